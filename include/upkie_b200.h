@@ -1,0 +1,295 @@
+/* SPDX-License-Identifier: Apache-2.0
+ *
+ * upkie_b200.h -- C ABI of the B200-native vectorised Upkie simulation and
+ * balance-control path (libupkie_b200.so).
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b). The reference has no
+ * FFI for this path (it is Python calling the pybullet C extension); the entry
+ * points below are what a binding of the reference's `Backend` ABC
+ * (upkie/envs/backends/backend.py:11-50) and of `MPCBalancer.step`
+ * (upkie/controllers/mpc_balancer.py:237-312) would call, vectorised over N
+ * independent robots. Plain pointers and sizes only: no torch types.
+ *
+ * Conventions
+ *  - every `const float*` / `float*` / `uint8_t*` argument of the non-`_host`
+ *    functions is a DEVICE pointer on the handle's device; the caller owns all
+ *    buffers, the library owns only the handle's internal state;
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default
+ *    stream); all launches are asynchronous on that stream;
+ *  - every function returns 0 on success and a negative UPKIE_B200_E* code on
+ *    failure, in which case `upkie_b200_last_error()` describes the failure
+ *    (thread-local string). Nothing throws across the boundary.
+ *  - joint order everywhere: left_hip, left_knee, left_wheel, right_hip,
+ *    right_knee, right_wheel (URDF order, upkie/cpp/interfaces/static_config.h:64-69).
+ */
+#ifndef UPKIE_B200_H_
+#define UPKIE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPKIE_B200_ABI_VERSION 1
+
+#define UPKIE_NJ 6 /* actuated joints */
+#define UPKIE_NB 7 /* moving bodies: base lump + 2 x (upper leg, lower leg, wheel) */
+
+/* ---- flat tensor layouts (all row-major, last index fastest) ------------- */
+
+/* action[N][6 joints][6 keys], keys in UpkieServos.ACTION_KEYS order
+ * (upkie/envs/upkie_servos.py:98-105). */
+#define UPKIE_ACT_POSITION 0
+#define UPKIE_ACT_VELOCITY 1
+#define UPKIE_ACT_FEEDFORWARD_TORQUE 2
+#define UPKIE_ACT_KP_SCALE 3
+#define UPKIE_ACT_KD_SCALE 4
+#define UPKIE_ACT_MAXIMUM_TORQUE 5
+#define UPKIE_ACT_KEYS 6
+#define UPKIE_ACT_DIM (UPKIE_NJ * UPKIE_ACT_KEYS) /* 36 */
+
+/* obs[N][6 joints][5 keys], keys in the servo observation space order
+ * (upkie/envs/upkie_servos.py:221-253). */
+#define UPKIE_OBS_POSITION 0
+#define UPKIE_OBS_VELOCITY 1
+#define UPKIE_OBS_TORQUE 2
+#define UPKIE_OBS_TEMPERATURE 3
+#define UPKIE_OBS_VOLTAGE 4
+#define UPKIE_OBS_KEYS 5
+#define UPKIE_OBS_DIM (UPKIE_NJ * UPKIE_OBS_KEYS) /* 30 */
+
+/* init_state[N][25]: what RobotState carries (upkie/utils/robot_state.py:37-92) */
+#define UPKIE_INIT_POS 0     /* position_base_in_world[3] */
+#define UPKIE_INIT_QUAT 3    /* orientation_base_in_world as (w, x, y, z) */
+#define UPKIE_INIT_LINVEL 7  /* linear_velocity_base_to_world_in_world[3] */
+#define UPKIE_INIT_ANGVEL 10 /* angular_velocity_base_in_base[3] */
+#define UPKIE_INIT_Q 13      /* joint_configuration[6] */
+#define UPKIE_INIT_QD 19     /* joint_velocity[6] (ignored by the PyBullet-mode reset, pybullet_backend.py:260-267) */
+#define UPKIE_INIT_DIM 25
+
+/* state[N][UPKIE_STATE_DIM]: full per-robot simulator + wrapper state
+ * (get_state / set_state; internally stored struct-of-arrays). */
+#define UPKIE_ST_POS 0          /* base position in world [3] */
+#define UPKIE_ST_QUAT 3         /* base orientation (w, x, y, z) */
+#define UPKIE_ST_LINVEL 7       /* base linear velocity, world frame [3] */
+#define UPKIE_ST_ANGVEL 10      /* base angular velocity, world frame [3] */
+#define UPKIE_ST_Q 13           /* joint angles [6] */
+#define UPKIE_ST_QD 19          /* joint velocities [6] */
+#define UPKIE_ST_PREV_IMU_VEL 25 /* __previous_imu_linear_velocity, pybullet_backend.py:157,405-408 */
+#define UPKIE_ST_TORQUE 28      /* __joint_torques: last commanded torques [6], pybullet_backend.py:163,294 */
+#define UPKIE_ST_LEG_TARGET 34  /* UpkieGyropod leg position targets: lh, lk, rh, rk (upkie_gyropod.py:246-267) */
+#define UPKIE_ST_YAW 38         /* UpkieGyropod commanded-yaw integral (upkie_gyropod.py:383-385) */
+#define UPKIE_ST_YAW_VEL 39
+#define UPKIE_ST_CONTACT 40     /* floor contact seen by the last collision pass (0/1) */
+#define UPKIE_ST_IMU_ACC 41     /* world-frame IMU linear acceleration of the last observation [3] (pybullet_backend.py:405-408) */
+#define UPKIE_STATE_DIM 44
+
+/* spine_obs[N][UPKIE_SPINE_DIM]: the observation dictionary of
+ * PyBulletBackend.get_spine_observation (pybullet_backend.py:313-331), flattened. */
+#define UPKIE_SP_BASE_ANGVEL 0   /* base_orientation.angular_velocity (base frame) [3] */
+#define UPKIE_SP_BASE_LINVEL 3   /* base_orientation.linear_velocity (world) [3] */
+#define UPKIE_SP_PITCH 6         /* base_orientation.pitch */
+#define UPKIE_SP_ROT 7           /* base_orientation.rotation_base_to_world, row-major [9] */
+#define UPKIE_SP_IMU_QUAT 16     /* imu.orientation (w, x, y, z) in the ARS frame */
+#define UPKIE_SP_IMU_ANGVEL 20   /* imu.angular_velocity (IMU frame) [3] */
+#define UPKIE_SP_IMU_LINACC 23   /* imu.linear_acceleration (IMU frame) [3] */
+#define UPKIE_SP_IMU_RAWACC 26   /* imu.raw_linear_acceleration (IMU frame) [3] */
+#define UPKIE_SP_CONTACT 29      /* floor_contact.contact (0/1) */
+#define UPKIE_SP_SERVO 30        /* servo[6][5] as in obs */
+#define UPKIE_SP_ODOM_POS 60     /* wheel_odometry.position */
+#define UPKIE_SP_ODOM_VEL 61     /* wheel_odometry.velocity */
+#define UPKIE_SPINE_DIM 62
+
+/* per-env error flags (sticky until reset) */
+#define UPKIE_ERR_NAN_VELOCITY 1u /* NaN target velocity (asserted in pybullet_backend.py:519) */
+#define UPKIE_ERR_NAN_STATE 2u    /* non-finite simulator state */
+#define UPKIE_ERR_CLAMPED 4u      /* some action entry was clamped (clamp_and_warn, upkie/utils/clamp.py:42-58) */
+
+/* status codes */
+#define UPKIE_B200_OK 0
+#define UPKIE_B200_EINVAL (-1)
+#define UPKIE_B200_ECUDA (-2)
+#define UPKIE_B200_ENOMEM (-3)
+#define UPKIE_B200_EMODEL (-4)
+
+/* ---- model and configuration (host-side, read once at create) ------------ */
+
+/* Rigid-body model after fixed-joint lumping. Body 0 is the floating base
+ * lump; body i (1..6) is attached to parent[i] by revolute joint i-1. Every body
+ * frame has its origin at its joint's origin and is aligned with the base frame
+ * at the zero configuration. This carries what upkie.model.Model provides
+ * (upkie/model/model.py:57-110: wheel radius, wheel base, left-wheeledness,
+ * base->IMU rotation, joint limits) plus the masses/inertias that live in the
+ * URDF of upkie_description. */
+typedef struct UpkieModel {
+  int32_t parent[UPKIE_NB];          /* parent[0] = -1 */
+  int32_t left_wheeled;              /* upkie/model/model.py:104 */
+  double joint_origin[UPKIE_NJ][3];  /* joint origin in the parent body frame */
+  double joint_axis[UPKIE_NJ][3];    /* unit rotation axis (same in parent and child frames) */
+  double mass[UPKIE_NB];
+  double com[UPKIE_NB][3];           /* centre of mass in the body frame */
+  double inertia[UPKIE_NB][6];       /* about the CoM, body axes: xx, yy, zz, xy, xz, yz */
+  double q_lower[UPKIE_NJ];          /* position limits (-inf/+inf for wheels) */
+  double q_upper[UPKIE_NJ];
+  double qd_max[UPKIE_NJ];           /* velocity limits */
+  double tau_max[UPKIE_NJ];          /* effort limits */
+  double wheel_radius;               /* tire collision cylinder radius, model.py:115-144 */
+  double wheel_base;                 /* distance between tire frames, model.py:82 */
+  double imu_position[3];            /* IMU frame origin in the base frame */
+  double rotation_base_to_imu[9];    /* row-major, model.py:106 */
+} UpkieModel;
+
+/* Simulation + environment configuration. Defaults are filled by
+ * upkie_b200_default_config(). */
+typedef struct UpkieSimConfig {
+  /* PyBulletBackend (upkie/envs/backends/pybullet_backend.py:55-112) */
+  double dt;                   /* agent period, 1/frequency (0.005) */
+  int32_t nb_substeps;         /* int(1000*dt) = 5 */
+  int32_t pgs_iterations;      /* Bullet numSolverIterations default (50) */
+  double gravity;              /* 9.81, pybullet_backend.py:110 */
+  double torque_control_kp;    /* 20.0 */
+  double torque_control_kd;    /* 1.0 */
+  double joint_friction[UPKIE_NJ]; /* JointProperties.friction, joint_properties.py:24-40 */
+  /* restated Bullet multibody behaviour (third-party) */
+  double linear_damping;       /* 0.04 */
+  double angular_damping;      /* 0.04 */
+  double max_coordinate_velocity; /* 100.0 */
+  double contact_stiffness;    /* tire <contact> stiffness */
+  double contact_damping;      /* tire <contact> damping */
+  double contact_breaking_threshold; /* 0.02 */
+  double friction;             /* combined lateral friction (plane 1.0 x tire) */
+  /* UpkieServos (upkie/envs/upkie_servos.py:114-170) */
+  double max_gain_scale;       /* 5.0 */
+  /* UpkieGyropod / UpkiePendulum (upkie/envs/upkie_gyropod.py:105-160) */
+  double fall_pitch;           /* 1.0 */
+  double leg_gain_scale;       /* 1.0 */
+  double max_ground_velocity;  /* 3.0 */
+  double max_yaw_velocity;     /* 1.0 */
+  /* extension: also terminate UpkieServos envs when
+   * |pitch| > fall_pitch or base height < min_base_height; 0 = reference behaviour */
+  int32_t servos_fall_termination;
+  int32_t reserved0;
+  double min_base_height;
+  /* RobotStateRandomization bounds used by the on-device sampler
+   * (upkie/utils/robot_state_randomization.py:135-189) */
+  double init_position[3];     /* nominal position_base_in_world (0, 0, 0.6) */
+  double init_quat[4];         /* nominal orientation (w, x, y, z) */
+  double rand_roll, rand_pitch, rand_x, rand_z;
+  double rand_omega_x, rand_omega_y;
+  double rand_linear_velocity[3];
+} UpkieSimConfig;
+
+/* MPCBalancer parameters (upkie/controllers/mpc_balancer.py:168-181) */
+typedef struct UpkieMpcConfig {
+  double fall_pitch;              /* 1.0 */
+  double leg_length;              /* 0.58 */
+  double max_ground_accel;        /* 10.0 */
+  double max_ground_velocity;     /* 3.0 */
+  int32_t nb_timesteps;           /* 50 */
+  int32_t max_iterations;         /* active-set iteration cap */
+  double sampling_period;         /* 0.02 */
+  double stage_input_cost_weight; /* 1e-3 */
+  double stage_state_cost_weight; /* 1e-3 */
+  double terminal_cost_weight;    /* 1.0 */
+  double gravity;                 /* 9.81 (qpmpc GRAVITY) */
+} UpkieMpcConfig;
+
+/* ---- library ------------------------------------------------------------ */
+
+int upkie_b200_abi_version(void);
+const char* upkie_b200_last_error(void);
+
+/* Fill `config` with the reference's defaults. */
+int upkie_b200_default_config(UpkieSimConfig* config);
+int upkie_b200_default_mpc_config(UpkieMpcConfig* config);
+
+/* ---- simulation handle --------------------------------------------------
+ * Replaces PyBulletBackend.__init__ (pybullet_backend.py:55-197). */
+int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config,
+                      int n_envs, int device, void** handle);
+void upkie_b200_destroy(void* handle);
+int upkie_b200_num_envs(void* handle);
+
+/* Vector-env auto-reset, fused into the step kernels (the reference has no
+ * auto-reset: "you are responsible for calling reset()", upkie_env.py:200-201;
+ * Gymnasium vector envs do). mode 0 = disabled (reference behaviour, default),
+ * 1 = next-step (an env that terminated at step t is re-initialised by the call
+ * at t+1, which returns its reset observation and ignores its action),
+ * 2 = same-step (re-initialised inside the terminating call, which returns the
+ * reset observation together with terminated = 1). Initial states are drawn on
+ * the device as in upkie_b200_reset(init_state = NULL). */
+int upkie_b200_set_autoreset(void* handle, int mode, uint64_t seed, uint64_t env_offset);
+
+/* Per-env domain randomisation; either pointer may be NULL (= nominal).
+ * friction[N]: combined floor friction (extension).
+ * inertia_eps[N][6]: epsilon of randomize_inertias (pybullet_backend.py:571-601),
+ * one per non-base body; mass and inertia scale by (1 + eps). */
+int upkie_b200_set_randomization(void* handle, const float* friction,
+                                 const float* inertia_eps, void* stream);
+
+/* Replaces UpkieEnv.reset -> PyBulletBackend.reset (upkie_env.py:162-194,
+ * pybullet_backend.py:220-267): set state, ONE physics substep, observe.
+ * mask[N] (u8) selects the envs to reset (NULL = all). init_state[N][25] gives
+ * the sampled RobotState per env; NULL = sample on the device from the
+ * configuration's RobotStateRandomization bounds with a counter-based generator
+ * keyed on (seed, global env index = env_offset + i). */
+int upkie_b200_reset(void* handle, const uint8_t* mask, const float* init_state,
+                     uint64_t seed, uint64_t env_offset, void* stream);
+
+/* Replaces UpkieServos.step = UpkieEnv.step -> get_spine_action ->
+ * PyBulletBackend.step -> get_env_observation (upkie_env.py:196-242,
+ * upkie_servos.py:288-344, pybullet_backend.py:269-311). */
+int upkie_b200_step_servos(void* handle, const float* action /* [N][6][6] */,
+                           float* obs /* [N][6][5] */, float* reward /* [N] */,
+                           uint8_t* terminated /* [N] */, uint8_t* truncated /* [N] */,
+                           void* stream);
+
+/* Replaces UpkieGyropod.step (act_dim = 2, obs[N][6]) and UpkiePendulum.step
+ * (act_dim = 1, obs[N][4]) (upkie_gyropod.py:354-392, upkie_pendulum.py:124-142). */
+int upkie_b200_step_gyropod(void* handle, const float* action /* [N][act_dim] */,
+                            int act_dim, float* obs, float* reward,
+                            uint8_t* terminated, uint8_t* truncated, void* stream);
+
+/* Same calls with HOST buffers: pinned staging, H2D, kernel, D2H, and a
+ * stream synchronisation inside the call (the `e2e` path of bench.py). */
+int upkie_b200_step_servos_host(void* handle, const float* action, float* obs,
+                                float* reward, uint8_t* terminated,
+                                uint8_t* truncated);
+int upkie_b200_step_gyropod_host(void* handle, const float* action, int act_dim,
+                                 float* obs, float* reward, uint8_t* terminated,
+                                 uint8_t* truncated);
+
+/* Replaces PyBulletBackend.get_spine_observation without side effects: returns
+ * the observation assembled by the last reset/step. out[N][UPKIE_SPINE_DIM]. */
+int upkie_b200_spine_obs(void* handle, float* out, void* stream);
+
+/* Gyropod observation after a reset (upkie_gyropod.py:216-244): obs[N][obs_dim],
+ * obs_dim 6 (gyropod) or 4 (pendulum); servo observation obs[N][6][5] for
+ * UpkieServos when obs_dim = 30. */
+int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream);
+
+int upkie_b200_get_state(void* handle, float* state /* [N][UPKIE_STATE_DIM] */, void* stream);
+int upkie_b200_set_state(void* handle, const float* state, void* stream);
+int upkie_b200_error_flags(void* handle, uint32_t* flags /* [N] */, void* stream);
+
+/* ---- MPC balancer handle -------------------------------------------------
+ * Replaces MPCBalancer.__init__/reset/step (mpc_balancer.py:168-312). */
+int upkie_b200_mpc_create(const UpkieMpcConfig* config, int n_robots, int device,
+                          void** mpc);
+void upkie_b200_mpc_destroy(void* mpc);
+int upkie_b200_mpc_reset(void* mpc, const uint8_t* mask, void* stream);
+/* x0[N][4] = (ground position, pitch, ground velocity, pitch velocity);
+ * v_cmd[N] is the commanded velocity, read and updated in place
+ * (MPCBalancer.commanded_velocity); first_input[N] (may be NULL) receives the
+ * first optimal ground acceleration; found[N] (may be NULL) the solver status. */
+int upkie_b200_mpc_step(void* mpc, const float* x0, const float* v_target,
+                        const uint8_t* floor_contact, float dt, float* v_cmd,
+                        float* first_input, uint8_t* found, void* stream);
+/* Full optimal input sequence of the last solve, plan[N][nb_timesteps]. */
+int upkie_b200_mpc_plan(void* mpc, float* plan, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPKIE_B200_H_ */

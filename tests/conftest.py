@@ -1,0 +1,68 @@
+# SPDX-License-Identifier: Apache-2.0
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def model():
+    from upkie_b200.model import Model
+
+    return Model.standard_upkie()
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import oracle
+
+    oracle.build()
+    return oracle
+
+
+def random_states(n, seed=0, z_range=(0.57, 0.62), vel=1.0, qd=5.0, tilt=0.3):
+    """Random simulator states [n, 44] (float64), quaternions normalised."""
+    from upkie_b200 import _abi
+
+    rng = np.random.default_rng(seed)
+    st = np.zeros((n, _abi.STATE_DIM))
+    st[:, 2] = rng.uniform(z_range[0], z_range[1], n)
+    quat = rng.normal(size=(n, 4)) * [1, 0.5 * tilt, tilt, 0.5 * tilt]
+    quat[:, 0] = 1.0
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    st[:, 3:7] = quat
+    st[:, 7:13] = rng.uniform(-vel, vel, (n, 6))
+    st[:, 13:19] = rng.uniform(-0.8, 0.8, (n, 6))
+    st[:, 19:25] = rng.uniform(-qd, qd, (n, 6))
+    return st
+
+
+def random_servo_actions(n, model, seed=1, torque_mode=False):
+    """Random UpkieServos actions [n, 6, 6] inside (and slightly outside) the box."""
+    rng = np.random.default_rng(seed)
+    a = np.zeros((n, 6, 6))
+    tau = np.asarray(model.tau_max)
+    if torque_mode:
+        a[:, :, 0] = np.nan
+        a[:, :, 2] = rng.uniform(-1, 1, (n, 6)) * tau
+        a[:, :, 5] = tau
+        return a
+    a[:, :, 0] = rng.uniform(-1.0, 1.0, (n, 6))
+    a[:, [2, 5], 0] = np.nan
+    nan_mask = rng.uniform(size=(n, 6)) < 0.2
+    a[:, :, 0] = np.where(nan_mask, np.nan, a[:, :, 0])
+    a[:, :, 1] = rng.uniform(-1, 1, (n, 6)) * np.asarray(model.qd_max) * 0.2
+    a[:, :, 2] = rng.uniform(-1.2, 1.2, (n, 6)) * tau * 0.3
+    a[:, :, 3] = rng.uniform(-0.5, 6.0, (n, 6))
+    a[:, :, 4] = rng.uniform(-0.5, 6.0, (n, 6))
+    a[:, :, 5] = rng.uniform(0.2, 1.1, (n, 6)) * tau
+    return a

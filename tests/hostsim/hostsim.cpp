@@ -1,0 +1,109 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// hostsim.cpp -- TEST INFRASTRUCTURE. Compiles the kernels' per-robot arithmetic
+// (upkie_b200/csrc/sim_core.cuh, __host__ __device__) with g++ so that the fp32
+// formulation can be checked against the oracle on machines without a GPU
+// (`pytest -m "not gpu"`). Never loaded by the product: upkie_b200/_lib.py
+// only opens libupkie_b200.so, which has no CPU path.
+#include <cstring>
+#include <string>
+
+#include "../../upkie_b200/csrc/params.h"
+
+using namespace upkie_b200;
+
+struct HostSim {
+  SimParams P;
+};
+
+static bool any_fn(bool p) { return p; }
+
+extern "C" {
+
+void* hostsim_create(const UpkieModel* m, const UpkieSimConfig* c) {
+  HostSim* h = new HostSim();
+  std::string err;
+  std::memset(&h->P, 0, sizeof(h->P));
+  if (make_sim_params(*m, *c, h->P, err) != 0) { delete h; return nullptr; }
+  return h;
+}
+void hostsim_destroy(void* h) { delete static_cast<HostSim*>(h); }
+
+void hostsim_reset(void* hv, int n, float* state, const float* init, const float* eps, const float* mu) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    reset_robot(h->P, S, init + size_t(i) * UPKIE_INIT_DIM, eps ? eps + size_t(i) * 6 : nullptr,
+                mu ? mu[i] : h->P.friction, any_fn);
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
+void hostsim_step_servos(void* hv, int n, float* state, const float* action, float* obs, const float* eps,
+                         const float* mu, uint32_t* err) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    float a[UPKIE_ACT_DIM];
+    std::memcpy(a, action + size_t(i) * UPKIE_ACT_DIM, sizeof(a));
+    const uint32_t e = step_servo_action(h->P, S, a, eps ? eps + size_t(i) * 6 : nullptr, mu ? mu[i] : h->P.friction, any_fn);
+    if (err) err[i] = e;
+    for (int j = 0; j < 6; ++j) {
+      float* o = obs + size_t(i) * UPKIE_OBS_DIM + j * 5;
+      o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = S.torque[j]; o[3] = 42.0f; o[4] = 18.0f;
+    }
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
+void hostsim_step_gyropod(void* hv, int n, float* state, const float* action, int act_dim, float* obs6,
+                          uint8_t* terminated) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    float a[UPKIE_ACT_DIM];
+    const float a0 = action[size_t(i) * act_dim];
+    const float a1 = act_dim > 1 ? action[size_t(i) * act_dim + 1] : 0.f;
+    gyropod_action(h->P, S, a0, a1, a);
+    step_servo_action(h->P, S, a, nullptr, h->P.friction, any_fn);
+    S.yaw += a1 * h->P.dt;
+    S.yaw_vel = a1;
+    gyropod_obs(h->P, S, obs6 + size_t(i) * 6);
+    terminated[i] = fabsf(obs6[size_t(i) * 6 + 1]) > h->P.fall_pitch ? 1 : 0;
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
+void hostsim_substep(void* hv, int n, float* state, const float* tau) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    physics_substep(h->P, S, tau + size_t(i) * 6, nullptr, h->P.friction, any_fn);
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
+void hostsim_spine_obs(void* hv, int n, const float* state, float* out) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    spine_observation(h->P, S, out + size_t(i) * UPKIE_SPINE_DIM);
+  }
+}
+
+void hostsim_sample_init(void* hv, int n, uint64_t seed, uint64_t env_offset, uint64_t episode, float* init) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) sample_init_state(h->P, seed, env_offset + i, episode, init + size_t(i) * UPKIE_INIT_DIM);
+}
+
+void hostsim_philox(uint64_t clo, uint64_t chi, uint64_t key, uint32_t* out) {
+  Philox4 r = philox4x32_10(clo, chi, key);
+  for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+# SPDX-License-Identifier: Apache-2.0
+"""ctypes mirror of ``include/upkie_b200.h`` (struct layouts and constants).
+
+Kept in one place so that the product loader (``upkie_b200._lib``) and the test
+infrastructure bind the very same layouts. The constants follow the reference:
+action keys ``upkie/envs/upkie_servos.py:98-105``, observation keys
+``upkie/envs/upkie_servos.py:221-253``, spine observation dictionary
+``upkie/envs/backends/pybullet_backend.py:313-331``.
+"""
+
+import ctypes as C
+
+ABI_VERSION = 1
+
+NJ = 6
+NB = 7
+
+ACT_KEYS = (
+    "position",
+    "velocity",
+    "feedforward_torque",
+    "kp_scale",
+    "kd_scale",
+    "maximum_torque",
+)
+OBS_KEYS = ("position", "velocity", "torque", "temperature", "voltage")
+JOINT_NAMES = (
+    "left_hip",
+    "left_knee",
+    "left_wheel",
+    "right_hip",
+    "right_knee",
+    "right_wheel",
+)
+UPPER_LEG_JOINTS = (0, 1, 3, 4)
+WHEEL_JOINTS = (2, 5)
+
+ACT_DIM = 36
+OBS_DIM = 30
+INIT_DIM = 25
+STATE_DIM = 44
+SPINE_DIM = 62
+
+# init_state offsets
+INIT_POS, INIT_QUAT, INIT_LINVEL, INIT_ANGVEL, INIT_Q, INIT_QD = 0, 3, 7, 10, 13, 19
+# state offsets
+ST_POS, ST_QUAT, ST_LINVEL, ST_ANGVEL, ST_Q, ST_QD = 0, 3, 7, 10, 13, 19
+ST_PREV_IMU_VEL, ST_TORQUE, ST_LEG_TARGET, ST_YAW, ST_YAW_VEL, ST_CONTACT = 25, 28, 34, 38, 39, 40
+ST_IMU_ACC = 41
+# spine observation offsets
+SP_BASE_ANGVEL, SP_BASE_LINVEL, SP_PITCH, SP_ROT = 0, 3, 6, 7
+SP_IMU_QUAT, SP_IMU_ANGVEL, SP_IMU_LINACC, SP_IMU_RAWACC = 16, 20, 23, 26
+SP_CONTACT, SP_SERVO, SP_ODOM_POS, SP_ODOM_VEL = 29, 30, 60, 61
+
+ERR_NAN_VELOCITY, ERR_NAN_STATE, ERR_CLAMPED = 1, 2, 4
+
+
+class UpkieModel(C.Structure):
+    _fields_ = [
+        ("parent", C.c_int32 * NB),
+        ("left_wheeled", C.c_int32),
+        ("joint_origin", (C.c_double * 3) * NJ),
+        ("joint_axis", (C.c_double * 3) * NJ),
+        ("mass", C.c_double * NB),
+        ("com", (C.c_double * 3) * NB),
+        ("inertia", (C.c_double * 6) * NB),
+        ("q_lower", C.c_double * NJ),
+        ("q_upper", C.c_double * NJ),
+        ("qd_max", C.c_double * NJ),
+        ("tau_max", C.c_double * NJ),
+        ("wheel_radius", C.c_double),
+        ("wheel_base", C.c_double),
+        ("imu_position", C.c_double * 3),
+        ("rotation_base_to_imu", C.c_double * 9),
+    ]
+
+
+class UpkieSimConfig(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double),
+        ("nb_substeps", C.c_int32),
+        ("pgs_iterations", C.c_int32),
+        ("gravity", C.c_double),
+        ("torque_control_kp", C.c_double),
+        ("torque_control_kd", C.c_double),
+        ("joint_friction", C.c_double * NJ),
+        ("linear_damping", C.c_double),
+        ("angular_damping", C.c_double),
+        ("max_coordinate_velocity", C.c_double),
+        ("contact_stiffness", C.c_double),
+        ("contact_damping", C.c_double),
+        ("contact_breaking_threshold", C.c_double),
+        ("friction", C.c_double),
+        ("max_gain_scale", C.c_double),
+        ("fall_pitch", C.c_double),
+        ("leg_gain_scale", C.c_double),
+        ("max_ground_velocity", C.c_double),
+        ("max_yaw_velocity", C.c_double),
+        ("servos_fall_termination", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("min_base_height", C.c_double),
+        ("init_position", C.c_double * 3),
+        ("init_quat", C.c_double * 4),
+        ("rand_roll", C.c_double),
+        ("rand_pitch", C.c_double),
+        ("rand_x", C.c_double),
+        ("rand_z", C.c_double),
+        ("rand_omega_x", C.c_double),
+        ("rand_omega_y", C.c_double),
+        ("rand_linear_velocity", C.c_double * 3),
+    ]
+
+
+class UpkieMpcConfig(C.Structure):
+    _fields_ = [
+        ("fall_pitch", C.c_double),
+        ("leg_length", C.c_double),
+        ("max_ground_accel", C.c_double),
+        ("max_ground_velocity", C.c_double),
+        ("nb_timesteps", C.c_int32),
+        ("max_iterations", C.c_int32),
+        ("sampling_period", C.c_double),
+        ("stage_input_cost_weight", C.c_double),
+        ("stage_state_cost_weight", C.c_double),
+        ("terminal_cost_weight", C.c_double),
+        ("gravity", C.c_double),
+    ]
+
+
+def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
+    """Reference defaults (``pybullet_backend.py:55-112``,
+    ``upkie_servos.py:114-124``, ``upkie_gyropod.py:105-112``,
+    ``upkie_env.py:87-90``) plus the restated Bullet constants.
+
+    Must stay equal to ``upkie_b200_default_config`` in the C library; a test
+    checks it.
+    """
+    c = UpkieSimConfig()
+    c.dt = 1.0 / frequency
+    c.nb_substeps = int(1000.0 * c.dt)
+    c.pgs_iterations = 50
+    c.gravity = 9.81
+    c.torque_control_kp = 20.0
+    c.torque_control_kd = 1.0
+    for j in range(NJ):
+        c.joint_friction[j] = 0.0
+    c.linear_damping = 0.04
+    c.angular_damping = 0.04
+    c.max_coordinate_velocity = 100.0
+    c.contact_stiffness = 30000.0
+    c.contact_damping = 1000.0
+    c.contact_breaking_threshold = 0.02
+    c.friction = 1.0
+    c.max_gain_scale = 5.0
+    c.fall_pitch = 1.0
+    c.leg_gain_scale = 1.0
+    c.max_ground_velocity = 3.0
+    c.max_yaw_velocity = 1.0
+    c.servos_fall_termination = 0
+    c.reserved0 = 0
+    c.min_base_height = 0.0
+    c.init_position[0], c.init_position[1], c.init_position[2] = 0.0, 0.0, 0.6
+    c.init_quat[0], c.init_quat[1], c.init_quat[2], c.init_quat[3] = 1.0, 0.0, 0.0, 0.0
+    c.rand_roll = c.rand_pitch = c.rand_x = c.rand_z = 0.0
+    c.rand_omega_x = c.rand_omega_y = 0.0
+    for k in range(3):
+        c.rand_linear_velocity[k] = 0.0
+    return c
+
+
+def default_mpc_config() -> UpkieMpcConfig:
+    """``MPCBalancer.__init__`` defaults (``mpc_balancer.py:168-181``)."""
+    c = UpkieMpcConfig()
+    c.fall_pitch = 1.0
+    c.leg_length = 0.58
+    c.max_ground_accel = 10.0
+    c.max_ground_velocity = 3.0
+    c.nb_timesteps = 50
+    c.max_iterations = 30
+    c.sampling_period = 0.02
+    c.stage_input_cost_weight = 1e-3
+    c.stage_state_cost_weight = 1e-3
+    c.terminal_cost_weight = 1.0
+    c.gravity = 9.81
+    return c
+
+
+def struct_to_dict(s: C.Structure) -> dict:
+    """Nested lists/floats view of a ctypes structure (for comparisons)."""
+    out = {}
+    for name, _ in s._fields_:
+        v = getattr(s, name)
+        if isinstance(v, C.Array):
+            out[name] = [list(x) if isinstance(x, C.Array) else x for x in v]
+        else:
+            out[name] = v
+    return out

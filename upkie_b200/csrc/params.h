@@ -1,0 +1,190 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// params.h -- host-side conversion of the public UpkieModel / UpkieSimConfig
+// (double precision, include/upkie_b200.h) into the fp32 kernel parameter block.
+#pragma once
+
+#include <cmath>
+#include <string>
+
+#include "sim_core.cuh"
+
+namespace upkie_b200 {
+
+inline void default_sim_config(UpkieSimConfig* c) {
+  // PyBulletBackend.__init__ defaults (upkie/envs/backends/pybullet_backend.py:55-112)
+  c->dt = 1.0 / 200.0;          // UpkieServos frequency=200 (upkie/envs/upkie_servos.py:118)
+  c->nb_substeps = 5;           // int(1000 * dt), pybullet_backend.py:85-87
+  c->pgs_iterations = 50;       // Bullet numSolverIterations default
+  c->gravity = 9.81;            // pybullet_backend.py:110
+  c->torque_control_kp = 20.0;  // pybullet_backend.py:65
+  c->torque_control_kd = 1.0;   // pybullet_backend.py:64
+  for (int j = 0; j < UPKIE_NJ; ++j) c->joint_friction[j] = 0.0;
+  c->linear_damping = 0.04;     // Bullet btMultiBody default
+  c->angular_damping = 0.04;
+  c->max_coordinate_velocity = 100.0;
+  c->contact_stiffness = 30000.0;
+  c->contact_damping = 1000.0;
+  c->contact_breaking_threshold = 0.02;
+  c->friction = 1.0;            // plane.urdf lateral_friction=1 (upkie/cpp/interfaces/bullet/plane/plane.urdf:5) x tire
+  c->max_gain_scale = 5.0;      // upkie_servos.py:120
+  c->fall_pitch = 1.0;          // upkie_gyropod.py:108
+  c->leg_gain_scale = 1.0;
+  c->max_ground_velocity = 3.0;
+  c->max_yaw_velocity = 1.0;
+  c->servos_fall_termination = 0;
+  c->reserved0 = 0;
+  c->min_base_height = 0.0;
+  c->init_position[0] = 0.0; c->init_position[1] = 0.0; c->init_position[2] = 0.6;  // upkie_env.py:87-90
+  c->init_quat[0] = 1.0; c->init_quat[1] = 0.0; c->init_quat[2] = 0.0; c->init_quat[3] = 0.0;
+  c->rand_roll = c->rand_pitch = c->rand_x = c->rand_z = 0.0;
+  c->rand_omega_x = c->rand_omega_y = 0.0;
+  for (int k = 0; k < 3; ++k) c->rand_linear_velocity[k] = 0.0;
+}
+
+inline void default_mpc_config(UpkieMpcConfig* c) {
+  // MPCBalancer.__init__ defaults (upkie/controllers/mpc_balancer.py:168-181)
+  c->fall_pitch = 1.0;
+  c->leg_length = 0.58;
+  c->max_ground_accel = 10.0;
+  c->max_ground_velocity = 3.0;
+  c->nb_timesteps = 50;
+  c->max_iterations = 30;
+  c->sampling_period = 0.02;
+  c->stage_input_cost_weight = 1e-3;
+  c->stage_state_cost_weight = 1e-3;
+  c->terminal_cost_weight = 1.0;
+  c->gravity = 9.81;
+}
+
+// Returns 0 on success; fills `err` otherwise.
+inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimParams& P, std::string& err) {
+  const int expect_parent[UPKIE_NB] = {-1, 0, 1, 2, 0, 4, 5};
+  for (int i = 0; i < UPKIE_NB; ++i)
+    if (m.parent[i] != expect_parent[i]) {
+      err = "model: kinematic tree must be base -> (hip, knee, wheel) x 2 in URDF joint order";
+      return UPKIE_B200_EMODEL;
+    }
+  for (int j = 0; j < UPKIE_NJ; ++j) {
+    const double ax = m.joint_axis[j][0], ay = m.joint_axis[j][1], az = m.joint_axis[j][2];
+    if (std::fabs(ax) > 1e-9 || std::fabs(az) > 1e-9 || std::fabs(std::fabs(ay) - 1.0) > 1e-9) {
+      err = "model: the sm_100a kernels specialise on joint axes along +-y of the base frame (Upkie, Cookie)";
+      return UPKIE_B200_EMODEL;
+    }
+    P.sgn[j] = ay > 0 ? 1.f : -1.f;
+    for (int k = 0; k < 3; ++k) P.jo[j][k] = float(m.joint_origin[j][k]);
+    P.q_lower[j] = float(m.q_lower[j]);
+    P.q_upper[j] = float(m.q_upper[j]);
+    P.qd_max[j] = float(m.qd_max[j]);
+    P.tau_max[j] = float(m.tau_max[j]);
+    P.joint_friction[j] = float(c.joint_friction[j]);
+  }
+  for (int i = 0; i < UPKIE_NB; ++i) {
+    if (!(m.mass[i] > 0.0)) { err = "model: body masses must be positive"; return UPKIE_B200_EMODEL; }
+    P.mass[i] = float(m.mass[i]);
+    for (int k = 0; k < 3; ++k) P.com[i][k] = float(m.com[i][k]);
+    for (int k = 0; k < 6; ++k) P.inertia[i][k] = float(m.inertia[i][k]);
+  }
+  auto wheel_sym = [&](int b) {
+    const double* I = m.inertia[b];
+    const double* cm = m.com[b];
+    return std::fabs(cm[0]) < 1e-12 && std::fabs(cm[2]) < 1e-12 && std::fabs(I[0] - I[2]) < 1e-12 &&
+           std::fabs(I[3]) < 1e-12 && std::fabs(I[4]) < 1e-12 && std::fabs(I[5]) < 1e-12;
+  };
+  P.wheel_symmetric = (wheel_sym(3) && wheel_sym(6)) ? 1 : 0;
+  if (!(m.wheel_radius > 0.0)) { err = "model: wheel_radius must be positive"; return UPKIE_B200_EMODEL; }
+  P.wheel_radius = float(m.wheel_radius);
+  P.half_wheel_base = float(0.5 * m.wheel_base);
+  P.left_sign = m.left_wheeled ? 1.f : -1.f;
+  for (int k = 0; k < 3; ++k) P.imu_pos[k] = float(m.imu_position[k]);
+  for (int k = 0; k < 9; ++k) P.Rbi[k] = float(m.rotation_base_to_imu[k]);
+
+  if (!(c.dt > 0.0) || c.nb_substeps < 1 || c.pgs_iterations < 0) {
+    err = "config: dt > 0, nb_substeps >= 1, pgs_iterations >= 0 required";
+    return UPKIE_B200_EINVAL;
+  }
+  const double h = c.dt / c.nb_substeps;
+  P.dt = float(c.dt);
+  P.inv_dt = float(1.0 / c.dt);
+  P.h = float(h);
+  P.inv_h = float(1.0 / h);
+  P.nb_substeps = c.nb_substeps;
+  P.pgs_iterations = c.pgs_iterations;
+  P.gravity = float(c.gravity);
+  P.kp = float(c.torque_control_kp);
+  P.kd = float(c.torque_control_kd);
+  P.lin_damp = float(c.linear_damping);
+  P.ang_damp = float(c.angular_damping);
+  P.vmax = float(c.max_coordinate_velocity);
+  // Bullet btMultiBodyConstraintSolver: cfm = 1/(h k + d), erp = h k/(h k + d), cfm *= 1/h
+  double denom = h * c.contact_stiffness + c.contact_damping;
+  if (denom < 1.1920929e-7) denom = 1.1920929e-7;
+  P.cfm = float((1.0 / denom) / h);
+  P.erp = float(h * c.contact_stiffness / denom);
+  P.breaking_threshold = float(c.contact_breaking_threshold);
+  P.friction = float(c.friction);
+  P.max_gain_scale = float(c.max_gain_scale);
+  P.fall_pitch = float(c.fall_pitch);
+  P.leg_gain_scale = float(c.leg_gain_scale);
+  P.max_ground_velocity = float(c.max_ground_velocity);
+  P.max_yaw_velocity = float(c.max_yaw_velocity);
+  P.servos_fall_termination = c.servos_fall_termination;
+  P.min_base_height = float(c.min_base_height);
+  for (int k = 0; k < 3; ++k) P.init_pos[k] = float(c.init_position[k]);
+  for (int k = 0; k < 4; ++k) P.init_quat[k] = float(c.init_quat[k]);
+  P.rand_roll = float(c.rand_roll);
+  P.rand_pitch = float(c.rand_pitch);
+  P.rand_x = float(c.rand_x);
+  P.rand_z = float(c.rand_z);
+  P.rand_omega_x = float(c.rand_omega_x);
+  P.rand_omega_y = float(c.rand_omega_y);
+  for (int k = 0; k < 3; ++k) P.rand_linvel[k] = float(c.rand_linear_velocity[k]);
+  return 0;
+}
+
+// AoS state row <-> registers
+UPKIE_HD void state_from_row(const float* r, RobotState& S) {
+  for (int i = 0; i < 3; ++i) {
+    S.pos[i] = r[UPKIE_ST_POS + i];
+    S.linvel[i] = r[UPKIE_ST_LINVEL + i];
+    S.angvel[i] = r[UPKIE_ST_ANGVEL + i];
+    S.prev_imu_vel[i] = r[UPKIE_ST_PREV_IMU_VEL + i];
+    S.imu_acc[i] = r[UPKIE_ST_IMU_ACC + i];
+  }
+  for (int i = 0; i < 4; ++i) {
+    S.quat[i] = r[UPKIE_ST_QUAT + i];
+    S.leg_target[i] = r[UPKIE_ST_LEG_TARGET + i];
+  }
+  for (int j = 0; j < 6; ++j) {
+    S.q[j] = r[UPKIE_ST_Q + j];
+    S.qd[j] = r[UPKIE_ST_QD + j];
+    S.torque[j] = r[UPKIE_ST_TORQUE + j];
+  }
+  S.yaw = r[UPKIE_ST_YAW];
+  S.yaw_vel = r[UPKIE_ST_YAW_VEL];
+  S.contact = r[UPKIE_ST_CONTACT];
+}
+
+UPKIE_HD void state_to_row(const RobotState& S, float* r) {
+  for (int i = 0; i < 3; ++i) {
+    r[UPKIE_ST_POS + i] = S.pos[i];
+    r[UPKIE_ST_LINVEL + i] = S.linvel[i];
+    r[UPKIE_ST_ANGVEL + i] = S.angvel[i];
+    r[UPKIE_ST_PREV_IMU_VEL + i] = S.prev_imu_vel[i];
+    r[UPKIE_ST_IMU_ACC + i] = S.imu_acc[i];
+  }
+  for (int i = 0; i < 4; ++i) {
+    r[UPKIE_ST_QUAT + i] = S.quat[i];
+    r[UPKIE_ST_LEG_TARGET + i] = S.leg_target[i];
+  }
+  for (int j = 0; j < 6; ++j) {
+    r[UPKIE_ST_Q + j] = S.q[j];
+    r[UPKIE_ST_QD + j] = S.qd[j];
+    r[UPKIE_ST_TORQUE + j] = S.torque[j];
+  }
+  r[UPKIE_ST_YAW] = S.yaw;
+  r[UPKIE_ST_YAW_VEL] = S.yaw_vel;
+  r[UPKIE_ST_CONTACT] = S.contact;
+}
+
+}  // namespace upkie_b200

@@ -1,0 +1,593 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// upkie_b200.cu -- sm_100a kernels and the C ABI of include/upkie_b200.h.
+//
+// Kernels (one thread = one robot, state struct-of-arrays, model in the kernel
+// parameter constant bank):
+//   k_step<MODE>   one 5 ms env tick: action front-end, 5 x (moteus torque law,
+//                  articulated-body dynamics, wheel-ground contact solve,
+//                  semi-implicit integration), observation, termination; optional
+//                  fused auto-reset.
+//   k_reset        masked reset: set state, one physics substep, observe.
+//   k_spine_obs / k_reset_obs / k_get_state / k_set_state   layout helpers.
+// MPC kernels live in mpc.cuh.
+//
+// There is deliberately NO CPU path in this library: every entry point needs a
+// CUDA device and fails with UPKIE_B200_ECUDA otherwise.
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "mpc.cuh"
+#include "params.h"
+
+using namespace upkie_b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return fail(UPKIE_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+enum { MODE_SERVOS = 0, MODE_GYROPOD = 1, MODE_PENDULUM = 2 };
+enum { AUTORESET_DISABLED = 0, AUTORESET_NEXT_STEP = 1, AUTORESET_SAME_STEP = 2 };
+
+struct Handle {
+  uint32_t magic;
+  int n, n_pad, device;
+  SimParams P;
+  float* state = nullptr;      // [STATE_DIM][n_pad]
+  float* eps = nullptr;        // [n][6] or null
+  float* mu = nullptr;         // [n] or null
+  uint32_t* err = nullptr;     // [n]
+  uint8_t* done_prev = nullptr;  // [n]
+  uint32_t* episode = nullptr;   // [n]
+  int autoreset = AUTORESET_DISABLED;
+  uint64_t seed = 0, env_offset = 0;
+  int block = 128;
+  // host-buffer staging (allocated on first use)
+  float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
+  uint8_t *h_term = nullptr, *h_trunc = nullptr;
+  float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
+  uint8_t *d_term = nullptr, *d_trunc = nullptr;
+  cudaStream_t host_stream = nullptr;
+};
+constexpr uint32_t kMagic = 0x55504B42u;  // "UPKB"
+
+Handle* as_handle(void* h) {
+  Handle* p = static_cast<Handle*>(h);
+  return (p && p->magic == kMagic) ? p : nullptr;
+}
+
+struct WarpAny {
+  __device__ __forceinline__ bool operator()(bool p) const { return __any_sync(__activemask(), p); }
+};
+
+__device__ __forceinline__ void load_state(const float* __restrict__ st, int n_pad, int i, RobotState& S) {
+  float r[UPKIE_STATE_DIM];
+#pragma unroll
+  for (int k = 0; k < UPKIE_STATE_DIM; ++k) r[k] = st[size_t(k) * n_pad + i];
+  state_from_row(r, S);
+}
+
+__device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, int i, const RobotState& S) {
+  float r[UPKIE_STATE_DIM];
+  state_to_row(S, r);
+#pragma unroll
+  for (int k = 0; k < UPKIE_STATE_DIM; ++k) st[size_t(k) * n_pad + i] = r[k];
+}
+
+// ---- the env-step kernel ------------------------------------------------------------
+template <int MODE, int AUTORESET>
+__global__ void __launch_bounds__(128)
+k_step(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict__ state,
+       const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+       uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
+       const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
+       uint32_t* __restrict__ episode, uint64_t seed, uint64_t env_offset) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = tid < n;
+  const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
+
+  RobotState S;
+  load_state(state, n_pad, i, S);
+  float epsv[6];
+  const float* eps = nullptr;
+  if (eps_all) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) epsv[k] = eps_all[size_t(i) * 6 + k];
+    eps = epsv;
+  }
+  const float mu = mu_all ? mu_all[i] : P.friction;
+
+  bool resetting = false;
+  if (AUTORESET == AUTORESET_NEXT_STEP) resetting = done_prev[i] != 0;
+
+  uint32_t e = 0;
+  float a[UPKIE_ACT_DIM];
+  float a0 = 0.f, a1 = 0.f;
+  if (MODE == MODE_SERVOS) {
+    const float4* ap = reinterpret_cast<const float4*>(action + size_t(i) * UPKIE_ACT_DIM);
+#pragma unroll
+    for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
+      const float4 v = __ldg(ap + k);
+      a[4 * k + 0] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+    }
+  } else if (MODE == MODE_GYROPOD) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(action) + i);
+    a0 = v.x; a1 = v.y;
+  } else {
+    a0 = __ldg(action + i);
+    a1 = 0.f;  // upkie_pendulum.py:137
+  }
+
+  if (resetting) {
+    // fused auto-reset: sample a new initial state, one zero-torque substep, observe
+    const uint32_t ep = episode[i] + 1u;
+    if (live) episode[i] = ep;
+    float init[UPKIE_INIT_DIM];
+    sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
+    reset_robot(P, S, init, eps, mu, WarpAny());
+  } else {
+    if (MODE != MODE_SERVOS) e |= gyropod_action(P, S, a0, a1, a);
+    e |= step_servo_action(P, S, a, eps, mu, WarpAny());
+    if (MODE != MODE_SERVOS) {
+      S.yaw += a1 * P.dt;  // integrates the unclamped action[1], upkie_gyropod.py:383-385
+      S.yaw_vel = a1;
+    }
+  }
+
+  // observation, reward, termination
+  bool term = false;
+  float o6[6];
+  if (MODE == MODE_SERVOS) {
+    if (P.servos_fall_termination) term = (fabsf(base_pitch(S)) > P.fall_pitch) || (S.pos[2] < P.min_base_height);
+  } else {
+    gyropod_obs(P, S, o6);
+    term = fabsf(o6[1]) > P.fall_pitch;  // strict, upkie_gyropod.py:345
+  }
+  if (resetting) term = false;
+
+  if (AUTORESET == AUTORESET_SAME_STEP) {
+    if (term) {
+      const uint32_t ep = episode[i] + 1u;
+      if (live) episode[i] = ep;
+      float init[UPKIE_INIT_DIM];
+      sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
+      reset_robot(P, S, init, eps, mu, WarpAny());
+      if (MODE != MODE_SERVOS) gyropod_obs(P, S, o6);
+    }
+  }
+
+  if (!live) return;
+  store_state(state, n_pad, i, S);
+  if (MODE == MODE_SERVOS) {
+    float2* op = reinterpret_cast<float2*>(obs + size_t(i) * UPKIE_OBS_DIM);
+    float o[UPKIE_OBS_DIM];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      o[j * 5 + 0] = S.q[j]; o[j * 5 + 1] = S.qd[j]; o[j * 5 + 2] = S.torque[j];
+      o[j * 5 + 3] = 42.0f;  // pybullet_backend.py:471
+      o[j * 5 + 4] = 18.0f;  // pybullet_backend.py:472
+    }
+#pragma unroll
+    for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) op[k] = make_float2(o[2 * k], o[2 * k + 1]);
+  } else if (MODE == MODE_GYROPOD) {
+    float2* op = reinterpret_cast<float2*>(obs + size_t(i) * 6);
+    op[0] = make_float2(o6[0], o6[1]);
+    op[1] = make_float2(o6[2], o6[3]);
+    op[2] = make_float2(o6[4], o6[5]);
+  } else {
+    // upkie_pendulum.py:17 _PENDULUM_OBS_INDICES = [1, 0, 4, 3]
+    reinterpret_cast<float4*>(obs)[i] = make_float4(o6[1], o6[0], o6[4], o6[3]);
+  }
+  reward[i] = 0.0f;  // upkie_env.py:230
+  terminated[i] = term ? 1 : 0;
+  truncated[i] = 0;
+  if (e) err[i] |= e;
+  if (AUTORESET == AUTORESET_NEXT_STEP) done_prev[i] = term ? 1 : 0;
+}
+
+// ---- masked reset ------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_reset(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict__ state,
+        const uint8_t* __restrict__ mask, const float* __restrict__ init_state, const float* __restrict__ eps_all,
+        const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
+        uint32_t* __restrict__ episode, uint64_t seed, uint64_t env_offset) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask && !mask[i]) return;
+  RobotState S;
+  load_state(state, n_pad, i, S);
+  float epsv[6];
+  const float* eps = nullptr;
+  if (eps_all) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) epsv[k] = eps_all[size_t(i) * 6 + k];
+    eps = epsv;
+  }
+  const float mu = mu_all ? mu_all[i] : P.friction;
+  float init[UPKIE_INIT_DIM];
+  if (init_state) {
+#pragma unroll
+    for (int k = 0; k < UPKIE_INIT_DIM; ++k) init[k] = init_state[size_t(i) * UPKIE_INIT_DIM + k];
+  } else {
+    const uint32_t ep = episode[i] + 1u;
+    episode[i] = ep;
+    sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
+  }
+  reset_robot(P, S, init, eps, mu, WarpAny());
+  store_state(state, n_pad, i, S);
+  err[i] = 0;
+  done_prev[i] = 0;
+}
+
+__global__ void k_spine_obs(const __grid_constant__ SimParams P, int n, int n_pad, const float* __restrict__ state,
+                            float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RobotState S;
+  load_state(state, n_pad, i, S);
+  float o[UPKIE_SPINE_DIM];
+  spine_observation(P, S, o);
+#pragma unroll
+  for (int k = 0; k < UPKIE_SPINE_DIM; ++k) out[size_t(i) * UPKIE_SPINE_DIM + k] = o[k];
+}
+
+__global__ void k_reset_obs(const __grid_constant__ SimParams P, int n, int n_pad, const float* __restrict__ state,
+                            int obs_dim, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  RobotState S;
+  load_state(state, n_pad, i, S);
+  if (obs_dim == UPKIE_OBS_DIM) {
+    for (int j = 0; j < 6; ++j) {
+      float* o = out + size_t(i) * UPKIE_OBS_DIM + j * 5;
+      o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = S.torque[j]; o[3] = 42.0f; o[4] = 18.0f;
+    }
+    return;
+  }
+  float o6[6];
+  gyropod_obs(P, S, o6);
+  if (obs_dim == 6) {
+    for (int k = 0; k < 6; ++k) out[size_t(i) * 6 + k] = o6[k];
+  } else {
+    out[size_t(i) * 4 + 0] = o6[1]; out[size_t(i) * 4 + 1] = o6[0];
+    out[size_t(i) * 4 + 2] = o6[4]; out[size_t(i) * 4 + 3] = o6[3];
+  }
+}
+
+// SoA <-> AoS state transposes
+__global__ void k_get_state(int n, int n_pad, const float* __restrict__ state, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < UPKIE_STATE_DIM; ++k) out[size_t(i) * UPKIE_STATE_DIM + k] = state[size_t(k) * n_pad + i];
+}
+__global__ void k_set_state(int n, int n_pad, float* __restrict__ state, const float* __restrict__ in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < UPKIE_STATE_DIM; ++k) state[size_t(k) * n_pad + i] = in[size_t(i) * UPKIE_STATE_DIM + k];
+}
+__global__ void k_init_state(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict__ state) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  for (int k = 0; k < UPKIE_STATE_DIM; ++k) state[size_t(k) * n_pad + i] = 0.f;
+  for (int k = 0; k < 3; ++k) state[size_t(UPKIE_ST_POS + k) * n_pad + i] = P.init_pos[k];
+  for (int k = 0; k < 4; ++k) state[size_t(UPKIE_ST_QUAT + k) * n_pad + i] = P.init_quat[k];
+  (void)n;
+}
+
+template <int MODE>
+int launch_step(Handle* h, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
+                cudaStream_t s) {
+  const int grid = (h->n + h->block - 1) / h->block;
+#define LAUNCH(AR)                                                                                           \
+  k_step<MODE, AR><<<grid, h->block, 0, s>>>(h->P, h->n, h->n_pad, h->state, action, obs, reward, term, trunc, \
+                                             h->eps, h->mu, h->err, h->done_prev, h->episode, h->seed, h->env_offset)
+  if (h->autoreset == AUTORESET_NEXT_STEP) LAUNCH(AUTORESET_NEXT_STEP);
+  else if (h->autoreset == AUTORESET_SAME_STEP) LAUNCH(AUTORESET_SAME_STEP);
+  else LAUNCH(AUTORESET_DISABLED);
+#undef LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int step_any(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
+             cudaStream_t s) {
+  if (!action || !obs || !reward || !term || !trunc) return fail(UPKIE_B200_EINVAL, "step: null buffer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (mode == MODE_SERVOS) return launch_step<MODE_SERVOS>(h, action, obs, reward, term, trunc, s);
+  if (mode == MODE_GYROPOD) return launch_step<MODE_GYROPOD>(h, action, obs, reward, term, trunc, s);
+  return launch_step<MODE_PENDULUM>(h, action, obs, reward, term, trunc, s);
+}
+
+int ensure_staging(Handle* h) {
+  if (h->h_act) return UPKIE_B200_OK;
+  const size_t n = size_t(h->n);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMallocHost(&h->h_act, n * UPKIE_ACT_DIM * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&h->h_obs, n * UPKIE_OBS_DIM * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&h->h_rew, n * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&h->h_term, n));
+  CUDA_TRY(cudaMallocHost(&h->h_trunc, n));
+  CUDA_TRY(cudaMalloc(&h->d_act, n * UPKIE_ACT_DIM * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&h->d_obs, n * UPKIE_OBS_DIM * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&h->d_rew, n * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&h->d_term, n));
+  CUDA_TRY(cudaMalloc(&h->d_trunc, n));
+  return UPKIE_B200_OK;
+}
+
+int step_host(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc) {
+  if (!action || !obs || !reward || !term || !trunc) return fail(UPKIE_B200_EINVAL, "step_host: null buffer");
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  const size_t n = size_t(h->n);
+  const size_t act_dim = mode == MODE_SERVOS ? UPKIE_ACT_DIM : (mode == MODE_GYROPOD ? 2 : 1);
+  const size_t obs_dim = mode == MODE_SERVOS ? UPKIE_OBS_DIM : (mode == MODE_GYROPOD ? 6 : 4);
+  cudaStream_t s = h->host_stream;
+  // caller memory may be pageable: stage through pinned buffers so the copies are truly asynchronous
+  std::memcpy(h->h_act, action, n * act_dim * sizeof(float));
+  CUDA_TRY(cudaMemcpyAsync(h->d_act, h->h_act, n * act_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  rc = step_any(h, mode, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, s);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->h_obs, h->d_obs, n * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_term, h->d_term, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_trunc, h->d_trunc, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  std::memcpy(obs, h->h_obs, n * obs_dim * sizeof(float));
+  std::memcpy(reward, h->h_rew, n * sizeof(float));
+  std::memcpy(term, h->h_term, n);
+  std::memcpy(trunc, h->h_trunc, n);
+  return UPKIE_B200_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ----------------------------------------------------------------------------
+
+extern "C" {
+
+int upkie_b200_abi_version(void) { return UPKIE_B200_ABI_VERSION; }
+const char* upkie_b200_last_error(void) { return g_last_error.c_str(); }
+
+int upkie_b200_default_config(UpkieSimConfig* config) {
+  if (!config) return fail(UPKIE_B200_EINVAL, "default_config: null");
+  default_sim_config(config);
+  return UPKIE_B200_OK;
+}
+int upkie_b200_default_mpc_config(UpkieMpcConfig* config) {
+  if (!config) return fail(UPKIE_B200_EINVAL, "default_mpc_config: null");
+  default_mpc_config(config);
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int n_envs, int device, void** handle) {
+  if (!model || !config || !handle) return fail(UPKIE_B200_EINVAL, "create: null argument");
+  if (n_envs < 1) return fail(UPKIE_B200_EINVAL, "create: n_envs must be >= 1");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(UPKIE_B200_ECUDA, "create: no CUDA device available (this library has no CPU path)");
+  if (device < 0 || device >= count) return fail(UPKIE_B200_EINVAL, "create: invalid device index");
+  Handle* h = new (std::nothrow) Handle();
+  if (!h) return fail(UPKIE_B200_ENOMEM, "create: out of host memory");
+  std::memset(&h->P, 0, sizeof(h->P));
+  std::string err;
+  int rc = make_sim_params(*model, *config, h->P, err);
+  if (rc) { delete h; return fail(rc, err); }
+  h->magic = kMagic;
+  h->n = n_envs;
+  h->n_pad = (n_envs + 31) / 32 * 32;
+  h->device = device;
+  if (const char* b = std::getenv("UPKIE_B200_BLOCK")) {
+    const int v = std::atoi(b);
+    if (v >= 32 && v <= 128 && v % 32 == 0) h->block = v;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&h->state, size_t(UPKIE_STATE_DIM) * h->n_pad * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->err, size_t(n_envs) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->done_prev, size_t(n_envs));
+  if (e == cudaSuccess) e = cudaMalloc(&h->episode, size_t(n_envs) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->err, 0, size_t(n_envs) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->done_prev, 0, size_t(n_envs));
+  if (e == cudaSuccess) e = cudaMemset(h->episode, 0, size_t(n_envs) * sizeof(uint32_t));
+  if (e == cudaSuccess) {
+    k_init_state<<<(h->n_pad + 127) / 128, 128>>>(h->P, h->n, h->n_pad, h->state);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    std::string msg = std::string("create: ") + cudaGetErrorString(e);
+    upkie_b200_destroy(h);
+    return fail(UPKIE_B200_ECUDA, msg);
+  }
+  *handle = h;
+  return UPKIE_B200_OK;
+}
+
+void upkie_b200_destroy(void* handle) {
+  Handle* h = as_handle(handle);
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->state); cudaFree(h->eps); cudaFree(h->mu); cudaFree(h->err); cudaFree(h->done_prev); cudaFree(h->episode);
+  cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_term); cudaFreeHost(h->h_trunc);
+  cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  h->magic = 0;
+  delete h;
+}
+
+int upkie_b200_num_envs(void* handle) {
+  Handle* h = as_handle(handle);
+  return h ? h->n : fail(UPKIE_B200_EINVAL, "invalid handle");
+}
+
+int upkie_b200_set_autoreset(void* handle, int mode, uint64_t seed, uint64_t env_offset) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  if (mode < 0 || mode > 2) return fail(UPKIE_B200_EINVAL, "set_autoreset: mode must be 0 (disabled), 1 (next step) or 2 (same step)");
+  h->autoreset = mode;
+  h->seed = seed;
+  h->env_offset = env_offset;
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_set_randomization(void* handle, const float* friction, const float* inertia_eps, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (friction) {
+    if (!h->mu) CUDA_TRY(cudaMalloc(&h->mu, size_t(h->n) * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(h->mu, friction, size_t(h->n) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else if (h->mu) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(h->mu);
+    h->mu = nullptr;
+  }
+  if (inertia_eps) {
+    if (!h->eps) CUDA_TRY(cudaMalloc(&h->eps, size_t(h->n) * 6 * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(h->eps, inertia_eps, size_t(h->n) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else if (h->eps) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(h->eps);
+    h->eps = nullptr;
+  }
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_reset(void* handle, const uint8_t* mask, const float* init_state, uint64_t seed, uint64_t env_offset,
+                     void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = (h->n + h->block - 1) / h->block;
+  k_reset<<<grid, h->block, 0, s>>>(h->P, h->n, h->n_pad, h->state, mask, init_state, h->eps, h->mu, h->err,
+                                    h->done_prev, h->episode, seed, env_offset);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_step_servos(void* handle, const float* action, float* obs, float* reward, uint8_t* terminated,
+                           uint8_t* truncated, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  return step_any(h, MODE_SERVOS, action, obs, reward, terminated, truncated, static_cast<cudaStream_t>(stream));
+}
+
+int upkie_b200_step_gyropod(void* handle, const float* action, int act_dim, float* obs, float* reward,
+                            uint8_t* terminated, uint8_t* truncated, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  if (act_dim != 1 && act_dim != 2) return fail(UPKIE_B200_EINVAL, "step_gyropod: act_dim must be 1 (pendulum) or 2 (gyropod)");
+  return step_any(h, act_dim == 2 ? MODE_GYROPOD : MODE_PENDULUM, action, obs, reward, terminated, truncated,
+                  static_cast<cudaStream_t>(stream));
+}
+
+int upkie_b200_step_servos_host(void* handle, const float* action, float* obs, float* reward, uint8_t* terminated,
+                                uint8_t* truncated) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  return step_host(h, MODE_SERVOS, action, obs, reward, terminated, truncated);
+}
+
+int upkie_b200_step_gyropod_host(void* handle, const float* action, int act_dim, float* obs, float* reward,
+                                 uint8_t* terminated, uint8_t* truncated) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  if (act_dim != 1 && act_dim != 2) return fail(UPKIE_B200_EINVAL, "step_gyropod_host: act_dim must be 1 or 2");
+  return step_host(h, act_dim == 2 ? MODE_GYROPOD : MODE_PENDULUM, action, obs, reward, terminated, truncated);
+}
+
+int upkie_b200_spine_obs(void* handle, float* out, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !out) return fail(UPKIE_B200_EINVAL, "spine_obs: invalid argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_spine_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, out);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !obs) return fail(UPKIE_B200_EINVAL, "reset_obs: invalid argument");
+  if (obs_dim != 4 && obs_dim != 6 && obs_dim != UPKIE_OBS_DIM) return fail(UPKIE_B200_EINVAL, "reset_obs: obs_dim must be 4, 6 or 30");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_reset_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, obs_dim, obs);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_get_state(void* handle, float* state, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !state) return fail(UPKIE_B200_EINVAL, "get_state: invalid argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_get_state<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, h->n_pad, h->state, state);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_set_state(void* handle, const float* state, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !state) return fail(UPKIE_B200_EINVAL, "set_state: invalid argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_set_state<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, h->n_pad, h->state, state);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_error_flags(void* handle, uint32_t* flags, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !flags) return fail(UPKIE_B200_EINVAL, "error_flags: invalid argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(flags, h->err, size_t(h->n) * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(stream)));
+  return UPKIE_B200_OK;
+}
+
+// ---- MPC ---------------------------------------------------------------------------------
+
+int upkie_b200_mpc_create(const UpkieMpcConfig* config, int n_robots, int device, void** mpc) {
+  if (!config || !mpc) return fail(UPKIE_B200_EINVAL, "mpc_create: null argument");
+  std::string err;
+  int rc = mpc_create_impl(*config, n_robots, device, mpc, err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+void upkie_b200_mpc_destroy(void* mpc) { mpc_destroy_impl(mpc); }
+int upkie_b200_mpc_reset(void* mpc, const uint8_t* mask, void* stream) {
+  std::string err;
+  int rc = mpc_reset_impl(mpc, mask, static_cast<cudaStream_t>(stream), err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+int upkie_b200_mpc_step(void* mpc, const float* x0, const float* v_target, const uint8_t* floor_contact, float dt,
+                        float* v_cmd, float* first_input, uint8_t* found, void* stream) {
+  std::string err;
+  int rc = mpc_step_impl(mpc, x0, v_target, floor_contact, dt, v_cmd, first_input, found,
+                         static_cast<cudaStream_t>(stream), err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+int upkie_b200_mpc_plan(void* mpc, float* plan, void* stream) {
+  std::string err;
+  int rc = mpc_plan_impl(mpc, plan, static_cast<cudaStream_t>(stream), err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+
+}  // extern "C"

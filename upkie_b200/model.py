@@ -1,0 +1,275 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Rigid-body model constants for the vectorised Upkie simulation.
+
+Mirrors what ``upkie.model.Model`` provides (``upkie/model/model.py:57-110``:
+``wheel_radius``, ``wheel_base``, ``left_wheeled``, ``rotation_base_to_imu``,
+``joints`` in URDF order with limits) and adds the masses / inertias the
+simulator needs.
+
+**Stand-in inertias.** The reference reads every mass, inertia and joint
+origin from the URDF of the un-vendored ``upkie_description`` 2.2.0 package,
+which is absent from this image. ``standard_upkie()`` therefore authors a
+7-body model (fixed joints lumped) that satisfies every aggregate the
+reference's own tests pin:
+
+- total mass 5.3382 kg and centre of mass (-0.0059, 0, -0.2455) in the base
+  frame at the zero configuration
+  (``upkie/cpp/interfaces/bullet/tests/utils_test.cpp:89-98``,
+  ``upkie/cpp/interfaces/tests/BulletInterfaceTest.cpp:328-330``);
+- wheel radius 0.05 m, wheel base 0.3048 m, left-wheeled,
+  ``rotation_base_to_imu = diag(-1, 1, -1)`` (``tests/model/test_model.py:64-92``);
+- joint limits of ``docs/kinematics.md:45-55``.
+
+Per-link values are *parity unpinned* (SURVEY.md section 8c).
+``Model.from_urdf`` overwrites them from a real ``upkie.urdf`` when one is
+available.
+"""
+
+import math
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi
+
+JOINT_NAMES = _abi.JOINT_NAMES
+
+
+@dataclass
+class JointLimit:
+    """Same fields as ``upkie.model.joint_limit.JointLimit``."""
+
+    lower: float
+    upper: float
+    velocity: float
+    effort: float
+
+
+@dataclass
+class Joint:
+    """Same fields as ``upkie.model.joint.Joint`` that the path uses."""
+
+    name: str
+    idx_q: int
+    limit: JointLimit
+
+
+@dataclass
+class Model:
+    """Upkie model: kinematic constants of ``upkie.model.Model`` + dynamics.
+
+    Body ``0`` is the floating-base lump, body ``i`` (1..6) hangs from
+    ``parent[i]`` through revolute joint ``i - 1``; body frames sit at their
+    joint origin and are aligned with the base frame at the zero configuration.
+    """
+
+    parent: List[int]
+    joint_origin: np.ndarray  # [6, 3] in the parent body frame
+    joint_axis: np.ndarray  # [6, 3]
+    mass: np.ndarray  # [7]
+    com: np.ndarray  # [7, 3]
+    inertia: np.ndarray  # [7, 6] xx, yy, zz, xy, xz, yz about the CoM
+    q_lower: np.ndarray
+    q_upper: np.ndarray
+    qd_max: np.ndarray
+    tau_max: np.ndarray
+    wheel_radius: float
+    wheel_base: float
+    left_wheeled: bool
+    imu_position: np.ndarray
+    rotation_base_to_imu: np.ndarray
+    rotation_ars_to_world: np.ndarray = field(
+        default_factory=lambda: np.diag([1.0, -1.0, -1.0])
+    )
+    source: str = "stand-in"
+
+    # ---- upkie.model.Model API ------------------------------------------
+    @property
+    def joints(self) -> List[Joint]:
+        """Actuated joints in URDF order (``model.py:111-114``)."""
+        return [
+            Joint(
+                name,
+                j,
+                JointLimit(
+                    float(self.q_lower[j]),
+                    float(self.q_upper[j]),
+                    float(self.qd_max[j]),
+                    float(self.tau_max[j]),
+                ),
+            )
+            for j, name in enumerate(JOINT_NAMES)
+        ]
+
+    @property
+    def joint_names(self) -> set:
+        return set(JOINT_NAMES)
+
+    @property
+    def upper_leg_joints(self):
+        return tuple(j for j in self.joints if "hip" in j.name or "knee" in j.name)
+
+    @property
+    def wheel_joints(self):
+        return tuple(j for j in self.joints if "wheel" in j.name)
+
+    # ---- aggregates --------------------------------------------------------
+    def total_mass(self) -> float:
+        return float(np.sum(self.mass))
+
+    def body_origins_zero_config(self) -> np.ndarray:
+        """Body frame origins in the base frame at the zero configuration."""
+        o = np.zeros((7, 3))
+        for i in range(1, 7):
+            o[i] = o[self.parent[i]] + self.joint_origin[i - 1]
+        return o
+
+    def com_zero_config(self) -> np.ndarray:
+        o = self.body_origins_zero_config()
+        return ((o + self.com) * self.mass[:, None]).sum(axis=0) / self.total_mass()
+
+    # ---- C ABI ---------------------------------------------------------------
+    def to_struct(self) -> _abi.UpkieModel:
+        s = _abi.UpkieModel()
+        for i in range(7):
+            s.parent[i] = int(self.parent[i])
+            s.mass[i] = float(self.mass[i])
+            for k in range(3):
+                s.com[i][k] = float(self.com[i, k])
+            for k in range(6):
+                s.inertia[i][k] = float(self.inertia[i, k])
+        s.left_wheeled = 1 if self.left_wheeled else 0
+        for j in range(6):
+            for k in range(3):
+                s.joint_origin[j][k] = float(self.joint_origin[j, k])
+                s.joint_axis[j][k] = float(self.joint_axis[j, k])
+            s.q_lower[j] = float(self.q_lower[j])
+            s.q_upper[j] = float(self.q_upper[j])
+            s.qd_max[j] = float(self.qd_max[j])
+            s.tau_max[j] = float(self.tau_max[j])
+        s.wheel_radius = float(self.wheel_radius)
+        s.wheel_base = float(self.wheel_base)
+        for k in range(3):
+            s.imu_position[k] = float(self.imu_position[k])
+        R = np.asarray(self.rotation_base_to_imu, dtype=float).reshape(9)
+        for k in range(9):
+            s.rotation_base_to_imu[k] = float(R[k])
+        return s
+
+    # ---- constructors ---------------------------------------------------------
+    @staticmethod
+    def standard_upkie() -> "Model":
+        """Stand-in for ``upkie_description`` (see module docstring)."""
+        half_base = 0.3048 / 2.0
+        y_hip, y_step = 0.1, (half_base - 0.1) / 2.0
+        z_hip, l_upper, l_lower = -0.19, 0.17, 0.17
+        joint_origin = np.array(
+            [
+                [0.0, +y_hip, z_hip],
+                [0.0, +y_step, -l_upper],
+                [0.0, +y_step, -l_lower],
+                [0.0, -y_hip, z_hip],
+                [0.0, -y_step, -l_upper],
+                [0.0, -y_step, -l_lower],
+            ]
+        )
+        # moteus convention: the left-wheel hub z-axis points along -y of the
+        # base and the joint axis is -z of the joint frame (docs/kinematics.md
+        # "Link and joint names"), i.e. +y in base coordinates: positive
+        # left-wheel velocity rolls forward (left_wheeled, model.py:104).
+        joint_axis = np.array(
+            [[0, 1, 0], [0, 1, 0], [0, 1, 0], [0, -1, 0], [0, -1, 0], [0, -1, 0]],
+            dtype=float,
+        )
+        m_upper, m_lower, m_wheel = 0.70, 0.35, 0.30
+        total_mass = 5.3382
+        target_com = np.array([-0.0059, 0.0, -0.2455])
+        mass = np.array(
+            [0.0, m_upper, m_lower, m_wheel, m_upper, m_lower, m_wheel]
+        )
+        mass[0] = total_mass - mass.sum()
+        com = np.array(
+            [
+                [0.0, 0.0, 0.0],
+                [0.0, +0.02, -0.10],
+                [0.0, +0.015, -0.10],
+                [0.0, 0.0, 0.0],
+                [0.0, -0.02, -0.10],
+                [0.0, -0.015, -0.10],
+                [0.0, 0.0, 0.0],
+            ]
+        )
+        parent = [-1, 0, 1, 2, 0, 4, 5]
+        # solve the base-lump CoM so that the aggregate CoM is the pinned one
+        o = np.zeros((7, 3))
+        for i in range(1, 7):
+            o[i] = o[parent[i]] + joint_origin[i - 1]
+        legs = ((o[1:] + com[1:]) * mass[1:, None]).sum(axis=0)
+        com[0] = (total_mass * target_com - legs) / mass[0]
+        bx, by, bz = 0.14, 0.22, 0.22  # torso box
+        inertia = np.array(
+            [
+                [
+                    mass[0] / 12.0 * (by**2 + bz**2),
+                    mass[0] / 12.0 * (bx**2 + bz**2),
+                    mass[0] / 12.0 * (bx**2 + by**2),
+                    0.0,
+                    0.0,
+                    0.0,
+                ],
+                [3.0e-3, 3.0e-3, 8.0e-4, 0, 0, 0],
+                [1.4e-3, 1.4e-3, 3.0e-4, 0, 0, 0],
+                [3.2e-4, 6.0e-4, 3.2e-4, 0, 0, 0],
+                [3.0e-3, 3.0e-3, 8.0e-4, 0, 0, 0],
+                [1.4e-3, 1.4e-3, 3.0e-4, 0, 0, 0],
+                [3.2e-4, 6.0e-4, 3.2e-4, 0, 0, 0],
+            ]
+        )
+        inf = math.inf
+        return Model(
+            parent=parent,
+            joint_origin=joint_origin,
+            joint_axis=joint_axis,
+            mass=mass,
+            com=com,
+            inertia=inertia,
+            q_lower=np.array([-1.26, -2.51, -inf, -1.26, -2.51, -inf]),
+            q_upper=np.array([+1.26, +2.51, +inf, +1.26, +2.51, +inf]),
+            qd_max=np.array([28.8, 28.8, 111.0, 28.8, 28.8, 111.0]),
+            tau_max=np.array([16.0, 16.0, 1.7, 16.0, 16.0, 1.7]),
+            wheel_radius=0.05,
+            wheel_base=2.0 * half_base,
+            left_wheeled=True,
+            imu_position=np.array([-0.01, 0.0, -0.06]),
+            rotation_base_to_imu=np.diag([-1.0, 1.0, -1.0]),
+        )
+
+    @staticmethod
+    def from_urdf(urdf_path: str) -> "Model":
+        """Build the 7-body model from a real ``upkie.urdf``.
+
+        Follows the parsing conventions of ``upkie/model/kinematic_tree.py:52-143``
+        (URDF roll-pitch-yaw -> rotation, joints in file order) and adds an
+        ``<inertial>`` parser; links attached by fixed joints are lumped into
+        their moving ancestor, frames are re-expressed aligned with the base at
+        the zero configuration.
+        """
+        from .urdf import load_urdf_model  # local import: optional path
+
+        return load_urdf_model(urdf_path)
+
+
+def default_model(urdf_path: Optional[str] = None) -> Model:
+    """``Model(urdf_path=None)`` of the reference defaults to
+    ``upkie_description.URDF_PATH`` (``model.py:63-65``); here it is the real
+    URDF when ``upkie_description`` is importable, else the stand-in."""
+    if urdf_path is not None:
+        return Model.from_urdf(urdf_path)
+    try:
+        import upkie_description  # type: ignore
+
+        return Model.from_urdf(upkie_description.URDF_PATH)
+    except ImportError:
+        return Model.standard_upkie()

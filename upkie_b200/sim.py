@@ -1,0 +1,225 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Tensor-level front end of the vectorised simulation (one handle = one GPU).
+
+``UpkieSim`` owns a ``libupkie_b200`` handle and exposes the flat fast path of
+SURVEY.md section 8(b): ``step_servos(action[N, 6, 6]) -> obs[N, 6, 5], reward[N],
+terminated[N], truncated[N]`` over PyTorch CUDA tensors (PyTorch is used for
+device memory and streams only; all arithmetic happens in the sm_100a kernels).
+"""
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._lib import check, lib
+from .exceptions import UpkieRuntimeError
+from .model import Model, default_model
+
+AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP = 0, 1, 2
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class UpkieSim:
+    """N independent robots on one CUDA device.
+
+    Replaces ``PyBulletBackend`` (``upkie/envs/backends/pybullet_backend.py:31``)
+    for N robots at once; same constructor knobs (``dt``, ``nb_substeps``,
+    ``torque_control_kp/kd``, ``joint_properties`` friction, ``inertia_variation``)
+    through ``config`` / ``set_randomization``.
+    """
+
+    def __init__(
+        self,
+        n_envs: int,
+        model: Optional[Model] = None,
+        config: Optional[_abi.UpkieSimConfig] = None,
+        device: int = 0,
+    ):
+        if not torch.cuda.is_available():
+            raise UpkieRuntimeError(
+                "upkie_b200 needs a CUDA device (there is no CPU fallback)"
+            )
+        self.model = model if model is not None else default_model()
+        self.config = config if config is not None else _abi.default_sim_config()
+        self.n = int(n_envs)
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self._model_struct = self.model.to_struct()
+        self._h = C.c_void_p()
+        check(
+            lib().upkie_b200_create(
+                C.byref(self._model_struct), C.byref(self.config), self.n, self.device_index, C.byref(self._h)
+            )
+        )
+        f32, u8 = torch.float32, torch.uint8
+        dev = self.device
+        self.reward = torch.empty(self.n, dtype=f32, device=dev)
+        self.terminated = torch.empty(self.n, dtype=u8, device=dev)
+        self.truncated = torch.empty(self.n, dtype=u8, device=dev)
+        self.obs_servos = torch.empty((self.n, 6, 5), dtype=f32, device=dev)
+        self.obs_gyropod = torch.empty((self.n, 6), dtype=f32, device=dev)
+        self.obs_pendulum = torch.empty((self.n, 4), dtype=f32, device=dev)
+        self.launches = 0  # kernels launched through this handle (bench.py reports it)
+
+    # ------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().upkie_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_tensor(self, t: torch.Tensor, shape, dtype=torch.float32, name="tensor"):
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise UpkieRuntimeError(
+                f"{name}: expected contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}, "
+                f"got {t.dtype} {tuple(t.shape)} on {t.device}"
+            )
+
+    # ------------------------------------------------------------------
+    def set_autoreset(self, mode: int, seed: int = 0, env_offset: int = 0) -> None:
+        check(lib().upkie_b200_set_autoreset(self._h, int(mode), int(seed), int(env_offset)))
+
+    def set_randomization(self, friction: Optional[torch.Tensor] = None, inertia_eps: Optional[torch.Tensor] = None):
+        """Per-env floor friction [N] and ``randomize_inertias`` epsilons [N, 6]
+        (``pybullet_backend.py:571-601``)."""
+        if friction is not None:
+            self._check_tensor(friction, (self.n,), name="friction")
+        if inertia_eps is not None:
+            self._check_tensor(inertia_eps, (self.n, 6), name="inertia_eps")
+        check(lib().upkie_b200_set_randomization(self._h, _ptr(friction), _ptr(inertia_eps), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def reset(
+        self,
+        mask: Optional[torch.Tensor] = None,
+        init_state: Optional[torch.Tensor] = None,
+        seed: int = 0,
+        env_offset: int = 0,
+    ) -> None:
+        """``PyBulletBackend.reset`` for the envs selected by ``mask`` (all if
+        None). ``init_state[N, 25]`` = sampled ``RobotState`` rows; None = sample
+        on the device."""
+        if mask is not None:
+            self._check_tensor(mask, (self.n,), torch.uint8, "mask")
+        if init_state is not None:
+            self._check_tensor(init_state, (self.n, _abi.INIT_DIM), name="init_state")
+        check(lib().upkie_b200_reset(self._h, _ptr(mask), _ptr(init_state), int(seed), int(env_offset), self._stream()))
+        self.launches += 1
+
+    def step_servos(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None):
+        self._check_tensor(action, (self.n, 6, 6), name="action")
+        obs = self.obs_servos if obs is None else obs
+        check(
+            lib().upkie_b200_step_servos(
+                self._h, _ptr(action), _ptr(obs), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
+                self._stream(),
+            )
+        )
+        self.launches += 1
+        return obs, self.reward, self.terminated, self.truncated
+
+    def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None):
+        self._check_tensor(action, (self.n, 2), name="action")
+        obs = self.obs_gyropod if obs is None else obs
+        check(
+            lib().upkie_b200_step_gyropod(
+                self._h, _ptr(action), 2, _ptr(obs), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
+                self._stream(),
+            )
+        )
+        self.launches += 1
+        return obs, self.reward, self.terminated, self.truncated
+
+    def step_pendulum(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None):
+        self._check_tensor(action, (self.n, 1), name="action")
+        obs = self.obs_pendulum if obs is None else obs
+        check(
+            lib().upkie_b200_step_gyropod(
+                self._h, _ptr(action), 1, _ptr(obs), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
+                self._stream(),
+            )
+        )
+        self.launches += 1
+        return obs, self.reward, self.terminated, self.truncated
+
+    # host-buffer path (H2D + kernel + D2H inside the call)
+    def step_servos_host(self, action: np.ndarray):
+        a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.n, 6, 6)
+        obs = np.empty((self.n, 6, 5), dtype=np.float32)
+        rew = np.empty(self.n, dtype=np.float32)
+        term = np.empty(self.n, dtype=np.uint8)
+        trunc = np.empty(self.n, dtype=np.uint8)
+        check(
+            lib().upkie_b200_step_servos_host(
+                self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data
+            )
+        )
+        self.launches += 1
+        return obs, rew, term, trunc
+
+    def step_gyropod_host(self, action: np.ndarray):
+        a = np.ascontiguousarray(action, dtype=np.float32)
+        act_dim = a.shape[1]
+        obs = np.empty((self.n, 6 if act_dim == 2 else 4), dtype=np.float32)
+        rew = np.empty(self.n, dtype=np.float32)
+        term = np.empty(self.n, dtype=np.uint8)
+        trunc = np.empty(self.n, dtype=np.uint8)
+        check(
+            lib().upkie_b200_step_gyropod_host(
+                self._h, a.ctypes.data, act_dim, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data
+            )
+        )
+        self.launches += 1
+        return obs, rew, term, trunc
+
+    # ------------------------------------------------------------------
+    def spine_obs(self) -> torch.Tensor:
+        """``get_spine_observation`` for all envs, flattened ``[N, 62]``."""
+        out = torch.empty((self.n, _abi.SPINE_DIM), dtype=torch.float32, device=self.device)
+        check(lib().upkie_b200_spine_obs(self._h, _ptr(out), self._stream()))
+        return out
+
+    def reset_obs(self, obs_dim: int) -> torch.Tensor:
+        shape = (self.n, 6, 5) if obs_dim == 30 else (self.n, obs_dim)
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        check(lib().upkie_b200_reset_obs(self._h, int(obs_dim), _ptr(out), self._stream()))
+        return out
+
+    def get_state(self) -> torch.Tensor:
+        out = torch.empty((self.n, _abi.STATE_DIM), dtype=torch.float32, device=self.device)
+        check(lib().upkie_b200_get_state(self._h, _ptr(out), self._stream()))
+        return out
+
+    def set_state(self, state: torch.Tensor) -> None:
+        self._check_tensor(state, (self.n, _abi.STATE_DIM), name="state")
+        check(lib().upkie_b200_set_state(self._h, _ptr(state), self._stream()))
+
+    def error_flags(self) -> torch.Tensor:
+        out = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        check(lib().upkie_b200_error_flags(self._h, _ptr(out), self._stream()))
+        return out
+
+
+def neutral_action(model: Model, n: int, device=None) -> torch.Tensor:
+    """``UpkieServos.get_neutral_action`` (``upkie_servos.py:255-262``) as a
+    ``[N, 6, 6]`` tensor."""
+    a = torch.zeros((n, 6, 6), dtype=torch.float32, device=device)
+    a[:, :, 0] = float("nan")
+    a[:, :, 3] = 1.0
+    a[:, :, 4] = 1.0
+    a[:, :, 5] = torch.tensor(model.tau_max, dtype=torch.float32, device=device)
+    return a
