@@ -107,3 +107,65 @@ void hostsim_philox(uint64_t clo, uint64_t chi, uint64_t key, uint32_t* out) {
 }
 
 }  // extern "C"
+
+// ---- MPC core on the host (float = what the kernel runs, double = formulation check) ----
+#include <vector>
+
+#include "../../upkie_b200/csrc/mpc_core.cuh"
+
+template <typename T>
+static void fill_mpc_params(const UpkieMpcConfig& c, MpcParams<T>& M) {
+  const double Ts = c.sampling_period, g = c.gravity;
+  const double om = std::sqrt(g / c.leg_length);
+  const double ch = std::cosh(Ts * om), sh = std::sinh(Ts * om);
+  M.Ts = T(Ts); M.ch = T(ch); M.sho = T(sh / om); M.osh = T(om * sh);
+  M.b0 = T(Ts * Ts / 2.0); M.b1 = T(-ch / g + 1.0 / g); M.b2 = T(Ts); M.b3 = T(-om * sh / g);
+  M.w_u = T(c.stage_input_cost_weight); M.w_x = T(c.stage_state_cost_weight); M.w_T = T(c.terminal_cost_weight);
+  M.a_max = T(c.max_ground_accel); M.v_max = T(c.max_ground_velocity); M.fall_pitch = T(c.fall_pitch);
+  M.N = c.nb_timesteps; M.max_iterations = c.max_iterations > 0 ? c.max_iterations : 30;
+}
+
+template <typename T>
+static void hostsim_mpc_impl(const UpkieMpcConfig* c, int n, const double* x0, const double* v_target,
+                             const uint8_t* contact, double dt, double* v_cmd, double* plan, uint8_t* found,
+                             int* iterations) {
+  MpcParams<T> M;
+  fill_mpc_params(*c, M);
+  std::vector<T> scratch(size_t(5) * M.N);
+  for (int i = 0; i < n; ++i) {
+    MpcScratch<T> sc{scratch.data(), 1};
+    const T x[4] = {T(x0[4 * i]), T(x0[4 * i + 1]), T(x0[4 * i + 2]), T(x0[4 * i + 3])};
+    uint64_t up = 0, lo = 0;
+    T u0 = 0;
+    // count iterations by running the solver with increasing caps is wasteful; replicate the loop here
+    bool ok = false;
+    int it = 0;
+    for (; it < M.max_iterations; ++it) {
+      mpc_backward(M, x[0], T(v_target[i]), up, lo, sc);
+      uint64_t nu, nl;
+      mpc_forward(M, x, up, lo, sc, nu, nl, u0);
+      if (nu == up && nl == lo) { ok = true; break; }
+      up = nu; lo = nl;
+    }
+    if (iterations) iterations[i] = it + 1;
+    for (int k = 0; k < M.N; ++k) {
+      double u = double(sc.at(k, 4));
+      if (u > c->max_ground_accel) u = c->max_ground_accel;
+      if (u < -c->max_ground_accel) u = -c->max_ground_accel;
+      plan[size_t(i) * M.N + k] = u;
+    }
+    found[i] = ok ? 1 : 0;
+    v_cmd[i] = double(mpc_command_update(M, T(v_cmd[i]), x[1], contact ? contact[i] != 0 : true, ok, u0, T(dt)));
+  }
+}
+
+extern "C" {
+void hostsim_mpc_step_f32(const UpkieMpcConfig* c, int n, const double* x0, const double* v_target, const uint8_t* contact,
+                          double dt, double* v_cmd, double* plan, uint8_t* found, int* iterations) {
+  hostsim_mpc_impl<float>(c, n, x0, v_target, contact, dt, v_cmd, plan, found, iterations);
+}
+void hostsim_mpc_step_f64(const UpkieMpcConfig* c, int n, const double* x0, const double* v_target, const uint8_t* contact,
+                          double dt, double* v_cmd, double* plan, uint8_t* found, int* iterations) {
+  hostsim_mpc_impl<double>(c, n, x0, v_target, contact, dt, v_cmd, plan, found, iterations);
+}
+}

@@ -1,0 +1,351 @@
+# SPDX-License-Identifier: Apache-2.0
+"""The kernels' per-robot arithmetic (sim_core.cuh / mpc_core.cuh compiled for the
+host, fp32) against the fp64 oracle. Runs without a GPU; the `-m gpu` tests repeat
+the comparisons through the C ABI on the device.
+
+Tolerances (DESIGN.md "Parity"): the fp32 common-frame formulation carries ~1e-5
+relative error on accelerations; the Bullet-style contact row has a sensitivity of
+1/h = 1000 s^-1 to the penetration depth at touchdown (times 1/r = 20 on wheel
+rates), so velocities at touchdown substeps can differ by ~1e-3..1e-2 while
+steady contact agrees to ~1e-5.
+"""
+import numpy as np
+import pytest
+
+from conftest import random_servo_actions, random_states
+from hostsim_wrap import HostSim, mpc_step, philox
+from upkie_b200 import _abi
+
+
+def _pair(model, oracle_lib, n, cfg=None, **kw):
+    cfg = cfg if cfg is not None else _abi.default_sim_config()
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return HostSim(model, cfg, n), oracle_lib.OracleSim(model, cfg, n, threads=4), cfg
+
+
+def test_free_flight_substep(model, oracle_lib):
+    n = 256
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    st = random_states(n, seed=11, z_range=(2.0, 3.0)).astype(np.float32)
+    tau = (np.random.default_rng(12).uniform(-1, 1, (n, 6)) * model.tau_max).astype(np.float32)
+    hs.set_state(st)
+    osim.set_state(st.astype(np.float64))
+    for _ in range(5):
+        hs.substep(tau)
+        osim.substep(tau.astype(np.float64), cfg.dt / cfg.nb_substeps)
+    d = np.abs(hs.state[:, :25].astype(np.float64) - osim.get_state()[:, :25])
+    assert d[:, :7].max() < 1e-6  # pose
+    assert d[:, 13:19].max() < 1e-5  # joint angles
+    assert d[:, 7:13].max() < 2e-4 and d[:, 19:25].max() < 2e-3  # velocities (accelerations up to 1e4 rad/s^2)
+
+
+def test_steady_contact_tick(model, oracle_lib):
+    """Robots standing on the ground under a PD action: one 5 ms tick."""
+    n = 128
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    rng = np.random.default_rng(5)
+    init = np.zeros((n, _abi.INIT_DIM), dtype=np.float32)
+    init[:, 2] = 0.58
+    pitch = rng.uniform(-0.1, 0.1, n)
+    init[:, 3], init[:, 5] = np.cos(pitch / 2), np.sin(pitch / 2)
+    hs.reset(init)
+    osim.reset(init.astype(np.float64))
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, [2, 5], 0] = np.nan
+    act[:, :, 3] = act[:, :, 4] = 1.0
+    act[:, :, 5] = 0.99 * model.tau_max  # float32(1.7) > 1.7: at the bound itself fp64 clamps, fp32 does not
+    act[:, [2, 5], 1] = rng.uniform(-3, 3, (n, 2))
+    for _ in range(10):  # settle on the ground
+        hs.step_servos(act)
+        osim.step_servos(act.astype(np.float64))
+    # re-synchronise, then compare one tick
+    osim.set_state(hs.state.astype(np.float64))
+    gobs, gerr = hs.step_servos(act)
+    oobs, _, _, _ = osim.step_servos(act.astype(np.float64))
+    d = np.abs(hs.state[:, :25].astype(np.float64) - osim.get_state()[:, :25])
+    assert (hs.state[:, 40] == 1).all()
+    assert d[:, :7].max() < 1e-6 and d[:, 13:19].max() < 1e-5
+    assert d[:, 7:13].max() < 1e-4 and d[:, 19:25].max() < 2e-3
+    assert np.abs(gobs[:, :, 2] - oobs[:, :, 2]).max() < 5e-3  # commanded torques
+    assert np.array_equal(gerr, osim.error_flags())
+
+
+def test_random_states_one_tick(model, oracle_lib):
+    n = 512
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    st = random_states(n, seed=3).astype(np.float32)
+    act = random_servo_actions(n, model, seed=4).astype(np.float32)
+    hs.set_state(st)
+    osim.set_state(st.astype(np.float64))
+    gobs, gerr = hs.step_servos(act)
+    oobs, orew, oterm, otrunc = osim.step_servos(act.astype(np.float64))
+    gs, os_ = hs.state.astype(np.float64), osim.get_state()
+    assert np.abs(gs[:, :7] - os_[:, :7]).max() < 2e-5
+    assert np.abs(gs[:, 13:19] - os_[:, 13:19]).max() < 2e-4
+    dv = np.abs(gs[:, 7:13] - os_[:, 7:13]).max(axis=1)
+    dqd = np.abs(gs[:, 19:25] - os_[:, 19:25]).max(axis=1)
+    assert np.median(dv) < 5e-5 and np.median(dqd) < 5e-4
+    assert dv.max() < 2e-2 and dqd.max() < 0.4  # touchdown outliers, see module docstring
+    assert np.array_equal(gs[:, 40], os_[:, 40])  # contact flags bit-exact
+    assert np.array_equal(gerr, osim.error_flags())  # clamp / NaN-velocity flags bit-exact
+    assert np.array_equal(gobs[:, :, 3:], np.tile(np.array([42.0, 18.0], dtype=np.float32), (n, 6, 1)))
+    assert (orew == 0.0).all() and not oterm.any() and not otrunc.any()
+
+
+def test_clamps_match_get_spine_action(model, oracle_lib):
+    """UpkieServos.get_spine_action clamps (upkie_servos.py:326-342): values
+    outside the box are clamped, NaN positions pass through, flags raised."""
+    n = 4
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, :, 0] = np.nan
+    act[:, :, 5] = 0.99 * model.tau_max
+    act[1, 0, 0] = 5.0  # beyond the hip limit 1.26
+    act[1, 0, 3] = 9.0  # kp_scale beyond max_gain_scale
+    act[2, 2, 2] = 50.0  # feedforward torque beyond 1.7
+    act[3, 1, 1] = np.nan  # NaN velocity: asserted in the reference (pybullet_backend.py:519)
+    st = random_states(n, seed=1, z_range=(2, 3)).astype(np.float32)
+    hs.set_state(st)
+    osim.set_state(st.astype(np.float64))
+    _, gerr = hs.step_servos(act)
+    osim.step_servos(act.astype(np.float64))
+    oerr = osim.error_flags()
+    # env 3 (NaN velocity) is undefined behaviour in the reference (assertion): the oracle lets the NaN
+    # poison the state (np.clip propagates NaN), the kernel's fminf/fmaxf clip drops it; both flag it
+    assert np.array_equal(gerr[:3], oerr[:3])
+    assert oerr[3] & _abi.ERR_NAN_VELOCITY
+    assert gerr[0] == 0
+    assert gerr[1] & _abi.ERR_CLAMPED and gerr[2] & _abi.ERR_CLAMPED
+    assert gerr[3] & _abi.ERR_NAN_VELOCITY
+    # the feedforward torque is clamped to the box, then clipped to maximum_torque (0.99 * 1.7)
+    assert hs.state[2, _abi.ST_TORQUE + 2] == np.float32(0.99 * 1.7)
+
+
+def test_gyropod_and_pendulum_wrappers(model, oracle_lib):
+    n = 64
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    rng = np.random.default_rng(9)
+    init = np.zeros((n, _abi.INIT_DIM), dtype=np.float32)
+    init[:, 2] = 0.6
+    pitch = rng.uniform(-0.2, 0.2, n)
+    init[:, 3], init[:, 5] = np.cos(pitch / 2), np.sin(pitch / 2)
+    init[:, 13:19] = rng.uniform(-0.3, 0.3, (n, 6))
+    hs.reset(init)
+    osim.reset(init.astype(np.float64))
+    # UpkieGyropod.reset: leg targets <- observed joint positions, yaw = 0 (upkie_gyropod.py:216-244)
+    assert np.allclose(hs.state[:, 34:38], hs.state[:, [13, 14, 16, 17]])
+    for t in range(20):
+        a = rng.uniform(-4, 4, (n, 2)).astype(np.float32)  # beyond the +-3 / +-1 boxes on purpose
+        osim.set_state(hs.state.astype(np.float64))
+        g6, gterm = hs.step_gyropod(a, 2)
+        o6, orew, oterm, otrunc = osim.step_gyropod(a.astype(np.float64), 2)
+        assert np.abs(g6[:, [0, 1, 2, 5]] - o6[:, [0, 1, 2, 5]]).max() < 1e-4
+        assert np.median(np.abs(g6[:, 3:5] - o6[:, 3:5])) < 1e-3
+        safe = np.abs(np.abs(o6[:, 1]) - cfg.fall_pitch) > 1e-4
+        assert np.array_equal(gterm[safe], oterm[safe])
+        # yaw integrates the UNCLAMPED action (upkie_gyropod.py:383-385)
+        assert np.allclose(g6[:, 5], a[:, 1])
+    # pendulum = gyropod with yaw command 0 and obs[[1, 0, 4, 3]] (upkie_pendulum.py:17,137-140)
+    a1 = rng.uniform(-3, 3, (n, 1)).astype(np.float32)
+    osim.set_state(hs.state.astype(np.float64))
+    g6, _ = hs.step_gyropod(a1, 1)
+    o4, _, _, _ = osim.step_gyropod(a1.astype(np.float64), 1)
+    assert np.abs(g6[:, [1, 0]] - o4[:, [0, 1]]).max() < 1e-4
+
+
+def test_leg_low_pass_and_wheel_velocity_targets(model, oracle_lib):
+    """Closed-form pieces of UpkieGyropod (tests/envs/test_upkie_gyropod.py:56-122):
+    pure yaw gives equal-sign wheel velocities, legs low-pass to zero with tau = 1 s."""
+    n = 1
+    cfg = _abi.default_sim_config()
+    cfg.nb_substeps = 1  # the stored torque is then the one computed from the initial (zero) wheel velocities
+    hs = HostSim(model, cfg, n)
+    st = np.zeros((1, _abi.STATE_DIM), dtype=np.float32)
+    st[0, 2], st[0, 3] = 5.0, 1.0
+    st[0, 34:38] = [0.4, -0.2, 0.1, 0.3]
+    hs.set_state(st)
+    hs.step_gyropod(np.array([[0.0, 1.0]], dtype=np.float32), 2)
+    alpha = cfg.dt / 1.0
+    assert np.allclose(hs.state[0, 34:38], np.array([0.4, -0.2, 0.1, 0.3]) * (1 - alpha), atol=1e-7)
+    # in free flight the wheel torques are kd * (target - qd) clipped to 1.7: same sign on both wheels
+    tl, tr = hs.state[0, _abi.ST_TORQUE + 2], hs.state[0, _abi.ST_TORQUE + 5]
+    assert tl > 0 and tr > 0
+
+
+def test_inertia_randomization_and_friction(model, oracle_lib):
+    n = 64
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    rng = np.random.default_rng(2)
+    eps = rng.uniform(-0.2, 0.2, (n, 6))
+    mu = rng.uniform(0.5, 1.2, n)
+    hs.set_randomization(friction=mu, inertia_eps=eps)
+    osim.set_randomization(friction=mu.astype(np.float32).astype(np.float64),
+                           inertia_eps=eps.astype(np.float32).astype(np.float64))
+    st = random_states(n, seed=21).astype(np.float32)
+    act = random_servo_actions(n, model, seed=22, torque_mode=True).astype(np.float32)
+    hs.set_state(st)
+    osim.set_state(st.astype(np.float64))
+    hs.step_servos(act)
+    osim.step_servos(act.astype(np.float64))
+    gs, os_ = hs.state.astype(np.float64), osim.get_state()
+    assert np.abs(gs[:, :7] - os_[:, :7]).max() < 2e-5
+    assert np.median(np.abs(gs[:, 19:25] - os_[:, 19:25]).max(axis=1)) < 1e-3
+    # randomisation changes the dynamics
+    hs2 = HostSim(model, cfg, n)
+    hs2.set_state(st)
+    hs2.step_servos(act)
+    assert np.abs(hs2.state[:, 19:25] - hs.state[:, 19:25]).max() > 1e-2
+
+
+def test_spine_observation(model, oracle_lib):
+    n = 128
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    st = random_states(n, seed=7).astype(np.float32)
+    act = random_servo_actions(n, model, seed=8).astype(np.float32)
+    hs.set_state(st)
+    osim.set_state(st.astype(np.float64))
+    hs.step_servos(act)
+    osim.step_servos(act.astype(np.float64))
+    g, o = hs.spine_obs().astype(np.float64), osim.spine_obs()
+    assert np.abs(g[:, 16:20] - o[:, 16:20]).max() < 1e-4  # IMU quaternion incl. scipy's sign convention
+    assert np.abs(g[:, 6] - o[:, 6]).max() < 1e-5  # pitch
+    assert np.abs(g[:, 7:16] - o[:, 7:16]).max() < 1e-5
+    assert np.array_equal(g[:, 29], o[:, 29])
+    assert np.abs(g[:, 60] - o[:, 60]).max() < 1e-5
+    assert np.array_equal(g[:, 30:60].reshape(n, 6, 5)[:, :, 3:], o[:, 30:60].reshape(n, 6, 5)[:, :, 3:])
+
+
+def test_twenty_tick_trajectory_under_pd(model, oracle_lib):
+    """Short closed-loop horizon without re-synchronisation (README PD policy,
+    README.md:62-64): fp32 and fp64 trajectories stay close for 0.1 s."""
+    n = 32
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    init = np.zeros((n, _abi.INIT_DIM), dtype=np.float32)
+    init[:, 2], init[:, 3] = 0.6, 1.0
+    hs.reset(init)
+    osim.reset(init.astype(np.float64))
+    go, oo = np.zeros((n, 6)), np.zeros((n, 4))
+    for t in range(20):
+        ga = (10.0 * go[:, 1] + 1.0 * go[:, 0] + 0.0 * go[:, 4] + 0.1 * go[:, 3]).reshape(n, 1)
+        oa = (10.0 * oo[:, 0] + 1.0 * oo[:, 1] + 0.0 * oo[:, 2] + 0.1 * oo[:, 3]).reshape(n, 1)
+        g6, gterm = hs.step_gyropod(ga.astype(np.float32), 1)
+        oo, _, oterm, _ = osim.step_gyropod(oa, 1)
+        go = g6.astype(np.float64)
+    assert np.abs(go[:, 1] - oo[:, 0]).max() < 1e-3  # pitch
+    assert np.abs(go[:, 0] - oo[:, 1]).max() < 1e-3  # ground position
+    assert np.array_equal(gterm, oterm)
+
+
+# ---- counter-based RNG ------------------------------------------------------------------------
+
+def test_philox4x32_10_known_answers():
+    """Random123 known-answer vectors of Philox4x32-10 (kat_vectors: counter words, key words, output)."""
+    kats = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for c, k, expect in kats:
+        assert philox(c[0] | (c[1] << 32), c[2] | (c[3] << 32), k[0] | (k[1] << 32)) == list(expect)
+
+
+def test_device_sampler_statistics_and_determinism(model):
+    cfg = _abi.default_sim_config()
+    cfg.rand_pitch, cfg.rand_roll, cfg.rand_x, cfg.rand_z = 0.3, 0.1, 0.05, 0.1
+    cfg.rand_omega_x, cfg.rand_omega_y = 0.2, 0.5
+    cfg.rand_linear_velocity[0], cfg.rand_linear_velocity[2] = 0.3, 0.1
+    n = 4096
+    hs = HostSim(model, cfg, n)
+    a = hs.sample_init(seed=7, env_offset=0, episode=1)
+    b = hs.sample_init(seed=7, env_offset=0, episode=1)
+    assert np.array_equal(a, b)
+    # sharding invariance: env i of a shard with offset k equals env k + i of the full batch
+    hs2 = HostSim(model, cfg, 128)
+    c = hs2.sample_init(seed=7, env_offset=1000, episode=1)
+    assert np.array_equal(c, a[1000:1128])
+    assert not np.array_equal(hs.sample_init(seed=7, env_offset=0, episode=2), a)
+    assert np.abs(a[:, 0]).max() <= 0.05 and a[:, 2].min() >= 0.6 and a[:, 2].max() <= 0.7
+    pitch = 2 * np.arctan2(a[:, 5], a[:, 3])
+    assert np.abs(pitch).max() <= 0.3 + 0.11 and abs(pitch.mean()) < 0.02 and pitch.std() > 0.1
+    assert np.abs(a[:, 10]).max() <= 0.2 and np.abs(a[:, 11]).max() <= 0.5 and (a[:, 12] == 0).all()
+    assert np.allclose(np.linalg.norm(a[:, 3:7], axis=1), 1.0, atol=1e-6)
+
+
+# ---- MPC ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("horizon", [16, 50])
+def test_mpc_riccati_active_set_matches_condensed_oracle(oracle_lib, horizon):
+    cfg = _abi.default_mpc_config()
+    cfg.nb_timesteps = horizon
+    om = oracle_lib.OracleMpc(cfg)
+    rng = np.random.default_rng(0)
+    n = 300
+    x0 = np.stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.2, 0.2, n), rng.uniform(-0.5, 0.5, n),
+                   rng.uniform(-1, 1, n)], 1)
+    x0[:20, 1] = rng.uniform(0.3, 0.9, 20)  # large pitch: many saturated inputs
+    x0[20:30, 1] = rng.uniform(1.05, 1.3, 10)  # fallen
+    vt = rng.uniform(-1, 1, n)
+    contact = np.ones(n, dtype=np.uint8)
+    contact[30:40] = 0
+    v0 = rng.uniform(-1, 1, n)
+    vc_o, first_o, found_o, plan_o = om.step(x0, vt, contact, 0.005, v0)
+    assert found_o.all()
+    # same formulation in fp64: agreement to round-off (two independent formulations, one optimum)
+    vc64, plan64, found64, it64 = mpc_step(cfg, x0, vt, contact, 0.005, v0, double=True)
+    assert found64.all() and np.abs(plan64 - plan_o).max() < 1e-8
+    # what the kernel runs (fp32): ProxQP's own tolerance is eps_abs = 1e-3 (mpc_balancer.py:76)
+    vc32, plan32, found32, it32 = mpc_step(cfg, x0, vt, contact, 0.005, v0, double=False)
+    assert found32.all()
+    assert np.abs(plan32[:, 0] - plan_o[:, 0]).max() < 1e-3
+    assert np.abs(plan32 - plan_o).max() < 5e-3
+    assert np.abs(vc32 - vc_o).max() < 1e-5
+    assert it32.max() <= 12
+    # MPCBalancer.step post-processing (mpc_balancer.py:295-311)
+    fallen = np.abs(x0[:, 1]) > 1.0
+    lp = fallen | (contact == 0)
+    assert np.allclose(vc_o[lp], v0[lp] * (1 - 0.005 / 0.1))
+    ok = ~lp
+    assert np.allclose(vc_o[ok], np.clip(v0[ok] + plan_o[ok, 0] * 0.005 / 2.0, -3, 3))
+    assert (np.abs(plan_o).max(axis=1) >= 10.0 - 1e-9).sum() >= 20  # saturated cases are exercised
+
+
+def test_mpc_oracle_against_scipy_bvls(oracle_lib):
+    """The oracle's QP solver against an independent bounded least-squares solver."""
+    from scipy.optimize import lsq_linear
+
+    cfg = _abi.default_mpc_config()
+    om = oracle_lib.OracleMpc(cfg)
+    P, A, B = om.matrices()
+    L = np.linalg.cholesky(P)
+    rng = np.random.default_rng(3)
+    for _ in range(8):
+        x0 = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-1, 1)])
+        q = om.cost_vector(x0, rng.uniform(-1, 1))
+        U, ok = om.solve(q)
+        r = lsq_linear(L.T, -np.linalg.solve(L, q), bounds=(-10, 10), method="bvls", tol=1e-14)
+        assert ok and np.abs(U - r.x).max() < 1e-8
+
+
+def test_mpc_model_matrices(oracle_lib):
+    """qpmpc WheeledInvertedPendulum discretisation: A, B satisfy theta'' = w^2 theta - u / l
+    and p'' = u."""
+    cfg = _abi.default_mpc_config()
+    om = oracle_lib.OracleMpc(cfg)
+    P, A, B = om.matrices()
+    T, g, l = cfg.sampling_period, cfg.gravity, cfg.leg_length
+    w = np.sqrt(g / l)
+    assert np.allclose(A[0], [1, 0, T, 0]) and np.allclose(A[2], [0, 0, 1, 0])
+    assert A[1, 1] == pytest.approx(np.cosh(T * w)) and A[3, 1] == pytest.approx(w * np.sinh(T * w))
+    assert np.allclose(B, [T * T / 2, (1 - np.cosh(T * w)) / g, T, -w * np.sinh(T * w) / g])
+    # zero-order-hold consistency against a fine explicit integration of the ODE
+    x = np.array([0.1, 0.05, -0.2, 0.3])
+    u = 2.0
+    y = x.copy()
+    m = 20000
+    for _ in range(m):
+        h = T / m
+        y = y + h * np.array([y[2], y[3], u, w * w * y[1] - u / l])
+    assert np.allclose(A @ x + B * u, y, atol=1e-5)
+    assert np.allclose(P, P.T) and np.linalg.eigvalsh(P).min() > 0

@@ -1,0 +1,347 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Pins the CPU oracle (and the host-side mirrors) to the reference.
+
+Two kinds of evidence, none of which reads /root/reference at test time:
+- golden vectors produced by importing the reference's own leaf modules
+  (tests/golden/make_golden.py -> tests/golden/reference_vectors.json);
+- known-answer values copied from the reference's own tests (cited inline).
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from upkie_b200 import _abi
+from upkie_b200.robot_state import RobotState, RobotStateRandomization
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(HERE, "golden", "reference_vectors.json")) as f:
+        return json.load(f)
+
+
+def _nan(x):
+    return float("nan") if x is None else x
+
+
+# ---- golden vectors -----------------------------------------------------------------
+
+def test_low_pass_filter_matches_reference(golden, oracle_lib):
+    for c in golden["low_pass_filter"]:
+        out = oracle_lib.low_pass_filter(c["prev"], c["cutoff"], c["new"], c["dt"])
+        assert out == pytest.approx(c["out"], rel=0, abs=1e-15)
+
+
+def test_clamp_matches_reference_including_nan(golden, oracle_lib):
+    for c in golden["clamp"]:
+        out = oracle_lib.clamp(_nan(c["value"]), c["lower"], c["upper"])
+        if c["out"] is None:
+            assert math.isnan(out)  # NaN passes through both comparisons (clamp.py:26-30)
+        else:
+            assert out == c["out"]
+
+
+def test_rotations_match_reference(golden, oracle_lib):
+    rot = golden["rotations"]
+    for q, R, qb in zip(rot["quat_wxyz"], rot["matrix"], rot["quat_from_matrix_wxyz"]):
+        R_o = oracle_lib.rotation_matrix_from_quaternion(q)
+        assert np.allclose(R_o, np.array(R), atol=1e-15)
+        q_o = oracle_lib.quaternion_from_rotation_matrix(np.array(R))
+        # same sign convention as scipy's from_matrix().as_quat(), not just the same rotation
+        assert np.allclose(q_o, np.array(qb), atol=1e-12)
+
+
+def test_robot_state_sampling_matches_reference(golden, oracle_lib):
+    for s in golden["robot_state_samples"]:
+        r = s["randomization"]
+        rand = RobotStateRandomization(
+            roll=r["roll"], pitch=r["pitch"], x=r["x"], z=r["z"], omega_x=r["omega_x"], omega_y=r["omega_y"],
+            linear_velocity=np.array(r["linear_velocity"]),
+        )
+        rs = RobotState(
+            position_base_in_world=np.array(s["nominal_position"]),
+            orientation_base_in_world=np.array(s["nominal_quat_wxyz"]),
+            randomization=rand,
+        )
+        out = rs.sample_state(np.random.default_rng(s["seed"]))
+        assert np.allclose(out.position_base_in_world, s["position"], atol=1e-14)
+        assert np.allclose(out.linear_velocity_base_to_world_in_world, s["linear_velocity"], atol=1e-14)
+        assert np.allclose(out.angular_velocity_base_in_base, s["angular_velocity"], atol=1e-14)
+        q = np.array(s["quat_wxyz"])
+        qo = out.orientation_quat_wxyz
+        assert min(np.abs(qo - q).max(), np.abs(qo + q).max()) < 1e-12
+        # the oracle's own restatement (used by the parity tests) agrees too
+        cfg = _abi.default_sim_config()
+        rs.apply_to_config(cfg)
+        row = oracle_lib.sample_init_state(cfg, np.random.default_rng(s["seed"]))
+        assert np.allclose(row[0:3], s["position"], atol=1e-14)
+        assert min(np.abs(row[3:7] - q).max(), np.abs(row[3:7] + q).max()) < 1e-12
+        assert np.allclose(row[7:10], s["linear_velocity"], atol=1e-14)
+        assert np.allclose(row[10:13], s["angular_velocity"], atol=1e-14)
+
+
+def test_robot_state_accepts_scipy_rotation():
+    from scipy.spatial.transform import Rotation
+
+    rs = RobotState(orientation_base_in_world=Rotation.from_euler("ZYX", [0.1, 0.2, 0.3]))
+    x, y, z, w = Rotation.from_euler("ZYX", [0.1, 0.2, 0.3]).as_quat()
+    assert np.allclose(rs.orientation_quat_wxyz, [w, x, y, z])
+    assert np.allclose(rs.orientation_base_in_world.as_quat(), [x, y, z, w])
+
+
+# ---- torque law: known answers of tests/envs/backends/test_pybullet_backend_mock.py --------
+
+def _sim(model, oracle_lib, **cfgkw):
+    cfg = _abi.default_sim_config()
+    for k, v in cfgkw.items():
+        setattr(cfg, k, v)
+    return oracle_lib.OracleSim(model, cfg, 1), cfg
+
+
+def test_torque_law_no_friction(model, oracle_lib):
+    # test_pybullet_backend_mock.py:134-173: expected -1.005
+    sim, _ = _sim(model, oracle_lib)
+    tau = sim.compute_joint_torque(0, 0.1, 0.005, 1.0, 0.0, 0.0, 1.0, 1.0, 10.0)
+    assert tau == pytest.approx(1.0 + 1.0 * (0.0 - 0.005) + 20.0 * (0.0 - 0.1), abs=1e-12)
+    assert tau == pytest.approx(-1.005, abs=1e-5)
+
+
+def test_torque_law_kinetic_friction_sign_and_stiction(model, oracle_lib):
+    # test_pybullet_backend_mock.py:179-315: friction 0.1 N.m opposes motion above 1e-3 rad/s (strict)
+    cfg = _abi.default_sim_config()
+    cfg.joint_friction[0] = 0.1
+    sim = oracle_lib.OracleSim(model, cfg, 1)
+    nan = float("nan")
+    pos = sim.compute_joint_torque(0, 0.0, +0.005, 0.0, nan, 0.0, 1.0, 1.0, 10.0)
+    neg = sim.compute_joint_torque(0, 0.0, -0.005, 0.0, nan, 0.0, 1.0, 1.0, 10.0)
+    assert pos == pytest.approx(-0.005 - 0.1, abs=1e-12)  # -0.105
+    assert neg == pytest.approx(+0.005 + 0.1, abs=1e-12)  # +0.105
+    at_threshold = sim.compute_joint_torque(0, 0.0, 1e-3, 0.0, nan, 0.0, 1.0, 1.0, 10.0)
+    assert at_threshold == pytest.approx(-1e-3, abs=1e-12)  # |qd| > 1e-3 is strict: no friction
+    below = sim.compute_joint_torque(0, 0.0, 0.0005, 0.0, nan, 0.0, 1.0, 1.0, 10.0)
+    assert below == pytest.approx(-0.0005, abs=1e-12)
+
+
+def test_torque_law_position_velocity_feedback(model, oracle_lib):
+    # test_pybullet_backend_mock.py:560-619: expected 2.05
+    sim, _ = _sim(model, oracle_lib)
+    tau = sim.compute_joint_torque(0, 0.1, 0.05, 0.0, 0.2, 0.1, 1.0, 1.0, 10.0)
+    assert tau == pytest.approx(2.05, abs=1e-12)
+
+
+def test_torque_law_clip_and_feedforward(model, oracle_lib):
+    # BulletInterfaceTest.cpp:163-183 ComputeJointFeedforwardTorque: kp=kd=0, ff=0.42, max 1.0 -> 0.42
+    sim, _ = _sim(model, oracle_lib)
+    nan = float("nan")
+    assert sim.compute_joint_torque(5, 0.3, 2.0, 0.42, nan, 0.0, 0.0, 0.0, 1.0) == pytest.approx(0.42, abs=1e-15)
+    assert sim.compute_joint_torque(0, 0.0, 0.0, 50.0, nan, 0.0, 1.0, 1.0, 16.0) == 16.0
+    assert sim.compute_joint_torque(0, 0.0, 0.0, -50.0, nan, 0.0, 1.0, 1.0, 16.0) == -16.0
+    # ComputeJointTorquesWhileMoving (:137-161): target velocity = measured velocity -> zero torque
+    assert sim.compute_joint_torque(2, 1.0, 3.0, 0.0, nan, 3.0, 1.0, 1.0, 1.0) == 0.0
+
+
+# ---- model aggregates: upkie/cpp/interfaces/bullet/tests/utils_test.cpp:89-98 -----------------
+
+def test_model_mass_and_com(model, oracle_lib):
+    sim, _ = _sim(model, oracle_lib)
+    mass, com = sim.mass_com()
+    assert mass == pytest.approx(5.3382, abs=1e-4)  # BulletInterfaceTest.cpp:328-330
+    assert com[0] == pytest.approx(-0.0059, abs=1e-4)
+    assert com[1] == pytest.approx(0.0, abs=1e-4)
+    assert com[2] == pytest.approx(-0.2455, abs=1e-4)
+    assert model.total_mass() == pytest.approx(5.3382, abs=1e-4)
+    assert np.allclose(model.com_zero_config(), [-0.0059, 0.0, -0.2455], atol=1e-4)
+
+
+def test_model_constants(model):
+    # tests/model/test_model.py:64-92
+    assert model.wheel_radius == pytest.approx(0.05)
+    assert model.wheel_base == pytest.approx(0.3048, abs=5e-3)
+    assert model.left_wheeled
+    assert np.allclose(model.rotation_base_to_imu, np.diag([-1.0, 1.0, -1.0]))
+    assert np.allclose(model.rotation_ars_to_world, np.diag([1.0, -1.0, -1.0]))
+    # docs/kinematics.md:45-55
+    lim = {j.name: j.limit for j in model.joints}
+    assert lim["left_hip"].upper == 1.26 and lim["right_knee"].upper == 2.51
+    assert lim["left_wheel"].velocity == 111.0 and lim["left_wheel"].effort == 1.7
+    assert lim["left_hip"].effort == 16.0 and lim["left_knee"].velocity == 28.8
+    assert [j.name for j in model.upper_leg_joints] == ["left_hip", "left_knee", "right_hip", "right_knee"]
+    assert [j.name for j in model.wheel_joints] == ["left_wheel", "right_wheel"]
+    # contact frames symmetric about y = 0 (tests/model/test_model.py:21-31)
+    o = model.body_origins_zero_config()
+    assert o[3][0] == pytest.approx(o[6][0]) and o[3][1] == pytest.approx(-o[6][1]) and o[3][2] == pytest.approx(o[6][2])
+
+
+# ---- free fall: upkie/cpp/interfaces/tests/BulletInterfaceTest.cpp:245-326 ------------------------
+
+def _free(model, oracle_lib, z=10.0, **kw):
+    cfg = _abi.default_sim_config()
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    sim = oracle_lib.OracleSim(model, cfg, 1)
+    st = np.zeros((1, _abi.STATE_DIM))
+    st[0, 2] = z
+    st[0, 3] = 1.0
+    sim.set_state(st)
+    return sim, cfg
+
+
+def test_semi_implicit_euler_two_cycles(model, oracle_lib):
+    # MonitorBaseState (:263-298): z after two cycles = 3 * (-g) * dt^2 (+-1e-6), orientation stays identity
+    dt = 1e-3
+    sim, cfg = _free(model, oracle_lib, z=0.0 + 100.0)
+    sim.substep(np.zeros((1, 6)), dt)
+    st = sim.get_state()[0]
+    assert st[9] == pytest.approx(-9.81 * dt, abs=1e-12)  # MonitorIMU (:245-261): v_z = -g dt after one cycle
+    sim.substep(np.zeros((1, 6)), dt)
+    st = sim.get_state()[0]
+    assert st[2] - 100.0 == pytest.approx(3 * -9.81 * dt**2, abs=1e-6)
+    assert st[0] == pytest.approx(0.0, abs=1e-12) and st[1] == pytest.approx(0.0, abs=1e-12)
+    assert st[3] == pytest.approx(1.0, abs=1e-12)
+    assert np.allclose(st[4:7], 0.0, atol=1e-12)
+
+
+def test_free_fall_base_position(model, oracle_lib):
+    # FreeFallBasePosition (:300-326): T = 0.05 s, z = -g T^2 / 2, v = -g T, both +-1e-3
+    T, dt = 0.05, 1e-3
+    sim, cfg = _free(model, oracle_lib, z=100.0)
+    for _ in range(int(round(T / dt))):
+        sim.substep(np.zeros((1, 6)), dt)
+    st = sim.get_state()[0]
+    assert st[0] == pytest.approx(0.0, abs=1e-4) and st[1] == pytest.approx(0.0, abs=1e-4)
+    assert st[2] - 100.0 == pytest.approx(-0.5 * 9.81 * T * T, abs=1e-3)
+    assert st[9] == pytest.approx(-9.81 * T, abs=1e-3)
+
+
+def test_imu_sees_gravity_in_free_fall(model, oracle_lib):
+    # read_imu_data_test.cpp:43-105: base pitched -pi/2 (IMU x-axis down), damping removed.
+    # With gravity 4.2 the filtered acceleration is +4.2 on IMU x; with gravity 9.81 the raw (proper)
+    # acceleration is zero.
+    for g, expect_lin, expect_raw in ((4.2, 4.2, None), (9.81, 9.81, 0.0)):
+        dt = 1.0 / 240.0
+        cfg = _abi.default_sim_config()
+        cfg.dt, cfg.nb_substeps, cfg.gravity = dt, 1, g
+        cfg.linear_damping = cfg.angular_damping = 0.0
+        sim = oracle_lib.OracleSim(model, cfg, 1)
+        st = np.zeros((1, _abi.STATE_DIM))
+        st[0, 2] = 100.0
+        st[0, 3:7] = [math.cos(-math.pi / 4), 0.0, math.sin(-math.pi / 4), 0.0]
+        sim.set_state(st)
+        sim.observe()
+        sim.substep(np.zeros((1, 6)), dt)
+        sim.observe()
+        sp = sim.spine_obs()[0]
+        lin = sp[_abi.SP_IMU_LINACC:_abi.SP_IMU_LINACC + 3]
+        assert lin[0] == pytest.approx(expect_lin, abs=1e-9)
+        assert lin[1] == pytest.approx(0.0, abs=1e-9) and lin[2] == pytest.approx(0.0, abs=1e-9)
+        if expect_raw is not None:
+            raw = sp[_abi.SP_IMU_RAWACC:_abi.SP_IMU_RAWACC + 3]
+            assert np.allclose(raw, 0.0, atol=1e-9)
+
+
+def test_imu_orientation_in_ars_frame(model, oracle_lib):
+    # BulletInterfaceTest.cpp:207-243 ObserveImuOrientation: q_base = (0, 1, 0, 0);
+    # R_imu_to_ars = diag(1,-1,-1) R_base_to_world diag(-1,1,-1)
+    sim, cfg = _free(model, oracle_lib, z=100.0)
+    st = np.zeros((1, _abi.STATE_DIM))
+    st[0, 2] = 100.0
+    st[0, 3:7] = [0.0, 1.0, 0.0, 0.0]
+    sim.set_state(st)
+    sim.observe()
+    q = sim.spine_obs()[0, _abi.SP_IMU_QUAT:_abi.SP_IMU_QUAT + 4]
+    R_bw = oracle_lib.rotation_matrix_from_quaternion([0.0, 1.0, 0.0, 0.0])
+    R_ia = np.diag([1.0, -1.0, -1.0]) @ R_bw @ np.diag([-1.0, 1.0, -1.0])
+    R_q = oracle_lib.rotation_matrix_from_quaternion(q)
+    assert np.allclose(R_q, R_ia, atol=1e-12)
+
+
+def test_reset_semantics(model, oracle_lib):
+    # ResetBaseState / ResetJointConfiguration (BulletInterfaceTest.cpp:84-119,332-351) in the
+    # PyBullet-backend flavour (pybullet_backend.py:234-267): joint velocities zeroed, angular velocity
+    # handed over unrotated, one stepSimulation afterwards.
+    cfg = _abi.default_sim_config()
+    cfg.linear_damping = cfg.angular_damping = 0.0
+    sim = oracle_lib.OracleSim(model, cfg, 1)
+    init = np.zeros((1, _abi.INIT_DIM))
+    init[0, 0:3] = [0.0, 0.0, 50.0]
+    init[0, 3:7] = [0.707, 0.0, -0.707, 0.0] / np.linalg.norm([0.707, 0.0, -0.707, 0.0])
+    init[0, 7:10] = [4.0, 5.0, 6.0]
+    init[0, 13:19] = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6]
+    init[0, 19:25] = 3.0
+    sim.reset(init)
+    st = sim.get_state()[0]
+    h = cfg.dt / cfg.nb_substeps
+    assert np.allclose(st[7:9], [4.0, 5.0], atol=1e-12)
+    assert st[9] == pytest.approx(6.0 - 9.81 * h, abs=1e-9)
+    assert np.allclose(st[0:3], [4.0 * h, 5.0 * h, 50.0 + (6.0 - 9.81 * h) * h], atol=1e-9)
+    assert np.allclose(st[13:19], [0.1, 0.2, 0.3, 0.4, 0.5, 0.6], atol=1e-4)
+    assert np.abs(st[19:25]).max() < 0.5  # zeroed by resetJointState, then one gravity substep
+    R = oracle_lib.rotation_matrix_from_quaternion(st[3:7])
+    assert R[0, 0] == pytest.approx(0.0, abs=1e-6) and R[0, 2] == pytest.approx(-1.0, abs=1e-6)
+    assert R[1, 1] == pytest.approx(1.0, abs=1e-6) and R[2, 0] == pytest.approx(1.0, abs=1e-6)
+
+
+# ---- tests/envs/backends/test_pybullet_backend.py:31-57 (real-pybullet smoke checks) ------------
+
+def _zero_torque_action():
+    a = np.zeros((1, 6, 6))
+    a[:, :, 0] = np.nan  # no position target, zero gains, zero maximum torque: step(action={})
+    return a
+
+
+def test_pitch_zero_after_one_step_and_fall_without_action(model, oracle_lib):
+    cfg = _abi.default_sim_config()
+    sim = oracle_lib.OracleSim(model, cfg, 1)
+    init = np.zeros((1, _abi.INIT_DIM))
+    init[0, 2] = 0.6
+    init[0, 3] = 1.0
+    sim.reset(init)
+    sim.step_servos(_zero_torque_action())
+    assert sim.spine_obs()[0, _abi.SP_PITCH] == pytest.approx(0.0, abs=1e-7)
+    for _ in range(100):
+        sim.step_servos(_zero_torque_action())
+    assert abs(sim.spine_obs()[0, _abi.SP_PITCH]) > 0.5  # the robot falls within 100 x 5 ms
+
+
+def test_fall_from_yaw_rotated_start(model, oracle_lib):
+    cfg = _abi.default_sim_config()
+    sim = oracle_lib.OracleSim(model, cfg, 1)
+    init = np.zeros((1, _abi.INIT_DIM))
+    init[0, 2] = 0.6
+    init[0, 3:7] = [math.cos(math.pi / 4), 0.0, 0.0, math.sin(math.pi / 4)]  # yaw = pi/2
+    sim.reset(init)
+    for _ in range(100):
+        sim.step_servos(_zero_torque_action())
+    assert abs(sim.spine_obs()[0, _abi.SP_PITCH]) > 0.5
+
+
+# ---- invariants of the restated dynamics (no reference value exists: parity unpinned) ---------------
+
+def test_energy_and_momentum_conservation_rate(model, oracle_lib):
+    cfg = _abi.default_sim_config()
+    cfg.linear_damping = cfg.angular_damping = 0.0
+    rng = np.random.default_rng(1)
+    st = np.zeros((1, _abi.STATE_DIM))
+    st[0, 2] = 50.0
+    q = np.array([0.9, 0.1, 0.3, -0.2])
+    st[0, 3:7] = q / np.linalg.norm(q)
+    st[0, 7:13] = rng.uniform(-1, 1, 6)
+    st[0, 13:19] = rng.uniform(-1, 1, 6)
+    st[0, 19:25] = rng.uniform(-3, 3, 6)
+    drift = []
+    for h in (1e-3, 1e-4):
+        sim = oracle_lib.OracleSim(model, cfg, 1)
+        sim.set_state(st)
+        e0 = sim.energy()
+        for _ in range(int(round(0.1 / h))):
+            sim.substep(np.zeros((1, 6)), h)
+        e1 = sim.energy()
+        drift.append(abs((e1["kinetic"] + e1["potential"]) - (e0["kinetic"] + e0["potential"])))
+        assert np.allclose(e1["linear_momentum"][:2], e0["linear_momentum"][:2], atol=2e-2 * h / 1e-3 * 0.1)
+    # first-order integrator: the energy error shrinks ~linearly with the step
+    assert drift[1] < 0.2 * drift[0]

@@ -1,0 +1,394 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Vectorised Upkie environments on the sm_100a kernels.
+
+``B200VectorEnv`` is a ``gymnasium.vector.VectorEnv`` whose
+``single_action_space`` / ``single_observation_space`` are identical to the
+reference's single-robot environments:
+
+- ``"servos"``   = ``UpkieServos``   (``upkie/envs/upkie_servos.py:20-344``)
+- ``"gyropod"``  = ``UpkieGyropod``  (``upkie/envs/upkie_gyropod.py:20-392``)
+- ``"pendulum"`` = ``UpkiePendulum`` (``upkie/envs/upkie_pendulum.py:20-142``)
+
+with the reference's reset semantics (seeded NumPy sampling of the initial
+state, ``upkie/envs/upkie_env.py:162-194``), ``reward == 0.0`` and
+``truncated == False`` (``upkie_env.py:230-232``), fall termination for the
+wheeled-inverted-pendulum wrappers (``upkie_gyropod.py:333-352``).
+"""
+
+from typing import Any, Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _abi
+from .exceptions import UpkieException, UpkieRuntimeError
+from .gym_compat import VectorEnv, batch_space, spaces
+from .model import Model, default_model
+from .robot_state import RobotState
+from .sim import AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP, UpkieSim
+
+ENV_TYPES = ("servos", "gyropod", "pendulum")
+_AUTORESET = {"disabled": AUTORESET_DISABLED, "next_step": AUTORESET_NEXT_STEP, "same_step": AUTORESET_SAME_STEP}
+
+
+# ---- spaces (host-side, no GPU needed) ------------------------------------------------
+
+def make_servo_spaces(model: Model, max_gain_scale: float = 5.0):
+    """``UpkieServos.__create_servo_spaces`` (``upkie_servos.py:173-286``).
+
+    Returns ``(action_space, observation_space, neutral_action, max_action,
+    min_action)``.
+    """
+    if not (0.0 < max_gain_scale < 10.0):
+        raise UpkieRuntimeError(f"Invalid value {max_gain_scale=}")
+    action_space, servo_space = {}, {}
+    neutral_action, max_action, min_action = {}, {}, {}
+    f32 = np.float32
+
+    def box(lo, hi):
+        return spaces.Box(low=lo, high=hi, shape=(1,), dtype=f32)
+
+    for joint in model.joints:
+        lim = joint.limit
+        action_space[joint.name] = spaces.Dict(
+            {
+                "position": box(lim.lower, lim.upper),
+                "velocity": box(-lim.velocity, +lim.velocity),
+                "feedforward_torque": box(-lim.effort, +lim.effort),
+                "kp_scale": box(0.0, max_gain_scale),
+                "kd_scale": box(0.0, max_gain_scale),
+                "maximum_torque": box(0.0, lim.effort),
+            }
+        )
+        servo_space[joint.name] = spaces.Dict(
+            {
+                "position": box(lim.lower, lim.upper),
+                "velocity": box(-lim.velocity, +lim.velocity),
+                "torque": box(-lim.effort, +lim.effort),
+                "temperature": box(0.0, 100.0),
+                "voltage": box(10.0, 44.0),  # moteus min 10 V, max 44 V
+            }
+        )
+        neutral_action[joint.name] = {
+            "position": np.nan,
+            "velocity": 0.0,
+            "feedforward_torque": 0.0,
+            "kp_scale": 1.0,
+            "kd_scale": 1.0,
+            "maximum_torque": lim.effort,
+        }
+        max_action[joint.name] = {
+            "position": lim.upper,
+            "velocity": lim.velocity,
+            "feedforward_torque": lim.effort,
+            "kp_scale": max_gain_scale,
+            "kd_scale": max_gain_scale,
+            "maximum_torque": lim.effort,
+        }
+        min_action[joint.name] = {
+            "position": lim.lower,
+            "velocity": -lim.velocity,
+            "feedforward_torque": -lim.effort,
+            "kp_scale": 0.0,
+            "kd_scale": 0.0,
+            "maximum_torque": 0.0,
+        }
+    return spaces.Dict(action_space), spaces.Dict(servo_space), neutral_action, max_action, min_action
+
+
+def make_gyropod_spaces(max_ground_velocity: float = 3.0, max_yaw_velocity: float = 1.0):
+    """``UpkieGyropod.__init__`` spaces (``upkie_gyropod.py:118-160``)."""
+    observation_limit = np.array(
+        [float("inf"), np.pi, float("inf"), max_ground_velocity, 1000.0, max_yaw_velocity], dtype=np.float32
+    )
+    action_limit = np.array([max_ground_velocity, max_yaw_velocity], dtype=np.float32)
+    obs = spaces.Box(-observation_limit, +observation_limit, shape=observation_limit.shape, dtype=observation_limit.dtype)
+    act = spaces.Box(-action_limit, +action_limit, shape=action_limit.shape, dtype=action_limit.dtype)
+    return act, obs
+
+
+PENDULUM_OBS_INDICES = [1, 0, 4, 3]  # upkie_pendulum.py:17
+
+
+def make_pendulum_spaces(max_ground_velocity: float = 3.0):
+    """``UpkiePendulum.__init__`` spaces (``upkie_pendulum.py:87-102``)."""
+    _, gyro_obs = make_gyropod_spaces(max_ground_velocity)
+    obs_limit = gyro_obs.high[PENDULUM_OBS_INDICES]
+    obs = spaces.Box(-obs_limit, +obs_limit, shape=obs_limit.shape, dtype=np.float32)
+    action_limit = np.array([max_ground_velocity], dtype=np.float32)
+    act = spaces.Box(-action_limit, +action_limit, shape=action_limit.shape, dtype=np.float32)
+    return act, obs
+
+
+def servo_action_dict_to_array(action: dict, neutral_action: dict, n: int) -> np.ndarray:
+    """Batched dict action ``{joint: {key: array[N, 1]}}`` -> ``[N, 6, 6]``.
+    Missing keys take the neutral action (``upkie_servos.py:326-331``)."""
+    out = np.empty((n, 6, 6), dtype=np.float32)
+    for j, name in enumerate(_abi.JOINT_NAMES):
+        ja = action.get(name, {}) if isinstance(action, dict) else {}
+        for k, key in enumerate(_abi.ACT_KEYS):
+            if key in ja:
+                out[:, j, k] = np.asarray(ja[key], dtype=np.float32).reshape(n)
+            else:
+                out[:, j, k] = neutral_action[name][key]
+    return out
+
+
+def servo_obs_array_to_dict(obs: np.ndarray) -> dict:
+    """``[N, 6, 5]`` -> batched dict ``{joint: {key: array[N, 1] float32}}``
+    (``UpkieServos.get_env_observation``, ``upkie_servos.py:288-306``)."""
+    return {
+        name: {key: obs[:, j, k : k + 1].astype(np.float32, copy=False) for k, key in enumerate(_abi.OBS_KEYS)}
+        for j, name in enumerate(_abi.JOINT_NAMES)
+    }
+
+
+class SpineObservations:
+    """Lazy ``info["spine_observation"]``: fetched from the device on first use.
+
+    ``obs[i]`` returns the reference's nested dictionary for env ``i``
+    (``pybullet_backend.py:325-331``); ``obs.array`` the flat ``[N, 62]`` array.
+    """
+
+    def __init__(self, sim: UpkieSim):
+        self._sim = sim
+        self._array = None
+
+    @property
+    def array(self) -> np.ndarray:
+        if self._array is None:
+            self._array = self._sim.spine_obs().cpu().numpy()
+        return self._array
+
+    def __len__(self):
+        return self._sim.n
+
+    def __getitem__(self, i: int) -> dict:
+        return spine_row_to_dict(self.array[i])
+
+
+def spine_row_to_dict(r: np.ndarray) -> dict:
+    """Flat spine observation row -> the dictionary of
+    ``PyBulletBackend.get_spine_observation``."""
+    A = _abi
+    return {
+        "base_orientation": {
+            "angular_velocity": [float(x) for x in r[A.SP_BASE_ANGVEL : A.SP_BASE_ANGVEL + 3]],
+            "linear_velocity": [float(x) for x in r[A.SP_BASE_LINVEL : A.SP_BASE_LINVEL + 3]],
+            "pitch": float(r[A.SP_PITCH]),
+            "rotation_base_to_world": np.asarray(r[A.SP_ROT : A.SP_ROT + 9], dtype=float).reshape(3, 3).tolist(),
+        },
+        "floor_contact": {"contact": bool(r[A.SP_CONTACT] > 0.5)},
+        "imu": {
+            "orientation": [float(x) for x in r[A.SP_IMU_QUAT : A.SP_IMU_QUAT + 4]],
+            "angular_velocity": [float(x) for x in r[A.SP_IMU_ANGVEL : A.SP_IMU_ANGVEL + 3]],
+            "linear_acceleration": np.asarray(r[A.SP_IMU_LINACC : A.SP_IMU_LINACC + 3], dtype=float),
+            "raw_linear_acceleration": [float(x) for x in r[A.SP_IMU_RAWACC : A.SP_IMU_RAWACC + 3]],
+        },
+        "servo": {
+            name: {
+                key: float(r[A.SP_SERVO + j * 5 + k]) for k, key in enumerate(A.OBS_KEYS)
+            }
+            for j, name in enumerate(A.JOINT_NAMES)
+        },
+        "wheel_odometry": {"position": float(r[A.SP_ODOM_POS]), "velocity": float(r[A.SP_ODOM_VEL])},
+    }
+
+
+def make_config(
+    frequency: float = 200.0,
+    nb_substeps: Optional[int] = None,
+    torque_control_kp: float = 20.0,
+    torque_control_kd: float = 1.0,
+    joint_properties: Optional[dict] = None,
+    max_gain_scale: float = 5.0,
+    fall_pitch: float = 1.0,
+    leg_gain_scale: float = 1.0,
+    max_ground_velocity: float = 3.0,
+    max_yaw_velocity: float = 1.0,
+    init_state: Optional[RobotState] = None,
+) -> _abi.UpkieSimConfig:
+    """Split of the keyword arguments the reference's factories forward to the
+    backend, the servo env and the wrappers (``upkie/envs/entry_points.py:41-61,99-109``)."""
+    if frequency is None:
+        raise UpkieException("This environment needs a loop frequency")
+    cfg = _abi.default_sim_config(frequency)
+    if nb_substeps is not None:
+        cfg.nb_substeps = int(nb_substeps)
+    if cfg.nb_substeps < 1:
+        cfg.nb_substeps = 1
+    cfg.torque_control_kp = torque_control_kp
+    cfg.torque_control_kd = torque_control_kd
+    for j, name in enumerate(_abi.JOINT_NAMES):
+        props = (joint_properties or {}).get(name)
+        if props is not None:
+            cfg.joint_friction[j] = float(getattr(props, "friction", 0.0))
+    cfg.max_gain_scale = max_gain_scale
+    cfg.fall_pitch = fall_pitch
+    cfg.leg_gain_scale = leg_gain_scale
+    cfg.max_ground_velocity = max_ground_velocity
+    cfg.max_yaw_velocity = max_yaw_velocity
+    if init_state is not None:
+        init_state.apply_to_config(cfg)
+    return cfg
+
+
+class B200VectorEnv(VectorEnv):
+    """N Upkie environments stepped by one kernel launch per ``step()``."""
+
+    metadata: Dict[str, Any] = {"autoreset_mode": "disabled"}
+
+    def __init__(
+        self,
+        num_envs: int,
+        env_type: str = "servos",
+        frequency: float = 200.0,
+        init_state: Optional[RobotState] = None,
+        model: Optional[Model] = None,
+        device: int = 0,
+        autoreset_mode: str = "disabled",
+        max_gain_scale: float = 5.0,
+        fall_pitch: float = 1.0,
+        leg_gain_scale: float = 1.0,
+        max_ground_velocity: float = 3.0,
+        max_yaw_velocity: float = 1.0,
+        nb_substeps: Optional[int] = None,
+        torque_control_kp: float = 20.0,
+        torque_control_kd: float = 1.0,
+        joint_properties: Optional[dict] = None,
+        inertia_variation: float = 0.0,
+        env_offset: int = 0,
+        config: Optional[_abi.UpkieSimConfig] = None,
+    ):
+        if env_type not in ENV_TYPES:
+            raise UpkieException(f"env_type must be one of {ENV_TYPES}")
+        if autoreset_mode not in _AUTORESET:
+            raise UpkieException(f"autoreset_mode must be one of {tuple(_AUTORESET)}")
+        self.env_type = env_type
+        self.num_envs = int(num_envs)
+        self.model = model if model is not None else default_model()
+        self.init_state = init_state if init_state is not None else RobotState(
+            position_base_in_world=np.array([0.0, 0.0, 0.6])
+        )
+        self.frequency = frequency
+        self.dt = 1.0 / frequency
+        self.env_offset = int(env_offset)
+        self.autoreset_mode = autoreset_mode
+        self.metadata = dict(self.metadata, autoreset_mode=autoreset_mode)
+        if config is None:
+            config = make_config(
+                frequency, nb_substeps, torque_control_kp, torque_control_kd, joint_properties, max_gain_scale,
+                fall_pitch, leg_gain_scale, max_ground_velocity, max_yaw_velocity, self.init_state,
+            )
+        self.config = config
+        (
+            servo_act, servo_obs, self._neutral_action, self._max_action, self._min_action,
+        ) = make_servo_spaces(self.model, max_gain_scale)
+        if env_type == "servos":
+            self.single_action_space, self.single_observation_space = servo_act, servo_obs
+        elif env_type == "gyropod":
+            self.single_action_space, self.single_observation_space = make_gyropod_spaces(
+                max_ground_velocity, max_yaw_velocity
+            )
+        else:
+            self.single_action_space, self.single_observation_space = make_pendulum_spaces(max_ground_velocity)
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+
+        self.sim = UpkieSim(self.num_envs, model=self.model, config=self.config, device=device)
+        self._seed = 0
+        self.sim.set_autoreset(_AUTORESET[autoreset_mode], self._seed, self.env_offset)
+        self.inertia_variation = inertia_variation
+        if abs(inertia_variation) > 1e-10:
+            self.randomize_inertias(inertia_variation)
+
+    # ------------------------------------------------------------------
+    def get_neutral_action(self) -> dict:
+        """``UpkieServos.get_neutral_action`` (``upkie_servos.py:308-314``)."""
+        return self._neutral_action.copy()
+
+    def randomize_inertias(self, inertia_variation: float, seed: Optional[int] = None) -> None:
+        """``PyBulletBackend.randomize_inertias`` (``pybullet_backend.py:571-601``):
+        one epsilon ~ U(-v, v) per non-base body and env."""
+        rng = np.random.default_rng(seed)
+        eps = rng.uniform(-inertia_variation, inertia_variation, size=(self.num_envs, 6)).astype(np.float32)
+        self.sim.set_randomization(inertia_eps=torch.from_numpy(eps).to(self.sim.device))
+
+    def update_init_rand(self, **kwargs) -> None:
+        """``UpkieEnv.update_init_rand`` (``upkie_env.py:244-251``)."""
+        self.init_state.randomization.update(**kwargs)
+
+    def close(self, **kwargs) -> None:
+        self.sim.close()
+
+    # ------------------------------------------------------------------
+    def _obs_dim(self) -> int:
+        return {"servos": 30, "gyropod": 6, "pendulum": 4}[self.env_type]
+
+    def _format_obs(self, obs: np.ndarray):
+        return servo_obs_array_to_dict(obs) if self.env_type == "servos" else obs
+
+    def reset(self, *, seed: Optional[Union[int, list]] = None, options: Optional[dict] = None):
+        """Reset all envs (or ``options["reset_mask"]``) and return the initial
+        observations. Env ``i`` samples its initial state from
+        ``np.random.default_rng(seed + i)`` exactly as ``UpkieEnv.reset(seed)``
+        does for a single env (``upkie_env.py:180-190``); with ``seed=None``
+        the envs draw from the vector env's own generator."""
+        n = self.num_envs
+        mask = None
+        if options and options.get("reset_mask") is not None:
+            mask = np.ascontiguousarray(options["reset_mask"], dtype=np.uint8).reshape(n)
+        parent = self.np_random
+        if seed is None:
+            seeds = [None] * n
+        elif isinstance(seed, (list, tuple, np.ndarray)):
+            seeds = list(seed)
+        else:
+            seeds = [int(seed) + self.env_offset + i for i in range(n)]
+            self._seed = int(seed)
+            self.sim.set_autoreset(_AUTORESET[self.autoreset_mode], self._seed, self.env_offset)
+        rows = np.zeros((n, _abi.INIT_DIM), dtype=np.float32)
+        for i in range(n):
+            if mask is not None and not mask[i]:
+                continue
+            rng = parent if seeds[i] is None else np.random.default_rng(seeds[i])
+            rows[i] = self.init_state.sample_state(rng).to_row()
+        dev = self.sim.device
+        self.sim.reset(
+            mask=torch.from_numpy(mask).to(dev) if mask is not None else None,
+            init_state=torch.from_numpy(rows).to(dev),
+        )
+        obs = self.sim.reset_obs(self._obs_dim()).cpu().numpy()
+        return self._format_obs(obs), {"spine_observation": SpineObservations(self.sim)}
+
+    def step(self, action):
+        """One 5 ms control tick for every env. ``action`` is a batched dict
+        (servos), an ndarray / CPU tensor, or a CUDA tensor (then the result
+        tensors stay on the device)."""
+        if isinstance(action, torch.Tensor) and action.is_cuda:
+            return self.step_tensors(action)
+        n = self.num_envs
+        if self.env_type == "servos":
+            a = (
+                servo_action_dict_to_array(action, self._neutral_action, n)
+                if isinstance(action, dict)
+                else np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, 6, 6))
+            )
+            obs, rew, term, trunc = self.sim.step_servos_host(a)
+        else:
+            d = 2 if self.env_type == "gyropod" else 1
+            a = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, d))
+            obs, rew, term, trunc = self.sim.step_gyropod_host(a)
+        info = {"spine_observation": SpineObservations(self.sim)}
+        return self._format_obs(obs), rew.astype(np.float64), term.astype(bool), trunc.astype(bool), info
+
+    def step_tensors(self, action: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, dict]:
+        """Zero-copy fast path: CUDA tensors in, CUDA tensors out
+        (``action[N, 6, 6]`` / ``[N, 2]`` / ``[N, 1]``)."""
+        if self.env_type == "servos":
+            obs, rew, term, trunc = self.sim.step_servos(action)
+        elif self.env_type == "gyropod":
+            obs, rew, term, trunc = self.sim.step_gyropod(action)
+        else:
+            obs, rew, term, trunc = self.sim.step_pendulum(action)
+        return obs, rew, term, trunc, {"spine_observation": SpineObservations(self.sim)}
