@@ -400,8 +400,11 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     launches0 = env.sim.launches
     events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     end = torch.cuda.Event(enable_timing=True)
+    profiling = bool(os.environ.get("UPKIE_BENCH_CUDA_PROFILER"))  # ncu --profile-from-start off
     with ClockSampler(dev.index) as clk:
         torch.cuda.synchronize()
+        if profiling:
+            torch.cuda.profiler.start()
         events[0].record()
         for k in range(K):
             o, r, te, tr = step(acts[k % N_ACTION_BUFFERS])
@@ -412,6 +415,8 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
                     dist.all_gather_into_tensor(gathered, rollout)
         end.record()  # after the last step / all-gather queued on this stream
         torch.cuda.synchronize()
+        if profiling:
+            torch.cuda.profiler.stop()
         if world > 1:
             dist.barrier()
     total_ms = events[0].elapsed_time(end)

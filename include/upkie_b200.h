@@ -169,8 +169,14 @@ typedef struct UpkieSimConfig {
   /* extension: also terminate UpkieServos envs when
    * |pitch| > fall_pitch or base height < min_base_height; 0 = reference behaviour */
   int32_t servos_fall_termination;
-  int32_t reserved0;
+  /* 1 = skip the UpkieServos.get_spine_action clamps (used by the single-env Backend adapter,
+   * which receives actions the reference's own UpkieServos already clamped) */
+  int32_t skip_action_clamps;
   double min_base_height;
+  /* PGS sweeps stop early once every impulse of a warp changed by less than
+   * pgs_tolerance * |impulse| + 1e-9 in one sweep (Bullet: m_leastSquaresResidualThreshold-style
+   * exit); 0 = always run pgs_iterations sweeps */
+  double pgs_tolerance;
   /* RobotStateRandomization bounds used by the on-device sampler
    * (upkie/utils/robot_state_randomization.py:135-189) */
   double init_position[3];     /* nominal position_base_in_world (0, 0, 0.6) */

@@ -1,0 +1,336 @@
+# SPDX-License-Identifier: Apache-2.0
+"""GPU tests through the C ABI: wrappers, reset, auto-reset, vector-env API, MPC,
+full-size invariants."""
+import numpy as np
+import pytest
+
+from conftest import random_servo_actions, random_states
+from upkie_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _sim(n, model, cfg=None):
+    from upkie_b200.sim import UpkieSim
+
+    return UpkieSim(n, model=model, config=cfg if cfg is not None else _abi.default_sim_config())
+
+
+def test_loaded_library_is_the_in_tree_cuda_build():
+    from upkie_b200 import _lib
+
+    assert _lib.LIB_PATH.endswith("upkie_b200/libupkie_b200.so")
+    with open("/proc/self/maps") as f:
+        _lib.lib()
+        assert any("libupkie_b200.so" in line for line in f.read().splitlines())
+
+
+def test_reset_matches_oracle(model, oracle_lib, torch):
+    n = 1024
+    cfg = _abi.default_sim_config()
+    cfg.rand_pitch, cfg.rand_roll, cfg.rand_z, cfg.rand_omega_y = 0.3, 0.1, 0.05, 0.5
+    rng = np.random.default_rng(0)
+    init = np.stack([oracle_lib.sample_init_state(cfg, np.random.default_rng(s)) for s in range(n)]).astype(np.float32)
+    init[:, 13:19] = rng.uniform(-0.3, 0.3, (n, 6))
+    sim = _sim(n, model, cfg)
+    osim = oracle_lib.OracleSim(model, cfg, n, threads=8)
+    sim.reset(init_state=torch.from_numpy(init).cuda())
+    osim.reset(init.astype(np.float64))
+    gs, os_ = sim.get_state().cpu().numpy().astype(np.float64), osim.get_state()
+    assert np.abs(gs[:, :7] - os_[:, :7]).max() < 1e-6
+    assert np.abs(gs[:, 7:13] - os_[:, 7:13]).max() < 2e-3  # one substep of gravity/contact
+    assert np.allclose(gs[:, 34:38], gs[:, [13, 14, 16, 17]])  # UpkieGyropod.reset leg targets
+    for dim in (30, 6, 4):
+        g = sim.reset_obs(dim).cpu().numpy().astype(np.float64).reshape(n, -1)
+        o = osim.reset_obs(dim).reshape(n, -1)
+        assert np.median(np.abs(g - o)) < 1e-5 and np.abs(g - o).max() < 5e-2
+    # masked reset leaves the other envs untouched
+    before = sim.get_state().clone()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::2] = 1
+    sim.reset(mask=mask, init_state=torch.from_numpy(init).cuda())
+    after = sim.get_state()
+    assert torch.equal(after[1::2], before[1::2])
+
+
+def test_gyropod_and_pendulum_match_oracle(model, oracle_lib, torch):
+    n = 1024
+    cfg = _abi.default_sim_config()
+    sim = _sim(n, model, cfg)
+    osim = oracle_lib.OracleSim(model, cfg, n, threads=8)
+    rng = np.random.default_rng(5)
+    init = np.zeros((n, _abi.INIT_DIM), dtype=np.float32)
+    init[:, 2] = 0.6
+    pitch = rng.uniform(-0.3, 0.3, n)
+    init[:, 3], init[:, 5] = np.cos(pitch / 2), np.sin(pitch / 2)
+    sim.reset(init_state=torch.from_numpy(init).cuda())
+    osim.reset(init.astype(np.float64))
+    mism = 0
+    for t in range(30):
+        a = rng.uniform(-3.5, 3.5, (n, 2)).astype(np.float32)
+        osim.set_state(sim.get_state().cpu().numpy().astype(np.float64))  # re-synchronise every tick
+        g6, grew, gterm, gtrunc = sim.step_gyropod(torch.from_numpy(a).cuda())
+        o6, orew, oterm, otrunc = osim.step_gyropod(a.astype(np.float64), 2)
+        g6 = g6.cpu().numpy().astype(np.float64)
+        assert np.abs(g6[:, [0, 1, 2, 5]] - o6[:, [0, 1, 2, 5]]).max() < 2e-4
+        assert np.median(np.abs(g6[:, 3:5] - o6[:, 3:5])) < 1e-3
+        safe = np.abs(np.abs(o6[:, 1]) - 1.0) > 1e-4
+        assert np.array_equal(gterm.cpu().numpy()[safe], oterm[safe])
+        mism += int((gterm.cpu().numpy()[~safe] != oterm[~safe]).sum())
+        assert not gtrunc.any().item() and (grew == 0).all().item()
+    assert mism <= 2
+    a1 = rng.uniform(-3, 3, (n, 1)).astype(np.float32)
+    osim.set_state(sim.get_state().cpu().numpy().astype(np.float64))
+    g4, _, _, _ = sim.step_pendulum(torch.from_numpy(a1).cuda())
+    o4, _, _, _ = osim.step_gyropod(a1.astype(np.float64), 1)
+    assert np.abs(g4.cpu().numpy()[:, :2] - o4[:, :2]).max() < 2e-4
+
+
+def test_randomization_matches_oracle(model, oracle_lib, torch):
+    n = 1024
+    cfg = _abi.default_sim_config()
+    sim = _sim(n, model, cfg)
+    osim = oracle_lib.OracleSim(model, cfg, n, threads=8)
+    rng = np.random.default_rng(2)
+    eps = rng.uniform(-0.2, 0.2, (n, 6)).astype(np.float32)
+    mu = rng.uniform(0.5, 1.2, n).astype(np.float32)
+    sim.set_randomization(friction=torch.from_numpy(mu).cuda(), inertia_eps=torch.from_numpy(eps).cuda())
+    osim.set_randomization(friction=mu.astype(np.float64), inertia_eps=eps.astype(np.float64))
+    st = random_states(n, seed=21).astype(np.float32)
+    act = random_servo_actions(n, model, seed=22, torque_mode=True).astype(np.float32)
+    sim.set_state(torch.from_numpy(st).cuda())
+    osim.set_state(st.astype(np.float64))
+    sim.step_servos(torch.from_numpy(act).cuda())
+    osim.step_servos(act.astype(np.float64))
+    gs, os_ = sim.get_state().cpu().numpy().astype(np.float64), osim.get_state()
+    assert np.abs(gs[:, :7] - os_[:, :7]).max() < 2e-5
+    assert np.median(np.abs(gs[:, 19:25] - os_[:, 19:25]).max(axis=1)) < 1e-3
+
+
+def test_host_buffer_api_equals_device_api(model, torch):
+    n = 4096
+    a = random_servo_actions(n, model, seed=1).astype(np.float32)
+    st = torch.from_numpy(random_states(n, seed=2).astype(np.float32)).cuda()
+    s1, s2 = _sim(n, model), _sim(n, model)
+    s1.set_state(st)
+    s2.set_state(st)
+    o1, r1, t1, u1 = s1.step_servos(torch.from_numpy(a).cuda())
+    o2, r2, t2, u2 = s2.step_servos_host(a)
+    assert np.array_equal(o1.cpu().numpy(), o2)  # same kernel: bit-exact
+    assert np.array_equal(t1.cpu().numpy(), t2) and np.array_equal(r1.cpu().numpy(), r2)
+    g = np.random.default_rng(3).uniform(-3, 3, (n, 2)).astype(np.float32)
+    o1, _, t1, _ = s1.step_gyropod(torch.from_numpy(g).cuda())
+    o2, _, t2, _ = s2.step_gyropod_host(g)
+    assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(t1.cpu().numpy(), t2)
+
+
+def test_vector_env_api_and_reference_semantics(model, torch):
+    from upkie_b200.envs import B200VectorEnv
+    from upkie_b200.robot_state import RobotState, RobotStateRandomization
+
+    n = 64
+    init = RobotState(randomization=RobotStateRandomization(pitch=0.2, z=0.05))
+    env = B200VectorEnv(n, "servos", model=model, init_state=init)
+    obs, info = env.reset(seed=42)
+    assert set(obs) == set(_abi.JOINT_NAMES) and obs["left_hip"]["position"].shape == (n, 1)
+    assert obs["left_hip"]["position"].dtype == np.float32
+    assert np.all(obs["right_wheel"]["temperature"] == 42.0) and np.all(obs["right_wheel"]["voltage"] == 18.0)
+    sp0 = info["spine_observation"][0]
+    assert set(sp0) == {"base_orientation", "floor_contact", "imu", "servo", "wheel_odometry"}
+    # seeding: env i draws from default_rng(seed + i), as UpkieEnv.reset(seed) would (upkie_env.py:180-190)
+    obs_b, info_b = env.reset(seed=42)
+    sa, sb = info["spine_observation"].array, info_b["spine_observation"].array
+    # everything but the IMU accelerations repeats: the reference does NOT reset
+    # __previous_imu_linear_velocity on reset (pybullet_backend.py:157,220-232), and neither do we
+    keep = [i for i in range(_abi.SPINE_DIM) if not (_abi.SP_IMU_LINACC <= i < _abi.SP_IMU_RAWACC + 3)]
+    assert np.array_equal(sa[:, keep], sb[:, keep])
+    expect_pitch = [init.sample_state(np.random.default_rng(42 + i)).to_row()[3:7] for i in range(n)]
+    st = env.sim.get_state().cpu().numpy()
+    got_pitch = 2 * np.arctan2(st[:, 5], st[:, 3])
+    want_pitch = np.array([2 * np.arctan2(q[2], q[0]) for q in expect_pitch])
+    assert np.abs(got_pitch - want_pitch).max() < 2e-3  # one 1 ms substep after the reset
+    action = {name: {"position": np.zeros((n, 1), np.float32), "velocity": np.zeros((n, 1), np.float32)}
+              for name in ("left_hip", "left_knee", "right_hip", "right_knee")}
+    obs, rew, term, trunc, info = env.step(action)
+    assert rew.shape == (n,) and (rew == 0.0).all()  # upkie_env.py:230
+    assert term.dtype == bool and not term.any() and not trunc.any()  # UpkieServos never terminates
+    flat = np.zeros((n, 6, 6), np.float32)
+    flat[:, :, 0] = np.nan
+    obs2, *_ = env.step(flat)
+    assert obs2["left_hip"]["torque"].shape == (n, 1)
+    env.close()
+
+    penv = B200VectorEnv(n, "pendulum", model=model)
+    o, _ = penv.reset(seed=0)
+    assert o.shape == (n, 4) and o.dtype == np.float32
+    o, r, te, tr, _ = penv.step(np.zeros((n, 1), np.float32))
+    assert o.shape == (n, 4) and penv.single_observation_space.shape == (4,)
+    # README policy keeps every env up for a second (README.md:62-64)
+    for _ in range(200):
+        a = (10.0 * o[:, 0] + 1.0 * o[:, 1] + 0.0 * o[:, 2] + 0.1 * o[:, 3]).reshape(n, 1).astype(np.float32)
+        o, r, te, tr, _ = penv.step(a)
+        assert not te.any()
+    assert np.abs(o[:, 0]).max() < 0.3
+    # without control the robot falls and `terminated` is raised, and stays up to the user to reset
+    fell = np.zeros(n, bool)
+    for _ in range(400):
+        o, r, te, tr, _ = penv.step(np.zeros((n, 1), np.float32))
+        fell |= te
+    assert fell.all()
+    penv.close()
+
+
+def test_autoreset_modes(model, torch):
+    from upkie_b200.envs import B200VectorEnv
+    from upkie_b200.robot_state import RobotState, RobotStateRandomization
+
+    n = 256
+    init = RobotState(randomization=RobotStateRandomization(pitch=0.4))
+    zero = torch.zeros((n, 1), device="cuda")
+    for mode in ("next_step", "same_step"):
+        env = B200VectorEnv(n, "pendulum", model=model, init_state=init, autoreset_mode=mode)
+        env.reset(seed=7)
+        total_done, after_done_pitch = 0, []
+        prev_term = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        for _ in range(600):
+            o, r, te, tr, _ = env.step_tensors(zero)
+            if mode == "next_step":
+                # the step after a termination returns the reset observation with terminated = 0
+                idx = prev_term.bool()
+                if idx.any():
+                    assert not te[idx].any().item()
+                    after_done_pitch.append(o[idx, 0].abs().max().item())
+            else:
+                idx = te.bool()
+                if idx.any():
+                    after_done_pitch.append(o[idx, 0].abs().max().item())
+            prev_term = te.clone()
+            total_done += int(te.sum().item())
+        assert total_done >= n  # every env fell at least once on average and kept running
+        assert max(after_done_pitch) <= 0.4 + 0.05  # reset observations: |pitch| within the sampling bounds
+        st = env.sim.get_state()
+        assert torch.isfinite(st).all().item()
+        env.close()
+
+
+def test_env_index_sharding_is_invariant(model, torch):
+    """Two shards of n/2 envs with env_offset reproduce one batch of n envs bit for bit
+    (results invariant to the GPU count)."""
+    from upkie_b200 import _abi as A
+
+    n = 512
+    cfg = A.default_sim_config()
+    cfg.rand_pitch, cfg.rand_omega_y = 0.3, 0.5
+    cfg.servos_fall_termination = 1
+    cfg.min_base_height = 0.15
+    acts = torch.from_numpy(random_servo_actions(n, model, seed=3, torque_mode=True).astype(np.float32)).cuda()
+    full = _sim(n, model, cfg)
+    full.set_autoreset(1, 99, 0)
+    full.reset(seed=99, env_offset=0)
+    halves = []
+    for k in range(2):
+        h = _sim(n // 2, model, cfg)
+        h.set_autoreset(1, 99, k * n // 2)
+        h.reset(seed=99, env_offset=k * n // 2)
+        halves.append(h)
+    for t in range(60):
+        of, _, tf, _ = full.step_servos(acts)
+        parts = [h.step_servos(acts[k * n // 2:(k + 1) * n // 2].contiguous()) for k, h in enumerate(halves)]
+        assert torch.equal(of, torch.cat([p[0] for p in parts]))
+        assert torch.equal(tf, torch.cat([p[2] for p in parts]))
+    assert torch.equal(full.get_state(), torch.cat([h.get_state() for h in halves]))
+
+
+def test_mpc_matches_oracle(oracle_lib, torch):
+    from upkie_b200.mpc import BatchedMPCBalancer
+
+    for horizon in (16, 50):
+        cfg = _abi.default_mpc_config()
+        cfg.nb_timesteps = horizon
+        n = 2048
+        rng = np.random.default_rng(0)
+        x0 = np.stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.2, 0.2, n), rng.uniform(-0.5, 0.5, n),
+                       rng.uniform(-1, 1, n)], 1).astype(np.float32)
+        x0[:64, 1] = rng.uniform(0.3, 0.9, 64)
+        x0[64:96, 1] = rng.uniform(1.05, 1.3, 32)
+        vt = rng.uniform(-1, 1, n).astype(np.float32)
+        contact = np.ones(n, np.uint8)
+        contact[96:128] = 0
+        mpc = BatchedMPCBalancer(n, config=cfg)
+        v0 = rng.uniform(-1, 1, n).astype(np.float32)
+        mpc.commanded_velocity.copy_(torch.from_numpy(v0).cuda())
+        v = mpc.step_tensors(torch.from_numpy(x0).cuda(), torch.from_numpy(vt).cuda(), torch.from_numpy(contact).cuda(), 0.005)
+        plan = mpc.plan().cpu().numpy().astype(np.float64)
+        om = oracle_lib.OracleMpc(cfg)
+        vc_o, first_o, found_o, plan_o = om.step(x0.astype(np.float64), vt.astype(np.float64), contact, 0.005,
+                                                 v0.astype(np.float64), threads=8)
+        assert mpc.found.all().item() and found_o.all()
+        assert np.abs(plan[:, 0] - plan_o[:, 0]).max() < 1e-3  # |u0 - u0_oracle| <= ProxQP eps_abs (mpc_balancer.py:76)
+        assert np.abs(plan - plan_o).max() < 5e-3
+        assert np.abs(v.cpu().numpy() - vc_o).max() < 1e-5
+        assert np.abs(v.cpu().numpy()).max() <= 3.0
+        # warm-started second tick stays consistent
+        v2 = mpc.step_tensors(torch.from_numpy(x0).cuda(), torch.from_numpy(vt).cuda(), torch.from_numpy(contact).cuda(), 0.005)
+        assert np.abs(mpc.plan().cpu().numpy() - plan_o).max() < 5e-3
+        mpc.reset()
+        assert (mpc.commanded_velocity == 0).all().item()
+
+
+def test_mpc_in_the_loop_balances(model, torch):
+    """UpkieBaseVelocity-style closed loop (upkie_base_velocity.py:164-202): MPC command -> gyropod env."""
+    from upkie_b200.envs import B200VectorEnv
+    from upkie_b200.mpc import BatchedMPCBalancer
+
+    n = 128
+    env = B200VectorEnv(n, "gyropod", model=model)
+    env.reset(seed=1)
+    mpc = BatchedMPCBalancer(n)
+    target = torch.full((n,), 0.3, device="cuda")
+    spine = env.sim.spine_obs()
+    fell = torch.zeros(n, dtype=torch.bool, device="cuda")
+    for _ in range(400):
+        v = mpc.step_spine(target, spine, env.dt)
+        a = torch.stack([v, torch.zeros_like(v)], dim=1).contiguous()
+        o, r, te, tr, info = env.step_tensors(a)
+        spine = env.sim.spine_obs()
+        fell |= te.bool()
+    assert not fell.any().item()
+    assert (o[:, 3] - 0.3).abs().max().item() < 0.2  # tracks the commanded ground velocity
+    assert o[:, 1].abs().max().item() < 0.3
+
+
+def test_full_size_invariants(model, torch):
+    """BASELINE-size batch (65536 envs): finite state, unit quaternions, contact physics sane,
+    reward/truncated constants, idempotent spine observation."""
+    n = 65536
+    cfg = _abi.default_sim_config()
+    cfg.rand_pitch = 0.3
+    sim = _sim(n, model, cfg)
+    sim.reset(seed=5)
+    a = torch.zeros((n, 6, 6), device="cuda")
+    a[:, :, 0] = float("nan")
+    a[:, :, 5] = torch.tensor(model.tau_max, dtype=torch.float32, device="cuda")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0)
+    for _ in range(40):
+        a[:, :, 2] = (torch.rand((n, 6), device="cuda", generator=gen) * 2 - 1) * a[:, :, 5] * 0.2
+        obs, rew, term, trunc = sim.step_servos(a)
+    st = sim.get_state()
+    assert torch.isfinite(st).all().item()
+    assert (st[:, 3:7].norm(dim=1) - 1).abs().max().item() < 1e-5
+    assert (rew == 0).all().item() and not trunc.any().item() and not term.any().item()
+    assert (st[:, 19:25].abs() <= 100.0 + 1e-3).all().item()  # max coordinate velocity clamp
+    on_ground = st[:, 40] > 0.5
+    assert on_ground.float().mean().item() > 0.5
+    s1, s2 = sim.spine_obs(), sim.spine_obs()
+    assert torch.equal(s1, s2)  # observation has no side effects
+    assert torch.equal(s1[:, 30:60].reshape(n, 6, 5), obs)
+    assert (sim.error_flags() & 2).sum().item() == 0

@@ -97,8 +97,9 @@ class UpkieSimConfig(C.Structure):
         ("max_ground_velocity", C.c_double),
         ("max_yaw_velocity", C.c_double),
         ("servos_fall_termination", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("skip_action_clamps", C.c_int32),
         ("min_base_height", C.c_double),
+        ("pgs_tolerance", C.c_double),
         ("init_position", C.c_double * 3),
         ("init_quat", C.c_double * 4),
         ("rand_roll", C.c_double),
@@ -157,8 +158,9 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.max_ground_velocity = 3.0
     c.max_yaw_velocity = 1.0
     c.servos_fall_termination = 0
-    c.reserved0 = 0
+    c.skip_action_clamps = 0
     c.min_base_height = 0.0
+    c.pgs_tolerance = 1e-6
     c.init_position[0], c.init_position[1], c.init_position[2] = 0.0, 0.0, 0.6
     c.init_quat[0], c.init_quat[1], c.init_quat[2], c.init_quat[3] = 1.0, 0.0, 0.0, 0.0
     c.rand_roll = c.rand_pitch = c.rand_x = c.rand_z = 0.0

@@ -13,7 +13,8 @@ from . import _abi
 from .exceptions import MissingOptionalDependency, UpkieRuntimeError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libupkie_b200.so")
+# UPKIE_B200_LIB: developer override used by tools/variants.py to load an alternative build
+LIB_PATH = os.environ.get("UPKIE_B200_LIB") or os.path.join(_HERE, "libupkie_b200.so")
 
 _lib = None
 

@@ -33,8 +33,9 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->max_ground_velocity = 3.0;
   c->max_yaw_velocity = 1.0;
   c->servos_fall_termination = 0;
-  c->reserved0 = 0;
+  c->skip_action_clamps = 0;
   c->min_base_height = 0.0;
+  c->pgs_tolerance = 1e-6;
   c->init_position[0] = 0.0; c->init_position[1] = 0.0; c->init_position[2] = 0.6;  // upkie_env.py:87-90
   c->init_quat[0] = 1.0; c->init_quat[1] = 0.0; c->init_quat[2] = 0.0; c->init_quat[3] = 0.0;
   c->rand_roll = c->rand_pitch = c->rand_x = c->rand_z = 0.0;
@@ -110,6 +111,8 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.inv_h = float(1.0 / h);
   P.nb_substeps = c.nb_substeps;
   P.pgs_iterations = c.pgs_iterations;
+  P.pgs_rtol = float(c.pgs_tolerance);
+  P.skip_action_clamps = c.skip_action_clamps;
   P.gravity = float(c.gravity);
   P.kp = float(c.torque_control_kp);
   P.kd = float(c.torque_control_kd);

@@ -54,6 +54,8 @@ struct SimParams {
   // backend
   float dt, inv_dt, h, inv_h;
   int nb_substeps, pgs_iterations;
+  float pgs_rtol;          // early-exit tolerance of the PGS sweeps (0 = fixed count)
+  int skip_action_clamps;
   float gravity, kp, kd;
   float joint_friction[6];
   float lin_damp, ang_damp, vmax;
@@ -624,7 +626,13 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
     }
     const float cfmrow = P.cfm;  // m_cfm = cfm * jacDiagABInv
     const float hiL = actL ? 1e10f : 0.f, hiR = actR ? 1e10f : 0.f;
+    // Projected Gauss-Seidel, at most Bullet's iteration count. The sweep is a
+    // contraction towards a fixed point; the loop leaves once a sweep changed no
+    // impulse of the warp by more than pgs_rtol * |impulse| + 1e-9 (with
+    // pgs_rtol = 0 and the 1e-9 floor removed it runs all sweeps).
+    const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
     for (int it = 0; it < P.pgs_iterations; ++it) {
+      bool changed = false;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         float jdv = 0.f;
@@ -636,8 +644,16 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
         if (k == 0) { lo = 0.f; hi = hiL; }
         else if (k == 1) { lo = 0.f; hi = hiR; }
         else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
-        lam[k] = fminf(fmaxf(sum, lo), hi);
+        const float nl = fminf(fmaxf(sum, lo), hi);
+        changed = changed || (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+        lam[k] = nl;
       }
+#ifdef UPKIE_PGS_STATS
+      if (!changed) { upkie_pgs_stats(it + 1); break; }
+      if (it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 2);
+#else
+      if (!warp_any(changed)) break;
+#endif
     }
     // apply the total wheel impulses
     float fL[6], fR[6];
@@ -811,6 +827,49 @@ UPKIE_HD void spine_observation(const SimParams& P, const RobotState& S, float* 
 
 // UpkieServos.get_spine_action clamps + PyBulletBackend.step + observation update.
 // `a` is the 6x6 servo action (modified in place by the clamps).
+// UpkieServos.get_spine_action clamps (upkie_servos.py:316-344), in place.
+UPKIE_HD uint32_t clamp_servo_action(const SimParams& P, float a[UPKIE_ACT_DIM]) {
+  uint32_t err = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float lo[6] = {P.q_lower[j], -P.qd_max[j], -P.tau_max[j], 0.f, 0.f, 0.f};
+    const float hi[6] = {P.q_upper[j], P.qd_max[j], P.tau_max[j], P.max_gain_scale, P.max_gain_scale, P.tau_max[j]};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float v = a[j * 6 + k];
+      const float c = P.skip_action_clamps ? v : clamp_ref(v, lo[k], hi[k]);
+      if (c != v && !(c != c && v != v)) err |= UPKIE_ERR_CLAMPED;
+      a[j * 6 + k] = c;
+    }
+    if (a[j * 6 + UPKIE_ACT_VELOCITY] != a[j * 6 + UPKIE_ACT_VELOCITY]) err |= UPKIE_ERR_NAN_VELOCITY;
+  }
+  return err;
+}
+
+// One substep of PyBulletBackend.step (pybullet_backend.py:276-306): torque law on
+// the live joint state, then one stepSimulation. `store_torque` is false for the
+// zero-torque substep of a reset (the reference keeps __joint_torques across resets).
+template <typename AnyFn>
+UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPKIE_ACT_DIM], bool zero_torque,
+                            const float* eps, float mu, AnyFn warp_any) {
+  float tau[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float* aj = a + j * 6;
+    const float t = joint_torque(P, j, S.q[j], S.qd[j], aj[UPKIE_ACT_FEEDFORWARD_TORQUE], aj[UPKIE_ACT_POSITION],
+                                 aj[UPKIE_ACT_VELOCITY], aj[UPKIE_ACT_KP_SCALE], aj[UPKIE_ACT_KD_SCALE],
+                                 aj[UPKIE_ACT_MAXIMUM_TORQUE]);
+    tau[j] = zero_torque ? 0.f : t;
+    if (!zero_torque) S.torque[j] = t;
+  }
+  physics_substep(P, S, tau, eps, mu, warp_any);
+}
+
+UPKIE_HD uint32_t state_sanity(const RobotState& S) {
+  const float chk = S.quat[0] + S.quat[1] + S.quat[2] + S.quat[3] + S.pos[2] + S.linvel[0];
+  return (fabsf(chk) <= 3.0e38f) ? 0u : UPKIE_ERR_NAN_STATE;
+}
+
 template <typename AnyFn>
 UPKIE_HD uint32_t step_servo_action(const SimParams& P, RobotState& S, float a[UPKIE_ACT_DIM], const float* eps, float mu,
                                     AnyFn warp_any) {
@@ -895,6 +954,30 @@ UPKIE_HD void gyropod_obs(const SimParams& P, const RobotState& S, float o6[6]) 
   o6[3] = 0.5f * (S.qd[2] - S.qd[5]) * signed_radius;
   o6[4] = R[1] * S.angvel[0] + R[4] * S.angvel[1] + R[7] * S.angvel[2];  // (R^T w).y
   o6[5] = S.yaw_vel;
+}
+
+// _reset_robot_state (pybullet_backend.py:234-267): pose and velocities only
+UPKIE_HD void reset_pose(RobotState& S, const float init[UPKIE_INIT_DIM]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    S.pos[i] = init[UPKIE_INIT_POS + i];
+    S.linvel[i] = init[UPKIE_INIT_LINVEL + i];
+    S.angvel[i] = init[UPKIE_INIT_ANGVEL + i];  // body-frame vector used as world-frame (:253-258)
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) S.quat[i] = init[UPKIE_INIT_QUAT + i];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    S.q[j] = init[UPKIE_INIT_Q + j];
+    S.qd[j] = 0.f;
+  }
+}
+
+// UpkieGyropod.reset (upkie_gyropod.py:216-244), after the reset's stepSimulation + observation
+UPKIE_HD void reset_wrapper_state(RobotState& S) {
+  S.leg_target[0] = S.q[0]; S.leg_target[1] = S.q[1]; S.leg_target[2] = S.q[3]; S.leg_target[3] = S.q[4];
+  S.yaw = 0.f;
+  S.yaw_vel = 0.f;
 }
 
 // PyBulletBackend.reset (pybullet_backend.py:220-267) + UpkieGyropod.reset (upkie_gyropod.py:216-244)

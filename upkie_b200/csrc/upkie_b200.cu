@@ -43,6 +43,17 @@ int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess) return fail(UPKIE_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// build-time tuning knobs (tools/variants.py explores them; defaults are the measured best)
+#ifndef UPKIE_MAX_THREADS
+#define UPKIE_MAX_THREADS 128
+#endif
+#ifndef UPKIE_MIN_BLOCKS
+#define UPKIE_MIN_BLOCKS 1
+#endif
+#ifndef UPKIE_DEFAULT_BLOCK
+#define UPKIE_DEFAULT_BLOCK 128
+#endif
+
 enum { MODE_SERVOS = 0, MODE_GYROPOD = 1, MODE_PENDULUM = 2 };
 enum { AUTORESET_DISABLED = 0, AUTORESET_NEXT_STEP = 1, AUTORESET_SAME_STEP = 2 };
 
@@ -58,7 +69,7 @@ struct Handle {
   uint32_t* episode = nullptr;   // [n]
   int autoreset = AUTORESET_DISABLED;
   uint64_t seed = 0, env_offset = 0;
-  int block = 128;
+  int block = UPKIE_DEFAULT_BLOCK;
   // host-buffer staging (allocated on first use)
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
@@ -93,7 +104,7 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
 
 // ---- the env-step kernel ------------------------------------------------------------
 template <int MODE, int AUTORESET>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(UPKIE_MAX_THREADS, UPKIE_MIN_BLOCKS)
 k_step(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict__ state,
        const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
        uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
@@ -135,16 +146,34 @@ k_step(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict_
     a1 = 0.f;  // upkie_pendulum.py:137
   }
 
+  // One inlined copy of the physics serves both the regular tick (nb_substeps
+  // substeps under the torque law) and the fused auto-reset (new initial state,
+  // ONE zero-torque substep, pybullet_backend.py:227-228): resetting lanes run a
+  // single iteration of the same loop, which keeps the kernel's code small
+  // (instruction-cache footprint) and the warp converged.
+  int nsub = P.nb_substeps;
   if (resetting) {
-    // fused auto-reset: sample a new initial state, one zero-torque substep, observe
     const uint32_t ep = episode[i] + 1u;
     if (live) episode[i] = ep;
     float init[UPKIE_INIT_DIM];
     sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
-    reset_robot(P, S, init, eps, mu, WarpAny());
+    reset_pose(S, init);
+    nsub = 1;
   } else {
     if (MODE != MODE_SERVOS) e |= gyropod_action(P, S, a0, a1, a);
-    e |= step_servo_action(P, S, a, eps, mu, WarpAny());
+    e |= clamp_servo_action(P, a);
+  }
+  for (int sub = 0; sub < P.nb_substeps; ++sub) {
+#ifdef UPKIE_SUBSTEP_SYNC
+    __syncthreads();  // keeps the block's warps on the same stretch of code (shared instruction fetch)
+#endif
+    if (sub < nsub) servo_substep(P, S, a, resetting, eps, mu, WarpAny());
+  }
+  observe_update(P, S);
+  if (resetting) {
+    reset_wrapper_state(S);
+  } else {
+    e |= state_sanity(S);
     if (MODE != MODE_SERVOS) {
       S.yaw += a1 * P.dt;  // integrates the unclamped action[1], upkie_gyropod.py:383-385
       S.yaw_vel = a1;
@@ -398,7 +427,7 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
   h->device = device;
   if (const char* b = std::getenv("UPKIE_B200_BLOCK")) {
     const int v = std::atoi(b);
-    if (v >= 32 && v <= 128 && v % 32 == 0) h->block = v;
+    if (v >= 32 && v <= UPKIE_MAX_THREADS && v % 32 == 0) h->block = v;
   }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaMalloc(&h->state, size_t(UPKIE_STATE_DIM) * h->n_pad * sizeof(float));
