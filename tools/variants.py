@@ -12,17 +12,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "upkie_b200", "csrc")
 OUT = os.path.join(ROOT, "variants")
 BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-        "-Xcompiler", "-fPIC"]
+        "-Xcompiler", "-fPIC", "--use_fast_math"]
 VARIANTS = {
     "base": [],
-    "r128_b128": ["-DUPKIE_MIN_BLOCKS=4"],
-    "r128_b64": ["-DUPKIE_MAX_THREADS=64", "-DUPKIE_MIN_BLOCKS=8", "-DUPKIE_DEFAULT_BLOCK=64"],
-    "r168_b128": ["-DUPKIE_MIN_BLOCKS=3"],
-    "r168_b64": ["-DUPKIE_MAX_THREADS=64", "-DUPKIE_MIN_BLOCKS=6", "-DUPKIE_DEFAULT_BLOCK=64"],
+    "nosync": ["-DUPKIE_NO_PHASE_SYNC"],
     "b64": ["-DUPKIE_MAX_THREADS=64", "-DUPKIE_DEFAULT_BLOCK=64"],
-    "sync": ["-DUPKIE_SUBSTEP_SYNC"],
-    "sync_r128_b128": ["-DUPKIE_SUBSTEP_SYNC", "-DUPKIE_MIN_BLOCKS=4"],
-    "fastmath": ["--use_fast_math"],
+    "b256": ["-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
+    "r168_b128": ["-DUPKIE_MIN_BLOCKS=3"],
+    "r128_b128": ["-DUPKIE_MIN_BLOCKS=4"],
+    "r128_b256": ["-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256", "-DUPKIE_MIN_BLOCKS=2"],
 }
 
 
@@ -45,15 +43,18 @@ def build():
 def run():
     names = sys.argv[2:] or list(VARIANTS)
     for name in names:
+      try:
         env = dict(os.environ, UPKIE_B200_LIB=os.path.join(OUT, f"lib_{name}.so"))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "300", "--warmup", "20",
-                            "--no-cpu-baseline"], env=env, capture_output=True, text=True)
+                            "--no-cpu-baseline"], env=env, capture_output=True, text=True, timeout=150)
         import json
         try:
             j = json.loads(r.stdout.strip().splitlines()[-1])
             print(f"{name:16s} value={j['value']:.4e} kernel_ms={j['roofline']['kernel_ms']:.4f} e2e={j['e2e']['value']:.3e}", flush=True)
         except Exception:
             print(name, "FAILED", r.stdout[-300:], r.stderr[-600:], flush=True)
+      except subprocess.TimeoutExpired:
+        print(name, "TIMEOUT", flush=True)
 
 
 if __name__ == "__main__":

@@ -13,6 +13,9 @@ DEPS = ["upkie_b200.cu", "sim_core.cuh", "params.h", "mpc.cuh", "mpc_core.cuh", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    # approximate division / sqrt / sincos (<= 2 ulp, arguments range-reduced in the code) and FTZ:
+    # -19% kernel time; the parity tolerances already absorb fp32 round-off of that size
+    "--use_fast_math",
     "-shared", "-Xcompiler", "-fPIC",
 ]
 

@@ -202,7 +202,9 @@ UPKIE_HD void leg_pass12(const SimParams& P, const float q[6], const float qd[6]
       lc.oz[k] = oz;
       phi += s * q[j];
       if (k < 2 || !P.wheel_symmetric) {
-        sincosf(phi, &sp, &cp);
+        // explicit range reduction: the fast-math sincos of the device build is only accurate on [-pi, pi]
+        const float red = phi - 6.28318530718f * rintf(phi * 0.15915494309f);
+        sincosf(red, &sp, &cp);
       }
       cphi[k] = cp;
       sphi[k] = sp;
@@ -475,9 +477,17 @@ UPKIE_HD void leg_impulse_down(const SimParams& P, int J0, const LegCache& lc, c
 // detection at the current configuration, ABA velocity update, PGS contact
 // solve on velocities, semi-implicit position integration. `any_contact_hint`
 // lets a warp skip the contact solve when no lane touches the ground.
-template <typename AnyFn>
+// `phase_sync` is called exactly kPhaseSyncs times per substep by every lane,
+// whatever its path: on the device it is a CTA-wide barrier that keeps the
+// block's warps on the same stretch of this (instruction-cache-sized) code.
+struct NoSync {
+  UPKIE_HD void operator()() const {}
+};
+constexpr int kPhaseSyncs = 6;
+
+template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
-                              AnyFn warp_any) {
+                              AnyFn warp_any, SyncFn phase_sync = SyncFn()) {
   float R[9];
   quat_to_rot(S.quat, R);
   float V0[6];
@@ -489,6 +499,7 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
   LegCache lcL, lcR;
   float ccL[3][6], ccR[3][6], uuL[3], uuR[3];
   leg_pass12<0>(P, S.q, S.qd, tau, V0, eps, lcL, ccL, uuL, IA0, pA0);
+  phase_sync();  // 1
   leg_pass12<1>(P, S.q, S.qd, tau, V0, eps, lcR, ccR, uuR, IA0, pA0);
   ldl6(IA0);
   float a0[6];
@@ -533,8 +544,14 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
   const bool actL = rim_ok && (distL < P.breaking_threshold);
   const bool actR = rim_ok && (distR < P.breaking_threshold);
   S.contact = (actL || actR) ? 1.f : 0.f;
+  phase_sync();  // 2
 
-  if (warp_any(actL || actR)) {
+  if (!warp_any(actL || actR)) {
+    phase_sync();  // 3
+    phase_sync();  // 4
+    phase_sync();  // 5
+    phase_sync();  // 6
+  } else {
     // contact directions in base coordinates: normal, rolling, lateral
     const float nB[3] = {zb[0], zb[1], zb[2]};
     float dirs[2][3][3];
@@ -601,6 +618,7 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
         for (int i = 0; i < 6; ++i) acc += J[k][i] * a[i];
         W[k][l] = acc;
       }
+      if (l & 1) phase_sync();  // 3, 4, 5
     }
     // right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
     float rhs[6], jdi[6], lam[6];
@@ -631,15 +649,21 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
     // impulse of the warp by more than pgs_rtol * |impulse| + 1e-9 (with
     // pgs_rtol = 0 and the 1e-9 floor removed it runs all sweeps).
     const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+    // row update lam_k <- clamp(lam_k + rhs_k - cfm_k lam_k - jdi_k sum_l W_kl lam_l) with the
+    // row pre-scaled: G_kl = -jdi_k W_kl (l != k), G_kk = 1 - cfm_k - jdi_k W_kk
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+      for (int l = 0; l < 6; ++l) W[k][l] = -jdi[k] * W[k][l];
+      W[k][k] += 1.f - (k < 2 ? cfmrow * jdi[k] : 0.f);
+    }
     for (int it = 0; it < P.pgs_iterations; ++it) {
       bool changed = false;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        float jdv = 0.f;
+        float sum = rhs[k];
 #pragma unroll
-        for (int l = 0; l < 6; ++l) jdv += W[k][l] * lam[l];
-        const float c = k < 2 ? cfmrow * jdi[k] : 0.f;
-        const float sum = lam[k] + (rhs[k] - lam[k] * c - jdv * jdi[k]);
+        for (int l = 0; l < 6; ++l) sum += W[k][l] * lam[l];
         float lo, hi;
         if (k == 0) { lo = 0.f; hi = hiL; }
         else if (k == 1) { lo = 0.f; hi = hiR; }
@@ -683,6 +707,7 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
       S.qd[i] = clampf(S.qd[i] + dqL[i], -P.vmax, P.vmax);
       S.qd[3 + i] = clampf(S.qd[3 + i] + dqR[i], -P.vmax, P.vmax);
     }
+    phase_sync();  // 6
   }
 
   // -- position integration with the new velocities
@@ -849,9 +874,9 @@ UPKIE_HD uint32_t clamp_servo_action(const SimParams& P, float a[UPKIE_ACT_DIM])
 // One substep of PyBulletBackend.step (pybullet_backend.py:276-306): torque law on
 // the live joint state, then one stepSimulation. `store_torque` is false for the
 // zero-torque substep of a reset (the reference keeps __joint_torques across resets).
-template <typename AnyFn>
+template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPKIE_ACT_DIM], bool zero_torque,
-                            const float* eps, float mu, AnyFn warp_any) {
+                            const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync = SyncFn()) {
   float tau[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
@@ -862,7 +887,7 @@ UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPK
     tau[j] = zero_torque ? 0.f : t;
     if (!zero_torque) S.torque[j] = t;
   }
-  physics_substep(P, S, tau, eps, mu, warp_any);
+  physics_substep(P, S, tau, eps, mu, warp_any, phase_sync);
 }
 
 UPKIE_HD uint32_t state_sanity(const RobotState& S) {

@@ -84,6 +84,18 @@ Handle* as_handle(void* h) {
   return (p && p->magic == kMagic) ? p : nullptr;
 }
 
+// CTA-wide barrier that tolerates intra-warp divergence (non-.aligned form): every
+// thread of the block arrives exactly kPhaseSyncs times per substep. It buys no
+// data exchange: it keeps the block's warps within the same instruction-cache
+// window of the ~100 KB substep body (ncu: stall_no_instruction was the top stall).
+struct PhaseSync {
+  __device__ __forceinline__ void operator()() const {
+#ifndef UPKIE_NO_PHASE_SYNC
+    asm volatile("barrier.sync 0;" ::: "memory");
+#endif
+  }
+};
+
 struct WarpAny {
   __device__ __forceinline__ bool operator()(bool p) const { return __any_sync(__activemask(), p); }
 };
@@ -164,10 +176,12 @@ k_step(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict_
     e |= clamp_servo_action(P, a);
   }
   for (int sub = 0; sub < P.nb_substeps; ++sub) {
-#ifdef UPKIE_SUBSTEP_SYNC
-    __syncthreads();  // keeps the block's warps on the same stretch of code (shared instruction fetch)
-#endif
-    if (sub < nsub) servo_substep(P, S, a, resetting, eps, mu, WarpAny());
+    if (sub < nsub) {
+      servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync());
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
+    }
   }
   observe_update(P, S);
   if (resetting) {
