@@ -381,16 +381,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     env.sim.reset(seed=2025, env_offset=rank * n)
 
     # rollout buffer gathered over NVLink once per T steps
-    rec_bytes = obs_bytes + 4 + 2
-    rollout = torch.empty((ROLLOUT_T, n, rec_bytes), dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world, ROLLOUT_T, n, rec_bytes), dtype=torch.uint8, device=dev) if world > 1 else None
+    from upkie_b200.sharding import RolloutBuffer
 
-    def record(t, obs, rew, term, trunc):
-        r = rollout[t % ROLLOUT_T]
-        r[:, :obs_bytes] = obs.reshape(n, -1).view(torch.uint8)
-        r[:, obs_bytes:obs_bytes + 4] = rew.view(torch.uint8).reshape(n, 4)
-        r[:, obs_bytes + 4] = term
-        r[:, obs_bytes + 5] = trunc
+    rollout = RolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev)
 
     for k in range(W):
         step(acts[k % N_ACTION_BUFFERS])
@@ -410,9 +403,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
             o, r, te, tr = step(acts[k % N_ACTION_BUFFERS])
             events[k + 1].record()
             if world > 1:
-                record(k, o, r, te, tr)
+                rollout.record(k, o, r, te, tr)
                 if (k + 1) % ROLLOUT_T == 0:
-                    dist.all_gather_into_tensor(gathered, rollout)
+                    rollout.gather()
         end.record()  # after the last step / all-gather queued on this stream
         torch.cuda.synchronize()
         if profiling:
@@ -429,7 +422,8 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     launches = env.sim.launches - launches0
 
     # e2e through the public VectorEnv API with HOST buffers (H2D + kernel + D2H per step)
-    host_acts = [a.cpu().numpy() for a in acts[:4]]
+    # this step's inputs live in pinned host memory (4 rotating buffers), outputs land in pinned memory
+    host_acts = [a.cpu().pin_memory().numpy() for a in acts[:4]]
     Ke = max(10, min(K, 50))
     for k in range(3):
         env.step(host_acts[k % 4])

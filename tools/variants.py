@@ -14,13 +14,15 @@ OUT = os.path.join(ROOT, "variants")
 BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
         "-Xcompiler", "-fPIC", "--use_fast_math"]
 VARIANTS = {
-    "base": [],
-    "nosync": ["-DUPKIE_NO_PHASE_SYNC"],
-    "b64": ["-DUPKIE_MAX_THREADS=64", "-DUPKIE_DEFAULT_BLOCK=64"],
-    "b256": ["-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
-    "r168_b128": ["-DUPKIE_MIN_BLOCKS=3"],
-    "r128_b128": ["-DUPKIE_MIN_BLOCKS=4"],
-    "r128_b256": ["-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256", "-DUPKIE_MIN_BLOCKS=2"],
+    "s0_b128": ["-DUPKIE_PHASE_SYNC_LEVEL=0"],
+    "s1_b128": ["-DUPKIE_PHASE_SYNC_LEVEL=1"],
+    "s2_b128": ["-DUPKIE_PHASE_SYNC_LEVEL=2"],
+    "s0_b64": ["-DUPKIE_PHASE_SYNC_LEVEL=0", "-DUPKIE_MAX_THREADS=64", "-DUPKIE_DEFAULT_BLOCK=64"],
+    "s1_b64": ["-DUPKIE_PHASE_SYNC_LEVEL=1", "-DUPKIE_MAX_THREADS=64", "-DUPKIE_DEFAULT_BLOCK=64"],
+    "s0_b256": ["-DUPKIE_PHASE_SYNC_LEVEL=0", "-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
+    "s1_b256": ["-DUPKIE_PHASE_SYNC_LEVEL=1", "-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
+    "s2_b256": ["-DUPKIE_PHASE_SYNC_LEVEL=2", "-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
+    "s0_b32": ["-DUPKIE_PHASE_SYNC_LEVEL=0", "-DUPKIE_MAX_THREADS=32", "-DUPKIE_DEFAULT_BLOCK=32"],
 }
 
 

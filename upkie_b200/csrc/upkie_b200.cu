@@ -45,13 +45,16 @@ int fail(int code, const std::string& msg) {
 
 // build-time tuning knobs (tools/variants.py explores them; defaults are the measured best)
 #ifndef UPKIE_MAX_THREADS
-#define UPKIE_MAX_THREADS 128
+#define UPKIE_MAX_THREADS 256
 #endif
 #ifndef UPKIE_MIN_BLOCKS
 #define UPKIE_MIN_BLOCKS 1
 #endif
 #ifndef UPKIE_DEFAULT_BLOCK
-#define UPKIE_DEFAULT_BLOCK 128
+#define UPKIE_DEFAULT_BLOCK 0  // 0 = pick per launch (pick_block)
+#endif
+#ifndef UPKIE_PHASE_SYNC_LEVEL  // 0 none, 1 one barrier per substep, 2 also six barriers inside the substep
+#define UPKIE_PHASE_SYNC_LEVEL 1
 #endif
 
 enum { MODE_SERVOS = 0, MODE_GYROPOD = 1, MODE_PENDULUM = 2 };
@@ -70,13 +73,16 @@ struct Handle {
   int autoreset = AUTORESET_DISABLED;
   uint64_t seed = 0, env_offset = 0;
   int block = UPKIE_DEFAULT_BLOCK;
+  int num_sms = 148;
   // host-buffer staging (allocated on first use)
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
-  cudaStream_t host_stream = nullptr;
+  cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
 };
+constexpr int kHostStreams = 3;  // H2D, kernel and D2H of different chunks overlap
+constexpr int kHostChunks = 4;
 constexpr uint32_t kMagic = 0x55504B42u;  // "UPKB"
 
 Handle* as_handle(void* h) {
@@ -90,7 +96,7 @@ Handle* as_handle(void* h) {
 // window of the ~100 KB substep body (ncu: stall_no_instruction was the top stall).
 struct PhaseSync {
   __device__ __forceinline__ void operator()() const {
-#ifndef UPKIE_NO_PHASE_SYNC
+#if UPKIE_PHASE_SYNC_LEVEL >= 2
     asm volatile("barrier.sync 0;" ::: "memory");
 #endif
   }
@@ -117,12 +123,13 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
 // ---- the env-step kernel ------------------------------------------------------------
 template <int MODE, int AUTORESET>
 __global__ void __launch_bounds__(UPKIE_MAX_THREADS, UPKIE_MIN_BLOCKS)
-k_step(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict__ state,
+k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __restrict__ state,
        const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
        uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
        const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
        uint32_t* __restrict__ episode, uint64_t seed, uint64_t env_offset) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  // this launch covers the envs [i0, n)
+  const int tid = i0 + blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = tid < n;
   const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
 
@@ -176,6 +183,9 @@ k_step(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict_
     e |= clamp_servo_action(P, a);
   }
   for (int sub = 0; sub < P.nb_substeps; ++sub) {
+#if UPKIE_PHASE_SYNC_LEVEL >= 1
+    __syncthreads();  // once per substep: all threads are converged here
+#endif
     if (sub < nsub) {
       servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync());
     } else {
@@ -334,13 +344,25 @@ __global__ void k_init_state(const __grid_constant__ SimParams P, int n, int n_p
   (void)n;
 }
 
+// Largest block (the block's warps run the substep body in lock-step and share its
+// instruction fetches; measured 256 > 128 > 64, profiles/r01_variants.md) that still
+// gives every SM at least one block.
+int pick_block(const Handle* h, int cnt) {
+  if (h->block > 0) return h->block;
+  for (int b = UPKIE_MAX_THREADS; b > 32; b >>= 1)
+    if ((cnt + b - 1) / b >= h->num_sms) return b;
+  return 32;
+}
+
 template <int MODE>
-int launch_step(Handle* h, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
-                cudaStream_t s) {
-  const int grid = (h->n + h->block - 1) / h->block;
-#define LAUNCH(AR)                                                                                           \
-  k_step<MODE, AR><<<grid, h->block, 0, s>>>(h->P, h->n, h->n_pad, h->state, action, obs, reward, term, trunc, \
-                                             h->eps, h->mu, h->err, h->done_prev, h->episode, h->seed, h->env_offset)
+int launch_step(Handle* h, int i0, int cnt, const float* action, float* obs, float* reward, uint8_t* term,
+                uint8_t* trunc, cudaStream_t s) {
+  const int block = pick_block(h, cnt);
+  const int grid = (cnt + block - 1) / block;
+#define LAUNCH(AR)                                                                                              \
+  k_step<MODE, AR><<<grid, block, 0, s>>>(h->P, i0, i0 + cnt, h->n_pad, h->state, action, obs, reward, term, \
+                                             trunc, h->eps, h->mu, h->err, h->done_prev, h->episode, h->seed,  \
+                                             h->env_offset)
   if (h->autoreset == AUTORESET_NEXT_STEP) LAUNCH(AUTORESET_NEXT_STEP);
   else if (h->autoreset == AUTORESET_SAME_STEP) LAUNCH(AUTORESET_SAME_STEP);
   else LAUNCH(AUTORESET_DISABLED);
@@ -349,20 +371,26 @@ int launch_step(Handle* h, const float* action, float* obs, float* reward, uint8
   return UPKIE_B200_OK;
 }
 
+// envs [i0, i0 + cnt): all buffers are indexed by the env index of the handle
+int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float* obs, float* reward, uint8_t* term,
+               uint8_t* trunc, cudaStream_t s) {
+  if (mode == MODE_SERVOS) return launch_step<MODE_SERVOS>(h, i0, cnt, action, obs, reward, term, trunc, s);
+  if (mode == MODE_GYROPOD) return launch_step<MODE_GYROPOD>(h, i0, cnt, action, obs, reward, term, trunc, s);
+  return launch_step<MODE_PENDULUM>(h, i0, cnt, action, obs, reward, term, trunc, s);
+}
+
 int step_any(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
              cudaStream_t s) {
   if (!action || !obs || !reward || !term || !trunc) return fail(UPKIE_B200_EINVAL, "step: null buffer");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (mode == MODE_SERVOS) return launch_step<MODE_SERVOS>(h, action, obs, reward, term, trunc, s);
-  if (mode == MODE_GYROPOD) return launch_step<MODE_GYROPOD>(h, action, obs, reward, term, trunc, s);
-  return launch_step<MODE_PENDULUM>(h, action, obs, reward, term, trunc, s);
+  return step_range(h, mode, 0, h->n, action, obs, reward, term, trunc, s);
 }
 
 int ensure_staging(Handle* h) {
-  if (h->h_act) return UPKIE_B200_OK;
+  if (h->d_act) return UPKIE_B200_OK;
   const size_t n = size_t(h->n);
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < kHostStreams; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&h->host_streams[k], cudaStreamNonBlocking));
   CUDA_TRY(cudaMallocHost(&h->h_act, n * UPKIE_ACT_DIM * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&h->h_obs, n * UPKIE_OBS_DIM * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&h->h_rew, n * sizeof(float)));
@@ -376,28 +404,66 @@ int ensure_staging(Handle* h) {
   return UPKIE_B200_OK;
 }
 
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Host-buffer step: the batch is cut into chunks that flow through H2D copy ->
+// kernel -> D2H copy on rotating streams, so the copies of one chunk overlap
+// the kernel of another (PCIe is full duplex). Pinned caller buffers are used
+// in place; pageable ones are staged through pinned memory chunk by chunk.
 int step_host(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc) {
   if (!action || !obs || !reward || !term || !trunc) return fail(UPKIE_B200_EINVAL, "step_host: null buffer");
   int rc = ensure_staging(h);
   if (rc) return rc;
-  const size_t n = size_t(h->n);
+  CUDA_TRY(cudaSetDevice(h->device));
   const size_t act_dim = mode == MODE_SERVOS ? UPKIE_ACT_DIM : (mode == MODE_GYROPOD ? 2 : 1);
   const size_t obs_dim = mode == MODE_SERVOS ? UPKIE_OBS_DIM : (mode == MODE_GYROPOD ? 6 : 4);
-  cudaStream_t s = h->host_stream;
-  // caller memory may be pageable: stage through pinned buffers so the copies are truly asynchronous
-  std::memcpy(h->h_act, action, n * act_dim * sizeof(float));
-  CUDA_TRY(cudaMemcpyAsync(h->d_act, h->h_act, n * act_dim * sizeof(float), cudaMemcpyHostToDevice, s));
-  rc = step_any(h, mode, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, s);
-  if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(h->h_obs, h->d_obs, n * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_term, h->d_term, n, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_trunc, h->d_trunc, n, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  std::memcpy(obs, h->h_obs, n * obs_dim * sizeof(float));
-  std::memcpy(reward, h->h_rew, n * sizeof(float));
-  std::memcpy(term, h->h_term, n);
-  std::memcpy(trunc, h->h_trunc, n);
+  const bool pin_in = is_pinned(action);
+  const bool pin_out = is_pinned(obs) && is_pinned(reward) && is_pinned(term) && is_pinned(trunc);
+  // chunk size: a multiple of the block size, at least 8192 envs, at most kHostChunks chunks
+  int chunks = h->n >= 4 * 8192 ? kHostChunks : (h->n >= 2 * 8192 ? 2 : 1);
+  int per = (h->n + chunks - 1) / chunks;
+  per = (per + 255) / 256 * 256;
+  chunks = (h->n + per - 1) / per;
+  const float* src_act = pin_in ? action : h->h_act;
+  float* dst_obs = pin_out ? obs : h->h_obs;
+  float* dst_rew = pin_out ? reward : h->h_rew;
+  uint8_t* dst_term = pin_out ? term : h->h_term;
+  uint8_t* dst_trunc = pin_out ? trunc : h->h_trunc;
+  for (int c = 0; c < chunks; ++c) {
+    const int i0 = c * per;
+    const int cnt = (i0 + per <= h->n) ? per : h->n - i0;
+    cudaStream_t s = h->host_streams[c % kHostStreams];
+    if (!pin_in) std::memcpy(h->h_act + size_t(i0) * act_dim, action + size_t(i0) * act_dim, size_t(cnt) * act_dim * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(h->d_act + size_t(i0) * act_dim, src_act + size_t(i0) * act_dim,
+                             size_t(cnt) * act_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = step_range(h, mode, i0, cnt, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst_obs + size_t(i0) * obs_dim, h->d_obs + size_t(i0) * obs_dim,
+                             size_t(cnt) * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(dst_rew + i0, h->d_rew + i0, size_t(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(dst_term + i0, h->d_term + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(dst_trunc + i0, h->d_trunc + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
+  }
+  for (int c = 0; c < chunks; ++c) {
+    const int i0 = c * per;
+    const int cnt = (i0 + per <= h->n) ? per : h->n - i0;
+    if (c < kHostStreams || !pin_out) CUDA_TRY(cudaStreamSynchronize(h->host_streams[c % kHostStreams]));
+    if (!pin_out) {
+      // stream order guarantees chunk c is complete once its stream drained up to here only if no later
+      // chunk shares the stream; with later chunks queued behind it the sync above waits for those as well
+      std::memcpy(obs + size_t(i0) * obs_dim, h->h_obs + size_t(i0) * obs_dim, size_t(cnt) * obs_dim * sizeof(float));
+      std::memcpy(reward + i0, h->h_rew + i0, size_t(cnt) * sizeof(float));
+      std::memcpy(term + i0, h->h_term + i0, size_t(cnt));
+      std::memcpy(trunc + i0, h->h_trunc + i0, size_t(cnt));
+    }
+  }
   return UPKIE_B200_OK;
 }
 
@@ -444,6 +510,7 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
     if (v >= 32 && v <= UPKIE_MAX_THREADS && v % 32 == 0) h->block = v;
   }
   cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaMalloc(&h->state, size_t(UPKIE_STATE_DIM) * h->n_pad * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&h->err, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&h->done_prev, size_t(n_envs));
@@ -472,7 +539,8 @@ void upkie_b200_destroy(void* handle) {
   cudaFree(h->state); cudaFree(h->eps); cudaFree(h->mu); cudaFree(h->err); cudaFree(h->done_prev); cudaFree(h->episode);
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_term); cudaFreeHost(h->h_trunc);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
-  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  for (int k = 0; k < kHostStreams; ++k)
+    if (h->host_streams[k]) cudaStreamDestroy(h->host_streams[k]);
   h->magic = 0;
   delete h;
 }
@@ -522,8 +590,9 @@ int upkie_b200_reset(void* handle, const uint8_t* mask, const float* init_state,
   if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = (h->n + h->block - 1) / h->block;
-  k_reset<<<grid, h->block, 0, s>>>(h->P, h->n, h->n_pad, h->state, mask, init_state, h->eps, h->mu, h->err,
+  const int rblock = 128;
+  const int grid = (h->n + rblock - 1) / rblock;
+  k_reset<<<grid, rblock, 0, s>>>(h->P, h->n, h->n_pad, h->state, mask, init_state, h->eps, h->mu, h->err,
                                     h->done_prev, h->episode, seed, env_offset);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;

@@ -380,7 +380,8 @@ class B200VectorEnv(VectorEnv):
             a = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, d))
             obs, rew, term, trunc = self.sim.step_gyropod_host(a)
         info = {"spine_observation": SpineObservations(self.sim)}
-        return self._format_obs(obs), rew.astype(np.float64), term.astype(bool), trunc.astype(bool), info
+        # views of the handle's pinned output buffers: valid until the next step() (copy to keep them)
+        return self._format_obs(obs), rew, term.view(np.bool_), trunc.view(np.bool_), info
 
     def step_tensors(self, action: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, dict]:
         """Zero-copy fast path: CUDA tensors in, CUDA tensors out

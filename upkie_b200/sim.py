@@ -156,35 +156,70 @@ class UpkieSim:
         self.launches += 1
         return obs, self.reward, self.terminated, self.truncated
 
-    # host-buffer path (H2D + kernel + D2H inside the call)
+    # host-buffer path (H2D + kernel + D2H inside the call) ---------------------
+    def _host_buffers(self):
+        """Pinned host arrays owned by the handle: ``host_action_buffer()`` (fill it
+        in place for a staging-free H2D copy) and the outputs returned by the
+        ``*_host`` calls (overwritten by the next call)."""
+        if getattr(self, "_hb", None) is None:
+            def pinned(shape, dtype):
+                return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
+
+            self._hb = {
+                "act36": pinned((self.n, 6, 6), torch.float32),
+                "act2": pinned((self.n, 2), torch.float32),
+                "act1": pinned((self.n, 1), torch.float32),
+                "obs30": pinned((self.n, 6, 5), torch.float32),
+                "obs6": pinned((self.n, 6), torch.float32),
+                "obs4": pinned((self.n, 4), torch.float32),
+                "rew": pinned((self.n,), torch.float32),
+                "term": pinned((self.n,), torch.uint8),
+                "trunc": pinned((self.n,), torch.uint8),
+            }
+        return self._hb
+
+    def host_action_buffer(self, act_dim: int = 36) -> np.ndarray:
+        """Pinned ``[N, 6, 6]`` / ``[N, 2]`` / ``[N, 1]`` action array to fill in place."""
+        return self._host_buffers()[f"act{act_dim}"]
+
     def step_servos_host(self, action: np.ndarray):
-        a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.n, 6, 6)
-        obs = np.empty((self.n, 6, 5), dtype=np.float32)
-        rew = np.empty(self.n, dtype=np.float32)
-        term = np.empty(self.n, dtype=np.uint8)
-        trunc = np.empty(self.n, dtype=np.uint8)
+        """``action[N, 6, 6]`` float32 on the host (ideally ``host_action_buffer()``).
+        Returns pinned arrays that the next ``*_host`` call overwrites."""
+        hb = self._host_buffers()
+        a = action
+        if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(action, dtype=np.float32)
+        if a.size != self.n * 36:
+            raise UpkieRuntimeError(f"action: expected {self.n * 36} float32 values, got {a.size}")
+        obs, rew, term, trunc = hb["obs30"], hb["rew"], hb["term"], hb["trunc"]
         check(
             lib().upkie_b200_step_servos_host(
                 self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data
             )
         )
-        self.launches += 1
+        self.launches += self.host_chunks
         return obs, rew, term, trunc
 
     def step_gyropod_host(self, action: np.ndarray):
+        hb = self._host_buffers()
         a = np.ascontiguousarray(action, dtype=np.float32)
-        act_dim = a.shape[1]
-        obs = np.empty((self.n, 6 if act_dim == 2 else 4), dtype=np.float32)
-        rew = np.empty(self.n, dtype=np.float32)
-        term = np.empty(self.n, dtype=np.uint8)
-        trunc = np.empty(self.n, dtype=np.uint8)
+        act_dim = a.shape[1] if a.ndim == 2 else a.size // self.n
+        if act_dim not in (1, 2) or a.size != self.n * act_dim:
+            raise UpkieRuntimeError("action: expected shape [N, 1] (pendulum) or [N, 2] (gyropod)")
+        obs = hb["obs6"] if act_dim == 2 else hb["obs4"]
+        rew, term, trunc = hb["rew"], hb["term"], hb["trunc"]
         check(
             lib().upkie_b200_step_gyropod_host(
                 self._h, a.ctypes.data, act_dim, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data
             )
         )
-        self.launches += 1
+        self.launches += self.host_chunks
         return obs, rew, term, trunc
+
+    @property
+    def host_chunks(self) -> int:
+        """Kernel launches per host-buffer step (the batch is pipelined in chunks)."""
+        return 4 if self.n >= 4 * 8192 else (2 if self.n >= 2 * 8192 else 1)
 
     # ------------------------------------------------------------------
     def spine_obs(self) -> torch.Tensor:
