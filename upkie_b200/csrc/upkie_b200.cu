@@ -344,14 +344,20 @@ __global__ void k_init_state(const __grid_constant__ SimParams P, int n, int n_p
   (void)n;
 }
 
-// Largest block (the block's warps run the substep body in lock-step and share its
-// instruction fetches; measured 256 > 128 > 64, profiles/r01_variants.md) that still
-// gives every SM at least one block.
+// Block size per launch. Two measured effects (profiles/r01_variants.md): (1) the warps of a block run the
+// substep body in lock-step (one barrier per substep) and share its instruction fetches, so large blocks win
+// (256 > 128 > 64); (2) with 255 registers/thread one 256-thread block fills an SM, so 65 536 envs = 256 blocks
+// = 1.73 waves left 25 % of the SM-time idle. Pick the number of waves k first, then the block size (multiple of
+// 32) that makes the grid k * num_sms blocks: every SM gets the same number of equally sized blocks.
 int pick_block(const Handle* h, int cnt) {
   if (h->block > 0) return h->block;
-  for (int b = UPKIE_MAX_THREADS; b > 32; b >>= 1)
-    if ((cnt + b - 1) / b >= h->num_sms) return b;
-  return 32;
+  const int per_wave = h->num_sms * UPKIE_MAX_THREADS;
+  const int waves = (cnt + per_wave - 1) / per_wave;
+  int block = (cnt + waves * h->num_sms - 1) / (waves * h->num_sms);
+  block = (block + 31) / 32 * 32;
+  if (block < 32) block = 32;
+  if (block > UPKIE_MAX_THREADS) block = UPKIE_MAX_THREADS;
+  return block;
 }
 
 template <int MODE>
