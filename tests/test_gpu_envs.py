@@ -307,6 +307,37 @@ def test_mpc_in_the_loop_balances(model, torch):
     assert o[:, 1].abs().max().item() < 0.3
 
 
+def test_base_velocity_env(model, torch):
+    """UpkieBaseVelocity semantics (tests/envs/test_upkie_base_velocity.py:35-105): zero observation at
+    reset, SE(2) dead reckoning of the commanded velocity, balance kept by the embedded MPC."""
+    import upkie_b200
+
+    n = 64
+    env = upkie_b200.make_vec("Upkie-B200-BaseVelocity", n, model=model)
+    assert env.single_action_space.shape == (2,) and env.single_observation_space.shape == (3,)
+    obs, info = env.reset(seed=3)
+    assert obs.shape == (n, 3) and obs.dtype == np.float32 and not obs.any()
+    a = np.tile(np.array([[0.2, 0.5]], dtype=np.float32), (n, 1))
+    fell = np.zeros(n, bool)
+    for k in range(300):
+        obs, rew, term, trunc, info = env.step(a)
+        fell |= term
+    assert not fell.any()
+    t = 300 * env.dt
+    yaw = 0.5 * t  # yaw integrates the commanded yaw velocity
+    assert np.allclose(obs[:, 2], yaw, atol=1e-3)
+    # x = int v cos(psi) dt with psi the post-step yaw (upkie_base_velocity.py:197-199)
+    k = np.arange(1, 301)
+    x = (0.2 * np.cos(0.5 * k * env.dt) * env.dt).sum()
+    y = (0.2 * np.sin(0.5 * k * env.dt) * env.dt).sum()
+    assert np.allclose(obs[:, 0], x, atol=1e-4) and np.allclose(obs[:, 1], y, atol=1e-4)
+    sp = info["spine_observation"].array
+    assert np.abs(sp[:, _abi.SP_PITCH]).max() < 0.3
+    obs, _ = env.reset(seed=3)
+    assert not obs.any() and (env.mpc_balancer.commanded_velocity == 0).all().item()
+    env.close()
+
+
 def test_full_size_invariants(model, torch):
     """BASELINE-size batch (65536 envs): finite state, unit quaternions, contact physics sane,
     reward/truncated constants, idempotent spine observation."""

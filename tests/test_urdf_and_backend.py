@@ -1,0 +1,84 @@
+# SPDX-License-Identifier: Apache-2.0
+"""URDF loader (fixed-joint lumping) and the single-robot Backend adapter."""
+import numpy as np
+import pytest
+
+from upkie_b200 import _abi
+from upkie_b200.exceptions import ModelError
+from upkie_b200.model import Model
+from upkie_b200.urdf import load_urdf_model, rotation_matrix_from_rpy, write_urdf
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_urdf_roundtrip_lumps_fixed_links(model, tmp_path, split):
+    path = str(tmp_path / "upkie.urdf")
+    write_urdf(model, path, split_fixed_links=split)
+    m2 = Model.from_urdf(path)
+    assert m2.parent == model.parent
+    assert np.allclose(m2.joint_origin, model.joint_origin, atol=1e-12)
+    assert np.allclose(m2.joint_axis, model.joint_axis, atol=1e-12)
+    assert np.allclose(m2.mass, model.mass, atol=1e-12)
+    assert np.allclose(m2.com, model.com, atol=1e-10)
+    assert np.allclose(m2.inertia, model.inertia, atol=1e-10)
+    assert np.allclose(m2.q_lower, model.q_lower) and np.allclose(m2.q_upper, model.q_upper)
+    assert np.allclose(m2.qd_max, model.qd_max) and np.allclose(m2.tau_max, model.tau_max)
+    assert m2.wheel_radius == pytest.approx(0.05) and m2.wheel_base == pytest.approx(0.3048)
+    assert m2.left_wheeled
+    assert np.allclose(m2.rotation_base_to_imu, np.diag([-1.0, 1.0, -1.0]), atol=1e-12)
+    assert np.allclose(m2.imu_position, model.imu_position, atol=1e-12)
+    # the aggregates the reference pins survive the round trip (utils_test.cpp:89-98)
+    assert m2.total_mass() == pytest.approx(5.3382, abs=1e-9)
+    assert np.allclose(m2.com_zero_config(), [-0.0059, 0.0, -0.2455], atol=1e-9)
+    # and the kernels accept the loaded model (axes along +-y)
+    s = m2.to_struct()
+    assert [round(s.joint_axis[j][1]) for j in range(6)] == [1, 1, 1, -1, -1, -1]
+
+
+def test_urdf_rpy_convention():
+    # rotation_matrix_from_rpy of the reference (upkie/utils/rotations.py:74-102): R = Rz Ry Rx
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        rpy = rng.uniform(-1.5, 1.5, 3)
+        assert np.allclose(rotation_matrix_from_rpy(rpy), Rotation.from_euler("xyz", rpy).as_matrix(), atol=1e-12)
+
+
+def test_urdf_errors(tmp_path):
+    p = tmp_path / "bad.urdf"
+    p.write_text('<robot name="x"><link name="a"/><link name="b"/></robot>')
+    with pytest.raises(ModelError):
+        load_urdf_model(str(p))
+
+
+@pytest.mark.gpu
+def test_backend_adapter_follows_the_backend_contract(model):
+    """Backend ABC (upkie/envs/backends/backend.py:11-50) + the action/observation dictionaries of
+    PyBulletBackend (pybullet_backend.py:276-331); mirrors tests/envs/backends/test_pybullet_backend.py."""
+    from upkie_b200.backend import B200Backend
+    from upkie_b200.robot_state import RobotState
+
+    backend = B200Backend(dt=0.005, model=model)
+    init = RobotState(position_base_in_world=np.array([0.0, 0.0, 0.6]))
+    obs = backend.reset(init)
+    assert set(obs) == {"base_orientation", "floor_contact", "imu", "servo", "wheel_odometry"}
+    assert set(obs["servo"]) == set(_abi.JOINT_NAMES)
+    assert obs["servo"]["left_hip"]["temperature"] == 42.0 and obs["servo"]["left_hip"]["voltage"] == 18.0
+    obs = backend.step({})  # legal: no torques (test_pybullet_backend.py:28-31)
+    assert isinstance(obs, dict)
+    assert obs["base_orientation"]["pitch"] == pytest.approx(0.0, abs=1e-5)  # :31-38
+    for _ in range(100):
+        obs = backend.step({})
+    assert abs(obs["base_orientation"]["pitch"]) > 0.5  # :40-47
+    # commanded joints follow the moteus law; uncommanded joints keep their last reported torque
+    backend.reset(init)
+    servo_action = {"position": 0.2, "velocity": 0.1, "kp_scale": 1.0, "kd_scale": 1.0, "maximum_torque": 10.0}
+    o1 = backend.step({"servo": {"left_hip": servo_action, "left_knee": servo_action, "unknown_joint": servo_action}})
+    assert o1["servo"]["left_hip"]["torque"] != 0.0
+    assert o1["servo"]["right_hip"]["torque"] == 0.0
+    o2 = backend.step({"servo": {"left_knee": servo_action}})
+    assert o2["servo"]["left_hip"]["torque"] == o1["servo"]["left_hip"]["torque"]
+    assert backend.get_spine_observation()["wheel_odometry"]["position"] == o2["wheel_odometry"]["position"]
+    with pytest.raises(AssertionError):
+        backend.step({"servo": {"left_hip": dict(servo_action, velocity=float("nan"))}})
+    backend.close()

@@ -27,7 +27,7 @@ from .model import Model, default_model
 from .robot_state import RobotState
 from .sim import AUTORESET_DISABLED, AUTORESET_NEXT_STEP, AUTORESET_SAME_STEP, UpkieSim
 
-ENV_TYPES = ("servos", "gyropod", "pendulum")
+ENV_TYPES = ("servos", "gyropod", "pendulum", "base_velocity")
 _AUTORESET = {"disabled": AUTORESET_DISABLED, "next_step": AUTORESET_NEXT_STEP, "same_step": AUTORESET_SAME_STEP}
 
 
@@ -117,6 +117,15 @@ def make_pendulum_spaces(max_ground_velocity: float = 3.0):
     obs = spaces.Box(-obs_limit, +obs_limit, shape=obs_limit.shape, dtype=np.float32)
     action_limit = np.array([max_ground_velocity], dtype=np.float32)
     act = spaces.Box(-action_limit, +action_limit, shape=action_limit.shape, dtype=np.float32)
+    return act, obs
+
+
+def make_base_velocity_spaces(max_ground_velocity: float = 3.0, max_yaw_velocity: float = 1.0):
+    """``UpkieBaseVelocity.__init__`` spaces (``upkie_base_velocity.py:96-115``)."""
+    observation_limit = np.full(3, float("inf"), dtype=np.float32)
+    action_limit = np.array([max_ground_velocity, max_yaw_velocity], dtype=np.float32)
+    obs = spaces.Box(-observation_limit, +observation_limit, shape=observation_limit.shape, dtype=observation_limit.dtype)
+    act = spaces.Box(-action_limit, +action_limit, shape=action_limit.shape, dtype=action_limit.dtype)
     return act, obs
 
 
@@ -259,6 +268,8 @@ class B200VectorEnv(VectorEnv):
         inertia_variation: float = 0.0,
         env_offset: int = 0,
         config: Optional[_abi.UpkieSimConfig] = None,
+        leg_length: float = 0.58,
+        max_ground_accel: float = 10.0,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")
@@ -290,6 +301,12 @@ class B200VectorEnv(VectorEnv):
             self.single_action_space, self.single_observation_space = make_gyropod_spaces(
                 max_ground_velocity, max_yaw_velocity
             )
+        elif env_type == "base_velocity":
+            if autoreset_mode != "disabled":
+                raise UpkieException("base_velocity envs support autoreset_mode='disabled' only")
+            self.single_action_space, self.single_observation_space = make_base_velocity_spaces(
+                max_ground_velocity, max_yaw_velocity
+            )
         else:
             self.single_action_space, self.single_observation_space = make_pendulum_spaces(max_ground_velocity)
         self.action_space = batch_space(self.single_action_space, self.num_envs)
@@ -297,6 +314,17 @@ class B200VectorEnv(VectorEnv):
 
         self.sim = UpkieSim(self.num_envs, model=self.model, config=self.config, device=device)
         self._seed = 0
+        self.mpc_balancer = None
+        if env_type == "base_velocity":
+            # UpkieBaseVelocity embeds an MPCBalancer (upkie_base_velocity.py:117-126)
+            from .mpc import BatchedMPCBalancer
+
+            self.mpc_balancer = BatchedMPCBalancer(
+                self.num_envs, fall_pitch=fall_pitch, leg_length=leg_length, max_ground_accel=max_ground_accel,
+                max_ground_velocity=max_ground_velocity, device=device,
+            )
+            self._xy = torch.zeros((self.num_envs, 2), dtype=torch.float32, device=self.sim.device)
+            self._spine = None
         self.sim.set_autoreset(_AUTORESET[autoreset_mode], self._seed, self.env_offset)
         self.inertia_variation = inertia_variation
         if abs(inertia_variation) > 1e-10:
@@ -323,7 +351,7 @@ class B200VectorEnv(VectorEnv):
 
     # ------------------------------------------------------------------
     def _obs_dim(self) -> int:
-        return {"servos": 30, "gyropod": 6, "pendulum": 4}[self.env_type]
+        return {"servos": 30, "gyropod": 6, "pendulum": 4, "base_velocity": 6}[self.env_type]
 
     def _format_obs(self, obs: np.ndarray):
         return servo_obs_array_to_dict(obs) if self.env_type == "servos" else obs
@@ -358,8 +386,15 @@ class B200VectorEnv(VectorEnv):
             mask=torch.from_numpy(mask).to(dev) if mask is not None else None,
             init_state=torch.from_numpy(rows).to(dev),
         )
+        info = {"spine_observation": SpineObservations(self.sim)}
+        if self.env_type == "base_velocity":
+            # UpkieBaseVelocity.reset (upkie_base_velocity.py:138-162): MPC reset, x = y = 0, zero observation
+            self.mpc_balancer.reset()
+            self._xy.zero_()
+            self._spine = self.sim.spine_obs()
+            return np.zeros((n, 3), dtype=np.float32), info
         obs = self.sim.reset_obs(self._obs_dim()).cpu().numpy()
-        return self._format_obs(obs), {"spine_observation": SpineObservations(self.sim)}
+        return self._format_obs(obs), info
 
     def step(self, action):
         """One 5 ms control tick for every env. ``action`` is a batched dict
@@ -368,6 +403,10 @@ class B200VectorEnv(VectorEnv):
         if isinstance(action, torch.Tensor) and action.is_cuda:
             return self.step_tensors(action)
         n = self.num_envs
+        if self.env_type == "base_velocity":
+            a = torch.from_numpy(np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, 2))).to(self.sim.device)
+            obs, rew, term, trunc, info = self.step_tensors(a)
+            return obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy().view(np.bool_), trunc.cpu().numpy().view(np.bool_), info
         if self.env_type == "servos":
             a = (
                 servo_action_dict_to_array(action, self._neutral_action, n)
@@ -390,6 +429,21 @@ class B200VectorEnv(VectorEnv):
             obs, rew, term, trunc = self.sim.step_servos(action)
         elif self.env_type == "gyropod":
             obs, rew, term, trunc = self.sim.step_gyropod(action)
+        elif self.env_type == "base_velocity":
+            # UpkieBaseVelocity.step (upkie_base_velocity.py:164-202): the MPC turns the commanded linear
+            # velocity into a ground velocity from the LAST spine observation, the gyropod env is stepped,
+            # (x, y) dead-reckon the commanded velocity along the post-step yaw
+            if self._spine is None:
+                self._spine = self.sim.spine_obs()
+            linear_velocity = action[:, 0].contiguous()
+            ground_velocity = self.mpc_balancer.step_spine(linear_velocity, self._spine, self.dt)
+            gyro_action = torch.stack([ground_velocity, action[:, 1]], dim=1).contiguous()
+            obs6, rew, term, trunc = self.sim.step_gyropod(gyro_action)
+            self._spine = self.sim.spine_obs()
+            yaw = obs6[:, 2]
+            self._xy[:, 0] += linear_velocity * torch.cos(yaw) * self.dt
+            self._xy[:, 1] += linear_velocity * torch.sin(yaw) * self.dt
+            obs = torch.cat([self._xy, yaw[:, None]], dim=1)
         else:
             obs, rew, term, trunc = self.sim.step_pendulum(action)
         return obs, rew, term, trunc, {"spine_observation": SpineObservations(self.sim)}
