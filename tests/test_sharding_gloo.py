@@ -42,26 +42,27 @@ def _worker(rank, world, port, n_global, T, obs_dim, out_dir):
         buf = RolloutBuffer(T, cnt, obs_dim, "cpu")
         idx = torch.arange(off, off + cnt, dtype=torch.float32)
         for t in range(T):
-            # every value is a function of (t, global env index) only
-            obs = (idx[:, None] * 10.0 + torch.arange(obs_dim)[None, :] + 1000.0 * t)
-            rew = idx * 0.5 + t
-            term = ((idx.long() + t) % 7 == 0).to(torch.uint8)
-            trunc = ((idx.long() + t) % 11 == 0).to(torch.uint8)
-            buf.record(t, obs, rew, term, trunc)
+            # every value is a function of (t, global env index) only; the producer writes INTO the slot
+            o, r, te, tr = buf.slot(t)
+            o.copy_(idx[:, None] * 10.0 + torch.arange(obs_dim)[None, :] + 1000.0 * t)
+            r.copy_(idx * 0.5 + t)
+            te.copy_(((idx.long() + t) % 7 == 0).to(torch.uint8))
+            tr.copy_(((idx.long() + t) % 11 == 0).to(torch.uint8))
         full = buf.gather()
-        assert full.shape == (T, n_global, 4 * obs_dim + 6)
-        obs, rew, term, trunc = RolloutBuffer.unpack(full, obs_dim)
-        np.save(os.path.join(out_dir, f"obs_{rank}.npy"), obs.numpy())
+        assert full["obs"].shape == (T, n_global, obs_dim) and full["terminated"].dtype == torch.uint8
+        np.save(os.path.join(out_dir, f"obs_{rank}.npy"), full["obs"].numpy())
         gidx = torch.arange(n_global, dtype=torch.float32)
         for t in range(T):
-            assert torch.equal(obs[t], gidx[:, None] * 10.0 + torch.arange(obs_dim)[None, :] + 1000.0 * t)
-            assert torch.equal(rew[t], gidx * 0.5 + t)
-            assert torch.equal(term[t], ((gidx.long() + t) % 7 == 0).to(torch.uint8))
-            assert torch.equal(trunc[t], ((gidx.long() + t) % 11 == 0).to(torch.uint8))
+            assert torch.equal(full["obs"][t], gidx[:, None] * 10.0 + torch.arange(obs_dim)[None, :] + 1000.0 * t)
+            assert torch.equal(full["reward"][t], gidx * 0.5 + t)
+            assert torch.equal(full["terminated"][t], ((gidx.long() + t) % 7 == 0).to(torch.uint8))
+            assert torch.equal(full["truncated"][t], ((gidx.long() + t) % 11 == 0).to(torch.uint8))
+        raw = buf.gather_raw()
+        assert raw.shape == (world, buf.nbytes) and torch.equal(raw[rank], buf.raw)
         # scalar statistics reduce across ranks (mask counts)
-        c = term[:, off:off + cnt].sum().to(torch.float64).reshape(1)
+        c = buf.terminated.sum().to(torch.float64).reshape(1)
         dist.all_reduce(c)
-        assert c.item() == term.sum().item()
+        assert c.item() == full["terminated"].sum().item()
     finally:
         dist.destroy_process_group()
 
@@ -86,7 +87,12 @@ def test_rollout_buffer_single_process_roundtrip():
         trunc = torch.zeros(n, dtype=torch.uint8)
         buf.record(t, obs, rew, term, trunc)
         ref.append((obs, term))
-    obs, rew, term, trunc = RolloutBuffer.unpack(buf.gather(), d)
+    full = buf.gather()
     for t in range(T):
-        assert torch.equal(obs[t], ref[t][0]) and torch.equal(term[t], ref[t][1])
+        assert torch.equal(full["obs"][t], ref[t][0]) and torch.equal(full["terminated"][t], ref[t][1])
     assert buf.rec == 4 * d + 6 and RolloutBuffer(1, 1, 30, "cpu").rec == 126  # 126 B/env/step
+    assert buf.nbytes >= T * n * buf.rec
+    # slots are views of the one byte buffer that gets gathered
+    o, r, te, tr = buf.slot(1)
+    o.fill_(7.0)
+    assert (buf.gather()["obs"][1] == 7.0).all()

@@ -9,7 +9,7 @@ The only exchange is one all-gather of the trajectory buffer per rollout, over
 NCCL (NVLink/NVSwitch) on GPUs or gloo in the CPU tests.
 """
 
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -27,12 +27,15 @@ def shard_range(num_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 
 class RolloutBuffer:
-    """``[T, n_local, record]`` byte buffer of one rollout on this rank.
+    """One rollout of this rank: ``obs[T, n, obs_dim]`` f32, ``reward[T, n]`` f32,
+    ``terminated[T, n]`` u8, ``truncated[T, n]`` u8, carved out of ONE byte buffer
+    (``4 * obs_dim + 6`` bytes per env and step: 126 B for UpkieServos).
 
-    A record is ``obs (obs_dim f32) | reward (f32) | terminated (u8) | truncated
-    (u8)`` = ``4 * obs_dim + 6`` bytes (126 B for UpkieServos). ``gather()``
-    returns the rollout of ALL envs, ``[T, N_global, record]``, ordered by global
-    env index, identical on every rank.
+    ``slot(t)`` returns the four views of time step ``t``; handing them to
+    ``UpkieSim.step_*`` as output tensors makes the step kernel write the rollout
+    in place (no copy kernels). ``gather()`` all-gathers the byte buffer once and
+    returns the rollout of ALL envs ordered by global env index, identical on
+    every rank.
     """
 
     def __init__(self, horizon: int, n_local: int, obs_dim: int, device, group: Optional[dist.ProcessGroup] = None):
@@ -40,32 +43,60 @@ class RolloutBuffer:
         self.rec = 4 * self.obs_dim + 6
         self.group = group
         self.device = torch.device(device)
-        self.data = torch.zeros((self.T, self.n, self.rec), dtype=torch.uint8, device=self.device)
+        T, n, d = self.T, self.n, self.obs_dim
+        self._sizes = [T * n * d * 4, T * n * 4, T * n, T * n]
+        total = sum(self._sizes)
+        self.nbytes = (total + 15) // 16 * 16
+        self.raw = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.obs, self.reward, self.terminated, self.truncated = self._views(self.raw, n)
+
+    def _views(self, raw: torch.Tensor, n: int):
+        T, d = self.T, self.obs_dim
+        o0 = 0
+        o1 = o0 + T * n * d * 4
+        o2 = o1 + T * n * 4
+        o3 = o2 + T * n
+        obs = raw[o0:o1].view(torch.float32).view(T, n, d)
+        rew = raw[o1:o2].view(torch.float32).view(T, n)
+        term = raw[o2:o3].view(T, n)
+        trunc = raw[o3:o3 + T * n].view(T, n)
+        return obs, rew, term, trunc
+
+    def slot(self, t: int):
+        """Output tensors of time step ``t`` (modulo the horizon)."""
+        k = t % self.T
+        return self.obs[k], self.reward[k], self.terminated[k], self.truncated[k]
 
     def record(self, t: int, obs: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor, truncated: torch.Tensor):
-        r = self.data[t % self.T]
-        ob = 4 * self.obs_dim
-        r[:, :ob] = obs.reshape(self.n, self.obs_dim).contiguous().view(torch.uint8).reshape(self.n, ob)
-        r[:, ob:ob + 4] = reward.contiguous().view(torch.uint8).reshape(self.n, 4)
-        r[:, ob + 4] = terminated
-        r[:, ob + 5] = truncated
+        """Copy-in variant of ``slot`` for producers that own their output tensors."""
+        o, r, te, tr = self.slot(t)
+        o.copy_(obs.reshape(self.n, self.obs_dim))
+        r.copy_(reward)
+        te.copy_(terminated)
+        tr.copy_(truncated)
 
-    def gather(self) -> torch.Tensor:
+    def gather(self) -> Dict[str, torch.Tensor]:
+        """``{"obs": [T, N, obs_dim], "reward": [T, N], "terminated": [T, N], "truncated": [T, N]}``
+        over all ranks (``N = world_size * n``; equal shards)."""
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            return self.data
+            return {"obs": self.obs, "reward": self.reward, "terminated": self.terminated, "truncated": self.truncated}
         world = dist.get_world_size(self.group)
-        # concatenated layout [G * T, n, rec] (the form both NCCL and gloo accept)
-        out = torch.empty((world * self.T, self.n, self.rec), dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(out, self.data, group=self.group)
-        # [G, T, n, rec] -> [T, G * n, rec]: rank-major = global env order for equal shards
-        return out.reshape(world, self.T, self.n, self.rec).permute(1, 0, 2, 3).reshape(self.T, world * self.n, self.rec)
+        out = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(out, self.raw, group=self.group)
+        parts = [self._views(out[r * self.nbytes:(r + 1) * self.nbytes], self.n) for r in range(world)]
+        return {
+            "obs": torch.cat([p[0] for p in parts], dim=1),
+            "reward": torch.cat([p[1] for p in parts], dim=1),
+            "terminated": torch.cat([p[2] for p in parts], dim=1),
+            "truncated": torch.cat([p[3] for p in parts], dim=1),
+        }
 
-    @staticmethod
-    def unpack(records: torch.Tensor, obs_dim: int):
-        """Split gathered records back into ``obs[T, N, obs_dim]`` (f32),
-        ``reward[T, N]`` (f32), ``terminated[T, N]``, ``truncated[T, N]`` (u8)."""
-        T, N, rec = records.shape
-        ob = 4 * obs_dim
-        obs = records[:, :, :ob].contiguous().view(torch.float32).reshape(T, N, obs_dim)
-        rew = records[:, :, ob:ob + 4].contiguous().view(torch.float32).reshape(T, N)
-        return obs, rew, records[:, :, ob + 4], records[:, :, ob + 5]
+    def gather_raw(self) -> torch.Tensor:
+        """The all-gather alone (``[world, nbytes]`` bytes, rank-major), without re-assembly."""
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return self.raw.view(1, -1)
+        world = dist.get_world_size(self.group)
+        if getattr(self, "_gathered", None) is None:
+            self._gathered = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(self._gathered, self.raw, group=self.group)
+        return self._gathered.view(world, self.nbytes)

@@ -120,41 +120,60 @@ class UpkieSim:
         check(lib().upkie_b200_reset(self._h, _ptr(mask), _ptr(init_state), int(seed), int(env_offset), self._stream()))
         self.launches += 1
 
-    def step_servos(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None):
+    def _outputs(self, obs, default_obs, reward, terminated, truncated):
+        """Caller-provided output tensors (e.g. ``RolloutBuffer.slot(t)``: the kernel then
+        writes the rollout in place) or the handle's own."""
+        obs = default_obs if obs is None else obs
+        reward = self.reward if reward is None else reward
+        terminated = self.terminated if terminated is None else terminated
+        truncated = self.truncated if truncated is None else truncated
+        if obs is not default_obs:
+            if obs.numel() != default_obs.numel() or obs.data_ptr() % 16 != 0:
+                raise UpkieRuntimeError("obs: wrong number of elements or not 16-byte aligned")
+            self._check_tensor(obs, obs.shape, name="obs")
+        if reward is not self.reward:
+            self._check_tensor(reward, (self.n,), name="reward")
+        if terminated is not self.terminated:
+            self._check_tensor(terminated, (self.n,), torch.uint8, "terminated")
+        if truncated is not self.truncated:
+            self._check_tensor(truncated, (self.n,), torch.uint8, "truncated")
+        return obs, reward, terminated, truncated
+
+    def step_servos(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
+                    truncated=None):
         self._check_tensor(action, (self.n, 6, 6), name="action")
-        obs = self.obs_servos if obs is None else obs
+        obs, reward, terminated, truncated = self._outputs(obs, self.obs_servos, reward, terminated, truncated)
         check(
             lib().upkie_b200_step_servos(
-                self._h, _ptr(action), _ptr(obs), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
-                self._stream(),
+                self._h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream(),
             )
         )
         self.launches += 1
-        return obs, self.reward, self.terminated, self.truncated
+        return obs, reward, terminated, truncated
 
-    def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None):
+    def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
+                     truncated=None):
         self._check_tensor(action, (self.n, 2), name="action")
-        obs = self.obs_gyropod if obs is None else obs
+        obs, reward, terminated, truncated = self._outputs(obs, self.obs_gyropod, reward, terminated, truncated)
         check(
             lib().upkie_b200_step_gyropod(
-                self._h, _ptr(action), 2, _ptr(obs), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
-                self._stream(),
+                self._h, _ptr(action), 2, _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream(),
             )
         )
         self.launches += 1
-        return obs, self.reward, self.terminated, self.truncated
+        return obs, reward, terminated, truncated
 
-    def step_pendulum(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None):
+    def step_pendulum(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
+                      truncated=None):
         self._check_tensor(action, (self.n, 1), name="action")
-        obs = self.obs_pendulum if obs is None else obs
+        obs, reward, terminated, truncated = self._outputs(obs, self.obs_pendulum, reward, terminated, truncated)
         check(
             lib().upkie_b200_step_gyropod(
-                self._h, _ptr(action), 1, _ptr(obs), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated),
-                self._stream(),
+                self._h, _ptr(action), 1, _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream(),
             )
         )
         self.launches += 1
-        return obs, self.reward, self.terminated, self.truncated
+        return obs, reward, terminated, truncated
 
     # host-buffer path (H2D + kernel + D2H inside the call) ---------------------
     def _host_buffers(self):
