@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="servos", choices=["servos", "pendulum", "mpc"])
+    ap.add_argument("--workload", default="servos", choices=["servos", "pendulum", "mpc", "plumbing"])
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -269,6 +269,9 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
 
+    if args.workload == "plumbing":
+        print(json.dumps(bench_plumbing(torch, dev, model)), flush=True)
+        return
     if args.workload == "mpc":
         result = bench_mpc(args, torch, dev, rank, world, K, W)
     else:
@@ -318,13 +321,20 @@ def main():
     if args.workload != "mpc":
         # secondary roofline: non-tensor fp32 issue slots
         sm_mhz = clocks.get("sm_mhz") or 1700.0
-        instr_per_env_step = 24_000  # counted from SASS, DESIGN.md "Roofline"
-        peak_slots = 148 * 4 * 32 * sm_mhz * 1e6
+        # warp instructions per env-step of the servos workload, ncu smsp__inst_executed.sum / warps
+        # (profiles/r01_ncu_summary.md); 84.5 % of them FFMA/FMUL/FADD
+        instr_per_env_step = 23_790
+        sched_cycles = 148 * 4 * sm_mhz * 1e6  # issue slots per second (one warp instruction each)
+        ipc = instr_per_env_step * (n_per_gpu / 32.0) / (kernel_ms * 1e-3) / sched_cycles
         line["roofline"]["fp32_issue"] = {
-            "achieved_lane_instr_per_s": instr_per_env_step * n_per_gpu / (kernel_ms * 1e-3),
-            "peak_lane_instr_per_s": peak_slots,
-            "frac": instr_per_env_step * n_per_gpu / (kernel_ms * 1e-3) / peak_slots,
+            "ipc_per_scheduler": ipc,
+            "peak_ipc": 1.0,
+            "frac": ipc,
+            # tools/micro/ffma2_bench.cu on this pool: three-register scalar FFMA saturates at 0.59 inst/cycle/scheduler
+            "measured_scalar_ffma_ceiling_ipc": 0.59,
+            "fp_instr_frac_of_ceiling": 0.845 * ipc / 0.59,
             "instr_per_env_step": instr_per_env_step,
+            "exact_for": "servos workload (the pendulum front-end changes the count by < 2 %)",
         }
     if world == 1 and not args.no_cpu_baseline and args.workload != "mpc":
         cores = os.cpu_count() or 1
@@ -383,7 +393,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     # rollout buffer gathered over NVLink once per T steps
     from upkie_b200.sharding import RolloutBuffer
 
-    rollout = RolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev)
+    # two buffers: the all-gather of rollout r (communication stream, NVLink) overlaps the simulation of r + 1
+    rollouts = [RolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev) for _ in range(2)]
+    works = [None, None]
 
     for k in range(W):
         step(acts[k % N_ACTION_BUFFERS])
@@ -401,11 +413,19 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         events[0].record()
         for k in range(K):
             # the kernel writes observation / reward / masks straight into the rollout slot of this step
-            so, sr, ste, stru = rollout.slot(k)
+            cur = (k // ROLLOUT_T) % 2
+            if k % ROLLOUT_T == 0 and works[cur] is not None:
+                works[cur].wait()  # the gather that last read this buffer must be done before it is overwritten
+                works[cur] = None
+            so, sr, ste, stru = rollouts[cur].slot(k)
             step(acts[k % N_ACTION_BUFFERS], obs=so, reward=sr, terminated=ste, truncated=stru)
             events[k + 1].record()
             if world > 1 and (k + 1) % ROLLOUT_T == 0:
-                rollout.gather_raw()  # one NCCL all-gather of the [T, n, 126 B] buffer per rollout
+                # one NCCL all-gather of the [T, n, 126 B] buffer per rollout, asynchronous
+                _, works[cur] = rollouts[cur].gather_raw(async_op=True)
+        for w_ in works:
+            if w_ is not None:
+                w_.wait()
         end.record()  # after the last step / all-gather queued on this stream
         torch.cuda.synchronize()
         if profiling:
@@ -461,6 +481,56 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
               " vs 126 MB L2); robot state stays resident by design",
     }
     return n * K, t_ms * K, kernel_ms, e2e, launches, clk.summary(), config, n
+
+
+def bench_plumbing(torch, dev, model, steps=10_000):
+    """BASELINE configs[0]: ONE Upkie-PyBullet-Pendulum-equivalent env at 200 Hz under the README PD policy
+    (README.md:62-64), 10 k steps, reset on `terminated`, through the public env API with host arrays; the same
+    loop on the CPU oracle beside it (single thread)."""
+    from oracle import oracle
+    from upkie_b200 import _abi
+    from upkie_b200.envs import B200VectorEnv
+
+    gains = np.array([10.0, 1.0, 0.0, 0.1], dtype=np.float32)
+    env = B200VectorEnv(1, "pendulum", model=model, device=dev.index)
+    obs, _ = env.reset(seed=0)
+    for _ in range(50):
+        obs, _, term, _, _ = env.step((gains @ obs[0]).reshape(1, 1))
+    t0 = time.perf_counter()
+    resets = 0
+    for _ in range(steps):
+        obs, _, term, _, _ = env.step((gains @ obs[0]).reshape(1, 1))
+        if term[0]:
+            obs, _ = env.reset()
+            resets += 1
+    gpu_rate = steps / (time.perf_counter() - t0)
+    pitch_final = float(obs[0, 0])
+    cfg = _abi.default_sim_config()
+    osim = oracle.OracleSim(model, cfg, 1)
+    init = np.zeros((1, 25))
+    init[0, 2], init[0, 3] = 0.6, 1.0
+    osim.reset(init)
+    o = osim.reset_obs(4)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o, _, oterm, _ = osim.step_gyropod((gains.astype(np.float64) @ o[0]).reshape(1, 1), 1)
+        if oterm[0]:
+            osim.reset(init)
+            o = osim.reset_obs(4)
+    cpu_rate = steps / (time.perf_counter() - t0)
+    return {
+        "metric": "env-steps/sec", "value": gpu_rate, "unit": "env-steps/s", "n_gpus": 1, "steps": steps, "warmup": 50,
+        "ms_per_step": 1e3 / gpu_rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "single UpkiePendulum env, 200 Hz, README PD policy, 10k steps (BASELINE configs[0]); "
+                               "latency-bound plumbing case, not the throughput configuration",
+                   "resets": resets, "final_pitch": pitch_final},
+        "e2e": {"value": gpu_rate, "unit": "env-steps/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 22,
+                "api": "B200VectorEnv(1, 'pendulum').step(numpy)"},
+        "gpu_launches": steps,
+        "cpu_baseline": {"value": cpu_rate, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                         "sample": f"{steps} steps of the same closed loop on the fp64 oracle, 1 thread"},
+    }
 
 
 def bench_mpc(args, torch, dev, rank, world, K, W):

@@ -91,12 +91,18 @@ class RolloutBuffer:
             "truncated": torch.cat([p[3] for p in parts], dim=1),
         }
 
-    def gather_raw(self) -> torch.Tensor:
-        """The all-gather alone (``[world, nbytes]`` bytes, rank-major), without re-assembly."""
+    def gather_raw(self, async_op: bool = False):
+        """The all-gather alone (``[world, nbytes]`` bytes, rank-major), without re-assembly.
+
+        With ``async_op=True`` returns ``(tensor, work)``: the collective runs on the
+        communication stream while the next rollout (in another buffer) is simulated;
+        call ``work.wait()`` before touching ``tensor`` or re-using this buffer's slots."""
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            return self.raw.view(1, -1)
+            out = self.raw.view(1, -1)
+            return (out, None) if async_op else out
         world = dist.get_world_size(self.group)
         if getattr(self, "_gathered", None) is None:
             self._gathered = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(self._gathered, self.raw, group=self.group)
-        return self._gathered.view(world, self.nbytes)
+        work = dist.all_gather_into_tensor(self._gathered, self.raw, group=self.group, async_op=async_op)
+        out = self._gathered.view(world, self.nbytes)
+        return (out, work) if async_op else out
