@@ -101,6 +101,19 @@ extern "C" {
 #define UPKIE_SP_ODOM_VEL 61     /* wheel_odometry.velocity */
 #define UPKIE_SPINE_DIM 62
 
+/* observers_out[N][UPKIE_OBSV_DIM]: outputs of the spine's observer pipeline
+ * (spines/common/observers.h:23-44) */
+#define UPKIE_OBSV_PITCH 0          /* base_orientation.pitch (upkie/cpp/observers/BaseOrientation.h:73-92) */
+#define UPKIE_OBSV_ANGVEL 1         /* base_orientation.angular_velocity [3] (BaseOrientation.h:144-148) */
+#define UPKIE_OBSV_ROT 4            /* base_orientation.rotation_base_to_world, row-major [9] */
+#define UPKIE_OBSV_CONTACT 13       /* floor_contact.contact (FloorContact.cpp:37-49) */
+#define UPKIE_OBSV_WHEEL_CONTACT 14 /* floor_contact.{left,right}_wheel.contact [2] (WheelContact.cpp:19-48) */
+#define UPKIE_OBSV_LEG_TORQUE 16    /* floor_contact.upper_leg_torque (FloorContact.cpp:73-91) */
+#define UPKIE_OBSV_WHEEL_INERTIA 17 /* floor_contact.{left,right}_wheel.inertia [2] */
+#define UPKIE_OBSV_ODOM_POS 19      /* wheel_odometry.position (WheelOdometry.cpp:16-24) */
+#define UPKIE_OBSV_ODOM_VEL 20      /* wheel_odometry.velocity */
+#define UPKIE_OBSV_DIM 21
+
 /* per-env error flags (sticky until reset) */
 #define UPKIE_ERR_NAN_VELOCITY 1u /* NaN target velocity (asserted in pybullet_backend.py:519) */
 #define UPKIE_ERR_NAN_STATE 2u    /* non-finite simulator state */
@@ -201,6 +214,20 @@ typedef struct UpkieMpcConfig {
   double gravity;                 /* 9.81 (qpmpc GRAVITY) */
 } UpkieMpcConfig;
 
+/* Observer pipeline parameters: spine configuration defaults of
+ * upkie/envs/backends/spine_backend.py:77-105,140-165 */
+typedef struct UpkieObserverConfig {
+  double dt;                          /* 1 / spine_frequency (0.001) */
+  double cutoff_period;               /* wheel_contact.cutoff_period (0.2) */
+  double liftoff_inertia;             /* 1e-3 */
+  double min_touchdown_acceleration;  /* 2.0 */
+  double min_touchdown_torque;        /* 0.015 */
+  double touchdown_inertia;           /* 4e-3 */
+  double upper_leg_torque_threshold;  /* floor_contact.upper_leg_torque_threshold (10.0) */
+  double signed_radius[2];            /* wheel_odometry.signed_radius: left, right */
+  double rotation_base_to_imu[9];     /* base_orientation.rotation_base_to_imu, row-major */
+} UpkieObserverConfig;
+
 /* ---- library ------------------------------------------------------------ */
 
 int upkie_b200_abi_version(void);
@@ -294,6 +321,17 @@ int upkie_b200_mpc_step(void* mpc, const float* x0, const float* v_target,
                         float* first_input, uint8_t* found, void* stream);
 /* Full optimal input sequence of the last solve, plan[N][nb_timesteps]. */
 int upkie_b200_mpc_plan(void* mpc, float* plan, void* stream);
+
+/* ---- observer pipeline handle --------------------------------------------
+ * Replaces the spine's BaseOrientation -> FloorContact -> WheelOdometry observers
+ * (upkie/cpp/observers/, spines/common/observers.h:23-44) for N robots: one call
+ * = one spine cycle. spine_obs[N][UPKIE_SPINE_DIM] supplies imu.orientation,
+ * imu.angular_velocity and servo.*.{torque, velocity}; out[N][UPKIE_OBSV_DIM]. */
+int upkie_b200_default_observer_config(const UpkieModel* model, UpkieObserverConfig* config);
+int upkie_b200_observers_create(const UpkieObserverConfig* config, int n_robots, int device, void** observers);
+void upkie_b200_observers_destroy(void* observers);
+int upkie_b200_observers_reset(void* observers, const uint8_t* mask, void* stream);
+int upkie_b200_observers_step(void* observers, const float* spine_obs, float* out, void* stream);
 
 #ifdef __cplusplus
 }

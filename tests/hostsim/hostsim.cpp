@@ -82,7 +82,7 @@ void hostsim_substep(void* hv, int n, float* state, const float* tau) {
   for (int i = 0; i < n; ++i) {
     RobotState S;
     state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
-    physics_substep(h->P, S, tau + size_t(i) * 6, nullptr, h->P.friction, any_fn);
+    substep(h->P, S, tau + size_t(i) * 6, nullptr, h->P.friction, any_fn);
     state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
   }
 }
@@ -167,5 +167,34 @@ void hostsim_mpc_step_f32(const UpkieMpcConfig* c, int n, const double* x0, cons
 void hostsim_mpc_step_f64(const UpkieMpcConfig* c, int n, const double* x0, const double* v_target, const uint8_t* contact,
                           double dt, double* v_cmd, double* plan, uint8_t* found, int* iterations) {
   hostsim_mpc_impl<double>(c, n, x0, v_target, contact, dt, v_cmd, plan, found, iterations);
+}
+}
+
+// ---- observer pipeline core on the host (fp32, what k_observers_step runs) ----
+#include "../../upkie_b200/csrc/observers_core.cuh"
+
+struct HostObservers {
+  ObserverParams<float> P;
+  std::vector<ObserverState<float>> st;
+};
+
+extern "C" {
+void* hostsim_observers_create(const UpkieObserverConfig* c, int n) {
+  HostObservers* h = new HostObservers();
+  h->P.dt = float(c->dt); h->P.cutoff_period = float(c->cutoff_period); h->P.liftoff_inertia = float(c->liftoff_inertia);
+  h->P.min_touchdown_acceleration = float(c->min_touchdown_acceleration);
+  h->P.min_touchdown_torque = float(c->min_touchdown_torque); h->P.touchdown_inertia = float(c->touchdown_inertia);
+  h->P.upper_leg_torque_threshold = float(c->upper_leg_torque_threshold);
+  h->P.signed_radius[0] = float(c->signed_radius[0]); h->P.signed_radius[1] = float(c->signed_radius[1]);
+  for (int k = 0; k < 9; ++k) h->P.Rbi[k] = float(c->rotation_base_to_imu[k]);
+  h->st.assign(size_t(n), ObserverState<float>());
+  for (auto& s : h->st) std::memset(&s, 0, sizeof(s));
+  return h;
+}
+void hostsim_observers_destroy(void* h) { delete static_cast<HostObservers*>(h); }
+void hostsim_observers_step(void* hv, const float* spine, float* out) {
+  HostObservers* h = static_cast<HostObservers*>(hv);
+  for (size_t i = 0; i < h->st.size(); ++i)
+    observers_step(h->P, h->st[i], spine + i * UPKIE_SPINE_DIM, out + i * UPKIE_OBSV_DIM);
 }
 }

@@ -14,15 +14,11 @@ OUT = os.path.join(ROOT, "variants")
 BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
         "-Xcompiler", "-fPIC", "--use_fast_math"]
 VARIANTS = {
-    "s0_b128": ["-DUPKIE_PHASE_SYNC_LEVEL=0"],
-    "s1_b128": ["-DUPKIE_PHASE_SYNC_LEVEL=1"],
-    "s2_b128": ["-DUPKIE_PHASE_SYNC_LEVEL=2"],
-    "s0_b64": ["-DUPKIE_PHASE_SYNC_LEVEL=0", "-DUPKIE_MAX_THREADS=64", "-DUPKIE_DEFAULT_BLOCK=64"],
-    "s1_b64": ["-DUPKIE_PHASE_SYNC_LEVEL=1", "-DUPKIE_MAX_THREADS=64", "-DUPKIE_DEFAULT_BLOCK=64"],
-    "s0_b256": ["-DUPKIE_PHASE_SYNC_LEVEL=0", "-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
-    "s1_b256": ["-DUPKIE_PHASE_SYNC_LEVEL=1", "-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
-    "s2_b256": ["-DUPKIE_PHASE_SYNC_LEVEL=2", "-DUPKIE_MAX_THREADS=256", "-DUPKIE_DEFAULT_BLOCK=256"],
-    "s0_b32": ["-DUPKIE_PHASE_SYNC_LEVEL=0", "-DUPKIE_MAX_THREADS=32", "-DUPKIE_DEFAULT_BLOCK=32"],
+    "paired_s1": [],
+    "paired_s0": ["-DUPKIE_PHASE_SYNC_LEVEL=0"],
+    "scalar_s1": ["-DUPKIE_PAIRED_LEGS=0"],
+    "paired_s1_r168": ["-DUPKIE_MAX_THREADS=384", "-DUPKIE_MIN_BLOCKS=1"],
+    "paired_s1_r128": ["-DUPKIE_MAX_THREADS=512", "-DUPKIE_MIN_BLOCKS=1"],
 }
 
 

@@ -128,6 +128,43 @@ class UpkieMpcConfig(C.Structure):
     ]
 
 
+class UpkieObserverConfig(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double),
+        ("cutoff_period", C.c_double),
+        ("liftoff_inertia", C.c_double),
+        ("min_touchdown_acceleration", C.c_double),
+        ("min_touchdown_torque", C.c_double),
+        ("touchdown_inertia", C.c_double),
+        ("upper_leg_torque_threshold", C.c_double),
+        ("signed_radius", C.c_double * 2),
+        ("rotation_base_to_imu", C.c_double * 9),
+    ]
+
+
+OBSV_PITCH, OBSV_ANGVEL, OBSV_ROT, OBSV_CONTACT, OBSV_WHEEL_CONTACT = 0, 1, 4, 13, 14
+OBSV_LEG_TORQUE, OBSV_WHEEL_INERTIA, OBSV_ODOM_POS, OBSV_ODOM_VEL, OBSV_DIM = 16, 17, 19, 20, 21
+
+
+def default_observer_config(model, spine_frequency: float = 1000.0) -> UpkieObserverConfig:
+    """Spine configuration defaults (``upkie/envs/backends/spine_backend.py:77-105,140-165``)."""
+    c = UpkieObserverConfig()
+    c.dt = 1.0 / spine_frequency
+    c.cutoff_period = 0.2
+    c.liftoff_inertia = 1e-3
+    c.min_touchdown_acceleration = 2.0
+    c.min_touchdown_torque = 0.015
+    c.touchdown_inertia = 4e-3
+    c.upper_leg_torque_threshold = 10.0
+    sign = 1.0 if model.left_wheeled else -1.0
+    c.signed_radius[0] = sign * model.wheel_radius
+    c.signed_radius[1] = -sign * model.wheel_radius
+    R = [float(x) for x in __import__("numpy").asarray(model.rotation_base_to_imu, dtype=float).reshape(9)]
+    for k in range(9):
+        c.rotation_base_to_imu[k] = R[k]
+    return c
+
+
 def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     """Reference defaults (``pybullet_backend.py:55-112``,
     ``upkie_servos.py:114-124``, ``upkie_gyropod.py:105-112``,

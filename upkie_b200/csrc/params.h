@@ -93,6 +93,18 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
            std::fabs(I[3]) < 1e-12 && std::fabs(I[4]) < 1e-12 && std::fabs(I[5]) < 1e-12;
   };
   P.wheel_symmetric = (wheel_sym(3) && wheel_sym(6)) ? 1 : 0;
+  for (int k = 0; k < 3; ++k) {
+    P.sgn2[k].x = P.sgn[k]; P.sgn2[k].y = P.sgn[k + 3];
+    P.mass2[k].x = P.mass[k + 1]; P.mass2[k].y = P.mass[k + 4];
+    float oyl = 0.f, oyr = 0.f;
+    for (int kk = 0; kk <= k; ++kk) { oyl += P.jo[kk][1]; oyr += P.jo[kk + 3][1]; }
+    P.oy2[k].x = oyl; P.oy2[k].y = oyr;
+    for (int i = 0; i < 3; ++i) {
+      P.jo2[k][i].x = P.jo[k][i]; P.jo2[k][i].y = P.jo[k + 3][i];
+      P.com2[k][i].x = P.com[k + 1][i]; P.com2[k][i].y = P.com[k + 4][i];
+    }
+    for (int i = 0; i < 6; ++i) { P.inertia2[k][i].x = P.inertia[k + 1][i]; P.inertia2[k][i].y = P.inertia[k + 4][i]; }
+  }
   if (!(m.wheel_radius > 0.0)) { err = "model: wheel_radius must be positive"; return UPKIE_B200_EMODEL; }
   P.wheel_radius = float(m.wheel_radius);
   P.half_wheel_base = float(0.5 * m.wheel_base);

@@ -36,6 +36,15 @@
 
 namespace upkie_b200 {
 
+#ifndef UPKIE_PAIRED_LEGS
+#define UPKIE_PAIRED_LEGS 1  // left/right leg arithmetic packed into f32x2 instructions (sim_pair.cuh)
+#endif
+
+// (left leg, right leg) pair; maps onto one 64-bit register pair / one FFMA2 operand
+struct alignas(8) f2 {
+  float x, y;
+};
+
 // ---- kernel parameters (constant bank) ----------------------------------------
 struct SimParams {
   // model (upkie.model.Model + URDF inertials)
@@ -51,6 +60,13 @@ struct SimParams {
   float imu_pos[3];
   float Rbi[9];            // rotation_base_to_imu
   int wheel_symmetric;     // wheel CoM on its axis and inertia axisymmetric: skip wheel-angle trig
+  // the per-leg constants again as (left, right) pairs, k = hip, knee, wheel (64-bit constant operands)
+  f2 sgn2[3];
+  f2 jo2[3][3];
+  f2 oy2[3];               // y of the body origin (sum of joint-origin y's down the chain)
+  f2 mass2[3];
+  f2 com2[3][3];
+  f2 inertia2[3][6];
   // backend
   float dt, inv_dt, h, inv_h;
   int nb_substeps, pgs_iterations;
@@ -734,6 +750,21 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
   for (int j = 0; j < 6; ++j) S.q[j] += P.h * S.qd[j];
 }
 
+}  // namespace upkie_b200
+#include "sim_pair.cuh"
+namespace upkie_b200 {
+
+// the substep the env-level functions below use
+template <typename AnyFn, typename SyncFn = NoSync>
+UPKIE_HD void substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu, AnyFn warp_any,
+                      SyncFn phase_sync = SyncFn()) {
+#if UPKIE_PAIRED_LEGS
+  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync);
+#else
+  physics_substep(P, S, tau, eps, mu, warp_any, phase_sync);
+#endif
+}
+
 // pybullet_backend.py:492-553 compute_joint_torque
 UPKIE_HD float joint_torque(const SimParams& P, int j, float q, float qd, float ff, float target_position,
                             float target_velocity, float kp_scale, float kd_scale, float maximum_torque) {
@@ -887,7 +918,7 @@ UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPK
     tau[j] = zero_torque ? 0.f : t;
     if (!zero_torque) S.torque[j] = t;
   }
-  physics_substep(P, S, tau, eps, mu, warp_any, phase_sync);
+  substep(P, S, tau, eps, mu, warp_any, phase_sync);
 }
 
 UPKIE_HD uint32_t state_sanity(const RobotState& S) {
@@ -1023,7 +1054,7 @@ UPKIE_HD void reset_robot(const SimParams& P, RobotState& S, const float init[UP
     S.qd[j] = 0.f;
   }
   const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  physics_substep(P, S, zero, eps, mu, warp_any);  // one stepSimulation (:228)
+  substep(P, S, zero, eps, mu, warp_any);  // one stepSimulation (:228)
   observe_update(P, S);
   S.leg_target[0] = S.q[0]; S.leg_target[1] = S.q[1]; S.leg_target[2] = S.q[3]; S.leg_target[3] = S.q[4];
   S.yaw = 0.f;

@@ -1,0 +1,550 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// sim_pair.cuh -- the physics substep with the LEFT and RIGHT leg packed into the
+// two lanes of sm_100a's f32x2 instructions (FFMA2 / FMUL2 / FADD2).
+//
+// Why: the step kernel is bound by the scalar fp32 pipe (profiles/r01_variants.md:
+// three-register scalar FFMA saturates at 0.59 inst/cycle/scheduler on B200, FFMA2
+// moves two FMAs per lane per instruction at the same issue cost). The two legs of
+// the robot run the same arithmetic on different data, so every per-leg scalar of
+// sim_core.cuh becomes an f2 = (left, right). SASS provides for free what the
+// pairing needs: per-operand negation, broadcast of a scalar register to both lanes
+// (`R.F32`), lane swap (`R.F32x2.LO_HI`, used for the cross-leg impulse responses)
+// and 64-bit constant-bank operands (the per-leg model constants are stored as
+// adjacent pairs in SimParams).
+//
+// Included by sim_core.cuh; same mathematics as the scalar functions there, which
+// remain available with -DUPKIE_PAIRED_LEGS=0.
+#pragma once
+
+namespace upkie_b200 {
+
+UPKIE_HD f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+UPKIE_HD f2 bc2(float a) { return mk2(a, a); }          // broadcast
+UPKIE_HD f2 swp2(f2 v) { return mk2(v.y, v.x); }       // lane swap (free: .LO_HI operand modifier)
+UPKIE_HD f2 neg2(f2 v) { return mk2(-v.x, -v.y); }     // free: operand negation
+
+#if defined(__CUDA_ARCH__)
+UPKIE_HD f2 fma2(f2 a, f2 b, f2 c) {
+  const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+  return mk2(r.x, r.y);
+}
+UPKIE_HD f2 mul2(f2 a, f2 b) {
+  const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return mk2(r.x, r.y);
+}
+UPKIE_HD f2 add2(f2 a, f2 b) {
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return mk2(r.x, r.y);
+}
+#else
+UPKIE_HD f2 fma2(f2 a, f2 b, f2 c) { return mk2(a.x * b.x + c.x, a.y * b.y + c.y); }
+UPKIE_HD f2 mul2(f2 a, f2 b) { return mk2(a.x * b.x, a.y * b.y); }
+UPKIE_HD f2 add2(f2 a, f2 b) { return mk2(a.x + b.x, a.y + b.y); }
+#endif
+UPKIE_HD f2 sub2(f2 a, f2 b) { return add2(a, neg2(b)); }
+
+UPKIE_HD void cross3_2(const f2 a[3], const f2 b[3], f2 c[3]) {
+  c[0] = fma2(a[1], b[2], neg2(mul2(a[2], b[1])));
+  c[1] = fma2(a[2], b[0], neg2(mul2(a[0], b[2])));
+  c[2] = fma2(a[0], b[1], neg2(mul2(a[1], b[0])));
+}
+
+// S^T x for S = s * [0 1 0 | -oz 0 ox], both legs
+UPKIE_HD f2 sdot2(f2 s, f2 ox, f2 oz, const f2 x[6]) { return mul2(s, fma2(ox, x[5], fma2(neg2(oz), x[3], x[1]))); }
+
+struct LegCache2 {
+  f2 ox[3], oz[3];
+  f2 U[3][6];
+  f2 invD[3];
+};
+
+// two right-hand sides at once against the scalar LDL^T factors of ldl6()
+UPKIE_HD void ldl6_solve2(const float A[21], f2 x[6]) {
+#pragma unroll
+  for (int i = 1; i < 6; ++i) {
+#pragma unroll
+    for (int k = 0; k < i; ++k) x[i] = fma2(bc2(-A[SI(k, i)]), x[k], x[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = mul2(x[i], bc2(A[SI(i, i)]));
+#pragma unroll
+  for (int i = 4; i >= 0; --i) {
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) x[i] = fma2(bc2(-A[SI(i, k)]), x[k], x[i]);
+  }
+}
+
+// Both legs of leg_pass12 at once.
+UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6], const float tau[6], const float V0[6],
+                          const float* eps, LegCache2& lc, f2 cc[3][6], f2 uu[3], float IA0[21], float pA0[6]) {
+  f2 cphi[3], sphi[3];
+  f2 V[3][6];
+  {
+    f2 phi = bc2(0.f), cp = bc2(1.f), sp = bc2(0.f), ox = bc2(0.f), oz = bc2(0.f);
+    f2 Vc[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Vc[i] = bc2(V0[i]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const f2 s = P.sgn2[k];
+      // origin of body k: parent origin + Ry(phi_parent) * joint origin
+      const f2 ox_n = fma2(cp, P.jo2[k][0], fma2(sp, P.jo2[k][2], ox));
+      const f2 oz_n = fma2(cp, P.jo2[k][2], fma2(neg2(sp), P.jo2[k][0], oz));
+      ox = ox_n;
+      oz = oz_n;
+      lc.ox[k] = ox;
+      lc.oz[k] = oz;
+      phi = fma2(s, mk2(q[k], q[k + 3]), phi);
+      if (k < 2 || !P.wheel_symmetric) {
+        float sx, cx, sy, cy;
+        sincosf(phi.x - 6.28318530718f * rintf(phi.x * 0.15915494309f), &sx, &cx);
+        sincosf(phi.y - 6.28318530718f * rintf(phi.y * 0.15915494309f), &sy, &cy);
+        sp = mk2(sx, sy);
+        cp = mk2(cx, cy);
+      }
+      cphi[k] = cp;
+      sphi[k] = sp;
+      const f2 w = mul2(s, mk2(qd[k], qd[k + 3]));
+      Vc[1] = add2(Vc[1], w);
+      Vc[3] = fma2(neg2(oz), w, Vc[3]);
+      Vc[5] = fma2(ox, w, Vc[5]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) V[k][i] = Vc[i];
+    }
+  }
+  f2 IA[21], pA[6];
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    const f2 s = P.sgn2[k];
+    const f2 ox = lc.ox[k], oz = lc.oz[k];
+    const f2 scale = eps ? mk2(1.f + eps[k], 1.f + eps[k + 3]) : bc2(1.f);
+    const f2 m = mul2(P.mass2[k], scale);
+    f2 C[3], Ib[6];
+    if (k == 2 && P.wheel_symmetric) {
+      C[0] = ox; C[1] = P.oy2[k]; C[2] = oz;
+      Ib[0] = mul2(P.inertia2[k][0], scale); Ib[1] = mul2(P.inertia2[k][1], scale); Ib[2] = mul2(P.inertia2[k][2], scale);
+      Ib[3] = bc2(0.f); Ib[4] = bc2(0.f); Ib[5] = bc2(0.f);
+    } else {
+      const f2 c = cphi[k], sn = sphi[k];
+      C[0] = fma2(c, P.com2[k][0], fma2(sn, P.com2[k][2], ox));
+      C[1] = add2(P.com2[k][1], P.oy2[k]);
+      C[2] = fma2(c, P.com2[k][2], fma2(neg2(sn), P.com2[k][0], oz));
+      const f2 a = mul2(P.inertia2[k][0], scale), bb = mul2(P.inertia2[k][1], scale), cz = mul2(P.inertia2[k][2], scale);
+      const f2 d = mul2(P.inertia2[k][3], scale), e = mul2(P.inertia2[k][4], scale), f = mul2(P.inertia2[k][5], scale);
+      const f2 c2 = mul2(c, c), s2 = mul2(sn, sn), cs = mul2(c, sn), cs2 = add2(cs, cs);
+      Ib[0] = fma2(c2, a, fma2(cs2, e, mul2(s2, cz)));
+      Ib[1] = bb;
+      Ib[2] = fma2(s2, a, fma2(neg2(cs2), e, mul2(c2, cz)));
+      Ib[3] = fma2(c, d, mul2(sn, f));
+      Ib[4] = fma2(cs, sub2(cz, a), mul2(sub2(c2, s2), e));
+      Ib[5] = fma2(c, f, neg2(mul2(sn, d)));
+    }
+    // spatial inertia about the base origin
+    f2 I[21];
+    {
+      const f2 cc2 = fma2(C[0], C[0], fma2(C[1], C[1], mul2(C[2], C[2])));
+      I[SI(0, 0)] = fma2(m, sub2(cc2, mul2(C[0], C[0])), Ib[0]);
+      I[SI(1, 1)] = fma2(m, sub2(cc2, mul2(C[1], C[1])), Ib[1]);
+      I[SI(2, 2)] = fma2(m, sub2(cc2, mul2(C[2], C[2])), Ib[2]);
+      const f2 hx = mul2(m, C[0]), hy = mul2(m, C[1]), hz = mul2(m, C[2]);
+      I[SI(0, 1)] = fma2(neg2(hx), C[1], Ib[3]);
+      I[SI(0, 2)] = fma2(neg2(hx), C[2], Ib[4]);
+      I[SI(1, 2)] = fma2(neg2(hy), C[2], Ib[5]);
+      I[SI(0, 3)] = bc2(0.f); I[SI(0, 4)] = neg2(hz); I[SI(0, 5)] = hy;
+      I[SI(1, 3)] = hz;       I[SI(1, 4)] = bc2(0.f); I[SI(1, 5)] = neg2(hx);
+      I[SI(2, 3)] = neg2(hy); I[SI(2, 4)] = hx;       I[SI(2, 5)] = bc2(0.f);
+      I[SI(3, 3)] = m; I[SI(4, 4)] = m; I[SI(5, 5)] = m;
+      I[SI(3, 4)] = bc2(0.f); I[SI(3, 5)] = bc2(0.f); I[SI(4, 5)] = bc2(0.f);
+    }
+    // momentum, bias force p = V x* (I V) - damping wrench
+    f2 p[6];
+    {
+      const f2* om = &V[k][0];
+      const f2* v = &V[k][3];
+      f2 t[3], vC[3];
+      cross3_2(om, C, t);
+      vC[0] = add2(v[0], t[0]); vC[1] = add2(v[1], t[1]); vC[2] = add2(v[2], t[2]);
+      const f2 f[3] = {mul2(m, vC[0]), mul2(m, vC[1]), mul2(m, vC[2])};
+      const f2 nC[3] = {fma2(Ib[0], om[0], fma2(Ib[3], om[1], mul2(Ib[4], om[2]))),
+                        fma2(Ib[3], om[0], fma2(Ib[1], om[1], mul2(Ib[5], om[2]))),
+                        fma2(Ib[4], om[0], fma2(Ib[5], om[1], mul2(Ib[2], om[2])))};
+      f2 n[3];
+      cross3_2(C, f, n);
+      n[0] = add2(n[0], nC[0]); n[1] = add2(n[1], nC[1]); n[2] = add2(n[2], nC[2]);
+      f2 a1[3], a2[3], a3[3];
+      cross3_2(om, n, a1);
+      cross3_2(v, f, a2);
+      cross3_2(om, f, a3);
+      // Bullet-style damping: F = -m vC (k + k|vC|), N = -Ic om (k + k|om|)
+      const f2 v2 = fma2(vC[0], vC[0], fma2(vC[1], vC[1], mul2(vC[2], vC[2])));
+      const f2 o2 = fma2(om[0], om[0], fma2(om[1], om[1], mul2(om[2], om[2])));
+      const f2 gl = fma2(bc2(P.lin_damp), mk2(sqrtf(v2.x), sqrtf(v2.y)), bc2(P.lin_damp));
+      const f2 ga = fma2(bc2(P.ang_damp), mk2(sqrtf(o2.x), sqrtf(o2.y)), bc2(P.ang_damp));
+      const f2 F[3] = {mul2(f[0], gl), mul2(f[1], gl), mul2(f[2], gl)};  // = -damping force
+      f2 cF[3];
+      cross3_2(C, F, cF);
+      p[0] = add2(add2(a1[0], a2[0]), fma2(nC[0], ga, cF[0]));
+      p[1] = add2(add2(a1[1], a2[1]), fma2(nC[1], ga, cF[1]));
+      p[2] = add2(add2(a1[2], a2[2]), fma2(nC[2], ga, cF[2]));
+      p[3] = add2(a3[0], F[0]);
+      p[4] = add2(a3[1], F[1]);
+      p[5] = add2(a3[2], F[2]);
+    }
+    if (k == 2) {
+#pragma unroll
+      for (int i = 0; i < 21; ++i) IA[i] = I[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) pA[i] = p[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 21; ++i) IA[i] = add2(IA[i], I[i]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) pA[i] = add2(pA[i], p[i]);
+    }
+    // velocity-product acceleration c = V x (S qd)
+    {
+      const f2 w = mul2(s, mk2(qd[k], qd[k + 3]));
+      const f2* om = &V[k][0];
+      const f2* v = &V[k][3];
+      cc[k][0] = neg2(mul2(om[2], w));
+      cc[k][1] = bc2(0.f);
+      cc[k][2] = mul2(om[0], w);
+      cc[k][3] = mul2(fma2(om[1], ox, neg2(v[2])), w);
+      cc[k][4] = neg2(mul2(fma2(om[2], oz, mul2(om[0], ox)), w));
+      cc[k][5] = mul2(fma2(om[1], oz, v[0]), w);
+    }
+    // U = IA S, D = S^T U, u = tau - S^T pA
+    f2 U[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) U[r] = mul2(s, fma2(ox, IA[SI(r, 5)], fma2(neg2(oz), IA[SI(r, 3)], IA[SI(r, 1)])));
+    const f2 D = sdot2(s, ox, oz, U);
+    const f2 invD = mk2(1.f / D.x, 1.f / D.y);
+    const f2 u = sub2(mk2(tau[k], tau[k + 3]), sdot2(s, ox, oz, pA));
+#pragma unroll
+    for (int r = 0; r < 6; ++r) lc.U[k][r] = U[r];
+    lc.invD[k] = invD;
+    uu[k] = u;
+    // Ia = IA - U U^T / D ; pa = pA + Ia c + U u / D
+    f2 Ud[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) Ud[r] = mul2(U[r], invD);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int c2 = r; c2 < 6; ++c2) IA[SI(r, c2)] = fma2(neg2(Ud[r]), U[c2], IA[SI(r, c2)]);
+    }
+    const f2 ud = mul2(u, invD);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      f2 acc = fma2(U[r], ud, pA[r]);
+#pragma unroll
+      for (int c2 = 0; c2 < 6; ++c2) acc = fma2(IA[SI(r, c2)], cc[k][c2], acc);
+      p[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) pA[r] = p[r];
+  }
+#pragma unroll
+  for (int i = 0; i < 21; ++i) IA0[i] += IA[i].x + IA[i].y;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) pA0[i] += pA[i].x + pA[i].y;
+}
+
+// joint accelerations down both legs given the base acceleration
+UPKIE_HD void legs_pass3(const SimParams& P, const LegCache2& lc, const f2 cc[3][6], const f2 uu[3], const float a0[6],
+                         float qdd[6]) {
+  f2 a[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a[i] = bc2(a0[i]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    f2 dot = bc2(0.f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      a[i] = add2(a[i], cc[k][i]);
+      dot = fma2(lc.U[k][i], a[i], dot);
+    }
+    const f2 dd = mul2(sub2(uu[k], dot), lc.invD[k]);
+    qdd[k] = dd.x;
+    qdd[k + 3] = dd.y;
+    const f2 w = mul2(P.sgn2[k], dd);
+    a[1] = add2(a[1], w);
+    a[3] = fma2(neg2(lc.oz[k]), w, a[3]);
+    a[5] = fma2(lc.ox[k], w, a[5]);
+  }
+}
+
+// lane x: impulse f.x on the LEFT wheel up the left leg; lane y: f.y on the RIGHT wheel up the right leg
+UPKIE_HD void legs_impulse_up(const SimParams& P, const LegCache2& lc, const f2 f[6], f2 uu[3], f2 ptop[6]) {
+  f2 p[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) p[i] = neg2(f[i]);
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    const f2 u = neg2(sdot2(P.sgn2[k], lc.ox[k], lc.oz[k], p));
+    uu[k] = u;
+    const f2 ud = mul2(u, lc.invD[k]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p[i] = fma2(lc.U[k][i], ud, p[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ptop[i] = p[i];
+}
+
+// Velocity changes down the legs. SWAP = false: lane x walks the left leg, lane y the right leg (with the
+// per-joint u's of legs_impulse_up). SWAP = true: lane x walks the RIGHT leg, lane y the LEFT leg with u = 0
+// (the leg the impulse was not applied to); the leg constants are read lane-swapped, which is free in SASS.
+template <bool SWAP>
+UPKIE_HD void legs_impulse_down(const SimParams& P, const LegCache2& lc, const f2 uu[3], const f2 a0[6], f2 aw[6],
+                                f2 dqd[3]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) aw[i] = a0[i];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    f2 dot = bc2(0.f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dot = fma2(SWAP ? swp2(lc.U[k][i]) : lc.U[k][i], aw[i], dot);
+    const f2 invD = SWAP ? swp2(lc.invD[k]) : lc.invD[k];
+    const f2 dd = SWAP ? mul2(neg2(dot), invD) : mul2(sub2(uu[k], dot), invD);
+    dqd[k] = dd;
+    const f2 w = mul2(SWAP ? swp2(P.sgn2[k]) : P.sgn2[k], dd);
+    aw[1] = add2(aw[1], w);
+    aw[3] = fma2(neg2(SWAP ? swp2(lc.oz[k]) : lc.oz[k]), w, aw[3]);
+    aw[5] = fma2(SWAP ? swp2(lc.ox[k]) : lc.ox[k], w, aw[5]);
+  }
+}
+
+// row / column index of (side, direction) in Bullet's order: nL nR t1L t2L t1R t2R
+UPKIE_HD constexpr int row_of(int side, int d) { return d == 0 ? side : 2 + 2 * side + (d - 1); }
+
+template <typename AnyFn, typename SyncFn = NoSync>
+UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
+                                     AnyFn warp_any, SyncFn phase_sync = SyncFn()) {
+  float R[9];
+  quat_to_rot(S.quat, R);
+  float V0[6];
+  rot_tmul(R, S.angvel, &V0[0]);
+  rot_tmul(R, S.linvel, &V0[3]);
+
+  float IA0[21], pA0[6];
+  base_inertia_bias(P, V0, IA0, pA0);
+  LegCache2 lc;
+  f2 cc[3][6], uu[3];
+  legs_pass12(P, S.q, S.qd, tau, V0, eps, lc, cc, uu, IA0, pA0);
+  phase_sync();  // 1
+  ldl6(IA0);
+  float a0[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a0[i] = -pA0[i];
+  ldl6_solve(IA0, a0);
+  float qdd[6];
+  legs_pass3(P, lc, cc, uu, a0, qdd);
+
+  // gravity as a uniform frame acceleration, classical acceleration of the origin
+  const float zb[3] = {R[6], R[7], R[8]};  // world z axis in base coordinates
+  {
+    float lin[3], wxv[3], dw[3], dv[3];
+    cross3(&V0[0], &V0[3], wxv);
+    lin[0] = a0[3] - P.gravity * zb[0] + wxv[0];
+    lin[1] = a0[4] - P.gravity * zb[1] + wxv[1];
+    lin[2] = a0[5] - P.gravity * zb[2] + wxv[2];
+    rot_mul(R, &a0[0], dw);
+    rot_mul(R, lin, dv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      S.angvel[i] = clampf(S.angvel[i] + P.h * dw[i], -P.vmax, P.vmax);
+      S.linvel[i] = clampf(S.linvel[i] + P.h * dv[i], -P.vmax, P.vmax);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) S.qd[j] = clampf(S.qd[j] + P.h * qdd[j], -P.vmax, P.vmax);
+  }
+
+  // -- collision detection: tire circle vs the plane z = 0 (base coordinates), both wheels
+  const float nxz = sqrtf(zb[0] * zb[0] + zb[2] * zb[2]);
+  const bool rim_ok = nxz > 1e-6f;
+  const float inv_n = rim_ok ? 1.f / nxz : 0.f;
+  const float dB0 = -zb[0] * inv_n * P.wheel_radius, dB2 = -zb[2] * inv_n * P.wheel_radius;
+  const f2 Pc[3] = {add2(lc.ox[2], bc2(dB0)), P.oy2[2], add2(lc.oz[2], bc2(dB2))};
+  const f2 dist = fma2(bc2(zb[0]), Pc[0], fma2(bc2(zb[1]), Pc[1], fma2(bc2(zb[2]), Pc[2], bc2(S.pos[2]))));
+  const bool actL = rim_ok && (dist.x < P.breaking_threshold);
+  const bool actR = rim_ok && (dist.y < P.breaking_threshold);
+  S.contact = (actL || actR) ? 1.f : 0.f;
+  phase_sync();  // 2
+
+  if (!warp_any(actL || actR)) {
+    phase_sync();  // 3
+    phase_sync();  // 4
+    phase_sync();  // 5
+    phase_sync();  // 6
+  } else {
+    // contact directions in base coordinates: d = 0 normal, 1 rolling (s * t1), 2 lateral (s * t2)
+    const float t1[3] = {zb[2] * inv_n, 0.f, -zb[0] * inv_n};
+    float t2[3];
+    cross3(zb, t1, t2);
+    const f2 sw = P.sgn2[2];
+    // J rows as spatial forces about the base origin, (left wheel, right wheel)
+    f2 J[3][6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      f2 dir[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dir[i] = d == 0 ? bc2(zb[i]) : mul2(sw, bc2(d == 1 ? t1[i] : t2[i]));
+      cross3_2(Pc, dir, &J[d][0]);
+      J[d][3] = dir[0]; J[d][4] = dir[1]; J[d][5] = dir[2];
+    }
+    // wheel spatial velocities at the predicted generalized velocity
+    f2 Vw[6];
+    {
+      float Vb[6];
+      rot_tmul(R, S.angvel, &Vb[0]);
+      rot_tmul(R, S.linvel, &Vb[3]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) Vw[i] = bc2(Vb[i]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const f2 w = mul2(P.sgn2[k], mk2(S.qd[k], S.qd[k + 3]));
+        Vw[1] = add2(Vw[1], w);
+        Vw[3] = fma2(neg2(lc.oz[k]), w, Vw[3]);
+        Vw[5] = fma2(lc.ox[k], w, Vw[5]);
+      }
+    }
+    // Delassus matrix W = J M^-1 J^T: three impulse responses, each for the (left, right) column pair
+    float W[6][6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      f2 u[3], da0[6];
+      legs_impulse_up(P, lc, J[d], u, da0);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) da0[i] = neg2(da0[i]);
+      ldl6_solve2(IA0, da0);  // lane x: base response to the left column, lane y: to the right column
+      f2 a_own[6], a_cross[6], dq[3];
+      legs_impulse_down<false>(P, lc, u, da0, a_own, dq);    // (left wheel | left col, right wheel | right col)
+      legs_impulse_down<true>(P, lc, u, da0, a_cross, dq);   // (right wheel | left col, left wheel | right col)
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        f2 wo = bc2(0.f), wc = bc2(0.f);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          wo = fma2(J[e][i], a_own[i], wo);
+          wc = fma2(swp2(J[e][i]), a_cross[i], wc);
+        }
+        W[row_of(0, e)][row_of(0, d)] = wo.x;
+        W[row_of(1, e)][row_of(1, d)] = wo.y;
+        W[row_of(1, e)][row_of(0, d)] = wc.x;
+        W[row_of(0, e)][row_of(1, d)] = wc.y;
+      }
+      phase_sync();  // 3, 4, 5
+    }
+    // right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
+    float rhs[6], jdi[6], lam[6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      f2 rel = bc2(0.f);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rel = fma2(J[d][i], Vw[i], rel);
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int k = row_of(side, d);
+        const float r = side == 0 ? rel.x : rel.y;
+        lam[k] = 0.f;
+        if (d == 0) {
+          const float pen = side == 0 ? dist.x : dist.y;
+          jdi[k] = 1.f / (W[k][k] + P.cfm);
+          float pos_err = 0.f, vel_err = -r;
+          if (pen > 0.f) vel_err -= pen * P.inv_h;
+          else pos_err = -pen * P.erp * P.inv_h;
+          rhs[k] = (pos_err + vel_err) * jdi[k];
+        } else {
+          jdi[k] = W[k][k] > 0.f ? 1.f / W[k][k] : 0.f;
+          rhs[k] = -r * jdi[k];
+        }
+      }
+    }
+    const float cfmrow = P.cfm;  // m_cfm = cfm * jacDiagABInv
+    const float hiL = actL ? 1e10f : 0.f, hiR = actR ? 1e10f : 0.f;
+    // Projected Gauss-Seidel, see physics_substep() for the exit rule
+    const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+      for (int l = 0; l < 6; ++l) W[k][l] = -jdi[k] * W[k][l];
+      W[k][k] += 1.f - (k < 2 ? cfmrow * jdi[k] : 0.f);
+    }
+    for (int it = 0; it < P.pgs_iterations; ++it) {
+      bool changed = false;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        float sum = rhs[k];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) sum += W[k][l] * lam[l];
+        float lo, hi;
+        if (k == 0) { lo = 0.f; hi = hiL; }
+        else if (k == 1) { lo = 0.f; hi = hiR; }
+        else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
+        const float nl = fminf(fmaxf(sum, lo), hi);
+        changed = changed || (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+        lam[k] = nl;
+      }
+#ifdef UPKIE_PGS_STATS
+      if (!changed) { upkie_pgs_stats(it + 1); break; }
+      if (it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 2);
+#else
+      if (!warp_any(changed)) break;
+#endif
+    }
+    // apply the total wheel impulses: both wheels up their legs at once, one base solve, both legs down
+    f2 F[6];
+    {
+      const f2 ln = mk2(lam[0], lam[1]), l1 = mk2(lam[2], lam[4]), l2 = mk2(lam[3], lam[5]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) F[i] = fma2(ln, J[0][i], fma2(l1, J[1][i], mul2(l2, J[2][i])));
+    }
+    f2 u[3], ptop[6];
+    legs_impulse_up(P, lc, F, u, ptop);
+    float da0[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) da0[i] = -(ptop[i].x + ptop[i].y);
+    ldl6_solve(IA0, da0);
+    f2 da2[6], aw[6], dq[3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) da2[i] = bc2(da0[i]);
+    legs_impulse_down<false>(P, lc, u, da2, aw, dq);
+    float dw[3], dv[3];
+    rot_mul(R, &da0[0], dw);
+    rot_mul(R, &da0[3], dv);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      S.angvel[i] = clampf(S.angvel[i] + dw[i], -P.vmax, P.vmax);
+      S.linvel[i] = clampf(S.linvel[i] + dv[i], -P.vmax, P.vmax);
+      S.qd[i] = clampf(S.qd[i] + dq[i].x, -P.vmax, P.vmax);
+      S.qd[3 + i] = clampf(S.qd[3 + i] + dq[i].y, -P.vmax, P.vmax);
+    }
+    phase_sync();  // 6
+  }
+
+  // -- position integration with the new velocities (as physics_substep)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.pos[i] += P.h * S.linvel[i];
+  {
+    const float* om = S.angvel;
+    const float ang2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+    const float ang = sqrtf(ang2);
+    float sc;
+    if (ang < 0.001f) sc = 0.5f * P.h - P.h * P.h * P.h * 0.020833333333f * ang2;
+    else sc = sinf(0.5f * ang * P.h) / ang;
+    const float ax = om[0] * sc, ay = om[1] * sc, az = om[2] * sc;
+    const float dqw = cosf(ang * P.h * 0.5f);
+    const float qw = S.quat[0], qx = S.quat[1], qy = S.quat[2], qz = S.quat[3];
+    const float nw = dqw * qw - ax * qx - ay * qy - az * qz;
+    const float nx = dqw * qx + ax * qw + ay * qz - az * qy;
+    const float ny = dqw * qy - ax * qz + ay * qw + az * qx;
+    const float nz = dqw * qz + ax * qy - ay * qx + az * qw;
+    const float inv = 1.f / sqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+    S.quat[0] = nw * inv; S.quat[1] = nx * inv; S.quat[2] = ny * inv; S.quat[3] = nz * inv;
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) S.q[j] += P.h * S.qd[j];
+}
+
+}  // namespace upkie_b200

@@ -24,6 +24,7 @@
 #include <string>
 
 #include "mpc.cuh"
+#include "observers.cuh"
 #include "params.h"
 
 using namespace upkie_b200;
@@ -705,6 +706,31 @@ int upkie_b200_mpc_step(void* mpc, const float* x0, const float* v_target, const
 int upkie_b200_mpc_plan(void* mpc, float* plan, void* stream) {
   std::string err;
   int rc = mpc_plan_impl(mpc, plan, static_cast<cudaStream_t>(stream), err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+
+// ---- observer pipeline --------------------------------------------------------------------
+
+int upkie_b200_default_observer_config(const UpkieModel* model, UpkieObserverConfig* config) {
+  if (!model || !config) return fail(UPKIE_B200_EINVAL, "default_observer_config: null");
+  default_observer_config(*model, config);
+  return UPKIE_B200_OK;
+}
+int upkie_b200_observers_create(const UpkieObserverConfig* config, int n_robots, int device, void** observers) {
+  if (!config || !observers) return fail(UPKIE_B200_EINVAL, "observers_create: null argument");
+  std::string err;
+  int rc = observers_create_impl(*config, n_robots, device, observers, err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+void upkie_b200_observers_destroy(void* observers) { observers_destroy_impl(observers); }
+int upkie_b200_observers_reset(void* observers, const uint8_t* mask, void* stream) {
+  std::string err;
+  int rc = observers_reset_impl(observers, mask, static_cast<cudaStream_t>(stream), err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+int upkie_b200_observers_step(void* observers, const float* spine_obs, float* out, void* stream) {
+  std::string err;
+  int rc = observers_step_impl(observers, spine_obs, out, static_cast<cudaStream_t>(stream), err);
   return rc ? fail(rc, err) : UPKIE_B200_OK;
 }
 
