@@ -83,7 +83,8 @@ extern "C" {
 #define UPKIE_ST_YAW_VEL 39
 #define UPKIE_ST_CONTACT 40     /* floor contact seen by the last collision pass (0/1) */
 #define UPKIE_ST_IMU_ACC 41     /* world-frame IMU linear acceleration of the last observation [3] (pybullet_backend.py:405-408) */
-#define UPKIE_STATE_DIM 44
+#define UPKIE_ST_CONTACT_IMPULSE 44 /* normal contact impulses of the last substep (left, right wheel): PGS warm start */
+#define UPKIE_STATE_DIM 46
 
 /* spine_obs[N][UPKIE_SPINE_DIM]: the observation dictionary of
  * PyBulletBackend.get_spine_observation (pybullet_backend.py:313-331), flattened. */
@@ -190,6 +191,10 @@ typedef struct UpkieSimConfig {
    * pgs_tolerance * |impulse| + 1e-9 in one sweep (Bullet: m_leastSquaresResidualThreshold-style
    * exit); 0 = always run pgs_iterations sweeps */
   double pgs_tolerance;
+  /* Bullet's SOLVER_USE_WARMSTARTING: normal contact impulses start each substep at
+   * warmstarting_factor x the previous substep's value while the contact persists (Bullet: 0.85), friction rows
+   * at 0. Default 0 = cold start: the fixed point is the same and the sweep count did not drop in measurements */
+  double warmstarting_factor;
   /* RobotStateRandomization bounds used by the on-device sampler
    * (upkie/utils/robot_state_randomization.py:135-189) */
   double init_position[3];     /* nominal position_base_in_world (0, 0, 0.6) */

@@ -198,6 +198,35 @@ def test_inertia_randomization_and_friction(model, oracle_lib):
     assert np.abs(hs2.state[:, 19:25] - hs.state[:, 19:25]).max() > 1e-2
 
 
+def test_warm_started_contact_impulses(model, oracle_lib):
+    """Optional Bullet-style warm start of the normal rows (warmstarting_factor = 0.85): kernel
+    arithmetic and oracle agree, the cached impulses are part of the state, and the converged
+    contact solution does not depend on the starting point."""
+    n = 128
+    hs, osim, cfg = _pair(model, oracle_lib, n, warmstarting_factor=0.85)
+    hs0, _, _ = _pair(model, oracle_lib, n)
+    init = np.zeros((n, _abi.INIT_DIM), dtype=np.float32)
+    init[:, 2], init[:, 3] = 0.58, 1.0
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, [2, 5], 0] = np.nan
+    act[:, :, 3] = act[:, :, 4] = 1.0
+    act[:, :, 5] = 0.99 * model.tau_max
+    act[:, [2, 5], 1] = np.random.default_rng(0).uniform(-3, 3, (n, 2))
+    for sim in (hs, osim, hs0):
+        sim.reset(init if sim is not osim else init.astype(np.float64))
+    for _ in range(10):
+        hs.step_servos(act)
+        hs0.step_servos(act)
+        osim.step_servos(act.astype(np.float64))
+    lam = hs.state[:, _abi.ST_CONTACT_IMPULSE:_abi.ST_CONTACT_IMPULSE + 2]
+    weight_impulse = 5.3382 * 9.81 * cfg.dt / cfg.nb_substeps / 2  # half the weight per wheel over one substep
+    assert np.abs(lam - weight_impulse).max() < 0.3 * weight_impulse
+    assert np.abs(lam - osim.get_state()[:, _abi.ST_CONTACT_IMPULSE:_abi.ST_CONTACT_IMPULSE + 2]).max() < 1e-4
+    d = np.abs(hs.state[:, :25].astype(np.float64) - osim.get_state()[:, :25])
+    assert d[:, :7].max() < 1e-5 and d[:, 19:25].max() < 5e-3
+    assert np.abs(hs.state[:, :25] - hs0.state[:, :25]).max() < 5e-3  # cold and warm start: same fixed point
+
+
 def test_spine_observation(model, oracle_lib):
     n = 128
     hs, osim, cfg = _pair(model, oracle_lib, n)

@@ -38,7 +38,7 @@ WHEEL_JOINTS = (2, 5)
 ACT_DIM = 36
 OBS_DIM = 30
 INIT_DIM = 25
-STATE_DIM = 44
+STATE_DIM = 46
 SPINE_DIM = 62
 
 # init_state offsets
@@ -47,6 +47,7 @@ INIT_POS, INIT_QUAT, INIT_LINVEL, INIT_ANGVEL, INIT_Q, INIT_QD = 0, 3, 7, 10, 13
 ST_POS, ST_QUAT, ST_LINVEL, ST_ANGVEL, ST_Q, ST_QD = 0, 3, 7, 10, 13, 19
 ST_PREV_IMU_VEL, ST_TORQUE, ST_LEG_TARGET, ST_YAW, ST_YAW_VEL, ST_CONTACT = 25, 28, 34, 38, 39, 40
 ST_IMU_ACC = 41
+ST_CONTACT_IMPULSE = 44
 # spine observation offsets
 SP_BASE_ANGVEL, SP_BASE_LINVEL, SP_PITCH, SP_ROT = 0, 3, 6, 7
 SP_IMU_QUAT, SP_IMU_ANGVEL, SP_IMU_LINACC, SP_IMU_RAWACC = 16, 20, 23, 26
@@ -100,6 +101,7 @@ class UpkieSimConfig(C.Structure):
         ("skip_action_clamps", C.c_int32),
         ("min_base_height", C.c_double),
         ("pgs_tolerance", C.c_double),
+        ("warmstarting_factor", C.c_double),
         ("init_position", C.c_double * 3),
         ("init_quat", C.c_double * 4),
         ("rand_roll", C.c_double),
@@ -198,6 +200,7 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.skip_action_clamps = 0
     c.min_base_height = 0.0
     c.pgs_tolerance = 1e-6
+    c.warmstarting_factor = 0.0  # measured: no fewer sweeps (friction rows dominate); Bullet's value would be 0.85
     c.init_position[0], c.init_position[1], c.init_position[2] = 0.0, 0.0, 0.6
     c.init_quat[0], c.init_quat[1], c.init_quat[2], c.init_quat[3] = 1.0, 0.0, 0.0, 0.0
     c.rand_roll = c.rand_pitch = c.rand_x = c.rand_z = 0.0

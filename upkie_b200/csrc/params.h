@@ -36,6 +36,7 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->skip_action_clamps = 0;
   c->min_base_height = 0.0;
   c->pgs_tolerance = 1e-6;
+  c->warmstarting_factor = 0.0;  // off by default (Bullet's m_warmstartingFactor is 0.85)
   c->init_position[0] = 0.0; c->init_position[1] = 0.0; c->init_position[2] = 0.6;  // upkie_env.py:87-90
   c->init_quat[0] = 1.0; c->init_quat[1] = 0.0; c->init_quat[2] = 0.0; c->init_quat[3] = 0.0;
   c->rand_roll = c->rand_pitch = c->rand_x = c->rand_z = 0.0;
@@ -124,6 +125,7 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.nb_substeps = c.nb_substeps;
   P.pgs_iterations = c.pgs_iterations;
   P.pgs_rtol = float(c.pgs_tolerance);
+  P.warm = float(c.warmstarting_factor);
   P.skip_action_clamps = c.skip_action_clamps;
   P.gravity = float(c.gravity);
   P.kp = float(c.torque_control_kp);
@@ -178,6 +180,8 @@ UPKIE_HD void state_from_row(const float* r, RobotState& S) {
   S.yaw = r[UPKIE_ST_YAW];
   S.yaw_vel = r[UPKIE_ST_YAW_VEL];
   S.contact = r[UPKIE_ST_CONTACT];
+  S.lam_n[0] = r[UPKIE_ST_CONTACT_IMPULSE];
+  S.lam_n[1] = r[UPKIE_ST_CONTACT_IMPULSE + 1];
 }
 
 UPKIE_HD void state_to_row(const RobotState& S, float* r) {
@@ -200,6 +204,8 @@ UPKIE_HD void state_to_row(const RobotState& S, float* r) {
   r[UPKIE_ST_YAW] = S.yaw;
   r[UPKIE_ST_YAW_VEL] = S.yaw_vel;
   r[UPKIE_ST_CONTACT] = S.contact;
+  r[UPKIE_ST_CONTACT_IMPULSE] = S.lam_n[0];
+  r[UPKIE_ST_CONTACT_IMPULSE + 1] = S.lam_n[1];
 }
 
 }  // namespace upkie_b200

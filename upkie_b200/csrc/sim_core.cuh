@@ -71,6 +71,7 @@ struct SimParams {
   float dt, inv_dt, h, inv_h;
   int nb_substeps, pgs_iterations;
   float pgs_rtol;          // early-exit tolerance of the PGS sweeps (0 = fixed count)
+  float warm;              // warm-starting factor of the normal contact impulses (Bullet: 0.85)
   int skip_action_clamps;
   float gravity, kp, kd;
   float joint_friction[6];
@@ -97,6 +98,7 @@ struct RobotState {
   float yaw, yaw_vel;
   float contact;
   float imu_acc[3];  // world-frame IMU acceleration of the last observation
+  float lam_n[2];    // normal contact impulses of the last substep (warm start)
 };
 
 // packed upper-triangular index of a symmetric 6x6
@@ -563,6 +565,8 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
   phase_sync();  // 2
 
   if (!warp_any(actL || actR)) {
+    S.lam_n[0] = 0.f;
+    S.lam_n[1] = 0.f;
     phase_sync();  // 3
     phase_sync();  // 4
     phase_sync();  // 5
@@ -645,7 +649,8 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
       float rel = 0.f;
 #pragma unroll
       for (int i = 0; i < 6; ++i) rel += J[k][i] * Vw[i];
-      lam[k] = 0.f;
+      // warm start (Bullet SOLVER_USE_WARMSTARTING): normals from the previous substep, frictions from 0
+      lam[k] = k == 0 ? (actL ? P.warm * S.lam_n[0] : 0.f) : (k == 1 ? (actR ? P.warm * S.lam_n[1] : 0.f) : 0.f);
       if (k < 2) {
         const float pen = k == 0 ? distL : distR;
         jdi[k] = 1.f / (W[k][k] + P.cfm);
@@ -695,6 +700,8 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
       if (!warp_any(changed)) break;
 #endif
     }
+    S.lam_n[0] = lam[0];
+    S.lam_n[1] = lam[1];
     // apply the total wheel impulses
     float fL[6], fR[6];
 #pragma unroll
@@ -1027,6 +1034,8 @@ UPKIE_HD void reset_pose(RobotState& S, const float init[UPKIE_INIT_DIM]) {
     S.q[j] = init[UPKIE_INIT_Q + j];
     S.qd[j] = 0.f;
   }
+  S.lam_n[0] = 0.f;  // new contact points carry no cached impulse
+  S.lam_n[1] = 0.f;
 }
 
 // UpkieGyropod.reset (upkie_gyropod.py:216-244), after the reset's stepSimulation + observation
@@ -1040,25 +1049,11 @@ UPKIE_HD void reset_wrapper_state(RobotState& S) {
 template <typename AnyFn>
 UPKIE_HD void reset_robot(const SimParams& P, RobotState& S, const float init[UPKIE_INIT_DIM], const float* eps, float mu,
                           AnyFn warp_any) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    S.pos[i] = init[UPKIE_INIT_POS + i];
-    S.linvel[i] = init[UPKIE_INIT_LINVEL + i];
-    S.angvel[i] = init[UPKIE_INIT_ANGVEL + i];  // body-frame vector used as world-frame (:253-258)
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) S.quat[i] = init[UPKIE_INIT_QUAT + i];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    S.q[j] = init[UPKIE_INIT_Q + j];
-    S.qd[j] = 0.f;
-  }
+  reset_pose(S, init);
   const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   substep(P, S, zero, eps, mu, warp_any);  // one stepSimulation (:228)
   observe_update(P, S);
-  S.leg_target[0] = S.q[0]; S.leg_target[1] = S.q[1]; S.leg_target[2] = S.q[3]; S.leg_target[3] = S.q[4];
-  S.yaw = 0.f;
-  S.yaw_vel = 0.f;
+  reset_wrapper_state(S);
 }
 
 // ---- counter-based RNG (Philox4x32-10) for on-device init-state sampling ------------

@@ -373,6 +373,8 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   phase_sync();  // 2
 
   if (!warp_any(actL || actR)) {
+    S.lam_n[0] = 0.f;
+    S.lam_n[1] = 0.f;
     phase_sync();  // 3
     phase_sync();  // 4
     phase_sync();  // 5
@@ -447,7 +449,8 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
       for (int side = 0; side < 2; ++side) {
         const int k = row_of(side, d);
         const float r = side == 0 ? rel.x : rel.y;
-        lam[k] = 0.f;
+        // warm start (Bullet SOLVER_USE_WARMSTARTING): normals from the previous substep, frictions from 0
+        lam[k] = d == 0 ? ((side == 0 ? actL : actR) ? P.warm * S.lam_n[side] : 0.f) : 0.f;
         if (d == 0) {
           const float pen = side == 0 ? dist.x : dist.y;
           jdi[k] = 1.f / (W[k][k] + P.cfm);
@@ -493,6 +496,8 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
       if (!warp_any(changed)) break;
 #endif
     }
+    S.lam_n[0] = lam[0];
+    S.lam_n[1] = lam[1];
     // apply the total wheel impulses: both wheels up their legs at once, one base solve, both legs down
     f2 F[6];
     {
