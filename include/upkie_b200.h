@@ -165,6 +165,11 @@ typedef struct UpkieSimConfig {
   double torque_control_kp;    /* 20.0 */
   double torque_control_kd;    /* 1.0 */
   double joint_friction[UPKIE_NJ]; /* JointProperties.friction, joint_properties.py:24-40 */
+  double torque_control_noise[UPKIE_NJ];     /* JointProperties.torque_control_noise: std of the Gaussian noise added to
+                                              * every commanded torque before the clip (pybullet_backend.py:545-550) */
+  double torque_measurement_noise[UPKIE_NJ]; /* std of the noise on the observed torque (pybullet_backend.py:461-466) */
+  uint64_t noise_seed;                       /* key of the counter-based generator (the reference draws from an unseeded
+                                              * np.random.default_rng(), pybullet_backend.py:160) */
   /* restated Bullet multibody behaviour (third-party) */
   double linear_damping;       /* 0.04 */
   double angular_damping;      /* 0.04 */

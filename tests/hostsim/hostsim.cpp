@@ -101,6 +101,35 @@ void hostsim_sample_init(void* hv, int n, uint64_t seed, uint64_t env_offset, ui
   for (int i = 0; i < n; ++i) sample_init_state(h->P, seed, env_offset + i, episode, init + size_t(i) * UPKIE_INIT_DIM);
 }
 
+void hostsim_gaussian8(uint64_t seed, uint64_t env, uint32_t tick, uint32_t slot, float* out) {
+  const NoiseCtx nz{env, tick};
+  gaussian8(seed, nz, slot, out);
+}
+
+// one env tick with the torque noise models on (same sequence as k_step<.., NOISE=1>)
+void hostsim_step_servos_noise(void* hv, int n, float* state, const float* action, uint32_t tick, uint64_t env_offset,
+                               float* obs) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    float a[UPKIE_ACT_DIM];
+    std::memcpy(a, action + size_t(i) * UPKIE_ACT_DIM, sizeof(a));
+    clamp_servo_action(h->P, a);
+    const NoiseCtx nz{env_offset + uint64_t(i), tick};
+    for (int sub = 0; sub < h->P.nb_substeps; ++sub)
+      servo_substep(h->P, S, a, false, nullptr, h->P.friction, any_fn, NoSync(), &nz, sub);
+    observe_update(h->P, S);
+    float tq[6];
+    measured_torques(h->P, S, &nz, tq);
+    for (int j = 0; j < 6; ++j) {
+      float* o = obs + size_t(i) * UPKIE_OBS_DIM + j * 5;
+      o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = tq[j]; o[3] = 42.0f; o[4] = 18.0f;
+    }
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
 void hostsim_philox(uint64_t clo, uint64_t chi, uint64_t key, uint32_t* out) {
   Philox4 r = philox4x32_10(clo, chi, key);
   for (int i = 0; i < 4; ++i) out[i] = r.v[i];

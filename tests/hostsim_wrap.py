@@ -46,6 +46,8 @@ def lib():
         L.hostsim_spine_obs.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.hostsim_sample_init.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, fp]
         L.hostsim_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.hostsim_gaussian8.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, fp]
+        L.hostsim_step_servos_noise.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_uint32, C.c_uint64, fp]
         for name in ("hostsim_mpc_step_f32", "hostsim_mpc_step_f64"):
             getattr(L, name).argtypes = [
                 C.POINTER(_abi.UpkieMpcConfig), C.c_int, dp, dp, u8p, C.c_double, dp, dp, u8p, C.POINTER(C.c_int),
@@ -101,6 +103,13 @@ class HostSim:
                                   self._opt(self.mu), err.ctypes.data_as(C.POINTER(C.c_uint32)))
         return obs, err
 
+    def step_servos_noise(self, action, tick, env_offset=0):
+        """One tick with the torque noise models, keyed like k_step<.., NOISE=1> at per-env tick ``tick``."""
+        a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.n, 36)
+        obs = np.empty((self.n, 6, 5), dtype=np.float32)
+        lib().hostsim_step_servos_noise(self._h, self.n, _f(self.state), _f(a), tick, env_offset, _f(obs))
+        return obs
+
     def step_gyropod(self, action, act_dim):
         a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.n, act_dim)
         obs6 = np.empty((self.n, 6), dtype=np.float32)
@@ -127,6 +136,12 @@ def philox(counter_lo, counter_hi, key):
     out = (C.c_uint32 * 4)()
     lib().hostsim_philox(counter_lo, counter_hi, key, out)
     return list(out)
+
+
+def gaussian8(seed, env, tick, slot):
+    out = np.empty(8, dtype=np.float32)
+    lib().hostsim_gaussian8(seed, env, tick, slot, _f(out))
+    return out
 
 
 def mpc_step(config, x0, v_target, contact, dt, v_cmd, double=False):

@@ -365,3 +365,71 @@ def test_full_size_invariants(model, torch):
     assert torch.equal(s1, s2)  # observation has no side effects
     assert torch.equal(s1[:, 30:60].reshape(n, 6, 5), obs)
     assert (sim.error_flags() & 2).sum().item() == 0
+
+
+def test_torque_noise_models(model, torch):
+    """The NOISE=1 instantiation of the step kernel: same draws as the CPU build of the same code (keyed on
+    seed, global env index, per-env tick), reproducible, invariant to sharding, inert at sigma = 0."""
+    from hostsim_wrap import HostSim
+    from upkie_b200.envs import B200VectorEnv
+    from upkie_b200.model import JointProperties
+
+    n = 2048
+    cfg = _abi.default_sim_config()
+    for j in range(6):
+        cfg.torque_control_noise[j] = (0.05, 0.0, 0.02)[j % 3]
+        cfg.torque_measurement_noise[j] = (0.0, 0.03, 0.01)[j % 3]
+    cfg.noise_seed = 99
+    st = random_states(n, seed=3, z_range=(2.0, 3.0)).astype(np.float32)
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, :, 0] = np.nan
+    act[:, :, 2] = 0.5 * np.asarray(model.tau_max, dtype=np.float32)
+    act[:, :, 5] = model.tau_max
+    sim = _sim(n, model, cfg)
+    sim.set_state(torch.from_numpy(st).cuda())
+    hs = HostSim(model, cfg, n)
+    hs.set_state(st)
+    a = torch.from_numpy(act).cuda()
+    for tick in (1, 2, 3):
+        obs = sim.step_servos(a)[0].cpu().numpy()
+        ref = hs.step_servos_noise(act, tick=tick)
+        # torques depend on the noise only (pure feedforward): fast-math logf/sincosf vs libm
+        assert np.abs(obs[:, :, 2] - ref[:, :, 2]).max() < 2e-5
+        applied = sim.get_state()[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6].cpu().numpy()
+        assert np.abs(applied - hs.state[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6]).max() < 2e-5
+        assert np.array_equal(obs[:, 1, 2] != applied[:, 1], np.ones(n, dtype=bool))  # measurement noise on knees
+        assert np.array_equal(obs[:, 0, 2], applied[:, 0])  # none on hips
+    spine = sim.spine_obs().cpu().numpy()[:, _abi.SP_SERVO:_abi.SP_SERVO + 30].reshape(n, 6, 5)
+    assert np.array_equal(spine[:, :, 2], obs[:, :, 2])  # the spine view repeats the step's draw
+
+    # reproducible for a given seed, different for another one, invariant to the sharding of the env index
+    def run(seed, offset=0, count=n):
+        c = _abi.default_sim_config()
+        for j in range(6):
+            c.torque_control_noise[j] = 0.05
+        c.noise_seed = seed
+        s = _sim(count, model, c)
+        s.set_autoreset(0, 0, offset)  # global env index of local env 0
+        s.set_state(torch.from_numpy(st[offset:offset + count]).cuda())
+        out = [s.step_servos(a[offset:offset + count])[0].clone() for _ in range(3)]
+        return torch.stack(out).cpu().numpy()
+
+    r1, r2, r3 = run(5), run(5), run(6)
+    assert np.array_equal(r1, r2) and not np.array_equal(r1, r3)
+    half = run(5, offset=n // 2, count=n // 2)
+    assert np.array_equal(half, r1[:, n // 2:])
+
+    # JointProperties through the env constructor; sigma = 0 is bit-identical to the default path
+    props = {name: JointProperties(friction=0.0, torque_control_noise=0.0) for name in _abi.JOINT_NAMES}
+    e0 = B200VectorEnv(64, "servos", model=model, joint_properties=props)
+    e1 = B200VectorEnv(64, "servos", model=model)
+    e0.reset(seed=1)
+    e1.reset(seed=1)
+    a64 = torch.from_numpy(act[:64]).cuda()
+    assert torch.equal(e0.sim.step_servos(a64)[0], e1.sim.step_servos(a64)[0])
+    noisy = {name: JointProperties(torque_control_noise=0.1, torque_measurement_noise=0.1) for name in _abi.JOINT_NAMES}
+    e2 = B200VectorEnv(64, "servos", model=model, joint_properties=noisy, noise_seed=3)
+    assert e2.config.torque_control_noise[2] == 0.1 and e2.config.noise_seed == 3
+    e2.reset(seed=1)
+    o2 = e2.sim.step_servos(torch.from_numpy(act[:64]).cuda())[0]
+    assert not torch.equal(o2[:, :, 2], e1.sim.step_servos(torch.from_numpy(act[:64]).cuda())[0][:, :, 2])

@@ -378,3 +378,67 @@ def test_mpc_model_matrices(oracle_lib):
         y = y + h * np.array([y[2], y[3], u, w * w * y[1] - u / l])
     assert np.allclose(A @ x + B * u, y, atol=1e-5)
     assert np.allclose(P, P.T) and np.linalg.eigvalsh(P).min() > 0
+
+
+def test_gaussian_noise_generator():
+    """Philox + Box-Muller normals of the torque noise models: moments, independence, determinism."""
+    from hostsim_wrap import gaussian8
+
+    x = np.stack([gaussian8(7, env, tick, slot) for env in range(40) for tick in range(1, 26) for slot in (0, 4, 255)])
+    assert x.shape == (3000, 8) and np.isfinite(x).all()
+    assert abs(x.mean()) < 0.02 and abs(x.std() - 1.0) < 0.02
+    assert abs(((x - x.mean()) ** 4).mean() / x.var() ** 2 - 3.0) < 0.15  # Gaussian kurtosis
+    c = np.corrcoef(x.T)
+    assert np.abs(c - np.eye(8)).max() < 0.08  # the 8 lanes are independent
+    assert np.array_equal(gaussian8(7, 3, 9, 2), gaussian8(7, 3, 9, 2))
+    for other in (gaussian8(8, 3, 9, 2), gaussian8(7, 4, 9, 2), gaussian8(7, 3, 10, 2), gaussian8(7, 3, 9, 3)):
+        assert not np.array_equal(gaussian8(7, 3, 9, 2), other)
+
+
+def test_torque_noise_models(model):
+    """JointProperties noise (pybullet_backend.py:457-466,545-552): control noise enters before the clip and
+    is redrawn every substep, measurement noise only touches the observed torque, sigma <= 1e-10 means off."""
+    n = 4000
+    cfg = _abi.default_sim_config()
+    sig_c = [0.05, 0.0, 0.02, 0.05, 0.0, 0.02]
+    sig_m = [0.0, 0.03, 0.01, 0.0, 0.03, 0.01]
+    for j in range(6):
+        cfg.torque_control_noise[j] = sig_c[j]
+        cfg.torque_measurement_noise[j] = sig_m[j]
+    cfg.noise_seed = 99
+    hs = HostSim(model, cfg, n)
+    st = random_states(n, seed=3, z_range=(2.0, 3.0)).astype(np.float32)
+    hs.set_state(st)
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, :, 0] = np.nan
+    act[:, :, 2] = 0.5 * model.tau_max  # pure feedforward torque, kp = kd = 0
+    act[:, :, 5] = model.tau_max
+    obs = hs.step_servos_noise(act, tick=1)
+    applied = hs.state[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6]  # torque of the last substep
+    ff = 0.5 * np.asarray(model.tau_max, dtype=np.float32)
+    for j in range(6):
+        d = applied[:, j] - ff[j]
+        if sig_c[j] == 0.0:
+            assert np.array_equal(applied[:, j], np.full(n, ff[j], dtype=np.float32))
+        else:
+            assert abs(d.mean()) < 4 * sig_c[j] / np.sqrt(n) and abs(d.std() / sig_c[j] - 1) < 0.05
+        m = obs[:, j, 2] - applied[:, j]
+        if sig_m[j] == 0.0:
+            assert np.array_equal(obs[:, j, 2], applied[:, j])
+        else:
+            assert abs(m.mean()) < 4 * sig_m[j] / np.sqrt(n) and abs(m.std() / sig_m[j] - 1) < 0.05
+    # noise of successive ticks is independent, and the same (seed, env, tick) reproduces it
+    first = applied.copy()
+    hs.step_servos_noise(act, tick=2)
+    second = hs.state[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6].copy()
+    assert abs(np.corrcoef(first[:, 0] - ff[0], second[:, 0] - ff[0])[0, 1]) < 0.06
+    hs.set_state(st)
+    hs.step_servos_noise(act, tick=1)
+    assert np.array_equal(hs.state[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6], first)
+    # control noise is clipped with the rest of the command
+    act[:, :, 2] = model.tau_max
+    act[:, :, 5] = 0.9 * np.asarray(model.tau_max, dtype=np.float32)
+    hs.set_state(st)
+    hs.step_servos_noise(act, tick=3)
+    lim = 0.9 * np.asarray(model.tau_max, dtype=np.float32)
+    assert (np.abs(hs.state[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6]) <= lim + 1e-6).all()

@@ -85,6 +85,9 @@ class UpkieSimConfig(C.Structure):
         ("torque_control_kp", C.c_double),
         ("torque_control_kd", C.c_double),
         ("joint_friction", C.c_double * NJ),
+        ("torque_control_noise", C.c_double * NJ),
+        ("torque_measurement_noise", C.c_double * NJ),
+        ("noise_seed", C.c_uint64),
         ("linear_damping", C.c_double),
         ("angular_damping", C.c_double),
         ("max_coordinate_velocity", C.c_double),
@@ -184,6 +187,9 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.torque_control_kd = 1.0
     for j in range(NJ):
         c.joint_friction[j] = 0.0
+        c.torque_control_noise[j] = 0.0
+        c.torque_measurement_noise[j] = 0.0
+    c.noise_seed = 0
     c.linear_damping = 0.04
     c.angular_damping = 0.04
     c.max_coordinate_velocity = 100.0

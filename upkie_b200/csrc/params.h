@@ -19,7 +19,12 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->gravity = 9.81;            // pybullet_backend.py:110
   c->torque_control_kp = 20.0;  // pybullet_backend.py:65
   c->torque_control_kd = 1.0;   // pybullet_backend.py:64
-  for (int j = 0; j < UPKIE_NJ; ++j) c->joint_friction[j] = 0.0;
+  for (int j = 0; j < UPKIE_NJ; ++j) {
+    c->joint_friction[j] = 0.0;
+    c->torque_control_noise[j] = 0.0;
+    c->torque_measurement_noise[j] = 0.0;
+  }
+  c->noise_seed = 0;
   c->linear_damping = 0.04;     // Bullet btMultiBody default
   c->angular_damping = 0.04;
   c->max_coordinate_velocity = 100.0;
@@ -67,6 +72,8 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
       err = "model: kinematic tree must be base -> (hip, knee, wheel) x 2 in URDF joint order";
       return UPKIE_B200_EMODEL;
     }
+  P.any_ctrl_noise = 0;
+  P.any_meas_noise = 0;
   for (int j = 0; j < UPKIE_NJ; ++j) {
     const double ax = m.joint_axis[j][0], ay = m.joint_axis[j][1], az = m.joint_axis[j][2];
     if (std::fabs(ax) > 1e-9 || std::fabs(az) > 1e-9 || std::fabs(std::fabs(ay) - 1.0) > 1e-9) {
@@ -80,6 +87,11 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
     P.qd_max[j] = float(m.qd_max[j]);
     P.tau_max[j] = float(m.tau_max[j]);
     P.joint_friction[j] = float(c.joint_friction[j]);
+    P.ctrl_noise[j] = float(c.torque_control_noise[j]);
+    P.meas_noise[j] = float(c.torque_measurement_noise[j]);
+    // thresholds of the reference: noise is drawn only when sigma > 1e-10 (pybullet_backend.py:464,548)
+    if (c.torque_control_noise[j] > 1e-10) P.any_ctrl_noise = 1;
+    if (c.torque_measurement_noise[j] > 1e-10) P.any_meas_noise = 1;
   }
   for (int i = 0; i < UPKIE_NB; ++i) {
     if (!(m.mass[i] > 0.0)) { err = "model: body masses must be positive"; return UPKIE_B200_EMODEL; }
@@ -94,6 +106,7 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
            std::fabs(I[3]) < 1e-12 && std::fabs(I[4]) < 1e-12 && std::fabs(I[5]) < 1e-12;
   };
   P.wheel_symmetric = (wheel_sym(3) && wheel_sym(6)) ? 1 : 0;
+  P.noise_seed = c.noise_seed;
   for (int k = 0; k < 3; ++k) {
     P.sgn2[k].x = P.sgn[k]; P.sgn2[k].y = P.sgn[k + 3];
     P.mass2[k].x = P.mass[k + 1]; P.mass2[k].y = P.mass[k + 4];

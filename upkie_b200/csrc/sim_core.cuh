@@ -75,6 +75,9 @@ struct SimParams {
   int skip_action_clamps;
   float gravity, kp, kd;
   float joint_friction[6];
+  float ctrl_noise[6], meas_noise[6];  // JointProperties noise standard deviations
+  int any_ctrl_noise, any_meas_noise;
+  uint64_t noise_seed;
   float lin_damp, ang_damp, vmax;
   float cfm, erp;          // from contact stiffness/damping and h (Bullet formulas)
   float breaking_threshold;
@@ -774,7 +777,8 @@ UPKIE_HD void substep(const SimParams& P, RobotState& S, const float tau[6], con
 
 // pybullet_backend.py:492-553 compute_joint_torque
 UPKIE_HD float joint_torque(const SimParams& P, int j, float q, float qd, float ff, float target_position,
-                            float target_velocity, float kp_scale, float kd_scale, float maximum_torque) {
+                            float target_velocity, float kp_scale, float kd_scale, float maximum_torque,
+                            float control_noise = 0.f) {
   const float kp = kp_scale * P.kp;
   const float kd = kd_scale * P.kd;
   float torque = ff;
@@ -784,6 +788,7 @@ UPKIE_HD float joint_torque(const SimParams& P, int j, float q, float qd, float 
     const float sign = qd > 0.f ? 1.f : -1.f;
     torque += -P.joint_friction[j] * sign;
   }
+  torque += control_noise;  // torque-control Gaussian white noise, before the clip (pybullet_backend.py:545-552)
   // np.clip(x, lo, hi) = minimum(maximum(x, lo), hi)
   return fminf(fmaxf(torque, -maximum_torque), maximum_torque);
 }
@@ -832,7 +837,7 @@ UPKIE_HD void quat_from_rot(const float M[9], float q_wxyz[4]) {
 }
 
 // full spine observation dictionary from the state (no side effects)
-UPKIE_HD void spine_observation(const SimParams& P, const RobotState& S, float* o) {
+UPKIE_HD void spine_observation(const SimParams& P, const RobotState& S, float* o, const float* torque_obs = nullptr) {
   float R[9];
   quat_to_rot(S.quat, R);
   float om_b[3];
@@ -877,7 +882,7 @@ UPKIE_HD void spine_observation(const SimParams& P, const RobotState& S, float* 
     float* so = o + UPKIE_SP_SERVO + j * UPKIE_OBS_KEYS;
     so[UPKIE_OBS_POSITION] = S.q[j];
     so[UPKIE_OBS_VELOCITY] = S.qd[j];
-    so[UPKIE_OBS_TORQUE] = S.torque[j];
+    so[UPKIE_OBS_TORQUE] = torque_obs ? torque_obs[j] : S.torque[j];
     so[UPKIE_OBS_TEMPERATURE] = 42.0f;
     so[UPKIE_OBS_VOLTAGE] = 18.0f;
   }
@@ -912,16 +917,34 @@ UPKIE_HD uint32_t clamp_servo_action(const SimParams& P, float a[UPKIE_ACT_DIM])
 // One substep of PyBulletBackend.step (pybullet_backend.py:276-306): torque law on
 // the live joint state, then one stepSimulation. `store_torque` is false for the
 // zero-torque substep of a reset (the reference keeps __joint_torques across resets).
+// Counter-based Gaussian noise: (seed, global env index, per-env tick, slot) -> 8 standard normals
+// (Philox4x32-10 + Box-Muller). Slots 0..nb_substeps-1 feed the torque-control noise of the substeps,
+// slot 255 the torque-measurement noise of the observation.
+struct Philox4;
+UPKIE_HD Philox4 philox4x32_10(uint64_t counter_lo, uint64_t counter_hi, uint64_t key);
+struct NoiseCtx {
+  uint64_t env;   // global env index
+  uint32_t tick;  // per-env step counter
+};
+UPKIE_HD void gaussian8(uint64_t seed, const NoiseCtx& nz, uint32_t slot, float out[8]);
+
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPKIE_ACT_DIM], bool zero_torque,
-                            const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync = SyncFn()) {
+                            const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync = SyncFn(),
+                            const NoiseCtx* nz = nullptr, int sub = 0) {
   float tau[6];
+  float noise[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (P.any_ctrl_noise && nz) {
+    gaussian8(P.noise_seed, *nz, uint32_t(sub), noise);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) noise[j] = P.ctrl_noise[j] > 1e-10f ? noise[j] * P.ctrl_noise[j] : 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     const float* aj = a + j * 6;
     const float t = joint_torque(P, j, S.q[j], S.qd[j], aj[UPKIE_ACT_FEEDFORWARD_TORQUE], aj[UPKIE_ACT_POSITION],
                                  aj[UPKIE_ACT_VELOCITY], aj[UPKIE_ACT_KP_SCALE], aj[UPKIE_ACT_KD_SCALE],
-                                 aj[UPKIE_ACT_MAXIMUM_TORQUE]);
+                                 aj[UPKIE_ACT_MAXIMUM_TORQUE], noise[j]);
     tau[j] = zero_torque ? 0.f : t;
     if (!zero_torque) S.torque[j] = t;
   }
@@ -1056,7 +1079,7 @@ UPKIE_HD void reset_robot(const SimParams& P, RobotState& S, const float init[UP
   reset_wrapper_state(S);
 }
 
-// ---- counter-based RNG (Philox4x32-10) for on-device init-state sampling ------------
+// ---- counter-based RNG (Philox4x32-10) for on-device init-state sampling and noise ----
 struct Philox4 { uint32_t v[4]; };
 
 UPKIE_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
@@ -1085,6 +1108,32 @@ UPKIE_HD Philox4 philox4x32_10(uint64_t counter_lo, uint64_t counter_hi, uint64_
 
 // uniform in [0, 1) with 24 bits
 UPKIE_HD float u01(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f); }
+
+UPKIE_HD void gaussian8(uint64_t seed, const NoiseCtx& nz, uint32_t slot, float out[8]) {
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const Philox4 r = philox4x32_10(nz.env, (uint64_t(nz.tick) << 10) | (uint64_t(slot) << 1) | uint64_t(b),
+                                    seed ^ 0x6E6F697365ull);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float u1 = (float(r.v[2 * p] >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+      const float u2 = u01(r.v[2 * p + 1]);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincosf(6.28318530718f * u2, &sn, &cs);
+      out[4 * b + 2 * p] = rad * cs;
+      out[4 * b + 2 * p + 1] = rad * sn;
+    }
+  }
+}
+
+// observed torques: commanded torque + measurement noise (pybullet_backend.py:457-466)
+UPKIE_HD void measured_torques(const SimParams& P, const RobotState& S, const NoiseCtx* nz, float out[6]) {
+  float noise[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (P.any_meas_noise && nz) gaussian8(P.noise_seed, *nz, 255u, noise);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) out[j] = S.torque[j] + (P.meas_noise[j] > 1e-10f ? noise[j] * P.meas_noise[j] : 0.f);
+}
 
 // RobotState.sample_state (robot_state.py:175-196) with a counter-based
 // generator keyed on (seed, global env index, episode): same draw order as the

@@ -71,10 +71,12 @@ struct Handle {
   uint32_t* err = nullptr;     // [n]
   uint8_t* done_prev = nullptr;  // [n]
   uint32_t* episode = nullptr;   // [n]
+  uint32_t* tick = nullptr;      // [n] env ticks since create: counter of the noise generator
   int autoreset = AUTORESET_DISABLED;
   uint64_t seed = 0, env_offset = 0;
   int block = UPKIE_DEFAULT_BLOCK;
   int num_sms = 148;
+  int host_chunks = 4;  // chunks of the pipelined host-buffer step
   // host-buffer staging (allocated on first use)
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
@@ -83,7 +85,6 @@ struct Handle {
   cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
 };
 constexpr int kHostStreams = 3;  // H2D, kernel and D2H of different chunks overlap
-constexpr int kHostChunks = 4;
 constexpr uint32_t kMagic = 0x55504B42u;  // "UPKB"
 
 Handle* as_handle(void* h) {
@@ -122,13 +123,13 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
 }
 
 // ---- the env-step kernel ------------------------------------------------------------
-template <int MODE, int AUTORESET>
+template <int MODE, int AUTORESET, int NOISE>
 __global__ void __launch_bounds__(UPKIE_MAX_THREADS, UPKIE_MIN_BLOCKS)
 k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __restrict__ state,
        const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
        uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
        const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
-       uint32_t* __restrict__ episode, uint64_t seed, uint64_t env_offset) {
+       uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset) {
   // this launch covers the envs [i0, n)
   const int tid = i0 + blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = tid < n;
@@ -171,6 +172,11 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
   // ONE zero-torque substep, pybullet_backend.py:227-228): resetting lanes run a
   // single iteration of the same loop, which keeps the kernel's code small
   // (instruction-cache footprint) and the warp converged.
+  NoiseCtx nz{env_offset + uint64_t(i), 0u};
+  if (NOISE) {
+    nz.tick = tick[i] + 1u;
+    if (live) tick[i] = nz.tick;
+  }
   int nsub = P.nb_substeps;
   if (resetting) {
     const uint32_t ep = episode[i] + 1u;
@@ -188,7 +194,7 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
     __syncthreads();  // once per substep: all threads are converged here
 #endif
     if (sub < nsub) {
-      servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync());
+      servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub);
     } else {
 #pragma unroll
       for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
@@ -232,9 +238,11 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
   if (MODE == MODE_SERVOS) {
     float2* op = reinterpret_cast<float2*>(obs + size_t(i) * UPKIE_OBS_DIM);
     float o[UPKIE_OBS_DIM];
+    float tq[6];
+    measured_torques(P, S, NOISE ? &nz : nullptr, tq);
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      o[j * 5 + 0] = S.q[j]; o[j * 5 + 1] = S.qd[j]; o[j * 5 + 2] = S.torque[j];
+      o[j * 5 + 0] = S.q[j]; o[j * 5 + 1] = S.qd[j]; o[j * 5 + 2] = tq[j];
       o[j * 5 + 3] = 42.0f;  // pybullet_backend.py:471
       o[j * 5 + 4] = 18.0f;  // pybullet_backend.py:472
     }
@@ -291,27 +299,34 @@ k_reset(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict
 }
 
 __global__ void k_spine_obs(const __grid_constant__ SimParams P, int n, int n_pad, const float* __restrict__ state,
-                            float* __restrict__ out) {
+                            const uint32_t* __restrict__ tick, uint64_t env_offset, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   RobotState S;
   load_state(state, n_pad, i, S);
   float o[UPKIE_SPINE_DIM];
-  spine_observation(P, S, o);
+  float tq[6];
+  const NoiseCtx nz{env_offset + uint64_t(i), tick[i]};  // same draw as the step that produced this state
+  measured_torques(P, S, &nz, tq);
+  spine_observation(P, S, o, tq);
 #pragma unroll
   for (int k = 0; k < UPKIE_SPINE_DIM; ++k) out[size_t(i) * UPKIE_SPINE_DIM + k] = o[k];
 }
 
 __global__ void k_reset_obs(const __grid_constant__ SimParams P, int n, int n_pad, const float* __restrict__ state,
-                            int obs_dim, float* __restrict__ out) {
+                            const uint32_t* __restrict__ tick, uint64_t env_offset, int obs_dim,
+                            float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   RobotState S;
   load_state(state, n_pad, i, S);
   if (obs_dim == UPKIE_OBS_DIM) {
+    float tq[6];
+    const NoiseCtx nz{env_offset + uint64_t(i), tick[i]};
+    measured_torques(P, S, &nz, tq);
     for (int j = 0; j < 6; ++j) {
       float* o = out + size_t(i) * UPKIE_OBS_DIM + j * 5;
-      o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = S.torque[j]; o[3] = 42.0f; o[4] = 18.0f;
+      o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = tq[j]; o[3] = 42.0f; o[4] = 18.0f;
     }
     return;
   }
@@ -366,14 +381,21 @@ int launch_step(Handle* h, int i0, int cnt, const float* action, float* obs, flo
                 uint8_t* trunc, cudaStream_t s) {
   const int block = pick_block(h, cnt);
   const int grid = (cnt + block - 1) / block;
-#define LAUNCH(AR)                                                                                              \
-  k_step<MODE, AR><<<grid, block, 0, s>>>(h->P, i0, i0 + cnt, h->n_pad, h->state, action, obs, reward, term, \
-                                             trunc, h->eps, h->mu, h->err, h->done_prev, h->episode, h->seed,  \
-                                             h->env_offset)
+  const bool noise = h->P.any_ctrl_noise || h->P.any_meas_noise;
+#define LAUNCH_N(AR, NZ)                                                                                            \
+  k_step<MODE, AR, NZ><<<grid, block, 0, s>>>(h->P, i0, i0 + cnt, h->n_pad, h->state, action, obs, reward, term, \
+                                                 trunc, h->eps, h->mu, h->err, h->done_prev, h->episode, h->tick,  \
+                                                 h->seed, h->env_offset)
+#define LAUNCH(AR)           \
+  do {                       \
+    if (noise) LAUNCH_N(AR, 1); \
+    else LAUNCH_N(AR, 0);    \
+  } while (0)
   if (h->autoreset == AUTORESET_NEXT_STEP) LAUNCH(AUTORESET_NEXT_STEP);
   else if (h->autoreset == AUTORESET_SAME_STEP) LAUNCH(AUTORESET_SAME_STEP);
   else LAUNCH(AUTORESET_DISABLED);
 #undef LAUNCH
+#undef LAUNCH_N
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }
@@ -433,8 +455,8 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
   const size_t obs_dim = mode == MODE_SERVOS ? UPKIE_OBS_DIM : (mode == MODE_GYROPOD ? 6 : 4);
   const bool pin_in = is_pinned(action);
   const bool pin_out = is_pinned(obs) && is_pinned(reward) && is_pinned(term) && is_pinned(trunc);
-  // chunk size: a multiple of the block size, at least 8192 envs, at most kHostChunks chunks
-  int chunks = h->n >= 4 * 8192 ? kHostChunks : (h->n >= 2 * 8192 ? 2 : 1);
+  // chunk size: a multiple of the block size, at least 8192 envs, at most host_chunks chunks
+  int chunks = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
   int per = (h->n + chunks - 1) / chunks;
   per = (per + 255) / 256 * 256;
   chunks = (h->n + per - 1) / per;
@@ -516,6 +538,10 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
     const int v = std::atoi(b);
     if (v >= 32 && v <= UPKIE_MAX_THREADS && v % 32 == 0) h->block = v;
   }
+  if (const char* b = std::getenv("UPKIE_B200_HOST_CHUNKS")) {  // developer knob
+    const int v = std::atoi(b);
+    if (v >= 1 && v <= 64) h->host_chunks = v;
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaMalloc(&h->state, size_t(UPKIE_STATE_DIM) * h->n_pad * sizeof(float));
@@ -525,6 +551,8 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
   if (e == cudaSuccess) e = cudaMemset(h->err, 0, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(h->done_prev, 0, size_t(n_envs));
   if (e == cudaSuccess) e = cudaMemset(h->episode, 0, size_t(n_envs) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->tick, size_t(n_envs) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->tick, 0, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) {
     k_init_state<<<(h->n_pad + 127) / 128, 128>>>(h->P, h->n, h->n_pad, h->state);
     e = cudaGetLastError();
@@ -544,6 +572,7 @@ void upkie_b200_destroy(void* handle) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->state); cudaFree(h->eps); cudaFree(h->mu); cudaFree(h->err); cudaFree(h->done_prev); cudaFree(h->episode);
+  cudaFree(h->tick);
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_term); cudaFreeHost(h->h_trunc);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
   for (int k = 0; k < kHostStreams; ++k)
@@ -640,7 +669,7 @@ int upkie_b200_spine_obs(void* handle, float* out, void* stream) {
   Handle* h = as_handle(handle);
   if (!h || !out) return fail(UPKIE_B200_EINVAL, "spine_obs: invalid argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  k_spine_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, out);
+  k_spine_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, h->tick, h->env_offset, out);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }
@@ -650,7 +679,7 @@ int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream) {
   if (!h || !obs) return fail(UPKIE_B200_EINVAL, "reset_obs: invalid argument");
   if (obs_dim != 4 && obs_dim != 6 && obs_dim != UPKIE_OBS_DIM) return fail(UPKIE_B200_EINVAL, "reset_obs: obs_dim must be 4, 6 or 30");
   CUDA_TRY(cudaSetDevice(h->device));
-  k_reset_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, obs_dim, obs);
+  k_reset_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, h->tick, h->env_offset, obs_dim, obs);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }

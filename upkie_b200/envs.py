@@ -216,6 +216,7 @@ def make_config(
     max_ground_velocity: float = 3.0,
     max_yaw_velocity: float = 1.0,
     init_state: Optional[RobotState] = None,
+    noise_seed: int = 0,
 ) -> _abi.UpkieSimConfig:
     """Split of the keyword arguments the reference's factories forward to the
     backend, the servo env and the wrappers (``upkie/envs/entry_points.py:41-61,99-109``)."""
@@ -232,6 +233,9 @@ def make_config(
         props = (joint_properties or {}).get(name)
         if props is not None:
             cfg.joint_friction[j] = float(getattr(props, "friction", 0.0))
+            cfg.torque_control_noise[j] = float(getattr(props, "torque_control_noise", 0.0))
+            cfg.torque_measurement_noise[j] = float(getattr(props, "torque_measurement_noise", 0.0))
+    cfg.noise_seed = int(noise_seed) & 0xFFFFFFFFFFFFFFFF
     cfg.max_gain_scale = max_gain_scale
     cfg.fall_pitch = fall_pitch
     cfg.leg_gain_scale = leg_gain_scale
@@ -270,6 +274,7 @@ class B200VectorEnv(VectorEnv):
         config: Optional[_abi.UpkieSimConfig] = None,
         leg_length: float = 0.58,
         max_ground_accel: float = 10.0,
+        noise_seed: int = 0,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")
@@ -289,7 +294,7 @@ class B200VectorEnv(VectorEnv):
         if config is None:
             config = make_config(
                 frequency, nb_substeps, torque_control_kp, torque_control_kd, joint_properties, max_gain_scale,
-                fall_pitch, leg_gain_scale, max_ground_velocity, max_yaw_velocity, self.init_state,
+                fall_pitch, leg_gain_scale, max_ground_velocity, max_yaw_velocity, self.init_state, noise_seed,
             )
         self.config = config
         (
@@ -354,7 +359,16 @@ class B200VectorEnv(VectorEnv):
         return {"servos": 30, "gyropod": 6, "pendulum": 4, "base_velocity": 6}[self.env_type]
 
     def _format_obs(self, obs: np.ndarray):
-        return servo_obs_array_to_dict(obs) if self.env_type == "servos" else obs
+        if self.env_type != "servos":
+            return obs
+        # the host-path observation lives in one persistent pinned buffer: build the dictionary of
+        # views once and hand the same (in-place updated) dictionary back on every step
+        cache = getattr(self, "_obs_dict_cache", None)
+        if cache is None or cache[0] is not obs:
+            cache = (obs, servo_obs_array_to_dict(obs))
+            if obs is self.sim._host_buffers()["obs30"]:
+                self._obs_dict_cache = cache
+        return cache[1]
 
     def reset(self, *, seed: Optional[Union[int, list]] = None, options: Optional[dict] = None):
         """Reset all envs (or ``options["reset_mask"]``) and return the initial

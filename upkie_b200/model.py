@@ -37,6 +37,22 @@ from . import _abi
 JOINT_NAMES = _abi.JOINT_NAMES
 
 
+class JointProperties:
+    """Per-joint simulation properties (``upkie/model/joint_properties.py:4-40``):
+    kinetic friction torque and the standard deviations of the Gaussian white
+    noise on the applied and on the observed torque, all in N·m."""
+
+    def __init__(
+        self,
+        friction: float = 0.0,
+        torque_control_noise: float = 0.0,
+        torque_measurement_noise: float = 0.0,
+    ):
+        self.friction = friction
+        self.torque_control_noise = torque_control_noise
+        self.torque_measurement_noise = torque_measurement_noise
+
+
 @dataclass
 class JointLimit:
     """Same fields as ``upkie.model.joint_limit.JointLimit``."""
