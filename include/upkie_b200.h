@@ -294,8 +294,16 @@ int upkie_b200_step_gyropod(void* handle, const float* action /* [N][act_dim] */
                             int act_dim, float* obs, float* reward,
                             uint8_t* terminated, uint8_t* truncated, void* stream);
 
-/* Same calls with HOST buffers: pinned staging, H2D, kernel, D2H, and a
- * stream synchronisation inside the call (the `e2e` path of bench.py). */
+/* Same calls with HOST buffers and a stream synchronisation inside the call
+ * (the `e2e` path of bench.py). When every buffer is pinned and mapped
+ * (cudaHostAlloc / cudaHostRegister(..Mapped), torch pin_memory) the step is
+ * ONE kernel launch that reads the action rows from host memory and writes the
+ * observation rows back over PCIe itself (coalesced through shared memory);
+ * pageable buffers go through pinned staging in pipelined chunks (H2D copy ->
+ * kernel -> D2H copy on rotating streams).
+ * `reward` and `truncated` may be NULL here and in the device-buffer calls: the
+ * reference returns constants for them (0.0, upkie_env.py:230; False,
+ * upkie_env.py:197) and a caller that knows it saves the bytes. */
 int upkie_b200_step_servos_host(void* handle, const float* action, float* obs,
                                 float* reward, uint8_t* terminated,
                                 uint8_t* truncated);
@@ -315,6 +323,10 @@ int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream);
 int upkie_b200_get_state(void* handle, float* state /* [N][UPKIE_STATE_DIM] */, void* stream);
 int upkie_b200_set_state(void* handle, const float* state, void* stream);
 int upkie_b200_error_flags(void* handle, uint32_t* flags /* [N] */, void* stream);
+
+/* Number of step-kernel launches issued through this handle since create
+ * (bench.py's `gpu_launches`). */
+int upkie_b200_launch_count(void* handle, uint64_t* count);
 
 /* ---- MPC balancer handle -------------------------------------------------
  * Replaces MPCBalancer.__init__/reset/step (mpc_balancer.py:168-312). */

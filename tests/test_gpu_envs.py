@@ -115,20 +115,39 @@ def test_randomization_matches_oracle(model, oracle_lib, torch):
     assert np.median(np.abs(gs[:, 19:25] - os_[:, 19:25]).max(axis=1)) < 1e-3
 
 
-def test_host_buffer_api_equals_device_api(model, torch):
-    n = 4096
+@pytest.mark.parametrize("n", [4096, 1003])
+def test_host_buffer_api_equals_device_api(model, torch, n):
+    """Pinned buffers: the kernel reads / writes host memory itself (zero-copy, one launch); pageable buffers:
+    staged chunks. Both must be bit-identical to the device-buffer call, full and partial warps alike."""
     a = random_servo_actions(n, model, seed=1).astype(np.float32)
     st = torch.from_numpy(random_states(n, seed=2).astype(np.float32)).cuda()
-    s1, s2 = _sim(n, model), _sim(n, model)
-    s1.set_state(st)
-    s2.set_state(st)
+    s1, s2, s3 = _sim(n, model), _sim(n, model), _sim(n, model)
+    for s in (s1, s2, s3):
+        s.set_state(st)
     o1, r1, t1, u1 = s1.step_servos(torch.from_numpy(a).cuda())
-    o2, r2, t2, u2 = s2.step_servos_host(a)
-    assert np.array_equal(o1.cpu().numpy(), o2)  # same kernel: bit-exact
-    assert np.array_equal(t1.cpu().numpy(), t2) and np.array_equal(r1.cpu().numpy(), r2)
+    l0 = s2.launches
+    pinned = s2.host_action_buffer(36)
+    pinned[:] = a
+    o2, r2, t2, u2 = s2.step_servos_host(pinned)  # zero-copy
+    assert s2.launches - l0 == 1
+    o3, r3, t3, u3 = s3.step_servos_host(a.copy())  # pageable action: staged
+    for o, r, t, u in ((o2, r2, t2, u2), (o3, r3, t3, u3)):
+        assert np.array_equal(o1.cpu().numpy(), o)  # same kernel: bit-exact
+        assert np.array_equal(t1.cpu().numpy(), t) and np.array_equal(r1.cpu().numpy(), r)
+        assert np.array_equal(u1.cpu().numpy(), u)
     g = np.random.default_rng(3).uniform(-3, 3, (n, 2)).astype(np.float32)
     o1, _, t1, _ = s1.step_gyropod(torch.from_numpy(g).cuda())
-    o2, _, t2, _ = s2.step_gyropod_host(g)
+    pg = s2.host_action_buffer(2)
+    pg[:] = g
+    o2, _, t2, _ = s2.step_gyropod_host(pg)
+    o3, _, t3, _ = s3.step_gyropod_host(g)
+    assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(t1.cpu().numpy(), t2)
+    assert np.array_equal(o1.cpu().numpy(), o3) and np.array_equal(t1.cpu().numpy(), t3)
+    p = np.random.default_rng(4).uniform(-3, 3, (n, 1)).astype(np.float32)
+    o1, _, t1, _ = s1.step_pendulum(torch.from_numpy(p).cuda())
+    pp = s2.host_action_buffer(1)
+    pp[:] = p
+    o2, _, t2, _ = s2.step_gyropod_host(pp)
     assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(t1.cpu().numpy(), t2)
 
 
@@ -397,7 +416,7 @@ def test_torque_noise_models(model, torch):
         assert np.abs(obs[:, :, 2] - ref[:, :, 2]).max() < 2e-5
         applied = sim.get_state()[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6].cpu().numpy()
         assert np.abs(applied - hs.state[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6]).max() < 2e-5
-        assert np.array_equal(obs[:, 1, 2] != applied[:, 1], np.ones(n, dtype=bool))  # measurement noise on knees
+        assert (obs[:, 1, 2] != applied[:, 1]).mean() > 0.99  # measurement noise on knees
         assert np.array_equal(obs[:, 0, 2], applied[:, 0])  # none on hips
     spine = sim.spine_obs().cpu().numpy()[:, _abi.SP_SERVO:_abi.SP_SERVO + 30].reshape(n, 6, 5)
     assert np.array_equal(spine[:, :, 2], obs[:, :, 2])  # the spine view repeats the step's draw

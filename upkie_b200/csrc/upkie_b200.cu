@@ -76,7 +76,9 @@ struct Handle {
   uint64_t seed = 0, env_offset = 0;
   int block = UPKIE_DEFAULT_BLOCK;
   int num_sms = 148;
-  int host_chunks = 4;  // chunks of the pipelined host-buffer step
+  int host_chunks = 4;           // chunks of the pipelined host-buffer step (pageable buffers)
+  uint64_t step_launches = 0;    // step kernels launched (upkie_b200_launch_count)
+  int zero_copy = 1;             // host-buffer steps read/write mapped pinned buffers from the kernel
   // host-buffer staging (allocated on first use)
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
@@ -124,16 +126,30 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
 
 // ---- the env-step kernel ------------------------------------------------------------
 template <int MODE, int AUTORESET, int NOISE>
+#ifdef UPKIE_MAXNREG
+__global__ void __maxnreg__(UPKIE_MAXNREG)
+#else
 __global__ void __launch_bounds__(UPKIE_MAX_THREADS, UPKIE_MIN_BLOCKS)
+#endif
 k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __restrict__ state,
        const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
        uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
        const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
-       uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset) {
+       uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset,
+       int coalesce) {
   // this launch covers the envs [i0, n)
   const int tid = i0 + blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = tid < n;
   const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
+  // Per-warp staging tile: the 32 action rows (144 B each) and observation rows (120 B each) of a warp
+  // are contiguous, so full warps move them with coalesced 16 B accesses through shared memory. This is
+  // what lets the kernel read actions from / write observations to mapped pinned HOST memory at PCIe line
+  // rate (per-thread strided accesses reach 1/10 of it, tools/micro/pcie_duplex.cu).
+  extern __shared__ float4 s_tile[];
+  const int lane = threadIdx.x & 31;
+  float4* tile4 = s_tile + (threadIdx.x >> 5) * (32 * UPKIE_ACT_DIM / 4);
+  const int wb = tid - lane;  // first env of this warp
+  const bool full = coalesce && (wb + 32 <= n);  // warp-uniform
 
   RobotState S;
   load_state(state, n_pad, i, S);
@@ -153,11 +169,24 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
   float a[UPKIE_ACT_DIM];
   float a0 = 0.f, a1 = 0.f;
   if (MODE == MODE_SERVOS) {
-    const float4* ap = reinterpret_cast<const float4*>(action + size_t(i) * UPKIE_ACT_DIM);
+    if (full) {
+      const float4* ap = reinterpret_cast<const float4*>(action + size_t(wb) * UPKIE_ACT_DIM);
 #pragma unroll
-    for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
-      const float4 v = __ldg(ap + k);
-      a[4 * k + 0] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) tile4[k * 32 + lane] = __ldg(ap + k * 32 + lane);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
+        const float4 v = tile4[lane * (UPKIE_ACT_DIM / 4) + k];
+        a[4 * k + 0] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+      }
+      __syncwarp();
+    } else {
+      const float4* ap = reinterpret_cast<const float4*>(action + size_t(i) * UPKIE_ACT_DIM);
+#pragma unroll
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
+        const float4 v = __ldg(ap + k);
+        a[4 * k + 0] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+      }
     }
   } else if (MODE == MODE_GYROPOD) {
     const float2 v = __ldg(reinterpret_cast<const float2*>(action) + i);
@@ -233,10 +262,8 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
     }
   }
 
-  if (!live) return;
-  store_state(state, n_pad, i, S);
+  if (live) store_state(state, n_pad, i, S);
   if (MODE == MODE_SERVOS) {
-    float2* op = reinterpret_cast<float2*>(obs + size_t(i) * UPKIE_OBS_DIM);
     float o[UPKIE_OBS_DIM];
     float tq[6];
     measured_torques(P, S, NOISE ? &nz : nullptr, tq);
@@ -246,20 +273,46 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
       o[j * 5 + 3] = 42.0f;  // pybullet_backend.py:471
       o[j * 5 + 4] = 18.0f;  // pybullet_backend.py:472
     }
+    if (full) {
+      float2* t2 = reinterpret_cast<float2*>(tile4) + lane * (UPKIE_OBS_DIM / 2);
 #pragma unroll
-    for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) op[k] = make_float2(o[2 * k], o[2 * k + 1]);
+      for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) t2[k] = make_float2(o[2 * k], o[2 * k + 1]);
+      __syncwarp();
+      float4* op = reinterpret_cast<float4*>(obs + size_t(wb) * UPKIE_OBS_DIM);
+#pragma unroll
+      for (int k = 0; k < (32 * UPKIE_OBS_DIM / 4 + 31) / 32; ++k) {
+        const int idx = k * 32 + lane;
+        if (idx < 32 * UPKIE_OBS_DIM / 4) op[idx] = tile4[idx];
+      }
+    } else if (live) {
+      float2* op = reinterpret_cast<float2*>(obs + size_t(i) * UPKIE_OBS_DIM);
+#pragma unroll
+      for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) op[k] = make_float2(o[2 * k], o[2 * k + 1]);
+    }
   } else if (MODE == MODE_GYROPOD) {
-    float2* op = reinterpret_cast<float2*>(obs + size_t(i) * 6);
-    op[0] = make_float2(o6[0], o6[1]);
-    op[1] = make_float2(o6[2], o6[3]);
-    op[2] = make_float2(o6[4], o6[5]);
-  } else {
+    if (full) {
+      float2* t2 = reinterpret_cast<float2*>(tile4) + lane * 3;
+      t2[0] = make_float2(o6[0], o6[1]);
+      t2[1] = make_float2(o6[2], o6[3]);
+      t2[2] = make_float2(o6[4], o6[5]);
+      __syncwarp();
+      float4* op = reinterpret_cast<float4*>(obs + size_t(wb) * 6);
+      op[lane] = tile4[lane];
+      if (lane < 16) op[32 + lane] = tile4[32 + lane];
+    } else if (live) {
+      float2* op = reinterpret_cast<float2*>(obs + size_t(i) * 6);
+      op[0] = make_float2(o6[0], o6[1]);
+      op[1] = make_float2(o6[2], o6[3]);
+      op[2] = make_float2(o6[4], o6[5]);
+    }
+  } else if (live) {
     // upkie_pendulum.py:17 _PENDULUM_OBS_INDICES = [1, 0, 4, 3]
     reinterpret_cast<float4*>(obs)[i] = make_float4(o6[1], o6[0], o6[4], o6[3]);
   }
-  reward[i] = 0.0f;  // upkie_env.py:230
+  if (!live) return;
+  if (reward) reward[i] = 0.0f;  // upkie_env.py:230
   terminated[i] = term ? 1 : 0;
-  truncated[i] = 0;
+  if (truncated) truncated[i] = 0;
   if (e) err[i] |= e;
   if (AUTORESET == AUTORESET_NEXT_STEP) done_prev[i] = term ? 1 : 0;
 }
@@ -382,10 +435,13 @@ int launch_step(Handle* h, int i0, int cnt, const float* action, float* obs, flo
   const int block = pick_block(h, cnt);
   const int grid = (cnt + block - 1) / block;
   const bool noise = h->P.any_ctrl_noise || h->P.any_meas_noise;
+  const size_t smem = size_t(block / 32) * 32 * UPKIE_ACT_DIM * sizeof(float);
+  // the coalesced tile path needs 16 B aligned rows of 32 envs; i0 is a multiple of 32 by construction
+  const int coalesce = ((reinterpret_cast<uintptr_t>(action) | reinterpret_cast<uintptr_t>(obs)) & 15) == 0 && (i0 % 32) == 0;
 #define LAUNCH_N(AR, NZ)                                                                                            \
-  k_step<MODE, AR, NZ><<<grid, block, 0, s>>>(h->P, i0, i0 + cnt, h->n_pad, h->state, action, obs, reward, term, \
-                                                 trunc, h->eps, h->mu, h->err, h->done_prev, h->episode, h->tick,  \
-                                                 h->seed, h->env_offset)
+  k_step<MODE, AR, NZ><<<grid, block, smem, s>>>(h->P, i0, i0 + cnt, h->n_pad, h->state, action, obs, reward,  \
+                                                    term, trunc, h->eps, h->mu, h->err, h->done_prev, h->episode, \
+                                                    h->tick, h->seed, h->env_offset, coalesce)
 #define LAUNCH(AR)           \
   do {                       \
     if (noise) LAUNCH_N(AR, 1); \
@@ -397,6 +453,7 @@ int launch_step(Handle* h, int i0, int cnt, const float* action, float* obs, flo
 #undef LAUNCH
 #undef LAUNCH_N
   CUDA_TRY(cudaGetLastError());
+  h->step_launches += 1;
   return UPKIE_B200_OK;
 }
 
@@ -410,7 +467,7 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
 
 int step_any(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
              cudaStream_t s) {
-  if (!action || !obs || !reward || !term || !trunc) return fail(UPKIE_B200_EINVAL, "step: null buffer");
+  if (!action || !obs || !term) return fail(UPKIE_B200_EINVAL, "step: null buffer");
   CUDA_TRY(cudaSetDevice(h->device));
   return step_range(h, mode, 0, h->n, action, obs, reward, term, trunc, s);
 }
@@ -442,19 +499,51 @@ bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+// device-side alias of a pinned host buffer (nullptr when the buffer is pageable or not mapped)
+template <typename T>
+T* mapped(T* p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+  return static_cast<T*>(at.devicePointer);
+}
+
 // Host-buffer step: the batch is cut into chunks that flow through H2D copy ->
 // kernel -> D2H copy on rotating streams, so the copies of one chunk overlap
 // the kernel of another (PCIe is full duplex). Pinned caller buffers are used
 // in place; pageable ones are staged through pinned memory chunk by chunk.
 int step_host(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc) {
-  if (!action || !obs || !reward || !term || !trunc) return fail(UPKIE_B200_EINVAL, "step_host: null buffer");
+  if (!action || !obs || !term) return fail(UPKIE_B200_EINVAL, "step_host: null buffer");
   int rc = ensure_staging(h);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->zero_copy) {
+    // All caller buffers pinned and mapped: ONE launch whose warps read their action rows from host memory
+    // and write their observation rows back over PCIe themselves (coalesced through the shared-memory
+    // tile). Reads, compute and writes of different warps overlap in both directions of the link, with no
+    // staging copies and no chunk boundaries.
+    const float* za = mapped(action);
+    float* zo = mapped(obs);
+    uint8_t* zt = mapped(term);
+    float* zr = mapped(reward);
+    uint8_t* zu = mapped(trunc);
+    if (za && zo && zt && (zr || !reward) && (zu || !trunc)) {
+      cudaStream_t s = h->host_streams[0];
+      rc = step_range(h, mode, 0, h->n, za, zo, zr, zt, zu, s);
+      if (rc) return rc;
+      CUDA_TRY(cudaStreamSynchronize(s));
+      return UPKIE_B200_OK;
+    }
+  }
+  // reward / truncated are constants of the reference (0.0 and false): callers may pass NULL for them
   const size_t act_dim = mode == MODE_SERVOS ? UPKIE_ACT_DIM : (mode == MODE_GYROPOD ? 2 : 1);
   const size_t obs_dim = mode == MODE_SERVOS ? UPKIE_OBS_DIM : (mode == MODE_GYROPOD ? 6 : 4);
   const bool pin_in = is_pinned(action);
-  const bool pin_out = is_pinned(obs) && is_pinned(reward) && is_pinned(term) && is_pinned(trunc);
+  const bool pin_out = is_pinned(obs) && (!reward || is_pinned(reward)) && is_pinned(term) && (!trunc || is_pinned(trunc));
   // chunk size: a multiple of the block size, at least 8192 envs, at most host_chunks chunks
   int chunks = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
   int per = (h->n + chunks - 1) / chunks;
@@ -476,9 +565,9 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(dst_obs + size_t(i0) * obs_dim, h->d_obs + size_t(i0) * obs_dim,
                              size_t(cnt) * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(dst_rew + i0, h->d_rew + i0, size_t(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward) CUDA_TRY(cudaMemcpyAsync(dst_rew + i0, h->d_rew + i0, size_t(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(dst_term + i0, h->d_term + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(dst_trunc + i0, h->d_trunc + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
+    if (trunc) CUDA_TRY(cudaMemcpyAsync(dst_trunc + i0, h->d_trunc + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
   }
   for (int c = 0; c < chunks; ++c) {
     const int i0 = c * per;
@@ -488,9 +577,9 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
       // stream order guarantees chunk c is complete once its stream drained up to here only if no later
       // chunk shares the stream; with later chunks queued behind it the sync above waits for those as well
       std::memcpy(obs + size_t(i0) * obs_dim, h->h_obs + size_t(i0) * obs_dim, size_t(cnt) * obs_dim * sizeof(float));
-      std::memcpy(reward + i0, h->h_rew + i0, size_t(cnt) * sizeof(float));
+      if (reward) std::memcpy(reward + i0, h->h_rew + i0, size_t(cnt) * sizeof(float));
       std::memcpy(term + i0, h->h_term + i0, size_t(cnt));
-      std::memcpy(trunc + i0, h->h_trunc + i0, size_t(cnt));
+      if (trunc) std::memcpy(trunc + i0, h->h_trunc + i0, size_t(cnt));
     }
   }
   return UPKIE_B200_OK;
@@ -538,6 +627,7 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
     const int v = std::atoi(b);
     if (v >= 32 && v <= UPKIE_MAX_THREADS && v % 32 == 0) h->block = v;
   }
+  if (const char* b = std::getenv("UPKIE_B200_ZERO_COPY")) h->zero_copy = std::atoi(b) != 0;  // developer knob
   if (const char* b = std::getenv("UPKIE_B200_HOST_CHUNKS")) {  // developer knob
     const int v = std::atoi(b);
     if (v >= 1 && v <= 64) h->host_chunks = v;
@@ -699,6 +789,13 @@ int upkie_b200_set_state(void* handle, const float* state, void* stream) {
   CUDA_TRY(cudaSetDevice(h->device));
   k_set_state<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, h->n_pad, h->state, state);
   CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_launch_count(void* handle, uint64_t* count) {
+  Handle* h = as_handle(handle);
+  if (!h || !count) return fail(UPKIE_B200_EINVAL, "launch_count: bad argument");
+  *count = h->step_launches;
   return UPKIE_B200_OK;
 }
 

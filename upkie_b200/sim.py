@@ -65,7 +65,6 @@ class UpkieSim:
         self.obs_servos = torch.empty((self.n, 6, 5), dtype=f32, device=dev)
         self.obs_gyropod = torch.empty((self.n, 6), dtype=f32, device=dev)
         self.obs_pendulum = torch.empty((self.n, 4), dtype=f32, device=dev)
-        self.launches = 0  # kernels launched through this handle (bench.py reports it)
 
     # ------------------------------------------------------------------
     def close(self) -> None:
@@ -118,7 +117,6 @@ class UpkieSim:
         if init_state is not None:
             self._check_tensor(init_state, (self.n, _abi.INIT_DIM), name="init_state")
         check(lib().upkie_b200_reset(self._h, _ptr(mask), _ptr(init_state), int(seed), int(env_offset), self._stream()))
-        self.launches += 1
 
     def _outputs(self, obs, default_obs, reward, terminated, truncated):
         """Caller-provided output tensors (e.g. ``RolloutBuffer.slot(t)``: the kernel then
@@ -148,7 +146,6 @@ class UpkieSim:
                 self._h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream(),
             )
         )
-        self.launches += 1
         return obs, reward, terminated, truncated
 
     def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
@@ -160,7 +157,6 @@ class UpkieSim:
                 self._h, _ptr(action), 2, _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream(),
             )
         )
-        self.launches += 1
         return obs, reward, terminated, truncated
 
     def step_pendulum(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
@@ -172,7 +168,6 @@ class UpkieSim:
                 self._h, _ptr(action), 1, _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream(),
             )
         )
-        self.launches += 1
         return obs, reward, terminated, truncated
 
     # host-buffer path (H2D + kernel + D2H inside the call) ---------------------
@@ -195,6 +190,8 @@ class UpkieSim:
                 "term": pinned((self.n,), torch.uint8),
                 "trunc": pinned((self.n,), torch.uint8),
             }
+            self._hb["rew"][:] = 0.0  # upkie_env.py:230
+            self._hb["trunc"][:] = 0  # upkie_env.py:197
         return self._hb
 
     def host_action_buffer(self, act_dim: int = 36) -> np.ndarray:
@@ -211,12 +208,8 @@ class UpkieSim:
         if a.size != self.n * 36:
             raise UpkieRuntimeError(f"action: expected {self.n * 36} float32 values, got {a.size}")
         obs, rew, term, trunc = hb["obs30"], hb["rew"], hb["term"], hb["trunc"]
-        check(
-            lib().upkie_b200_step_servos_host(
-                self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data
-            )
-        )
-        self.launches += self.host_chunks
+        # reward and truncated are constants of the reference (upkie_env.py:197,230): not transported
+        check(lib().upkie_b200_step_servos_host(self._h, a.ctypes.data, obs.ctypes.data, None, term.ctypes.data, None))
         return obs, rew, term, trunc
 
     def step_gyropod_host(self, action: np.ndarray):
@@ -228,17 +221,16 @@ class UpkieSim:
         obs = hb["obs6"] if act_dim == 2 else hb["obs4"]
         rew, term, trunc = hb["rew"], hb["term"], hb["trunc"]
         check(
-            lib().upkie_b200_step_gyropod_host(
-                self._h, a.ctypes.data, act_dim, obs.ctypes.data, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data
-            )
+            lib().upkie_b200_step_gyropod_host(self._h, a.ctypes.data, act_dim, obs.ctypes.data, None, term.ctypes.data, None)
         )
-        self.launches += self.host_chunks
         return obs, rew, term, trunc
 
     @property
-    def host_chunks(self) -> int:
-        """Kernel launches per host-buffer step (the batch is pipelined in chunks)."""
-        return 4 if self.n >= 4 * 8192 else (2 if self.n >= 2 * 8192 else 1)
+    def launches(self) -> int:
+        """Step kernels launched through this handle, counted by the library (bench.py's ``gpu_launches``)."""
+        c = C.c_uint64(0)
+        check(lib().upkie_b200_launch_count(self._h, C.byref(c)))
+        return int(c.value)
 
     # ------------------------------------------------------------------
     def spine_obs(self) -> torch.Tensor:
