@@ -7,8 +7,11 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libupkie_b200.so")
-SOURCES = ["upkie_b200.cu"]
-DEPS = ["upkie_b200.cu", "sim_core.cuh", "params.h", "mpc.cuh", "mpc_core.cuh", "../../include/upkie_b200.h"]
+SOURCES = ["upkie_b200.cu", "step_device.cu", "step_host.cu"]  # compiled in parallel, then linked
+DEPS = SOURCES + [
+    "sim_core.cuh", "sim_pair.cuh", "kernel_common.cuh", "step_kernel.cuh", "params.h", "mpc.cuh", "mpc_core.cuh",
+    "observers.cuh", "observers_core.cuh", "../../include/upkie_b200.h",
+]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -16,7 +19,7 @@ NVCC_FLAGS = [
     # approximate division / sqrt / sincos (<= 2 ulp, arguments range-reduced in the code) and FTZ:
     # -19% kernel time; the parity tolerances already absorb fp32 round-off of that size
     "--use_fast_math",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -32,7 +35,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]))
+    failed = [src for src, p in zip(SOURCES, procs) if p.wait() != 0]
+    if failed:
+        raise RuntimeError(f"nvcc failed on {failed}")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs)
     return LIB_PATH

@@ -1,0 +1,7 @@
+// SPDX-License-Identifier: Apache-2.0
+// Device-buffer instantiations of the env-step kernel (TILE=0), see kernel_common.cuh.
+#include "step_kernel.cuh"
+
+namespace upkie_b200 {
+cudaError_t launch_step_device(const StepArgs& a) { return launch_step_kernels<0>(a); }
+}  // namespace upkie_b200

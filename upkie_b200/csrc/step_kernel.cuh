@@ -1,0 +1,241 @@
+// SPDX-License-Identifier: Apache-2.0
+//
+// step_kernel.cuh -- the env-step kernel (one thread = one robot) and its launcher template.
+//   k_step<MODE, AUTORESET, NOISE, TILE>   one 5 ms env tick: action front-end, 5 x (moteus torque law,
+//       articulated-body dynamics, wheel-ground contact solve, semi-implicit integration), observation,
+//       termination; optional fused auto-reset; optional torque noise models.
+// Included by step_device.cu (TILE=0) and step_host.cu (TILE=1) only, see kernel_common.cuh.
+#pragma once
+
+#include "kernel_common.cuh"
+
+namespace upkie_b200 {
+namespace {
+
+// ---- the env-step kernel ------------------------------------------------------------
+template <int MODE, int AUTORESET, int NOISE, int TILE>
+#ifdef UPKIE_MAXNREG
+__global__ void __maxnreg__(UPKIE_MAXNREG)
+#else
+__global__ void __launch_bounds__(UPKIE_MAX_THREADS, UPKIE_MIN_BLOCKS)
+#endif
+k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __restrict__ state,
+       const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+       uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
+       const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
+       uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset,
+       int coalesce) {
+  // this launch covers the envs [i0, n)
+  const int tid = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = tid < n;
+  const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
+  // Per-warp staging tile: the 32 action rows (144 B each) and observation rows (120 B each) of a warp
+  // are contiguous, so full warps move them with coalesced 16 B accesses through shared memory. This is
+  // what lets the kernel read actions from / write observations to mapped pinned HOST memory at PCIe line
+  // rate (per-thread strided accesses reach 1/10 of it, tools/micro/pcie_duplex.cu).
+  extern __shared__ float4 s_tile[];
+  const int lane = threadIdx.x & 31;
+  float4* tile4 = s_tile + (threadIdx.x >> 5) * (32 * UPKIE_ACT_DIM / 4);
+  const int wb = tid - lane;  // first env of this warp
+  const bool full = TILE && coalesce && (wb + 32 <= n);  // warp-uniform; compiled out when TILE == 0
+
+  RobotState S;
+  load_state(state, n_pad, i, S);
+  float epsv[6];
+  const float* eps = nullptr;
+  if (eps_all) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) epsv[k] = eps_all[size_t(i) * 6 + k];
+    eps = epsv;
+  }
+  const float mu = mu_all ? mu_all[i] : P.friction;
+
+  bool resetting = false;
+  if (AUTORESET == AUTORESET_NEXT_STEP) resetting = done_prev[i] != 0;
+
+  uint32_t e = 0;
+  float a[UPKIE_ACT_DIM];
+  float a0 = 0.f, a1 = 0.f;
+  if (MODE == MODE_SERVOS) {
+    if (full) {
+      const float4* ap = reinterpret_cast<const float4*>(action + size_t(wb) * UPKIE_ACT_DIM);
+#pragma unroll
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) tile4[k * 32 + lane] = __ldg(ap + k * 32 + lane);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
+        const float4 v = tile4[lane * (UPKIE_ACT_DIM / 4) + k];
+        a[4 * k + 0] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+      }
+      __syncwarp();
+    } else {
+      const float4* ap = reinterpret_cast<const float4*>(action + size_t(i) * UPKIE_ACT_DIM);
+#pragma unroll
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
+        const float4 v = __ldg(ap + k);
+        a[4 * k + 0] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+      }
+    }
+  } else if (MODE == MODE_GYROPOD) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(action) + i);
+    a0 = v.x; a1 = v.y;
+  } else {
+    a0 = __ldg(action + i);
+    a1 = 0.f;  // upkie_pendulum.py:137
+  }
+
+  // One inlined copy of the physics serves both the regular tick (nb_substeps
+  // substeps under the torque law) and the fused auto-reset (new initial state,
+  // ONE zero-torque substep, pybullet_backend.py:227-228): resetting lanes run a
+  // single iteration of the same loop, which keeps the kernel's code small
+  // (instruction-cache footprint) and the warp converged.
+  NoiseCtx nz{env_offset + uint64_t(i), 0u};
+  if (NOISE) {
+    nz.tick = tick[i] + 1u;
+    if (live) tick[i] = nz.tick;
+  }
+  int nsub = P.nb_substeps;
+  if (resetting) {
+    const uint32_t ep = episode[i] + 1u;
+    if (live) episode[i] = ep;
+    float init[UPKIE_INIT_DIM];
+    sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
+    reset_pose(S, init);
+    nsub = 1;
+  } else {
+    if (MODE != MODE_SERVOS) e |= gyropod_action(P, S, a0, a1, a);
+    e |= clamp_servo_action(P, a);
+  }
+  for (int sub = 0; sub < P.nb_substeps; ++sub) {
+#if UPKIE_PHASE_SYNC_LEVEL >= 1
+    __syncthreads();  // once per substep: all threads are converged here
+#endif
+    if (sub < nsub) {
+      servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
+    }
+  }
+  observe_update(P, S);
+  if (resetting) {
+    reset_wrapper_state(S);
+  } else {
+    e |= state_sanity(S);
+    if (MODE != MODE_SERVOS) {
+      S.yaw += a1 * P.dt;  // integrates the unclamped action[1], upkie_gyropod.py:383-385
+      S.yaw_vel = a1;
+    }
+  }
+
+  // observation, reward, termination
+  bool term = false;
+  float o6[6];
+  if (MODE == MODE_SERVOS) {
+    if (P.servos_fall_termination) term = (fabsf(base_pitch(S)) > P.fall_pitch) || (S.pos[2] < P.min_base_height);
+  } else {
+    gyropod_obs(P, S, o6);
+    term = fabsf(o6[1]) > P.fall_pitch;  // strict, upkie_gyropod.py:345
+  }
+  if (resetting) term = false;
+
+  if (AUTORESET == AUTORESET_SAME_STEP) {
+    if (term) {
+      const uint32_t ep = episode[i] + 1u;
+      if (live) episode[i] = ep;
+      float init[UPKIE_INIT_DIM];
+      sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
+      reset_robot(P, S, init, eps, mu, WarpAny());
+      if (MODE != MODE_SERVOS) gyropod_obs(P, S, o6);
+    }
+  }
+
+  if (live) store_state(state, n_pad, i, S);
+  if (MODE == MODE_SERVOS) {
+    float o[UPKIE_OBS_DIM];
+    float tq[6];
+    measured_torques(P, S, NOISE ? &nz : nullptr, tq);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      o[j * 5 + 0] = S.q[j]; o[j * 5 + 1] = S.qd[j]; o[j * 5 + 2] = tq[j];
+      o[j * 5 + 3] = 42.0f;  // pybullet_backend.py:471
+      o[j * 5 + 4] = 18.0f;  // pybullet_backend.py:472
+    }
+    if (full) {
+      float2* t2 = reinterpret_cast<float2*>(tile4) + lane * (UPKIE_OBS_DIM / 2);
+#pragma unroll
+      for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) t2[k] = make_float2(o[2 * k], o[2 * k + 1]);
+      __syncwarp();
+      float4* op = reinterpret_cast<float4*>(obs + size_t(wb) * UPKIE_OBS_DIM);
+#pragma unroll
+      for (int k = 0; k < (32 * UPKIE_OBS_DIM / 4 + 31) / 32; ++k) {
+        const int idx = k * 32 + lane;
+        if (idx < 32 * UPKIE_OBS_DIM / 4) op[idx] = tile4[idx];
+      }
+    } else if (live) {
+      float2* op = reinterpret_cast<float2*>(obs + size_t(i) * UPKIE_OBS_DIM);
+#pragma unroll
+      for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) op[k] = make_float2(o[2 * k], o[2 * k + 1]);
+    }
+  } else if (MODE == MODE_GYROPOD) {
+    if (full) {
+      float2* t2 = reinterpret_cast<float2*>(tile4) + lane * 3;
+      t2[0] = make_float2(o6[0], o6[1]);
+      t2[1] = make_float2(o6[2], o6[3]);
+      t2[2] = make_float2(o6[4], o6[5]);
+      __syncwarp();
+      float4* op = reinterpret_cast<float4*>(obs + size_t(wb) * 6);
+      op[lane] = tile4[lane];
+      if (lane < 16) op[32 + lane] = tile4[32 + lane];
+    } else if (live) {
+      float2* op = reinterpret_cast<float2*>(obs + size_t(i) * 6);
+      op[0] = make_float2(o6[0], o6[1]);
+      op[1] = make_float2(o6[2], o6[3]);
+      op[2] = make_float2(o6[4], o6[5]);
+    }
+  } else if (live) {
+    // upkie_pendulum.py:17 _PENDULUM_OBS_INDICES = [1, 0, 4, 3]
+    reinterpret_cast<float4*>(obs)[i] = make_float4(o6[1], o6[0], o6[4], o6[3]);
+  }
+  if (!live) return;
+  if (reward) reward[i] = 0.0f;  // upkie_env.py:230
+  terminated[i] = term ? 1 : 0;
+  if (truncated) truncated[i] = 0;
+  if (e) err[i] |= e;
+  if (AUTORESET == AUTORESET_NEXT_STEP) done_prev[i] = term ? 1 : 0;
+}
+
+
+template <int TILE, int MODE>
+cudaError_t launch_step_mode(const StepArgs& a) {
+  const int grid = (a.cnt + a.block - 1) / a.block;
+  const size_t smem = TILE ? size_t(a.block / 32) * 32 * UPKIE_ACT_DIM * sizeof(float) : 0;
+  // the tile path needs 16 B aligned rows of 32 envs
+  const int coalesce =
+      ((reinterpret_cast<uintptr_t>(a.action) | reinterpret_cast<uintptr_t>(a.obs)) & 15) == 0 && (a.i0 % 32) == 0;
+#define LAUNCH_N(AR, NZ)                                                                                         \
+  k_step<MODE, AR, NZ, TILE><<<grid, a.block, smem, a.stream>>>(                                                 \
+      *a.P, a.i0, a.i0 + a.cnt, a.n_pad, a.state, a.action, a.obs, a.reward, a.terminated, a.truncated, a.eps,   \
+      a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, coalesce)
+#define LAUNCH(AR)                \
+  do {                            \
+    if (a.noise) LAUNCH_N(AR, 1); \
+    else LAUNCH_N(AR, 0);         \
+  } while (0)
+  if (a.autoreset == AUTORESET_NEXT_STEP) LAUNCH(AUTORESET_NEXT_STEP);
+  else if (a.autoreset == AUTORESET_SAME_STEP) LAUNCH(AUTORESET_SAME_STEP);
+  else LAUNCH(AUTORESET_DISABLED);
+#undef LAUNCH
+#undef LAUNCH_N
+  return cudaGetLastError();
+}
+
+template <int TILE>
+cudaError_t launch_step_kernels(const StepArgs& a) {
+  if (a.mode == MODE_SERVOS) return launch_step_mode<TILE, MODE_SERVOS>(a);
+  if (a.mode == MODE_GYROPOD) return launch_step_mode<TILE, MODE_GYROPOD>(a);
+  return launch_step_mode<TILE, MODE_PENDULUM>(a);
+}
+
+}  // namespace
+}  // namespace upkie_b200
