@@ -322,8 +322,8 @@ def main():
         # secondary roofline: non-tensor fp32 issue slots
         sm_mhz = clocks.get("sm_mhz") or 1700.0
         # warp instructions per env-step of the servos workload, ncu smsp__inst_executed.sum / warps
-        # (profiles/r01_ncu_summary.md); 84.5 % of them FFMA/FMUL/FADD
-        instr_per_env_step = 23_790
+        # (profiles/r01_ncu_summary.md, paired f32x2 legs); 78.5 % of them FFMA(2)/FMUL(2)/FADD(2)
+        instr_per_env_step = 17_771
         sched_cycles = 148 * 4 * sm_mhz * 1e6  # issue slots per second (one warp instruction each)
         ipc = instr_per_env_step * (n_per_gpu / 32.0) / (kernel_ms * 1e-3) / sched_cycles
         line["roofline"]["fp32_issue"] = {
@@ -332,7 +332,7 @@ def main():
             "frac": ipc,
             # tools/micro/ffma2_bench.cu on this pool: three-register scalar FFMA saturates at 0.59 inst/cycle/scheduler
             "measured_scalar_ffma_ceiling_ipc": 0.59,
-            "fp_instr_frac_of_ceiling": 0.845 * ipc / 0.59,
+            "fp_instr_frac_of_ceiling": 0.785 * ipc / 0.59,
             "instr_per_env_step": instr_per_env_step,
             "exact_for": "servos workload (the pendulum front-end changes the count by < 2 %)",
         }
@@ -462,7 +462,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         "value": n * world * Ke / float(te.item()),
         "unit": "env-steps/s",
         "h2d_bytes_per_step": n * act_bytes,
-        "d2h_bytes_per_step": n * (obs_bytes + 4 + 1 + 1),
+        # servos: position/velocity/torque rows (72 B) + terminated; temperature, voltage, reward and truncated
+        # are constants of the reference that the env fills once on the host (host path)
+        "d2h_bytes_per_step": n * ((72 if servos else obs_bytes) + 1),
         "steps": Ke,
         "api": "B200VectorEnv.step(numpy action) -> numpy obs/reward/terminated/truncated",
     }

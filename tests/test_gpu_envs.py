@@ -135,6 +135,16 @@ def test_host_buffer_api_equals_device_api(model, torch, n):
         assert np.array_equal(o1.cpu().numpy(), o)  # same kernel: bit-exact
         assert np.array_equal(t1.cpu().numpy(), t) and np.array_equal(r1.cpu().numpy(), r)
         assert np.array_equal(u1.cpu().numpy(), u)
+    # compact transport: only position / velocity / torque rows cross PCIe
+    s4, s5 = _sim(n, model), _sim(n, model)
+    s4.set_state(st)
+    s5.set_state(st)
+    p4 = s4.host_action_buffer(36)
+    p4[:] = a
+    c4, ct4 = s4.step_servos_host_compact(p4)
+    c5, ct5 = s5.step_servos_host_compact(a.copy())  # pageable: staged through the handle's pinned buffers
+    for c, ct in ((c4, ct4), (c5, ct5)):
+        assert c.shape == (n, 6, 3) and np.array_equal(c, o1.cpu().numpy()[:, :, :3]) and np.array_equal(ct, t1.cpu().numpy())
     g = np.random.default_rng(3).uniform(-3, 3, (n, 2)).astype(np.float32)
     o1, _, t1, _ = s1.step_gyropod(torch.from_numpy(g).cuda())
     pg = s2.host_action_buffer(2)

@@ -31,43 +31,8 @@ def timed(fn, reps=50):
 def main():
     n = 65536
     m = Model.standard_upkie()
-    for nbytes, name in ((n * 144, "H2D action 144 B/env"), (n * 126, "D2H obs+flags 126 B/env"), (n * 73, "D2H compact 73 B/env")):
-        h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-        d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        if name.startswith("H2D"):
-            t = timed(lambda: d.copy_(h, non_blocking=True))
-        else:
-            t = timed(lambda: h.copy_(d, non_blocking=True))
-        print(f"{name}: {nbytes / 1e6:.2f} MB  {t:.4f} ms  {nbytes / t / 1e6:.1f} GB/s")
-    # full duplex
-    ha = torch.empty(n * 144, dtype=torch.uint8).pin_memory()
-    da = torch.empty(n * 144, dtype=torch.uint8, device="cuda")
-    ho = torch.empty(n * 126, dtype=torch.uint8).pin_memory()
-    do = torch.empty(n * 126, dtype=torch.uint8, device="cuda")
-    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-
-    def duplex():
-        cur = torch.cuda.current_stream()
-        s1.wait_stream(cur)
-        s2.wait_stream(cur)
-        with torch.cuda.stream(s1):
-            da.copy_(ha, non_blocking=True)
-        with torch.cuda.stream(s2):
-            ho.copy_(do, non_blocking=True)
-        cur.wait_stream(s1)
-        cur.wait_stream(s2)
-
-    print(f"duplex H2D 9.4 MB + D2H 8.3 MB: {timed(duplex):.4f} ms")
-    # chunked H2D: 4 copies of a quarter
-    def h2d_chunks(k):
-        q = n * 144 // k
-        for c in range(k):
-            da[c * q:(c + 1) * q].copy_(ha[c * q:(c + 1) * q], non_blocking=True)
-    for k in (1, 2, 4, 8):
-        print(f"H2D in {k} chunks: {timed(lambda: h2d_chunks(k)):.4f} ms")
-
     # kernel time vs envs per launch (standing robots, PD action)
-    for cnt in (4096, 8192, 16384, 32768, 65536):
+    for cnt in ((4096, 8192, 16384, 32768, 65536) if "--kernel" in sys.argv else ()):
         sim = UpkieSim(cnt, model=m, config=_abi.default_sim_config())
         sim.reset(seed=1)
         a = torch.zeros((cnt, 6, 6), device="cuda")
@@ -78,9 +43,20 @@ def main():
             sim.step_servos(a)
         t = timed(lambda: sim.step_servos(a), reps=100)
         print(f"kernel {cnt} envs: {t:.4f} ms  {cnt / t / 1e3:.1f} M env-steps/s")
-    # host path as shipped
-    for chunks in (1, 2, 3, 4, 6, 8):
-        os.environ["UPKIE_B200_HOST_CHUNKS"] = str(chunks)
+    # host path as shipped: zero-copy persistent kernel (block, blocks/SM) and the staged pipeline (chunks)
+    import time
+    configs = []
+    for compact in ("1", ""):
+        configs += [{"compact": compact, "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": str(c),
+                     "UPKIE_B200_HOST_KERNEL_STREAMS": str(k), "UPKIE_B200_HOST_BLOCK": str(b)}
+                    for c, k, b in ((4, 1, 128), (2, 1, 128), (8, 2, 128), (8, 2, 64), (4, 2, 128))]
+        configs += [{"compact": compact, "UPKIE_B200_ZERO_COPY": "1", "UPKIE_B200_HOST_BLOCK": "128", "UPKIE_B200_HOST_BLOCKS_PER_SM": "1"}]
+    configs += [{"UPKIE_B200_ZERO_COPY": "0", "UPKIE_B200_HOST_CHUNKS": "4"}]
+    for cfg in configs:
+        for k in ("UPKIE_B200_ZERO_COPY", "UPKIE_B200_HOST_BLOCK", "UPKIE_B200_HOST_BLOCKS_PER_SM", "UPKIE_B200_HOST_CHUNKS",
+                  "UPKIE_B200_HOST_KERNEL_STREAMS"):
+            os.environ.pop(k, None)
+        os.environ.update({k: v for k, v in cfg.items() if k != "compact"})
         sim = UpkieSim(n, model=m, config=_abi.default_sim_config())
         sim.reset(seed=1)
         act = sim.host_action_buffer(36)
@@ -88,15 +64,15 @@ def main():
         act.reshape(n, 6, 6)[:, :, 0] = np.nan
         act.reshape(n, 6, 6)[:, :, 3:5] = 1.0
         act.reshape(n, 6, 6)[:, :, 5] = m.tau_max
+        step = sim.step_servos_host_compact if cfg.get("compact") else sim.step_servos_host
         for _ in range(30):
-            sim.step_servos_host(act)
-        import time
+            step(act)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(200):
-            sim.step_servos_host(act)
+            step(act)
         dt = (time.perf_counter() - t0) / 200
-        print(f"step_servos_host, {chunks} chunks: {dt * 1e3:.4f} ms  {n / dt / 1e6:.1f} M env-steps/s")
+        print(f"step_servos_host {cfg}: {dt * 1e3:.4f} ms  {n / dt / 1e6:.1f} M env-steps/s", flush=True)
 
 
 if __name__ == "__main__":

@@ -23,6 +23,49 @@ __global__ void zc_env(const float4* __restrict__ act, float2* __restrict__ obs,
   for (int k = 0; k < 15; ++k) obs[size_t(i) * 15 + k] = make_float2(s, s + k);
 }
 
+
+// Persistent-block pipeline shaped like k_step<TILE=1>: cp.async prefetch of the next tile's action rows, a spin of
+// `delay` cycles standing in for the physics, coalesced observation rows out. mode bit0 = read actions from `act`
+// (else skip), bit1 = write observations.
+__device__ __forceinline__ void cpa16(void* d, const void* s) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(d))), "l"(s) : "memory");
+}
+__global__ void zc_pipeline(const float4* __restrict__ act, float4* __restrict__ obs, int n, long long delay, int mode) {
+  extern __shared__ float4 sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float4* buf[2] = {sm + warp * 288, sm + (nw + warp) * 288};
+  const int ntiles = n / blockDim.x;
+  auto prefetch = [&](int t, float4* dst) {
+    if (mode & 1) {
+      const float4* src = act + size_t(t * blockDim.x + warp * 32) * 9;
+      for (int k = 0; k < 9; ++k) cpa16(dst + k * 32 + lane, src + k * 32 + lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int t = blockIdx.x, it = 0;
+  if (t < ntiles) prefetch(t, buf[0]);
+  for (; t < ntiles; t += gridDim.x, ++it) {
+    const int nt = t + gridDim.x;
+    if (nt < ntiles) { prefetch(nt, buf[(it + 1) & 1]); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    float4* b = buf[it & 1];
+    float s = 0.f;
+    for (int k = 0; k < 9; ++k) { const float4 v = b[lane * 9 + k]; s += v.x + v.y + v.z + v.w; }
+    const long long t0 = clock64();
+    while (clock64() - t0 < delay) {}
+    __syncwarp();
+    float2* t2 = reinterpret_cast<float2*>(b) + lane * 15;
+    for (int k = 0; k < 15; ++k) t2[k] = make_float2(s, s + k);
+    __syncwarp();
+    if (mode & 2) {
+      float4* dst = obs + size_t(t * blockDim.x + warp * 32) * 30 / 4;
+      for (int k = 0; k < 8; ++k) { const int idx = k * 32 + lane; if (idx < 240) dst[idx] = b[idx]; }
+    }
+    __syncwarp();
+  }
+}
+
 template <typename F>
 double wall_ms(F f, int reps) {
   for (int i = 0; i < 3; ++i) f();
@@ -95,5 +138,14 @@ int main() {
   // launch + sync floor
   t = wall_ms([&] { zc_env<<<1, 32, 0, s1>>>(reinterpret_cast<float4*>(da), reinterpret_cast<float2*>(dob), 32); cudaStreamSynchronize(s1); }, R);
   printf("empty launch + stream sync: %.4f ms\n", t);
+  // pipeline model of the zero-copy step kernel
+  for (int block : {128, 64}) {
+    for (long long delay : {0LL, 35000LL, 70000LL}) {  // cycles at ~1.9 GHz: 0, ~18 us, ~37 us
+      for (int mode : {1, 2, 3}) {
+        t = wall_ms([&] { zc_pipeline<<<148, block, 2 * (block / 32) * 4608, s1>>>(zha, reinterpret_cast<float4*>(zho), n, delay, mode); cudaStreamSynchronize(s1); }, R);
+        printf("zc_pipeline 148 x %d, delay %lld cycles, %s: %.4f ms\n", block, delay, mode == 1 ? "read only" : mode == 2 ? "write only" : "read+write", t);
+      }
+    }
+  }
   return 0;
 }

@@ -41,6 +41,7 @@ SYMBOLS = {
     "upkie_b200_step_gyropod": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_servos_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_gyropod_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "upkie_b200_step_servos_host_compact": (C.c_int, [_vp, _vp, _vp, _vp]),
     "upkie_b200_spine_obs": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_reset_obs": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "upkie_b200_get_state": (C.c_int, [_vp, _vp, _vp]),

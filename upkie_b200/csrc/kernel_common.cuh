@@ -68,6 +68,8 @@ struct StepArgs {
   const SimParams* P;
   int mode, autoreset, noise;
   int i0, cnt, n_pad, block;
+  int compact_obs;      // TILE=1, servos: observation rows [6][3] (position, velocity, torque) instead of [6][5]
+  int grid;             // TILE=1: number of persistent blocks (0 = one block per tile)
   float* state;
   const float* action;
   float* obs;

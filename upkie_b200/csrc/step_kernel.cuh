@@ -12,32 +12,20 @@
 namespace upkie_b200 {
 namespace {
 
-// ---- the env-step kernel ------------------------------------------------------------
+// ---- one env tick of the robot `tid` --------------------------------------------------
+// `tile4` is this warp's staging tile (TILE=1): on entry it holds the warp's 32 action rows when
+// `full` (prefetched by the caller), and it is reused to transpose the observation rows on the way out.
 template <int MODE, int AUTORESET, int NOISE, int TILE>
-#ifdef UPKIE_MAXNREG
-__global__ void __maxnreg__(UPKIE_MAXNREG)
-#else
-__global__ void __launch_bounds__(UPKIE_MAX_THREADS, UPKIE_MIN_BLOCKS)
-#endif
-k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __restrict__ state,
-       const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
-       uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
-       const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
-       uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset,
-       int coalesce) {
-  // this launch covers the envs [i0, n)
-  const int tid = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void step_env(
+    const SimParams& P, int tid, int n, int n_pad, float* __restrict__ state, const float* __restrict__ action,
+    float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ terminated,
+    uint8_t* __restrict__ truncated, const float* __restrict__ eps_all, const float* __restrict__ mu_all,
+    uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev, uint32_t* __restrict__ episode,
+    uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset, float4* tile4, bool full, bool compact) {
   const bool live = tid < n;
   const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
-  // Per-warp staging tile: the 32 action rows (144 B each) and observation rows (120 B each) of a warp
-  // are contiguous, so full warps move them with coalesced 16 B accesses through shared memory. This is
-  // what lets the kernel read actions from / write observations to mapped pinned HOST memory at PCIe line
-  // rate (per-thread strided accesses reach 1/10 of it, tools/micro/pcie_duplex.cu).
-  extern __shared__ float4 s_tile[];
   const int lane = threadIdx.x & 31;
-  float4* tile4 = s_tile + (threadIdx.x >> 5) * (32 * UPKIE_ACT_DIM / 4);
   const int wb = tid - lane;  // first env of this warp
-  const bool full = TILE && coalesce && (wb + 32 <= n);  // warp-uniform; compiled out when TILE == 0
 
   RobotState S;
   load_state(state, n_pad, i, S);
@@ -57,11 +45,7 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
   float a[UPKIE_ACT_DIM];
   float a0 = 0.f, a1 = 0.f;
   if (MODE == MODE_SERVOS) {
-    if (full) {
-      const float4* ap = reinterpret_cast<const float4*>(action + size_t(wb) * UPKIE_ACT_DIM);
-#pragma unroll
-      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) tile4[k * 32 + lane] = __ldg(ap + k * 32 + lane);
-      __syncwarp();
+    if (TILE && full) {
 #pragma unroll
       for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
         const float4 v = tile4[lane * (UPKIE_ACT_DIM / 4) + k];
@@ -161,7 +145,29 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
       o[j * 5 + 3] = 42.0f;  // pybullet_backend.py:471
       o[j * 5 + 4] = 18.0f;  // pybullet_backend.py:472
     }
-    if (full) {
+    if (TILE && compact) {
+      // compact rows [6 joints][position, velocity, torque]: temperature / voltage are constants the
+      // host fills once (pybullet_backend.py:471-472), 72 B per env instead of 120 B over PCIe
+      float c[18];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { c[3 * j] = o[5 * j]; c[3 * j + 1] = o[5 * j + 1]; c[3 * j + 2] = o[5 * j + 2]; }
+      if (full) {
+        float2* t2 = reinterpret_cast<float2*>(tile4) + lane * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t2[k] = make_float2(c[2 * k], c[2 * k + 1]);
+        __syncwarp();
+        float4* op = reinterpret_cast<float4*>(obs + size_t(wb) * 18);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int idx = k * 32 + lane;
+          if (idx < 32 * 18 / 4) op[idx] = tile4[idx];
+        }
+      } else if (live) {
+        float2* op = reinterpret_cast<float2*>(obs + size_t(i) * 18);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) op[k] = make_float2(c[2 * k], c[2 * k + 1]);
+      }
+    } else if (TILE && full) {
       float2* t2 = reinterpret_cast<float2*>(tile4) + lane * (UPKIE_OBS_DIM / 2);
 #pragma unroll
       for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) t2[k] = make_float2(o[2 * k], o[2 * k + 1]);
@@ -178,7 +184,7 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
       for (int k = 0; k < UPKIE_OBS_DIM / 2; ++k) op[k] = make_float2(o[2 * k], o[2 * k + 1]);
     }
   } else if (MODE == MODE_GYROPOD) {
-    if (full) {
+    if (TILE && full) {
       float2* t2 = reinterpret_cast<float2*>(tile4) + lane * 3;
       t2[0] = make_float2(o6[0], o6[1]);
       t2[1] = make_float2(o6[2], o6[3]);
@@ -205,14 +211,87 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
   if (AUTORESET == AUTORESET_NEXT_STEP) done_prev[i] = term ? 1 : 0;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- the env-step kernel ------------------------------------------------------------
+// TILE=0 (device buffers): one env per thread, grid = ceil(cnt / block).
+// TILE=1 (host buffers, zero-copy): persistent blocks walk the tiles of `blockDim.x` envs with stride
+// gridDim.x. The action rows of the NEXT tile are fetched over PCIe with cp.async into the second
+// shared-memory buffer while the current tile computes, and observation rows leave through coalesced
+// 16 B stores, so the link streams in both directions for the whole launch instead of in bursts
+// between compute phases.
+template <int MODE, int AUTORESET, int NOISE, int TILE>
+#ifdef UPKIE_MAXNREG
+__global__ void __maxnreg__(UPKIE_MAXNREG)
+#else
+__global__ void __launch_bounds__(UPKIE_MAX_THREADS, UPKIE_MIN_BLOCKS)
+#endif
+k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __restrict__ state,
+       const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+       uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
+       const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
+       uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset,
+       int coalesce) {
+  // this launch covers the envs [i0, n)
+  if (!TILE) {
+    step_env<MODE, AUTORESET, NOISE, 0>(P, i0 + blockIdx.x * blockDim.x + threadIdx.x, n, n_pad, state, action, obs,
+                                        reward, terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick,
+                                        seed, env_offset, nullptr, false, false);
+    return;
+  }
+  extern __shared__ float4 s_tile[];
+  constexpr int kRow4 = 32 * UPKIE_ACT_DIM / 4;  // float4 per warp tile
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float4* buf[2] = {s_tile + warp * kRow4, s_tile + (nwarps + warp) * kRow4};
+  const int ntiles = (n - i0 + blockDim.x - 1) / blockDim.x;
+  // a warp's rows are prefetched when all 32 envs exist and the rows are 16 B aligned
+  auto warp_full = [&](int t) { return (coalesce & 1) && (i0 + t * int(blockDim.x) + warp * 32 + 32 <= n); };
+  auto prefetch = [&](int t, float4* dst) {
+    if (MODE == MODE_SERVOS && warp_full(t)) {
+      const float4* src =
+          reinterpret_cast<const float4*>(action + size_t(i0 + t * int(blockDim.x) + warp * 32) * UPKIE_ACT_DIM);
+#pragma unroll
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) cp_async16(dst + k * 32 + lane, src + k * 32 + lane);
+    }
+    cp_async_commit();
+  };
+  int t = blockIdx.x, it = 0;
+  if (t < ntiles) prefetch(t, buf[0]);
+  for (; t < ntiles; t += gridDim.x, ++it) {
+    const int nt = t + gridDim.x;
+    if (nt < ntiles) {
+      prefetch(nt, buf[(it + 1) & 1]);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    step_env<MODE, AUTORESET, NOISE, 1>(P, i0 + t * blockDim.x + threadIdx.x, n, n_pad, state, action, obs, reward,
+                                        terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick, seed,
+                                        env_offset, buf[it & 1], warp_full(t), (coalesce & 2) != 0);
+    __syncwarp();  // the tile is free again before the next prefetch lands in it
+  }
+}
+
 
 template <int TILE, int MODE>
 cudaError_t launch_step_mode(const StepArgs& a) {
-  const int grid = (a.cnt + a.block - 1) / a.block;
-  const size_t smem = TILE ? size_t(a.block / 32) * 32 * UPKIE_ACT_DIM * sizeof(float) : 0;
+  const int tiles = (a.cnt + a.block - 1) / a.block;
+  const int grid = (TILE && a.grid > 0 && a.grid < tiles) ? a.grid : tiles;
+  const size_t smem = TILE ? size_t(2) * (a.block / 32) * 32 * UPKIE_ACT_DIM * sizeof(float) : 0;
   // the tile path needs 16 B aligned rows of 32 envs
-  const int coalesce =
+  const int aligned =
       ((reinterpret_cast<uintptr_t>(a.action) | reinterpret_cast<uintptr_t>(a.obs)) & 15) == 0 && (a.i0 % 32) == 0;
+  const int coalesce = (aligned ? 1 : 0) | ((TILE && a.compact_obs) ? 2 : 0);  // bit 0 tile path, bit 1 compact rows
 #define LAUNCH_N(AR, NZ)                                                                                         \
   k_step<MODE, AR, NZ, TILE><<<grid, a.block, smem, a.stream>>>(                                                 \
       *a.P, a.i0, a.i0 + a.cnt, a.n_pad, a.state, a.action, a.obs, a.reward, a.terminated, a.truncated, a.eps,   \

@@ -60,15 +60,19 @@ struct Handle {
   uint64_t seed = 0, env_offset = 0;
   int block = UPKIE_DEFAULT_BLOCK;
   int num_sms = 148;
-  int host_chunks = 4;           // chunks of the pipelined host-buffer step (pageable buffers)
+  int host_chunks = 2;           // chunks of the pipelined host-buffer step (measured best of 2..16, tools/e2e_parts.py)
   uint64_t step_launches = 0;    // step kernels launched (upkie_b200_launch_count)
-  int zero_copy = 1;             // host-buffer steps read/write mapped pinned buffers from the kernel
+  int host_block = 128;          // zero-copy step: persistent blocks of 4 warps, one per SM: ~3.5 tiles per block at
+  int host_blocks_per_sm = 1;    // 65536 envs, so PCIe reads of tile k+1 overlap the compute of tile k
+  int zero_copy = 2;             // pinned host buffers: 0 staged copies, 1 kernel reads+writes host memory, 2 hybrid
   // host-buffer staging (allocated on first use)
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
   cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t host_events[64] = {};
+  int host_kernel_streams = 1;   // hybrid host step: kernels of successive chunks alternate over this many streams
 };
 constexpr int kHostStreams = 3;  // H2D, kernel and D2H of different chunks overlap
 constexpr uint32_t kMagic = 0x55504B42u;  // "UPKB"
@@ -193,7 +197,7 @@ int pick_block(const Handle* h, int cnt) {
 // envs [i0, i0 + cnt): all buffers are indexed by the env index of the handle. `tile` selects the
 // shared-memory-tile instantiation (host buffers), see kernel_common.cuh.
 int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float* obs, float* reward, uint8_t* term,
-               uint8_t* trunc, cudaStream_t s, bool tile = false) {
+               uint8_t* trunc, cudaStream_t s, bool tile = false, bool persistent = true, bool compact = false) {
   StepArgs a;
   a.P = &h->P;
   a.mode = mode;
@@ -202,7 +206,9 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
   a.i0 = i0;
   a.cnt = cnt;
   a.n_pad = h->n_pad;
-  a.block = pick_block(h, cnt);
+  a.block = tile ? h->host_block : pick_block(h, cnt);
+  a.grid = (tile && persistent) ? h->num_sms * h->host_blocks_per_sm : 0;
+  a.compact_obs = compact ? 1 : 0;
   a.state = h->state;
   a.action = action;
   a.obs = obs;
@@ -235,6 +241,7 @@ int ensure_staging(Handle* h) {
   const size_t n = size_t(h->n);
   CUDA_TRY(cudaSetDevice(h->device));
   for (int k = 0; k < kHostStreams; ++k) CUDA_TRY(cudaStreamCreateWithFlags(&h->host_streams[k], cudaStreamNonBlocking));
+  for (int k = 0; k < 64; ++k) CUDA_TRY(cudaEventCreateWithFlags(&h->host_events[k], cudaEventDisableTiming));
   CUDA_TRY(cudaMallocHost(&h->h_act, n * UPKIE_ACT_DIM * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&h->h_obs, n * UPKIE_OBS_DIM * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&h->h_rew, n * sizeof(float)));
@@ -246,15 +253,6 @@ int ensure_staging(Handle* h) {
   CUDA_TRY(cudaMalloc(&h->d_term, n));
   CUDA_TRY(cudaMalloc(&h->d_trunc, n));
   return UPKIE_B200_OK;
-}
-
-bool is_pinned(const void* p) {
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return at.type == cudaMemoryTypeHost;
 }
 
 // device-side alias of a pinned host buffer (nullptr when the buffer is pageable or not mapped)
@@ -270,75 +268,87 @@ T* mapped(T* p) {
   return static_cast<T*>(at.devicePointer);
 }
 
-// Host-buffer step: the batch is cut into chunks that flow through H2D copy ->
-// kernel -> D2H copy on rotating streams, so the copies of one chunk overlap
-// the kernel of another (PCIe is full duplex). Pinned caller buffers are used
-// in place; pageable ones are staged through pinned memory chunk by chunk.
-int step_host(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc) {
+// Host-buffer step. Pageable caller buffers are first staged through the handle's pinned buffers; on
+// pinned (mapped) buffers one of three pipelines runs, `zero_copy` selecting it:
+//   2 (default, servos)  hybrid: the copy engine streams the action rows in, chunk by chunk on one stream; each
+//                        chunk's TILE=1 kernel waits for its rows only and writes observations / flags straight
+//                        to host memory. Copy-engine reads overlap SM writes on the link, SM reads do not
+//                        (63 GB/s combined, tools/micro/pcie_duplex.cu).
+//   1                    one persistent TILE=1 launch reading actions from and writing observations to host memory.
+//   0                    H2D copy -> TILE=0 kernel -> D2H copies per chunk on rotating streams.
+// `compact` (servos): observation rows [6][3] = position, velocity, torque; needs a TILE=1 pipeline.
+int step_host(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
+              bool compact = false) {
   if (!action || !obs || !term) return fail(UPKIE_B200_EINVAL, "step_host: null buffer");
   int rc = ensure_staging(h);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
-  if (h->zero_copy) {
-    // All caller buffers pinned and mapped: ONE launch whose warps read their action rows from host memory
-    // and write their observation rows back over PCIe themselves (coalesced through the shared-memory
-    // tile). Reads, compute and writes of different warps overlap in both directions of the link, with no
-    // staging copies and no chunk boundaries.
-    const float* za = mapped(action);
-    float* zo = mapped(obs);
-    uint8_t* zt = mapped(term);
-    float* zr = mapped(reward);
-    uint8_t* zu = mapped(trunc);
-    if (za && zo && zt && (zr || !reward) && (zu || !trunc)) {
-      cudaStream_t s = h->host_streams[0];
-      rc = step_range(h, mode, 0, h->n, za, zo, zr, zt, zu, s, /*tile=*/true);
-      if (rc) return rc;
-      CUDA_TRY(cudaStreamSynchronize(s));
-      return UPKIE_B200_OK;
-    }
-  }
-  // reward / truncated are constants of the reference (0.0 and false): callers may pass NULL for them
+  const size_t n = size_t(h->n);
   const size_t act_dim = mode == MODE_SERVOS ? UPKIE_ACT_DIM : (mode == MODE_GYROPOD ? 2 : 1);
-  const size_t obs_dim = mode == MODE_SERVOS ? UPKIE_OBS_DIM : (mode == MODE_GYROPOD ? 6 : 4);
-  const bool pin_in = is_pinned(action);
-  const bool pin_out = is_pinned(obs) && (!reward || is_pinned(reward)) && is_pinned(term) && (!trunc || is_pinned(trunc));
-  // chunk size: a multiple of the block size, at least 8192 envs, at most host_chunks chunks
-  int chunks = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
-  int per = (h->n + chunks - 1) / chunks;
-  per = (per + 255) / 256 * 256;
-  chunks = (h->n + per - 1) / per;
+  const size_t obs_dim = mode == MODE_SERVOS ? (compact ? 18 : UPKIE_OBS_DIM) : (mode == MODE_GYROPOD ? 6 : 4);
+  // reward / truncated are constants of the reference (0.0 and false): callers may pass NULL for them
+  const bool pin_in = mapped(action) != nullptr;
+  const bool pin_out = mapped(obs) && (!reward || mapped(reward)) && mapped(term) && (!trunc || mapped(trunc));
+  if (!pin_in) std::memcpy(h->h_act, action, n * act_dim * sizeof(float));
   const float* src_act = pin_in ? action : h->h_act;
   float* dst_obs = pin_out ? obs : h->h_obs;
-  float* dst_rew = pin_out ? reward : h->h_rew;
+  float* dst_rew = reward ? (pin_out ? reward : h->h_rew) : nullptr;
   uint8_t* dst_term = pin_out ? term : h->h_term;
-  uint8_t* dst_trunc = pin_out ? trunc : h->h_trunc;
-  for (int c = 0; c < chunks; ++c) {
-    const int i0 = c * per;
-    const int cnt = (i0 + per <= h->n) ? per : h->n - i0;
-    cudaStream_t s = h->host_streams[c % kHostStreams];
-    if (!pin_in) std::memcpy(h->h_act + size_t(i0) * act_dim, action + size_t(i0) * act_dim, size_t(cnt) * act_dim * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(h->d_act + size_t(i0) * act_dim, src_act + size_t(i0) * act_dim,
-                             size_t(cnt) * act_dim * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = step_range(h, mode, i0, cnt, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, s);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(dst_obs + size_t(i0) * obs_dim, h->d_obs + size_t(i0) * obs_dim,
-                             size_t(cnt) * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reward) CUDA_TRY(cudaMemcpyAsync(dst_rew + i0, h->d_rew + i0, size_t(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(dst_term + i0, h->d_term + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
-    if (trunc) CUDA_TRY(cudaMemcpyAsync(dst_trunc + i0, h->d_trunc + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
-  }
-  for (int c = 0; c < chunks; ++c) {
-    const int i0 = c * per;
-    const int cnt = (i0 + per <= h->n) ? per : h->n - i0;
-    if (c < kHostStreams || !pin_out) CUDA_TRY(cudaStreamSynchronize(h->host_streams[c % kHostStreams]));
-    if (!pin_out) {
-      // stream order guarantees chunk c is complete once its stream drained up to here only if no later
-      // chunk shares the stream; with later chunks queued behind it the sync above waits for those as well
-      std::memcpy(obs + size_t(i0) * obs_dim, h->h_obs + size_t(i0) * obs_dim, size_t(cnt) * obs_dim * sizeof(float));
-      if (reward) std::memcpy(reward + i0, h->h_rew + i0, size_t(cnt) * sizeof(float));
-      std::memcpy(term + i0, h->h_term + i0, size_t(cnt));
-      if (trunc) std::memcpy(trunc + i0, h->h_trunc + i0, size_t(cnt));
+  uint8_t* dst_trunc = trunc ? (pin_out ? trunc : h->h_trunc) : nullptr;
+
+  int pipeline = h->zero_copy;
+  if (pipeline == 2 && mode != MODE_SERVOS) pipeline = 1;  // tiny rows: nothing to stream
+  if (compact && pipeline == 0) pipeline = 2;
+  const int want = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
+  int per = (h->n + want - 1) / want;
+  per = (per + 255) / 256 * 256;
+  const int chunks = (h->n + per - 1) / per;
+  auto chunk_count = [&](int c) { return (c * per + per <= h->n) ? per : h->n - c * per; };
+
+  if (pipeline == 2) {
+    cudaStream_t sc = h->host_streams[0];
+    for (int c = 0; c < chunks; ++c) {
+      const size_t i0 = size_t(c) * per;
+      CUDA_TRY(cudaMemcpyAsync(h->d_act + i0 * act_dim, src_act + i0 * act_dim, size_t(chunk_count(c)) * act_dim * sizeof(float),
+                               cudaMemcpyHostToDevice, sc));
+      CUDA_TRY(cudaEventRecord(h->host_events[c], sc));
     }
+    for (int c = 0; c < chunks; ++c) {
+      cudaStream_t sk = h->host_streams[1 + (c % h->host_kernel_streams)];
+      CUDA_TRY(cudaStreamWaitEvent(sk, h->host_events[c], 0));
+      rc = step_range(h, mode, c * per, chunk_count(c), h->d_act, mapped(dst_obs), mapped(dst_rew), mapped(dst_term),
+                      mapped(dst_trunc), sk, /*tile=*/true, /*persistent=*/false, compact);
+      if (rc) return rc;
+    }
+    for (int k = 0; k < h->host_kernel_streams; ++k) CUDA_TRY(cudaStreamSynchronize(h->host_streams[1 + k]));
+  } else if (pipeline == 1) {
+    cudaStream_t s = h->host_streams[0];
+    rc = step_range(h, mode, 0, h->n, mapped(src_act), mapped(dst_obs), mapped(dst_rew), mapped(dst_term),
+                    mapped(dst_trunc), s, /*tile=*/true, /*persistent=*/true, compact);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
+  } else {
+    for (int c = 0; c < chunks; ++c) {
+      const int i0 = c * per;
+      const int cnt = chunk_count(c);
+      cudaStream_t s = h->host_streams[c % kHostStreams];
+      CUDA_TRY(cudaMemcpyAsync(h->d_act + size_t(i0) * act_dim, src_act + size_t(i0) * act_dim,
+                               size_t(cnt) * act_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+      rc = step_range(h, mode, i0, cnt, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, s);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(dst_obs + size_t(i0) * obs_dim, h->d_obs + size_t(i0) * obs_dim,
+                               size_t(cnt) * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+      if (dst_rew) CUDA_TRY(cudaMemcpyAsync(dst_rew + i0, h->d_rew + i0, size_t(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaMemcpyAsync(dst_term + i0, h->d_term + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
+      if (dst_trunc) CUDA_TRY(cudaMemcpyAsync(dst_trunc + i0, h->d_trunc + i0, size_t(cnt), cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < kHostStreams; ++k) CUDA_TRY(cudaStreamSynchronize(h->host_streams[k]));
+  }
+  if (!pin_out) {
+    std::memcpy(obs, h->h_obs, n * obs_dim * sizeof(float));
+    if (reward) std::memcpy(reward, h->h_rew, n * sizeof(float));
+    std::memcpy(term, h->h_term, n);
+    if (trunc) std::memcpy(trunc, h->h_trunc, n);
   }
   return UPKIE_B200_OK;
 }
@@ -385,7 +395,19 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
     const int v = std::atoi(b);
     if (v >= 32 && v <= UPKIE_MAX_THREADS && v % 32 == 0) h->block = v;
   }
-  if (const char* b = std::getenv("UPKIE_B200_ZERO_COPY")) h->zero_copy = std::atoi(b) != 0;  // developer knob
+  if (const char* b = std::getenv("UPKIE_B200_HOST_BLOCK")) {  // developer knob
+    const int v = std::atoi(b);
+    if (v >= 32 && v <= 160 && v % 32 == 0) h->host_block = v;  // 2 x 4608 B of tile per warp: <= 48 KB
+  }
+  if (const char* b = std::getenv("UPKIE_B200_HOST_BLOCKS_PER_SM")) {  // developer knob
+    const int v = std::atoi(b);
+    if (v >= 1 && v <= 8) h->host_blocks_per_sm = v;
+  }
+  if (const char* b = std::getenv("UPKIE_B200_ZERO_COPY")) h->zero_copy = std::atoi(b);  // developer knob: 0, 1, 2
+  if (const char* b = std::getenv("UPKIE_B200_HOST_KERNEL_STREAMS")) {  // developer knob
+    const int v = std::atoi(b);
+    if (v >= 1 && v <= 2) h->host_kernel_streams = v;
+  }
   if (const char* b = std::getenv("UPKIE_B200_HOST_CHUNKS")) {  // developer knob
     const int v = std::atoi(b);
     if (v >= 1 && v <= 64) h->host_chunks = v;
@@ -425,6 +447,8 @@ void upkie_b200_destroy(void* handle) {
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
   for (int k = 0; k < kHostStreams; ++k)
     if (h->host_streams[k]) cudaStreamDestroy(h->host_streams[k]);
+  for (int k = 0; k < 64; ++k)
+    if (h->host_events[k]) cudaEventDestroy(h->host_events[k]);
   h->magic = 0;
   delete h;
 }
@@ -503,6 +527,11 @@ int upkie_b200_step_servos_host(void* handle, const float* action, float* obs, f
   Handle* h = as_handle(handle);
   if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
   return step_host(h, MODE_SERVOS, action, obs, reward, terminated, truncated);
+}
+int upkie_b200_step_servos_host_compact(void* handle, const float* action, float* obs, uint8_t* terminated) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "step_servos_host_compact: bad handle");
+  return step_host(h, MODE_SERVOS, action, obs, nullptr, terminated, nullptr, /*compact=*/true);
 }
 
 int upkie_b200_step_gyropod_host(void* handle, const float* action, int act_dim, float* obs, float* reward,

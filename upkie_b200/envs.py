@@ -370,6 +370,31 @@ class B200VectorEnv(VectorEnv):
                 self._obs_dict_cache = cache
         return cache[1]
 
+    def _servo_obs_dict(self, obs18: np.ndarray) -> dict:
+        """Batched observation dictionary over the persistent pinned ``[N, 6, 3]`` buffer the kernel writes
+        (position, velocity, torque): built once, updated in place by every step. Temperature and voltage
+        are the simulator's constants (``pybullet_backend.py:471-472``) and never cross PCIe."""
+        cache = getattr(self, "_obs18_cache", None)
+        if cache is None or cache[0] is not obs18:
+            n = self.num_envs
+            temperature = np.full((n, 1), 42.0, dtype=np.float32)
+            voltage = np.full((n, 1), 18.0, dtype=np.float32)
+            temperature.flags.writeable = False
+            voltage.flags.writeable = False
+            d = {
+                name: {
+                    "position": obs18[:, j, 0:1],
+                    "velocity": obs18[:, j, 1:2],
+                    "torque": obs18[:, j, 2:3],
+                    "temperature": temperature,
+                    "voltage": voltage,
+                }
+                for j, name in enumerate(_abi.JOINT_NAMES)
+            }
+            cache = (obs18, d)
+            self._obs18_cache = cache
+        return cache[1]
+
     def reset(self, *, seed: Optional[Union[int, list]] = None, options: Optional[dict] = None):
         """Reset all envs (or ``options["reset_mask"]``) and return the initial
         observations. Env ``i`` samples its initial state from
@@ -427,7 +452,10 @@ class B200VectorEnv(VectorEnv):
                 if isinstance(action, dict)
                 else np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, 6, 6))
             )
-            obs, rew, term, trunc = self.sim.step_servos_host(a)
+            obs18, term = self.sim.step_servos_host_compact(a)
+            hb = self.sim._host_buffers()
+            info = {"spine_observation": SpineObservations(self.sim)}
+            return self._servo_obs_dict(obs18), hb["rew"], term.view(np.bool_), hb["trunc"].view(np.bool_), info
         else:
             d = 2 if self.env_type == "gyropod" else 1
             a = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, d))

@@ -184,6 +184,7 @@ class UpkieSim:
                 "act2": pinned((self.n, 2), torch.float32),
                 "act1": pinned((self.n, 1), torch.float32),
                 "obs30": pinned((self.n, 6, 5), torch.float32),
+                "obs18": pinned((self.n, 6, 3), torch.float32),
                 "obs6": pinned((self.n, 6), torch.float32),
                 "obs4": pinned((self.n, 4), torch.float32),
                 "rew": pinned((self.n,), torch.float32),
@@ -211,6 +212,20 @@ class UpkieSim:
         # reward and truncated are constants of the reference (upkie_env.py:197,230): not transported
         check(lib().upkie_b200_step_servos_host(self._h, a.ctypes.data, obs.ctypes.data, None, term.ctypes.data, None))
         return obs, rew, term, trunc
+
+    def step_servos_host_compact(self, action: np.ndarray):
+        """Like ``step_servos_host`` but only the changing part of the observation crosses PCIe:
+        returns ``obs[N, 6, 3]`` (position, velocity, torque per joint) and ``terminated``; temperature,
+        voltage, reward and truncated are constants of the reference the caller fills once."""
+        hb = self._host_buffers()
+        a = action
+        if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(action, dtype=np.float32)
+        if a.size != self.n * 36:
+            raise UpkieRuntimeError(f"action: expected {self.n * 36} float32 values, got {a.size}")
+        obs, term = hb["obs18"], hb["term"]
+        check(lib().upkie_b200_step_servos_host_compact(self._h, a.ctypes.data, obs.ctypes.data, term.ctypes.data))
+        return obs, term
 
     def step_gyropod_host(self, action: np.ndarray):
         hb = self._host_buffers()
