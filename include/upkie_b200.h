@@ -168,6 +168,10 @@ typedef struct UpkieSimConfig {
   double torque_control_noise[UPKIE_NJ];     /* JointProperties.torque_control_noise: std of the Gaussian noise added to
                                               * every commanded torque before the clip (pybullet_backend.py:545-550) */
   double torque_measurement_noise[UPKIE_NJ]; /* std of the noise on the observed torque (pybullet_backend.py:461-466) */
+  double imu_accelerometer_bias[3]; /* ImuUncertainty (upkie/cpp/interfaces/ImuUncertainty.h:29-69): bias and white */
+  double imu_accelerometer_noise;   /* noise added to the IMU-frame accelerations (filtered and raw) and angular    */
+  double imu_gyroscope_bias[3];     /* velocity of the spine observation (BulletInterface.cpp:252-258)             */
+  double imu_gyroscope_noise;
   uint64_t noise_seed;                       /* key of the counter-based generator (the reference draws from an unseeded
                                               * np.random.default_rng(), pybullet_backend.py:160) */
   /* restated Bullet multibody behaviour (third-party) */
@@ -330,6 +334,16 @@ int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream);
 int upkie_b200_get_state(void* handle, float* state /* [N][UPKIE_STATE_DIM] */, void* stream);
 int upkie_b200_set_state(void* handle, const float* state, void* stream);
 int upkie_b200_error_flags(void* handle, uint32_t* flags /* [N] */, void* stream);
+
+/* Replaces PyBulletBackend.set_external_forces (pybullet_backend.py:603-625):
+ * force[N][UPKIE_NB][3] (device pointer, newtons) acts at the centre of mass of
+ * body b of env i on every substep of every following step, until overwritten;
+ * NULL clears. Bit b of `local_mask`: the force on body b is expressed in the
+ * body frame (ExternalForce.local, upkie/utils/external_force.py:20-23) instead
+ * of the world frame. The substep of a reset runs without them (:227-228).
+ * Bodies are the lumps of UpkieModel (a force on a fixed-joint link acts at the
+ * centre of mass of its lump). */
+int upkie_b200_set_external_forces(void* handle, const float* force, uint32_t local_mask, void* stream);
 
 /* Number of step-kernel launches issued through this handle since create
  * (bench.py's `gpu_launches`). */

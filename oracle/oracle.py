@@ -56,6 +56,7 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
         L.oracle_set_randomization.argtypes = [C.c_void_p, _dp, _dp]
+        L.oracle_set_external_forces.argtypes = [C.c_void_p, _dp, C.c_uint32]
         L.oracle_reset.argtypes = [C.c_void_p, _u8p, _dp]
         L.oracle_step_servos.argtypes = [C.c_void_p, _dp, _dp, _dp, _u8p, _u8p]
         L.oracle_step_gyropod.argtypes = [
@@ -140,6 +141,12 @@ class OracleSim:
         lib().oracle_set_randomization(
             self._h, _d(f) if f is not None else None, _d(e) if e is not None else None
         )
+
+    def set_external_forces(self, force=None, local_mask=0):
+        """``force[n, 7, 3]`` newtons at the bodies' centres of mass (None clears); bit i of
+        ``local_mask``: the force on body i is expressed in the body frame."""
+        f = _f64(force, (self.n, 7, 3)) if force is not None else None
+        lib().oracle_set_external_forces(self._h, _d(f) if f is not None else None, int(local_mask))
 
     def reset(self, init_state, mask=None):
         init = _f64(init_state, (self.n, _abi.INIT_DIM))

@@ -101,6 +101,28 @@ void hostsim_sample_init(void* hv, int n, uint64_t seed, uint64_t env_offset, ui
   for (int i = 0; i < n; ++i) sample_init_state(h->P, seed, env_offset + i, episode, init + size_t(i) * UPKIE_INIT_DIM);
 }
 
+// one env tick with external forces ext[n][7][3] (same code path as k_step with forces set)
+void hostsim_step_servos_ext(void* hv, int n, float* state, const float* action, const float* ext, uint32_t local_mask,
+                             float* obs) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    float a[UPKIE_ACT_DIM];
+    std::memcpy(a, action + size_t(i) * UPKIE_ACT_DIM, sizeof(a));
+    clamp_servo_action(h->P, a);
+    const ExtForces X{ext + size_t(i) * 21, 1, local_mask};
+    for (int sub = 0; sub < h->P.nb_substeps; ++sub)
+      servo_substep(h->P, S, a, false, nullptr, h->P.friction, any_fn, NoSync(), nullptr, sub, &X);
+    observe_update(h->P, S);
+    for (int j = 0; j < 6; ++j) {
+      float* o = obs + size_t(i) * UPKIE_OBS_DIM + j * 5;
+      o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = S.torque[j]; o[3] = 42.0f; o[4] = 18.0f;
+    }
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
 void hostsim_gaussian8(uint64_t seed, uint64_t env, uint32_t tick, uint32_t slot, float* out) {
   const NoiseCtx nz{env, tick};
   gaussian8(seed, nz, slot, out);

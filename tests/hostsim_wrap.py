@@ -46,6 +46,7 @@ def lib():
         L.hostsim_spine_obs.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.hostsim_sample_init.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, fp]
         L.hostsim_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.hostsim_step_servos_ext.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_uint32, fp]
         L.hostsim_gaussian8.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, fp]
         L.hostsim_step_servos_noise.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_uint32, C.c_uint64, fp]
         for name in ("hostsim_mpc_step_f32", "hostsim_mpc_step_f64"):
@@ -102,6 +103,14 @@ class HostSim:
         lib().hostsim_step_servos(self._h, self.n, _f(self.state), _f(a), _f(obs), self._opt(self.eps),
                                   self._opt(self.mu), err.ctypes.data_as(C.POINTER(C.c_uint32)))
         return obs, err
+
+    def step_servos_ext(self, action, ext, local_mask=0):
+        """One tick under external forces ``ext[n, 7, 3]`` (newtons at the bodies' centres of mass)."""
+        a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.n, 36)
+        e = np.ascontiguousarray(ext, dtype=np.float32).reshape(self.n, 21)
+        obs = np.empty((self.n, 6, 5), dtype=np.float32)
+        lib().hostsim_step_servos_ext(self._h, self.n, _f(self.state), _f(a), _f(e), int(local_mask), _f(obs))
+        return obs
 
     def step_servos_noise(self, action, tick, env_offset=0):
         """One tick with the torque noise models, keyed like k_step<.., NOISE=1> at per-env tick ``tick``."""

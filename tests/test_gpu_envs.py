@@ -462,3 +462,77 @@ def test_torque_noise_models(model, torch):
     e2.reset(seed=1)
     o2 = e2.sim.step_servos(torch.from_numpy(act[:64]).cuda())[0]
     assert not torch.equal(o2[:, :, 2], e1.sim.step_servos(torch.from_numpy(act[:64]).cuda())[0][:, :, 2])
+
+
+def test_external_forces_and_imu_uncertainty(model, oracle_lib, torch):
+    """External forces through the C ABI against the oracle's native formulation (free flight), their
+    persistence / clearing, and ImuUncertainty on the spine observation."""
+    from upkie_b200.envs import B200VectorEnv
+    from upkie_b200.model import ExternalForce
+
+    n = 1024
+    cfg = _abi.default_sim_config()
+    rng = np.random.default_rng(31)
+    st = random_states(n, seed=32, z_range=(2.0, 3.0)).astype(np.float32)
+    ext = rng.uniform(-20.0, 20.0, (n, 7, 3)).astype(np.float32)
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, :, 0] = np.nan
+    act[:, :, 2] = rng.uniform(-0.5, 0.5, (n, 6)) * model.tau_max
+    act[:, :, 5] = 0.99 * np.asarray(model.tau_max, dtype=np.float32)
+    a = torch.from_numpy(act).cuda()
+    for mask in (0, 0b1001001):
+        sim = _sim(n, model, cfg)
+        osim = oracle_lib.OracleSim(model, cfg, n, threads=8)
+        sim.set_state(torch.from_numpy(st).cuda())
+        osim.set_state(st.astype(np.float64))
+        sim.set_external_forces(torch.from_numpy(ext).cuda(), mask)
+        osim.set_external_forces(ext.astype(np.float64), mask)
+        for _ in range(2):  # forces persist across steps
+            sim.step_servos(a)
+            osim.step_servos(act.astype(np.float64))
+        d = np.abs(sim.get_state().cpu().numpy()[:, :25].astype(np.float64) - osim.get_state()[:, :25])
+        assert d[:, :7].max() < 5e-6 and d[:, 13:19].max() < 5e-5
+        assert d[:, 7:13].max() < 1e-3 and d[:, 19:25].max() < 1e-2
+    # cleared forces: back to the plain kernel, bit-identical to a handle that never had any
+    s1, s2 = _sim(n, model, cfg), _sim(n, model, cfg)
+    for s in (s1, s2):
+        s.set_state(torch.from_numpy(st).cuda())
+    s1.set_external_forces(torch.from_numpy(ext).cuda(), 0)
+    s1.set_external_forces(None)
+    assert torch.equal(s1.step_servos(a)[0], s2.step_servos(a)[0])
+
+    # env-level API: a sideways push on the torso of every other env
+    env = B200VectorEnv(64, "servos", model=model)
+    env.reset(seed=3)
+    push = np.zeros((64, 3))
+    push[::2, 1] = 30.0
+    env.set_external_forces({"torso": ExternalForce(push)})
+    a64 = torch.from_numpy(act[:64]).cuda()
+    for _ in range(20):
+        env.sim.step_servos(a64)
+    vy = env.sim.get_state()[:, _abi.ST_LINVEL + 1].cpu().numpy()
+    assert (vy[::2] > 0.05).all() and (np.abs(vy[1::2]) < 1e-3).all()
+
+    # ImuUncertainty (ImuUncertainty.h:63-69): bias + white noise on the IMU part of the spine observation only
+    cfg2 = _abi.default_sim_config()
+    cfg2.imu_accelerometer_bias[0], cfg2.imu_accelerometer_noise = 0.3, 0.05
+    cfg2.imu_gyroscope_bias[2], cfg2.imu_gyroscope_noise = -0.1, 0.02
+    cfg2.noise_seed = 4
+    sa, sb = _sim(n, model, cfg2), _sim(n, model, cfg)
+    for s in (sa, sb):
+        s.set_state(torch.from_numpy(st).cuda())
+        s.step_servos(a)
+    pa, pb = sa.spine_obs().cpu().numpy(), sb.spine_obs().cpu().numpy()
+    assert np.array_equal(sa.get_state().cpu().numpy(), sb.get_state().cpu().numpy())  # the physics is untouched
+    other = np.ones(_abi.SPINE_DIM, dtype=bool)
+    other[_abi.SP_IMU_ANGVEL:_abi.SP_IMU_ANGVEL + 3] = False
+    other[_abi.SP_IMU_LINACC:_abi.SP_IMU_RAWACC + 3] = False
+    assert np.array_equal(pa[:, other], pb[:, other])
+    dacc = pa[:, _abi.SP_IMU_LINACC:_abi.SP_IMU_LINACC + 3] - pb[:, _abi.SP_IMU_LINACC:_abi.SP_IMU_LINACC + 3]
+    draw = pa[:, _abi.SP_IMU_RAWACC:_abi.SP_IMU_RAWACC + 3] - pb[:, _abi.SP_IMU_RAWACC:_abi.SP_IMU_RAWACC + 3]
+    dgyr = pa[:, _abi.SP_IMU_ANGVEL:_abi.SP_IMU_ANGVEL + 3] - pb[:, _abi.SP_IMU_ANGVEL:_abi.SP_IMU_ANGVEL + 3]
+    for d_, bias, sig in ((dacc, [0.3, 0, 0], 0.05), (draw, [0.3, 0, 0], 0.05), (dgyr, [0, 0, -0.1], 0.02)):
+        assert np.abs(d_.mean(axis=0) - bias).max() < 5 * sig / np.sqrt(n)
+        assert np.abs(d_.std(axis=0) / sig - 1).max() < 0.1
+    assert abs(np.corrcoef(dacc[:, 0], draw[:, 0])[0, 1]) < 0.12  # independent draws for the raw acceleration
+    assert np.array_equal(sa.spine_obs().cpu().numpy(), pa)  # same tick, same draw

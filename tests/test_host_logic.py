@@ -240,3 +240,26 @@ def test_model_struct_roundtrip_and_kernel_support(model):
     assert s.wheel_radius == 0.05 and s.left_wheeled == 1
     assert [s.joint_axis[j][1] for j in range(6)] == [1, 1, 1, -1, -1, -1]
     assert sum(s.mass) == pytest.approx(5.3382, abs=1e-9)
+
+
+def test_external_force_rows(model):
+    """Link names -> lumped bodies, frames -> mask bits, unknown links raise as in the reference
+    (pybullet_backend.py:615-619)."""
+    from upkie_b200.exceptions import UpkieRuntimeError
+    from upkie_b200.model import ExternalForce
+
+    rows, mask = model.external_force_rows(
+        {"torso": ExternalForce([1.0, 2.0, 3.0]), "imu": ExternalForce([1.0, 0.0, 0.0]),
+         "right_wheel_tire": ExternalForce([0.0, 0.0, -5.0], local=True)}, n=3)
+    assert rows.shape == (3, 7, 3) and mask == 1 << 6
+    assert np.allclose(rows[:, 0], [2.0, 2.0, 3.0]) and np.allclose(rows[:, 6], [0.0, 0.0, -5.0])
+    assert not rows[:, 1:6].any()
+    per_env = np.arange(9.0).reshape(3, 3)
+    rows, mask = model.external_force_rows({"base": ExternalForce(per_env)}, n=3)
+    assert mask == 0 and np.allclose(rows[:, 0], per_env)
+    with pytest.raises(UpkieRuntimeError):
+        model.external_force_rows({"no_such_link": ExternalForce([0, 0, 1])}, n=1)
+    with pytest.raises(UpkieRuntimeError):
+        model.external_force_rows({"torso": ExternalForce([0, 0, 1]), "imu": ExternalForce([0, 0, 1], local=True)}, n=1)
+    with pytest.raises(ValueError):
+        ExternalForce([1.0, 2.0])

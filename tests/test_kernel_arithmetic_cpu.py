@@ -442,3 +442,49 @@ def test_torque_noise_models(model):
     hs.step_servos_noise(act, tick=3)
     lim = 0.9 * np.asarray(model.tau_max, dtype=np.float32)
     assert (np.abs(hs.state[:, _abi.ST_TORQUE:_abi.ST_TORQUE + 6]) <= lim + 1e-6).all()
+
+
+@pytest.mark.parametrize("local_mask", [0, 0x7F, 0b0101010])
+def test_external_forces_match_oracle(model, oracle_lib, local_mask):
+    """set_external_forces (pybullet_backend.py:603-658): the kernel applies a force on body i as J_i^T w
+    (ancestor joint torques + base wrench); the oracle puts it into the ABA bias force of the body itself."""
+    n = 256
+    hs, osim, cfg = _pair(model, oracle_lib, n)
+    rng = np.random.default_rng(21)
+    st = random_states(n, seed=22, z_range=(2.0, 3.0)).astype(np.float32)  # free flight: no contact sensitivity
+    ext = rng.uniform(-20.0, 20.0, (n, 7, 3)).astype(np.float32)
+    ext[: n // 4, 1:] = 0.0  # base-only pushes
+    ext[n // 4: n // 2, 0] = 0.0
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, :, 0] = np.nan
+    act[:, :, 2] = rng.uniform(-0.5, 0.5, (n, 6)) * model.tau_max
+    act[:, :, 5] = 0.99 * np.asarray(model.tau_max, dtype=np.float32)
+    hs.set_state(st)
+    osim.set_state(st.astype(np.float64))
+    osim.set_external_forces(ext.astype(np.float64), local_mask)
+    hs.step_servos_ext(act, ext, local_mask)
+    osim.step_servos(act.astype(np.float64))
+    d = np.abs(hs.state[:, :25].astype(np.float64) - osim.get_state()[:, :25])
+    assert d[:, :7].max() < 2e-6 and d[:, 13:19].max() < 2e-5
+    assert d[:, 7:13].max() < 3e-4 and d[:, 19:25].max() < 4e-3
+    # and the forces do something: same tick without them differs
+    hs2 = HostSim(model, cfg, n)
+    hs2.set_state(st)
+    hs2.step_servos(act)
+    assert np.abs(hs2.state[:, 7:10] - hs.state[:, 7:10]).max() > 1e-3
+    # physics check of the oracle itself: from rest, one substep changes the total linear momentum by
+    # (sum of external forces + weight) * h, wherever the forces act
+    if local_mask == 0:
+        mass = float(np.sum(model.mass))
+        o2 = oracle_lib.OracleSim(model, cfg, 4, threads=1)
+        s4 = random_states(4, seed=5, z_range=(2.0, 3.0))
+        s4[:, 7:13] = 0.0
+        s4[:, 19:25] = 0.0
+        o2.set_state(s4)
+        f4 = rng.uniform(-20.0, 20.0, (4, 7, 3))
+        o2.set_external_forces(f4, 0)
+        o2.substep(np.zeros((4, 6)), 1e-5)
+        for i in range(4):
+            expect = (f4[i].sum(axis=0) + np.array([0.0, 0.0, -mass * cfg.gravity])) * 1e-5
+            # O(h^2) slack: the momentum is read after the position update
+            assert np.allclose(o2.energy(i)["linear_momentum"], expect, atol=1e-8, rtol=1e-4)

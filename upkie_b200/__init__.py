@@ -16,7 +16,7 @@ from .exceptions import (  # noqa: F401
     UpkieException,
     UpkieRuntimeError,
 )
-from .model import JointProperties, Model, default_model  # noqa: F401
+from .model import ExternalForce, JointProperties, Model, default_model  # noqa: F401
 from .robot_state import RobotState, RobotStateRandomization  # noqa: F401
 
 ENV_IDS = {

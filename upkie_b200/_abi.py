@@ -87,6 +87,10 @@ class UpkieSimConfig(C.Structure):
         ("joint_friction", C.c_double * NJ),
         ("torque_control_noise", C.c_double * NJ),
         ("torque_measurement_noise", C.c_double * NJ),
+        ("imu_accelerometer_bias", C.c_double * 3),
+        ("imu_accelerometer_noise", C.c_double),
+        ("imu_gyroscope_bias", C.c_double * 3),
+        ("imu_gyroscope_noise", C.c_double),
         ("noise_seed", C.c_uint64),
         ("linear_damping", C.c_double),
         ("angular_damping", C.c_double),
@@ -189,6 +193,11 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
         c.joint_friction[j] = 0.0
         c.torque_control_noise[j] = 0.0
         c.torque_measurement_noise[j] = 0.0
+    for k in range(3):
+        c.imu_accelerometer_bias[k] = 0.0
+        c.imu_gyroscope_bias[k] = 0.0
+    c.imu_accelerometer_noise = 0.0
+    c.imu_gyroscope_noise = 0.0
     c.noise_seed = 0
     c.linear_damping = 0.04
     c.angular_damping = 0.04

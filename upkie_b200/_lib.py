@@ -47,6 +47,7 @@ SYMBOLS = {
     "upkie_b200_get_state": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_set_state": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_error_flags": (C.c_int, [_vp, _vp, _vp]),
+    "upkie_b200_set_external_forces": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "upkie_b200_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "upkie_b200_mpc_create": (C.c_int, [C.POINTER(_abi.UpkieMpcConfig), C.c_int, C.c_int, C.POINTER(_vp)]),
     "upkie_b200_mpc_destroy": (None, [_vp]),

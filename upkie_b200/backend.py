@@ -77,6 +77,14 @@ class B200Backend(_Base):
         eps = np.random.default_rng().uniform(-inertia_variation, inertia_variation, size=(1, 6)).astype(np.float32)
         self._sim.set_randomization(inertia_eps=torch.from_numpy(eps).to(self._sim.device))
 
+    def set_external_forces(self, external_forces: dict) -> None:
+        """``PyBulletBackend.set_external_forces`` (``pybullet_backend.py:603-625``): forces persist, link
+        by link, until overwritten."""
+        self._external_forces = dict(getattr(self, "_external_forces", {}))
+        self._external_forces.update(external_forces)
+        rows, mask = self._sim.model.external_force_rows(self._external_forces, 1)
+        self._sim.set_external_forces(torch.from_numpy(rows).to(self._sim.device), mask)
+
     def reset(self, init_state: RobotState) -> dict:
         row = torch.from_numpy(init_state.to_row().astype(np.float32)).reshape(1, _abi.INIT_DIM).to(self._sim.device)
         self._sim.reset(init_state=row)

@@ -66,7 +66,7 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
 // One launch of the env-step kernel over the envs [i0, i0 + cnt) of a handle.
 struct StepArgs {
   const SimParams* P;
-  int mode, autoreset, noise;
+  int mode, autoreset, noise;  // noise: the "extras" instantiation (torque noise models, external forces)
   int i0, cnt, n_pad, block;
   int compact_obs;      // TILE=1, servos: observation rows [6][3] (position, velocity, torque) instead of [6][5]
   int grid;             // TILE=1: number of persistent blocks (0 = one block per tile)
@@ -83,6 +83,8 @@ struct StepArgs {
   uint32_t* episode;
   uint32_t* tick;
   uint64_t seed, env_offset;
+  const float* ext;     // external forces [21][n_pad] or null (noise != 0 when set)
+  uint32_t ext_local;
   cudaStream_t stream;
 };
 

@@ -24,6 +24,8 @@ inline void default_sim_config(UpkieSimConfig* c) {
     c->torque_control_noise[j] = 0.0;
     c->torque_measurement_noise[j] = 0.0;
   }
+  for (int k = 0; k < 3; ++k) c->imu_accelerometer_bias[k] = c->imu_gyroscope_bias[k] = 0.0;
+  c->imu_accelerometer_noise = c->imu_gyroscope_noise = 0.0;
   c->noise_seed = 0;
   c->linear_damping = 0.04;     // Bullet btMultiBody default
   c->angular_damping = 0.04;
@@ -107,6 +109,15 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   };
   P.wheel_symmetric = (wheel_sym(3) && wheel_sym(6)) ? 1 : 0;
   P.noise_seed = c.noise_seed;
+  P.any_imu_uncertainty = 0;
+  for (int k = 0; k < 3; ++k) {
+    P.imu_acc_bias[k] = float(c.imu_accelerometer_bias[k]);
+    P.imu_gyro_bias[k] = float(c.imu_gyroscope_bias[k]);
+    if (c.imu_accelerometer_bias[k] != 0.0 || c.imu_gyroscope_bias[k] != 0.0) P.any_imu_uncertainty = 1;
+  }
+  P.imu_acc_noise = float(c.imu_accelerometer_noise);
+  P.imu_gyro_noise = float(c.imu_gyroscope_noise);
+  if (c.imu_accelerometer_noise > 0.0 || c.imu_gyroscope_noise > 0.0) P.any_imu_uncertainty = 1;
   for (int k = 0; k < 3; ++k) {
     P.sgn2[k].x = P.sgn[k]; P.sgn2[k].y = P.sgn[k + 3];
     P.mass2[k].x = P.mass[k + 1]; P.mass2[k].y = P.mass[k + 4];

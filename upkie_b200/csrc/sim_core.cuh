@@ -77,6 +77,8 @@ struct SimParams {
   float joint_friction[6];
   float ctrl_noise[6], meas_noise[6];  // JointProperties noise standard deviations
   int any_ctrl_noise, any_meas_noise;
+  float imu_acc_bias[3], imu_gyro_bias[3], imu_acc_noise, imu_gyro_noise;  // ImuUncertainty.h:29-69
+  int any_imu_uncertainty;
   uint64_t noise_seed;
   float lin_damp, ang_damp, vmax;
   float cfm, erp;          // from contact stiffness/damping and h (Bullet formulas)
@@ -508,7 +510,7 @@ constexpr int kPhaseSyncs = 6;
 
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
-                              AnyFn warp_any, SyncFn phase_sync = SyncFn()) {
+                              AnyFn warp_any, SyncFn phase_sync = SyncFn(), const float* wext = nullptr) {
   float R[9];
   quat_to_rot(S.quat, R);
   float V0[6];
@@ -525,7 +527,7 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
   ldl6(IA0);
   float a0[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) a0[i] = -pA0[i];
+  for (int i = 0; i < 6; ++i) a0[i] = wext ? wext[i] - pA0[i] : -pA0[i];
   ldl6_solve(IA0, a0);
   float qdd[6];
   leg_pass3<0>(P, lcL, ccL, uuL, a0, qdd);
@@ -765,14 +767,82 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
 namespace upkie_b200 {
 
 // the substep the env-level functions below use
+// `wext`: external wrench on the base (moment about the base origin, force; base coordinates) or null
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu, AnyFn warp_any,
-                      SyncFn phase_sync = SyncFn()) {
+                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr) {
 #if UPKIE_PAIRED_LEGS
-  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync);
+  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext);
 #else
-  physics_substep(P, S, tau, eps, mu, warp_any, phase_sync);
+  physics_substep(P, S, tau, eps, mu, warp_any, phase_sync, wext);
 #endif
+}
+
+// External forces (PyBulletBackend.set_external_forces / __apply_external_forces,
+// pybullet_backend.py:603-658): one force per body acting at the body's centre of mass, expressed in the
+// world frame or (bit i of `local`) in the body frame, constant over the substeps of a tick. A wrench on
+// body i enters the equations of motion only through the generalized force J_i^T w, so it is applied as
+// joint torques on the ancestors of the body plus a wrench on the base, outside the ABA core.
+struct ExtForces {
+  const float* f;  // this env's forces, element (body b, axis k) at f[(3 * b + k) * stride]
+  size_t stride;
+  uint32_t local;
+};
+
+UPKIE_HD void external_generalized_forces(const SimParams& P, const RobotState& S, const ExtForces& X,
+                                          float tau_add[6], float wbase[6]) {
+  float R[9];
+  quat_to_rot(S.quat, R);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { tau_add[k] = 0.f; wbase[k] = 0.f; }
+  auto body_force = [&](int b, float out[3]) {
+    out[0] = X.f[(3 * b + 0) * X.stride];
+    out[1] = X.f[(3 * b + 1) * X.stride];
+    out[2] = X.f[(3 * b + 2) * X.stride];
+  };
+  auto add_base = [&](const float c[3], const float f[3]) {
+    wbase[0] += c[1] * f[2] - c[2] * f[1];
+    wbase[1] += c[2] * f[0] - c[0] * f[2];
+    wbase[2] += c[0] * f[1] - c[1] * f[0];
+    wbase[3] += f[0]; wbase[4] += f[1]; wbase[5] += f[2];
+  };
+  {
+    float F[3], fb[3];
+    body_force(0, F);
+    if (X.local & 1u) { fb[0] = F[0]; fb[1] = F[1]; fb[2] = F[2]; }
+    else rot_tmul(R, F, fb);
+    add_base(P.com[0], fb);
+  }
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    float th = 0.f, o[3][3], cs = 1.f, sn = 0.f;  // rotation of the parent body about +y, joint origins
+    float prev[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int j = 3 * side + k, b = j + 1;
+      // joint origin: parent origin + R_y(theta_parent) * joint offset
+      o[k][0] = prev[0] + cs * P.jo[j][0] + sn * P.jo[j][2];
+      o[k][1] = prev[1] + P.jo[j][1];
+      o[k][2] = prev[2] - sn * P.jo[j][0] + cs * P.jo[j][2];
+      th += P.sgn[j] * S.q[j];
+      sincosf(th - 6.28318530718f * rintf(th * 0.15915494309f), &sn, &cs);  // fast-math sincos: reduce to [-pi, pi]
+      prev[0] = o[k][0]; prev[1] = o[k][1]; prev[2] = o[k][2];
+      float F[3], fb[3], c[3];
+      body_force(b, F);
+      if ((X.local >> b) & 1u) {
+        fb[0] = cs * F[0] + sn * F[2]; fb[1] = F[1]; fb[2] = -sn * F[0] + cs * F[2];
+      } else {
+        rot_tmul(R, F, fb);
+      }
+      c[0] = o[k][0] + cs * P.com[b][0] + sn * P.com[b][2];
+      c[1] = o[k][1] + P.com[b][1];
+      c[2] = o[k][2] - sn * P.com[b][0] + cs * P.com[b][2];
+      add_base(c, fb);
+#pragma unroll
+      for (int m = 0; m <= k; ++m)  // torque of the force about every ancestor joint axis (+-y)
+        tau_add[3 * side + m] += P.sgn[3 * side + m] * ((c[2] - o[m][2]) * fb[0] - (c[0] - o[m][0]) * fb[2]);
+    }
+  }
 }
 
 // pybullet_backend.py:492-553 compute_joint_torque
@@ -931,7 +1001,7 @@ UPKIE_HD void gaussian8(uint64_t seed, const NoiseCtx& nz, uint32_t slot, float 
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPKIE_ACT_DIM], bool zero_torque,
                             const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync = SyncFn(),
-                            const NoiseCtx* nz = nullptr, int sub = 0) {
+                            const NoiseCtx* nz = nullptr, int sub = 0, const ExtForces* ext = nullptr) {
   float tau[6];
   float noise[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (P.any_ctrl_noise && nz) {
@@ -948,7 +1018,15 @@ UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPK
     tau[j] = zero_torque ? 0.f : t;
     if (!zero_torque) S.torque[j] = t;
   }
-  substep(P, S, tau, eps, mu, warp_any, phase_sync);
+  if (ext && !zero_torque) {  // the substep of a reset runs without external forces (pybullet_backend.py:227-228)
+    float tau_add[6], wbase[6];
+    external_generalized_forces(P, S, *ext, tau_add, wbase);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tau[j] += tau_add[j];
+    substep(P, S, tau, eps, mu, warp_any, phase_sync, wbase);
+  } else {
+    substep(P, S, tau, eps, mu, warp_any, phase_sync);
+  }
 }
 
 UPKIE_HD uint32_t state_sanity(const RobotState& S) {
@@ -1124,6 +1202,22 @@ UPKIE_HD void gaussian8(uint64_t seed, const NoiseCtx& nz, uint32_t slot, float 
       out[4 * b + 2 * p] = rad * cs;
       out[4 * b + 2 * p + 1] = rad * sn;
     }
+  }
+}
+
+// ImuUncertainty::apply on the IMU part of a spine observation (BulletInterface.cpp:252-258): bias plus
+// white noise on the filtered acceleration and the angular velocity, and with independent draws on the
+// raw acceleration. One draw per env tick, repeatable (slots 254 / 253 of the tick's generator).
+UPKIE_HD void apply_imu_uncertainty(const SimParams& P, const NoiseCtx& nz, float* o) {
+  if (!P.any_imu_uncertainty) return;
+  float g1[8], g2[8];
+  gaussian8(P.noise_seed, nz, 254u, g1);
+  gaussian8(P.noise_seed, nz, 253u, g2);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o[UPKIE_SP_IMU_LINACC + k] += P.imu_acc_bias[k] + P.imu_acc_noise * g1[k];
+    o[UPKIE_SP_IMU_ANGVEL + k] += P.imu_gyro_bias[k] + P.imu_gyro_noise * g1[3 + k];
+    o[UPKIE_SP_IMU_RAWACC + k] += P.imu_acc_bias[k] + P.imu_acc_noise * g2[k];
   }
 }
 

@@ -320,7 +320,7 @@ UPKIE_HD constexpr int row_of(int side, int d) { return d == 0 ? side : 2 + 2 * 
 
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
-                                     AnyFn warp_any, SyncFn phase_sync = SyncFn()) {
+                                     AnyFn warp_any, SyncFn phase_sync = SyncFn(), const float* wext = nullptr) {
   float R[9];
   quat_to_rot(S.quat, R);
   float V0[6];
@@ -336,7 +336,7 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   ldl6(IA0);
   float a0[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) a0[i] = -pA0[i];
+  for (int i = 0; i < 6; ++i) a0[i] = wext ? wext[i] - pA0[i] : -pA0[i];
   ldl6_solve(IA0, a0);
   float qdd[6];
   legs_pass3(P, lc, cc, uu, a0, qdd);

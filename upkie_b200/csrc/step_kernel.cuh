@@ -21,7 +21,8 @@ __device__ __forceinline__ void step_env(
     float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ terminated,
     uint8_t* __restrict__ truncated, const float* __restrict__ eps_all, const float* __restrict__ mu_all,
     uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev, uint32_t* __restrict__ episode,
-    uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset, float4* tile4, bool full, bool compact) {
+    uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset, const float* __restrict__ ext,
+    uint32_t ext_local, float4* tile4, bool full, bool compact) {
   const bool live = tid < n;
   const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
   const int lane = threadIdx.x & 31;
@@ -78,6 +79,8 @@ __device__ __forceinline__ void step_env(
     nz.tick = tick[i] + 1u;
     if (live) tick[i] = nz.tick;
   }
+  // external forces ride on the NOISE ("extras") instantiations so the plain kernels stay untouched
+  const ExtForces xf{ext ? ext + i : nullptr, size_t(n_pad), ext_local};
   int nsub = P.nb_substeps;
   if (resetting) {
     const uint32_t ep = episode[i] + 1u;
@@ -95,7 +98,8 @@ __device__ __forceinline__ void step_env(
     __syncthreads();  // once per substep: all threads are converged here
 #endif
     if (sub < nsub) {
-      servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub);
+      servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
+                    (NOISE && ext) ? &xf : nullptr);
     } else {
 #pragma unroll
       for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
@@ -240,12 +244,12 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
        uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
        const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
        uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset,
-       int coalesce) {
+       const float* __restrict__ ext, uint32_t ext_local, int coalesce) {
   // this launch covers the envs [i0, n)
   if (!TILE) {
     step_env<MODE, AUTORESET, NOISE, 0>(P, i0 + blockIdx.x * blockDim.x + threadIdx.x, n, n_pad, state, action, obs,
                                         reward, terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick,
-                                        seed, env_offset, nullptr, false, false);
+                                        seed, env_offset, ext, ext_local, nullptr, false, false);
     return;
   }
   extern __shared__ float4 s_tile[];
@@ -277,7 +281,7 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
     __syncwarp();
     step_env<MODE, AUTORESET, NOISE, 1>(P, i0 + t * blockDim.x + threadIdx.x, n, n_pad, state, action, obs, reward,
                                         terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick, seed,
-                                        env_offset, buf[it & 1], warp_full(t), (coalesce & 2) != 0);
+                                        env_offset, ext, ext_local, buf[it & 1], warp_full(t), (coalesce & 2) != 0);
     __syncwarp();  // the tile is free again before the next prefetch lands in it
   }
 }
@@ -295,7 +299,7 @@ cudaError_t launch_step_mode(const StepArgs& a) {
 #define LAUNCH_N(AR, NZ)                                                                                         \
   k_step<MODE, AR, NZ, TILE><<<grid, a.block, smem, a.stream>>>(                                                 \
       *a.P, a.i0, a.i0 + a.cnt, a.n_pad, a.state, a.action, a.obs, a.reward, a.terminated, a.truncated, a.eps,   \
-      a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, coalesce)
+      a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, a.ext, a.ext_local, coalesce)
 #define LAUNCH(AR)                \
   do {                            \
     if (a.noise) LAUNCH_N(AR, 1); \

@@ -56,6 +56,8 @@ struct Handle {
   uint8_t* done_prev = nullptr;  // [n]
   uint32_t* episode = nullptr;   // [n]
   uint32_t* tick = nullptr;      // [n] env ticks since create: counter of the noise generator
+  float* ext = nullptr;          // [7 * 3][n_pad] external forces, null = none
+  uint32_t ext_local = 0;
   int autoreset = AUTORESET_DISABLED;
   uint64_t seed = 0, env_offset = 0;
   int block = UPKIE_DEFAULT_BLOCK;
@@ -127,6 +129,7 @@ __global__ void k_spine_obs(const __grid_constant__ SimParams P, int n, int n_pa
   const NoiseCtx nz{env_offset + uint64_t(i), tick[i]};  // same draw as the step that produced this state
   measured_torques(P, S, &nz, tq);
   spine_observation(P, S, o, tq);
+  apply_imu_uncertainty(P, nz, o);
 #pragma unroll
   for (int k = 0; k < UPKIE_SPINE_DIM; ++k) out[size_t(i) * UPKIE_SPINE_DIM + k] = o[k];
 }
@@ -169,6 +172,11 @@ __global__ void k_set_state(int n, int n_pad, float* __restrict__ state, const f
   if (i >= n) return;
   for (int k = 0; k < UPKIE_STATE_DIM; ++k) state[size_t(k) * n_pad + i] = in[size_t(i) * UPKIE_STATE_DIM + k];
 }
+__global__ void k_set_ext(int n, int n_pad, float* __restrict__ ext, const float* __restrict__ in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < 3 * UPKIE_NB; ++k) ext[size_t(k) * n_pad + i] = in[size_t(i) * 3 * UPKIE_NB + k];
+}
 __global__ void k_init_state(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict__ state) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
@@ -202,7 +210,9 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
   a.P = &h->P;
   a.mode = mode;
   a.autoreset = h->autoreset;
-  a.noise = (h->P.any_ctrl_noise || h->P.any_meas_noise) ? 1 : 0;
+  a.noise = (h->P.any_ctrl_noise || h->P.any_meas_noise || h->ext) ? 1 : 0;
+  a.ext = h->ext;
+  a.ext_local = h->ext_local;
   a.i0 = i0;
   a.cnt = cnt;
   a.n_pad = h->n_pad;
@@ -442,7 +452,7 @@ void upkie_b200_destroy(void* handle) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->state); cudaFree(h->eps); cudaFree(h->mu); cudaFree(h->err); cudaFree(h->done_prev); cudaFree(h->episode);
-  cudaFree(h->tick);
+  cudaFree(h->tick); cudaFree(h->ext);
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_term); cudaFreeHost(h->h_trunc);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
   for (int k = 0; k < kHostStreams; ++k)
@@ -575,6 +585,29 @@ int upkie_b200_set_state(void* handle, const float* state, void* stream) {
   if (!h || !state) return fail(UPKIE_B200_EINVAL, "set_state: invalid argument");
   CUDA_TRY(cudaSetDevice(h->device));
   k_set_state<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, h->n_pad, h->state, state);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_set_external_forces(void* handle, const float* force, uint32_t local_mask, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "set_external_forces: invalid handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  h->ext_local = local_mask;
+  if (!force) {
+    if (h->ext) {
+      CUDA_TRY(cudaStreamSynchronize(s));
+      cudaFree(h->ext);
+      h->ext = nullptr;
+    }
+    return UPKIE_B200_OK;
+  }
+  if (!h->ext) {
+    CUDA_TRY(cudaMalloc(&h->ext, size_t(3 * UPKIE_NB) * h->n_pad * sizeof(float)));
+    CUDA_TRY(cudaMemsetAsync(h->ext, 0, size_t(3 * UPKIE_NB) * h->n_pad * sizeof(float), s));
+  }
+  k_set_ext<<<(h->n + 127) / 128, 128, 0, s>>>(h->n, h->n_pad, h->ext, force);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }

@@ -370,6 +370,15 @@ class B200VectorEnv(VectorEnv):
                 self._obs_dict_cache = cache
         return cache[1]
 
+    def set_external_forces(self, external_forces: Optional[dict]) -> None:
+        """Batched ``PyBulletBackend.set_external_forces``: ``{link name: ExternalForce}`` whose ``force`` is
+        ``[3]`` (all envs) or ``[N, 3]``; ``None`` or ``{}`` clears."""
+        if not external_forces:
+            self.sim.set_external_forces(None)
+            return
+        rows, mask = self.model.external_force_rows(external_forces, self.num_envs)
+        self.sim.set_external_forces(torch.from_numpy(rows).to(self.sim.device), mask)
+
     def _servo_obs_dict(self, obs18: np.ndarray) -> dict:
         """Batched observation dictionary over the persistent pinned ``[N, 6, 3]`` buffer the kernel writes
         (position, velocity, torque): built once, updated in place by every step. Temperature and voltage

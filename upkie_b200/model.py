@@ -37,6 +37,28 @@ from . import _abi
 JOINT_NAMES = _abi.JOINT_NAMES
 
 
+_STANDIN_LINK_BODY = {
+    "base": 0, "torso": 0, "imu": 0,
+    "left_upper_leg": 1, "left_lower_leg": 2, "left_wheel_hub": 3, "left_wheel_tire": 3,
+    "right_upper_leg": 4, "right_lower_leg": 5, "right_wheel_hub": 6, "right_wheel_tire": 6,
+}
+
+
+class ExternalForce:
+    """External force applied to a robot link (``upkie/utils/external_force.py:9-43``): a force vector in
+    newtons, in the world frame or (``local=True``) in the link frame."""
+
+    def __init__(self, force, local: bool = False):
+        force = np.array(force, dtype=np.float64)
+        if force.shape != (3,) and not (force.ndim == 2 and force.shape[1] == 3):  # [N, 3]: one per env (vector envs)
+            raise ValueError(f"Force must be a 3D vector, got shape {force.shape}")
+        self.force = force
+        self.local = local
+
+    def __repr__(self) -> str:
+        return f"ExternalForce(force={self.force.tolist()}, local={self.local})"
+
+
 class JointProperties:
     """Per-joint simulation properties (``upkie/model/joint_properties.py:4-40``):
     kinetic friction torque and the standard deviations of the Gaussian white
@@ -100,6 +122,34 @@ class Model:
         default_factory=lambda: np.diag([1.0, -1.0, -1.0])
     )
     source: str = "stand-in"
+    # URDF link name -> index of the moving body (lump) it belongs to; what PyBulletBackend keeps as
+    # ``__link_index`` (pybullet_backend.py:125-147), after fixed-joint lumping
+    link_body: dict = field(default_factory=lambda: dict(_STANDIN_LINK_BODY))
+    # link frame -> body (lump) frame rotation at the zero configuration, identity when absent
+    link_rotation: dict = field(default_factory=dict)
+
+    def external_force_rows(self, external_forces: dict, n: int = 1):
+        """``{link name: ExternalForce}`` (``PyBulletBackend.set_external_forces``, ``pybullet_backend.py:603-625``)
+        -> ``(force[n, 7, 3] float32, local_mask)`` for ``UpkieSim.set_external_forces``. ``force`` vectors may
+        be ``[3]`` (same for every env) or ``[n, 3]``."""
+        from .exceptions import UpkieRuntimeError
+
+        rows = np.zeros((n, 7, 3), dtype=np.float32)
+        frame = {}
+        for name, ef in external_forces.items():
+            b = self.link_body.get(name)
+            if b is None:
+                raise UpkieRuntimeError(f"Robot does not have a link named '{name}'")
+            f = np.asarray(ef.force, dtype=np.float64)
+            f = np.broadcast_to(f, (n, 3))
+            local = bool(ef.local)
+            if frame.setdefault(b, local) != local:
+                raise UpkieRuntimeError(f"links lumped into body {b} carry forces in different frames")
+            if local and name in self.link_rotation:
+                f = f @ np.asarray(self.link_rotation[name], dtype=np.float64).T
+            rows[:, b] += f.astype(np.float32)
+        mask = sum(1 << b for b, loc in frame.items() if loc)
+        return rows, mask
 
     # ---- upkie.model.Model API ------------------------------------------
     @property

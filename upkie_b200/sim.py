@@ -102,6 +102,15 @@ class UpkieSim:
         check(lib().upkie_b200_set_randomization(self._h, _ptr(friction), _ptr(inertia_eps), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
 
+    def set_external_forces(self, force: Optional[torch.Tensor] = None, local_mask: int = 0) -> None:
+        """``force[N, 7, 3]`` newtons at the centres of mass of the 7 bodies, applied on every substep of
+        the following steps until overwritten; ``None`` clears. Bit ``b`` of ``local_mask``: the force on
+        body ``b`` is expressed in the body frame (``pybullet_backend.py:603-658``)."""
+        if force is not None:
+            self._check_tensor(force, (self.n, _abi.NB, 3), name="force")
+        check(lib().upkie_b200_set_external_forces(self._h, _ptr(force), int(local_mask), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
     def reset(
         self,
         mask: Optional[torch.Tensor] = None,

@@ -178,6 +178,8 @@ def load_urdf_model(urdf_path: str):
         imu_position=p_imu.copy(),
         rotation_base_to_imu=R_base_from_imu.T.copy(),
         source=urdf_path,
+        link_body=dict(body_of),
+        link_rotation={name: T[name][0].copy() for name in body_of},
     )
 
 
