@@ -242,6 +242,24 @@ typedef struct UpkieObserverConfig {
   double rotation_base_to_imu[9];     /* base_orientation.rotation_base_to_imu, row-major */
 } UpkieObserverConfig;
 
+/* WheelBalancer::Parameters (upkie/cpp/controllers/WheelBalancer.h:48-91) */
+typedef struct UpkieWheelBalancerConfig {
+  double contact_radius;       /* 0.1524 */
+  double dt;                   /* 1 / spine_frequency (spines/common/controllers.h:34) */
+  double fall_pitch;           /* 1.0 */
+  double max_ground_velocity;  /* 2.0 */
+  double pitch_damping;        /* 1.8 */
+  double pitch_stiffness;      /* 20.0 */
+  double position_damping;     /* 0.7 */
+  double position_stiffness;   /* 1.6 */
+  double stiff_yaw_velocity;   /* 0.1 */
+  double wheel_radius;         /* 0.06 (spines/common/controllers.h:35) */
+} UpkieWheelBalancerConfig;
+
+/* where a controller reads pitch / floor contact / wheel-odometry position */
+#define UPKIE_OBS_LAYOUT_SPINE 0     /* spine_obs rows [N][UPKIE_SPINE_DIM] */
+#define UPKIE_OBS_LAYOUT_OBSERVERS 1 /* observers_out rows [N][UPKIE_OBSV_DIM] */
+
 /* ---- library ------------------------------------------------------------ */
 
 int upkie_b200_abi_version(void);
@@ -375,6 +393,24 @@ int upkie_b200_observers_create(const UpkieObserverConfig* config, int n_robots,
 void upkie_b200_observers_destroy(void* observers);
 int upkie_b200_observers_reset(void* observers, const uint8_t* mask, void* stream);
 int upkie_b200_observers_step(void* observers, const float* spine_obs, float* out, void* stream);
+
+/* ---- controller pipeline handle -------------------------------------------
+ * Replaces the spine's "wheel_balancer" controller pipeline
+ * (spines/common/controllers.h:24-44): WheelStopper::write (WheelStopper.cpp:15-22)
+ * then WheelBalancer::read / write (WheelBalancer.cpp:35-110) for N robots, one
+ * call = one controller cycle of period config.dt. `obs` rows in `obs_layout`
+ * supply base_orientation.pitch, floor_contact.contact and
+ * wheel_odometry.position; target[N][2] = (target_ground_velocity,
+ * target_yaw_velocity) of the "bullet" action key, NULL = zeros; action[N][6][6]
+ * is updated in place: wheel entries overwritten, leg kp/kd scales set. */
+int upkie_b200_default_wheel_balancer_config(UpkieWheelBalancerConfig* config);
+int upkie_b200_wheel_balancer_create(const UpkieWheelBalancerConfig* config, int n_robots, int device, void** balancer);
+void upkie_b200_wheel_balancer_destroy(void* balancer);
+int upkie_b200_wheel_balancer_reset(void* balancer, const uint8_t* mask, void* stream);
+int upkie_b200_wheel_balancer_step(void* balancer, const float* obs, int obs_layout, const float* target,
+                                   float* action, void* stream);
+/* controller state [N][4]: ground_velocity, integral_velocity, target_ground_position, target_yaw_velocity */
+int upkie_b200_wheel_balancer_state(void* balancer, float* state, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,9 +5,11 @@
 // formulation can be checked against the oracle on machines without a GPU
 // (`pytest -m "not gpu"`). Never loaded by the product: upkie_b200/_lib.py
 // only opens libupkie_b200.so, which has no CPU path.
+#include <cmath>
 #include <cstring>
 #include <string>
 
+#include "../../upkie_b200/csrc/controllers_core.cuh"
 #include "../../upkie_b200/csrc/params.h"
 
 using namespace upkie_b200;
@@ -120,6 +122,23 @@ void hostsim_step_servos_ext(void* hv, int n, float* state, const float* action,
       o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = S.torque[j]; o[3] = 42.0f; o[4] = 18.0f;
     }
     state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
+// fp32 controller arithmetic of the kernel, state[n][4] in/out, obs[n][3] = pitch, contact, odometry position
+void hostsim_wheel_balancer_step(const UpkieWheelBalancerConfig* c, int n, float* state, const float* obs,
+                                 const float* target, float* action) {
+  const WheelBalancerParams<float> P{float(c->contact_radius), float(c->dt), float(c->fall_pitch),
+                                     float(c->max_ground_velocity), float(c->pitch_damping), float(c->pitch_stiffness),
+                                     float(c->position_damping), float(c->position_stiffness),
+                                     float(c->stiff_yaw_velocity), float(c->wheel_radius)};
+  for (int i = 0; i < n; ++i) {
+    WheelBalancerState<float> s{state[4 * i], state[4 * i + 1], state[4 * i + 2], state[4 * i + 3]};
+    wheel_balancer_read(P, s, obs[3 * i], obs[3 * i + 2], obs[3 * i + 1] != 0.f, target ? target[2 * i] : 0.f,
+                        target ? target[2 * i + 1] : 0.f);
+    wheel_balancer_write(P, s, action + size_t(i) * UPKIE_ACT_DIM, std::nanf(""));
+    state[4 * i] = s.ground_velocity; state[4 * i + 1] = s.integral_velocity;
+    state[4 * i + 2] = s.target_ground_position; state[4 * i + 3] = s.target_yaw_velocity;
   }
 }
 

@@ -25,7 +25,7 @@ u8p = C.POINTER(C.c_uint8)
 def build():
     src = os.path.join(_HERE, "hostsim.cpp")
     csrc = os.path.join(os.path.dirname(_HERE), "..", "upkie_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("sim_core.cuh", "params.h", "mpc_core.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("sim_core.cuh", "sim_pair.cuh", "params.h", "mpc_core.cuh", "controllers_core.cuh", "observers_core.cuh")]
     if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", _LIB, src])
     return _LIB
@@ -47,6 +47,7 @@ def lib():
         L.hostsim_sample_init.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, fp]
         L.hostsim_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
         L.hostsim_step_servos_ext.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_uint32, fp]
+        L.hostsim_wheel_balancer_step.argtypes = [C.POINTER(_abi.UpkieWheelBalancerConfig), C.c_int, fp, fp, fp, fp]
         L.hostsim_gaussian8.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, fp]
         L.hostsim_step_servos_noise.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_uint32, C.c_uint64, fp]
         for name in ("hostsim_mpc_step_f32", "hostsim_mpc_step_f64"):
@@ -145,6 +146,14 @@ def philox(counter_lo, counter_hi, key):
     out = (C.c_uint32 * 4)()
     lib().hostsim_philox(counter_lo, counter_hi, key, out)
     return list(out)
+
+
+def wheel_balancer_step(config, state, obs3, target, action):
+    """fp32 kernel arithmetic of the wheel_balancer pipeline; ``state[n, 4]`` and ``action[n, 6, 6]`` in place."""
+    n = state.shape[0]
+    o = np.ascontiguousarray(obs3, dtype=np.float32)
+    t = None if target is None else np.ascontiguousarray(target, dtype=np.float32)
+    lib().hostsim_wheel_balancer_step(C.byref(config), n, _f(state), _f(o), _f(t) if t is not None else None, _f(action))
 
 
 def gaussian8(seed, env, tick, slot):

@@ -501,17 +501,26 @@ def test_external_forces_and_imu_uncertainty(model, oracle_lib, torch):
     s1.set_external_forces(None)
     assert torch.equal(s1.step_servos(a)[0], s2.step_servos(a)[0])
 
-    # env-level API: a sideways push on the torso of every other env
+    # env-level API: a sideways push on the torso of every other env, robots in free flight at rest
     env = B200VectorEnv(64, "servos", model=model)
     env.reset(seed=3)
+    s0 = env.sim.get_state().clone()
+    s0[:, _abi.ST_POS + 2] = 3.0
+    s0[:, _abi.ST_LINVEL:_abi.ST_LINVEL + 6] = 0.0
+    s0[:, _abi.ST_QD:_abi.ST_QD + 6] = 0.0
+    env.sim.set_state(s0)
     push = np.zeros((64, 3))
     push[::2, 1] = 30.0
     env.set_external_forces({"torso": ExternalForce(push)})
-    a64 = torch.from_numpy(act[:64]).cuda()
+    zero = torch.zeros((64, 6, 6), device="cuda")
+    zero[:, :, 0] = float("nan")
     for _ in range(20):
-        env.sim.step_servos(a64)
+        env.sim.step_servos(zero)
     vy = env.sim.get_state()[:, _abi.ST_LINVEL + 1].cpu().numpy()
-    assert (vy[::2] > 0.05).all() and (np.abs(vy[1::2]) < 1e-3).all()
+    com_speed = 30.0 * 0.1 / float(np.sum(model.mass))  # F t / m at the robot's centre of mass; the base origin
+    # also picks up the roll the off-centre push induces
+    assert (vy[::2] > 0.5 * com_speed).all() and (vy[::2] < 3.0 * com_speed).all() and (np.abs(vy[1::2]) < 1e-4).all()
+    env.set_external_forces(None)
 
     # ImuUncertainty (ImuUncertainty.h:63-69): bias + white noise on the IMU part of the spine observation only
     cfg2 = _abi.default_sim_config()

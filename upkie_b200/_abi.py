@@ -151,6 +151,39 @@ class UpkieObserverConfig(C.Structure):
     ]
 
 
+class UpkieWheelBalancerConfig(C.Structure):
+    _fields_ = [
+        ("contact_radius", C.c_double),
+        ("dt", C.c_double),
+        ("fall_pitch", C.c_double),
+        ("max_ground_velocity", C.c_double),
+        ("pitch_damping", C.c_double),
+        ("pitch_stiffness", C.c_double),
+        ("position_damping", C.c_double),
+        ("position_stiffness", C.c_double),
+        ("stiff_yaw_velocity", C.c_double),
+        ("wheel_radius", C.c_double),
+    ]
+
+
+def default_wheel_balancer_config(spine_frequency: float = 1000.0) -> UpkieWheelBalancerConfig:
+    """``WheelBalancer::Parameters`` defaults (``upkie/cpp/controllers/WheelBalancer.h:60-90``) with the spine's
+    overrides ``dt = 1 / spine_frequency``, ``wheel_radius = 0.06`` (``spines/common/controllers.h:33-36``)."""
+    c = UpkieWheelBalancerConfig()
+    c.contact_radius = 0.1524
+    c.dt = 1.0 / spine_frequency
+    c.fall_pitch = 1.0
+    c.max_ground_velocity = 2.0
+    c.pitch_damping = 1.8
+    c.pitch_stiffness = 20.0
+    c.position_damping = 0.7
+    c.position_stiffness = 1.6
+    c.stiff_yaw_velocity = 0.1
+    c.wheel_radius = 0.06
+    return c
+
+
+OBS_LAYOUT_SPINE, OBS_LAYOUT_OBSERVERS = 0, 1
 OBSV_PITCH, OBSV_ANGVEL, OBSV_ROT, OBSV_CONTACT, OBSV_WHEEL_CONTACT = 0, 1, 4, 13, 14
 OBSV_LEG_TORQUE, OBSV_WHEEL_INERTIA, OBSV_ODOM_POS, OBSV_ODOM_VEL, OBSV_DIM = 16, 17, 19, 20, 21
 

@@ -48,6 +48,12 @@ SYMBOLS = {
     "upkie_b200_set_state": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_error_flags": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_set_external_forces": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "upkie_b200_default_wheel_balancer_config": (C.c_int, [_vp]),
+    "upkie_b200_wheel_balancer_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "upkie_b200_wheel_balancer_destroy": (None, [_vp]),
+    "upkie_b200_wheel_balancer_reset": (C.c_int, [_vp, _vp, _vp]),
+    "upkie_b200_wheel_balancer_step": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "upkie_b200_wheel_balancer_state": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "upkie_b200_mpc_create": (C.c_int, [C.POINTER(_abi.UpkieMpcConfig), C.c_int, C.c_int, C.POINTER(_vp)]),
     "upkie_b200_mpc_destroy": (None, [_vp]),

@@ -24,6 +24,7 @@
 #include <string>
 
 #include "mpc.cuh"
+#include "controllers.cuh"
 #include "observers.cuh"
 #include "kernel_common.cuh"
 #include "params.h"
@@ -662,6 +663,55 @@ int upkie_b200_default_observer_config(const UpkieModel* model, UpkieObserverCon
   default_observer_config(*model, config);
   return UPKIE_B200_OK;
 }
+int upkie_b200_default_wheel_balancer_config(UpkieWheelBalancerConfig* config) {
+  if (!config) return fail(UPKIE_B200_EINVAL, "default_wheel_balancer_config: null");
+  default_wheel_balancer_config(config);
+  return UPKIE_B200_OK;
+}
+int upkie_b200_wheel_balancer_create(const UpkieWheelBalancerConfig* config, int n_robots, int device, void** balancer) {
+  if (!config || !balancer) return fail(UPKIE_B200_EINVAL, "wheel_balancer_create: null argument");
+  std::string err;
+  int rc = wheel_balancer_create_impl(*config, n_robots, device, balancer, err);
+  return rc ? fail(rc, err) : UPKIE_B200_OK;
+}
+void upkie_b200_wheel_balancer_destroy(void* balancer) { wheel_balancer_destroy_impl(balancer); }
+int upkie_b200_wheel_balancer_reset(void* balancer, const uint8_t* mask, void* stream) {
+  WheelBalancerHandle* h = as_wheel_balancer(balancer);
+  if (!h) return fail(UPKIE_B200_EINVAL, "wheel_balancer_reset: invalid handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_wheel_balancer_reset<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, mask, h->state);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+int upkie_b200_wheel_balancer_step(void* balancer, const float* obs, int obs_layout, const float* target, float* action,
+                                   void* stream) {
+  WheelBalancerHandle* h = as_wheel_balancer(balancer);
+  if (!h || !obs || !action) return fail(UPKIE_B200_EINVAL, "wheel_balancer_step: invalid argument");
+  int stride, pitch, contact, odom;
+  if (obs_layout == UPKIE_OBS_LAYOUT_SPINE) {
+    stride = UPKIE_SPINE_DIM; pitch = UPKIE_SP_PITCH; contact = UPKIE_SP_CONTACT; odom = UPKIE_SP_ODOM_POS;
+  } else if (obs_layout == UPKIE_OBS_LAYOUT_OBSERVERS) {
+    stride = UPKIE_OBSV_DIM; pitch = UPKIE_OBSV_PITCH; contact = UPKIE_OBSV_CONTACT; odom = UPKIE_OBSV_ODOM_POS;
+  } else {
+    return fail(UPKIE_B200_EINVAL, "wheel_balancer_step: unknown observation layout");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_wheel_balancer_step<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->P, h->n, h->state, obs, stride, pitch, contact, odom, target, action);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+int upkie_b200_wheel_balancer_state(void* balancer, float* state, void* stream) {
+  WheelBalancerHandle* h = as_wheel_balancer(balancer);
+  if (!h || !state) return fail(UPKIE_B200_EINVAL, "wheel_balancer_state: invalid argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // [4][n] -> [n][4]
+  for (int k = 0; k < 4; ++k)
+    CUDA_TRY(cudaMemcpy2DAsync(state + k, 4 * sizeof(float), h->state + size_t(k) * h->n, sizeof(float), sizeof(float), h->n,
+                               cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return UPKIE_B200_OK;
+}
+
 int upkie_b200_observers_create(const UpkieObserverConfig* config, int n_robots, int device, void** observers) {
   if (!config || !observers) return fail(UPKIE_B200_EINVAL, "observers_create: null argument");
   std::string err;
