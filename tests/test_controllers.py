@@ -130,29 +130,30 @@ def test_gpu_pipeline_matches_oracle_and_balances(model, oracle_lib):
         wb.reset()
         assert not wb.state().cpu().numpy().any()
 
-    # 2. closed loop at 200 Hz: simulator -> spine observation -> observers -> wheel_balancer -> simulator.
-    # The reference runs the pipeline at the spine frequency (1 kHz); the env tick is 5 ms, so dt = 1/200 here.
+    # 2. closed loop at 250 Hz: simulator -> spine observation -> observers -> wheel_balancer -> simulator.
+    # The reference runs the pipeline at the spine frequency (1 kHz); here one cycle per 4 ms env tick. (At the
+    # default 200 Hz the FloorContact low-pass, cutoff 0.01 s, violates cutoff > 2 dt and the reference throws.)
     n = 256
-    sim = UpkieSim(n, model=model, config=A.default_sim_config())
+    sim = UpkieSim(n, model=model, config=A.default_sim_config(250.0))
     init = np.zeros((n, A.INIT_DIM), dtype=np.float32)
     init[:, 2] = 0.58
     pitch0 = np.random.default_rng(3).uniform(-0.15, 0.15, n)
     init[:, 3], init[:, 5] = np.cos(pitch0 / 2), np.sin(pitch0 / 2)
     sim.reset(init_state=torch.from_numpy(init).cuda())
-    obs_pipe = ObserverPipeline(n, model=model, spine_frequency=200.0)
-    wbc = A.default_wheel_balancer_config(200.0)
+    obs_pipe = ObserverPipeline(n, model=model, spine_frequency=250.0)
+    wbc = A.default_wheel_balancer_config(250.0)
     wbc.wheel_radius = float(model.wheel_radius)
     wb = WheelBalancerPipeline(n, config=wbc)
     neutral = torch.zeros((n, 6, 6), device="cuda")
     neutral[:, :, 3:5] = 1.0
     neutral[:, :, 5] = torch.tensor(model.tau_max, device="cuda", dtype=torch.float32)
     pitches = []
-    for k in range(600):  # 3 s
+    for k in range(750):  # 3 s
         spine = sim.spine_obs()
         rows = obs_pipe.step(spine)
         act = wb.step(rows, neutral.clone())
         sim.step_servos(act)
         pitches.append(rows[:, A.OBSV_PITCH].abs().max().item())
     st = sim.get_state().cpu().numpy()
-    assert max(pitches[200:]) < 0.3, max(pitches[200:])  # every robot upright after the transient
+    assert max(pitches[250:]) < 0.3, max(pitches[250:])  # every robot upright after the transient
     assert (st[:, A.ST_POS + 2] > 0.4).all()
