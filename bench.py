@@ -405,7 +405,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     launches0 = env.sim.launches
     events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     end = torch.cuda.Event(enable_timing=True)
-    profiling = bool(os.environ.get("UPKIE_BENCH_CUDA_PROFILER"))  # ncu --profile-from-start off
+    # ncu --profile-from-start off: "1" brackets the timed device loop, "e2e" the host-buffer loop
+    profiling = os.environ.get("UPKIE_BENCH_CUDA_PROFILER", "") not in ("", "e2e")
+    profiling_e2e = os.environ.get("UPKIE_BENCH_CUDA_PROFILER", "") == "e2e"
     with ClockSampler(dev.index) as clk:
         torch.cuda.synchronize()
         if profiling:
@@ -450,11 +452,15 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if profiling_e2e:
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
     for k in range(Ke):
         env.step(host_acts[k % 4])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if profiling_e2e:
+        torch.cuda.profiler.stop()
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -66,3 +66,21 @@ def random_servo_actions(n, model, seed=1, torque_mode=False):
     a[:, :, 4] = rng.uniform(-0.5, 6.0, (n, 6))
     a[:, :, 5] = rng.uniform(0.2, 1.1, (n, 6)) * tau
     return a
+
+
+def mpc_kkt_residual(P, q, U, bound):
+    """Infinity-norm KKT residual of ``min 1/2 U'PU + q'U  s.t. |U| <= bound`` at ``U`` (the accuracy gate of
+    SURVEY.md 8d config 4: <= 1e-3, ProxQP's eps_abs at mpc_balancer.py:76). With g = PU + q the multipliers of
+    the box are max(-g, 0) on the upper and max(g, 0) on the lower side: stationarity holds by construction,
+    what remains is complementarity (g must vanish, or push outwards, exactly where a bound is active) and
+    primal feasibility."""
+    U = np.asarray(U, dtype=np.float64)
+    g = P @ U + q
+    tol_active = 1e-6 * max(1.0, bound)
+    upper = U >= bound - tol_active
+    lower = U <= -bound + tol_active
+    r = np.abs(g)
+    r[upper] = np.maximum(g[upper], 0.0)   # at the upper bound the gradient may only point down (g <= 0)
+    r[lower] = np.maximum(-g[lower], 0.0)  # at the lower bound only up
+    primal = max(0.0, float(np.max(np.abs(U)) - bound))
+    return max(float(r.max()), primal)

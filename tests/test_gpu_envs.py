@@ -4,7 +4,7 @@ full-size invariants."""
 import numpy as np
 import pytest
 
-from conftest import random_servo_actions, random_states
+from conftest import mpc_kkt_residual, random_servo_actions, random_states
 from upkie_b200 import _abi
 
 pytestmark = pytest.mark.gpu
@@ -305,6 +305,12 @@ def test_mpc_matches_oracle(oracle_lib, torch):
         assert np.abs(plan[:, 0] - plan_o[:, 0]).max() < 1e-3  # |u0 - u0_oracle| <= ProxQP eps_abs (mpc_balancer.py:76)
         assert np.abs(plan - plan_o).max() < 5e-3
         assert np.abs(v.cpu().numpy() - vc_o).max() < 1e-5
+        # accuracy gate of config 4: KKT residual of the device plan in the fp64 condensed QP
+        Pm, _, _ = om.matrices()
+        live = np.flatnonzero((np.abs(x0[:, 1]) <= 1.0) & (contact != 0))[:128]
+        worst = max(mpc_kkt_residual(Pm, om.cost_vector(x0[i].astype(np.float64), float(vt[i])), plan[i], cfg.max_ground_accel)
+                    for i in live)
+        assert worst < 1e-3, worst
         assert np.abs(v.cpu().numpy()).max() <= 3.0
         # warm-started second tick stays consistent
         v2 = mpc.step_tensors(torch.from_numpy(x0).cuda(), torch.from_numpy(vt).cuda(), torch.from_numpy(contact).cuda(), 0.005)

@@ -12,7 +12,7 @@ steady contact agrees to ~1e-5.
 import numpy as np
 import pytest
 
-from conftest import random_servo_actions, random_states
+from conftest import mpc_kkt_residual, random_servo_actions, random_states
 from hostsim_wrap import HostSim, mpc_step, philox
 from upkie_b200 import _abi
 
@@ -328,6 +328,13 @@ def test_mpc_riccati_active_set_matches_condensed_oracle(oracle_lib, horizon):
     vc32, plan32, found32, it32 = mpc_step(cfg, x0, vt, contact, 0.005, v0, double=False)
     assert found32.all()
     assert np.abs(plan32[:, 0] - plan_o[:, 0]).max() < 1e-3
+    # accuracy gate of config 4: KKT residual of the fp32 plan in the fp64 condensed QP <= 1e-3
+    om = oracle_lib.OracleMpc(cfg)
+    Pm, _, _ = om.matrices()
+    live = np.flatnonzero((np.abs(x0[:, 1]) <= 1.0) & (contact != 0))[:96]
+    worst = max(mpc_kkt_residual(Pm, om.cost_vector(x0[i].astype(np.float64), float(vt[i])), plan32[i], cfg.max_ground_accel)
+                for i in live)
+    assert worst < 1e-3, worst
     assert np.abs(plan32 - plan_o).max() < 5e-3
     assert np.abs(vc32 - vc_o).max() < 1e-5
     assert it32.max() <= 12
