@@ -287,7 +287,7 @@ T* mapped(T* p) {
 //                        (63 GB/s combined, tools/micro/pcie_duplex.cu).
 //   1                    one persistent TILE=1 launch reading actions from and writing observations to host memory.
 //   0                    H2D copy -> TILE=0 kernel -> D2H copies per chunk on rotating streams.
-// `compact` (servos): observation rows [6][3] = position, velocity, torque; needs a TILE=1 pipeline.
+// `compact` (servos): observation rows [6][3] = position, velocity, torque (TILE=1 kernels).
 int step_host(Handle* h, int mode, const float* action, float* obs, float* reward, uint8_t* term, uint8_t* trunc,
               bool compact = false) {
   if (!action || !obs || !term) return fail(UPKIE_B200_EINVAL, "step_host: null buffer");
@@ -309,7 +309,6 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
 
   int pipeline = h->zero_copy;
   if (pipeline == 2 && mode != MODE_SERVOS) pipeline = 1;  // tiny rows: nothing to stream
-  if (compact && pipeline == 0) pipeline = 2;
   const int want = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
   int per = (h->n + want - 1) / want;
   per = (per + 255) / 256 * 256;
@@ -345,7 +344,9 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
       cudaStream_t s = h->host_streams[c % kHostStreams];
       CUDA_TRY(cudaMemcpyAsync(h->d_act + size_t(i0) * act_dim, src_act + size_t(i0) * act_dim,
                                size_t(cnt) * act_dim * sizeof(float), cudaMemcpyHostToDevice, s));
-      rc = step_range(h, mode, i0, cnt, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, s);
+      // compact rows exist in the TILE=1 kernels only; device staging buffers either way
+      rc = step_range(h, mode, i0, cnt, h->d_act, h->d_obs, h->d_rew, h->d_term, h->d_trunc, s, /*tile=*/compact,
+                      /*persistent=*/false, compact);
       if (rc) return rc;
       CUDA_TRY(cudaMemcpyAsync(dst_obs + size_t(i0) * obs_dim, h->d_obs + size_t(i0) * obs_dim,
                                size_t(cnt) * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
