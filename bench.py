@@ -140,6 +140,8 @@ def servos_config():
     cfg.servos_fall_termination = 1
     cfg.min_base_height = 0.15
     cfg.rand_pitch = 0.3
+    if os.environ.get("UPKIE_BENCH_PGS_TOL"):  # developer knob (profiles/r01_variants.md)
+        cfg.pgs_tolerance = float(os.environ["UPKIE_BENCH_PGS_TOL"])
     return cfg
 
 

@@ -198,7 +198,8 @@ typedef struct UpkieSimConfig {
   double min_base_height;
   /* PGS sweeps stop early once every impulse of a warp changed by less than
    * pgs_tolerance * |impulse| + 1e-9 in one sweep (Bullet: m_leastSquaresResidualThreshold-style
-   * exit); 0 = always run pgs_iterations sweeps */
+   * exit); 0 = always run pgs_iterations sweeps. Default 1e-5: ~50 ulp of the fp32 impulses, the converged
+   * contact impulses then differ from 50 full sweeps by < 1e-6 m/s on velocities (profiles/r01_variants.md) */
   double pgs_tolerance;
   /* Bullet's SOLVER_USE_WARMSTARTING: normal contact impulses start each substep at
    * warmstarting_factor x the previous substep's value while the contact persists (Bullet: 0.85), friction rows

@@ -46,12 +46,11 @@ def main():
     # host path as shipped: zero-copy persistent kernel (block, blocks/SM) and the staged pipeline (chunks)
     import time
     configs = []
-    for compact in ("1", ""):
-        configs += [{"compact": compact, "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": str(c),
-                     "UPKIE_B200_HOST_KERNEL_STREAMS": str(k), "UPKIE_B200_HOST_BLOCK": str(b)}
-                    for c, k, b in ((4, 1, 128), (2, 1, 128), (8, 2, 128), (8, 2, 64), (4, 2, 128))]
-        configs += [{"compact": compact, "UPKIE_B200_ZERO_COPY": "1", "UPKIE_B200_HOST_BLOCK": "128", "UPKIE_B200_HOST_BLOCKS_PER_SM": "1"}]
-    configs += [{"UPKIE_B200_ZERO_COPY": "0", "UPKIE_B200_HOST_CHUNKS": "4"}]
+    for c in (2, 3, 4):
+        configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "0", "UPKIE_B200_HOST_CHUNKS": str(c)})
+    configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": "2", "UPKIE_B200_HOST_KERNEL_STREAMS": "1"})
+    configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": "3", "UPKIE_B200_HOST_KERNEL_STREAMS": "2"})
+    configs.append({"compact": "", "UPKIE_B200_ZERO_COPY": "0", "UPKIE_B200_HOST_CHUNKS": "4"})
     for cfg in configs:
         for k in ("UPKIE_B200_ZERO_COPY", "UPKIE_B200_HOST_BLOCK", "UPKIE_B200_HOST_BLOCKS_PER_SM", "UPKIE_B200_HOST_CHUNKS",
                   "UPKIE_B200_HOST_KERNEL_STREAMS"):

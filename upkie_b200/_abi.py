@@ -247,7 +247,7 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.servos_fall_termination = 0
     c.skip_action_clamps = 0
     c.min_base_height = 0.0
-    c.pgs_tolerance = 1e-6
+    c.pgs_tolerance = 1e-5
     c.warmstarting_factor = 0.0  # measured: no fewer sweeps (friction rows dominate); Bullet's value would be 0.85
     c.init_position[0], c.init_position[1], c.init_position[2] = 0.0, 0.0, 0.6
     c.init_quat[0], c.init_quat[1], c.init_quat[2], c.init_quat[3] = 1.0, 0.0, 0.0, 0.0

@@ -42,7 +42,7 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->servos_fall_termination = 0;
   c->skip_action_clamps = 0;
   c->min_base_height = 0.0;
-  c->pgs_tolerance = 1e-6;
+  c->pgs_tolerance = 1e-5;
   c->warmstarting_factor = 0.0;  // off by default (Bullet's m_warmstartingFactor is 0.85)
   c->init_position[0] = 0.0; c->init_position[1] = 0.0; c->init_position[2] = 0.6;  // upkie_env.py:87-90
   c->init_quat[0] = 1.0; c->init_quat[1] = 0.0; c->init_quat[2] = 0.0; c->init_quat[3] = 0.0;

@@ -508,6 +508,46 @@ struct NoSync {
 };
 constexpr int kPhaseSyncs = 6;
 
+// Projected Gauss-Seidel over the six contact rows in Bullet's order (nL nR t1L t2L t1R t2R), residual form:
+// r_k = rhs_k + sum_l G_kl lam_l is kept up to date for every row, so a row update is clamp(r_k) and the change
+// delta = lam_k' - lam_k is pushed into all six residuals with independent FMAs (r_m += G_mk delta). Same
+// iterates as the textbook sweep that re-sums each row, but the dependent chain per row is clamp -> delta -> one
+// FMA instead of a six-term sum (the solver is latency-bound: ~1.75 warps per scheduler), and the six updates
+// pair into three f32x2 FMAs in the paired build (sim_pair.cuh).
+template <typename AnyFn>
+UPKIE_HD void pgs_solve(const SimParams& P, const float G[6][6], const float rhs[6], float lam[6], float mu,
+                        float hiL, float hiR, float pgs_atol, AnyFn warp_any) {
+  float r[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    r[k] = rhs[k];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) r[k] += G[k][l] * lam[l];  // warm-started normals; frictions start from 0
+  }
+  for (int it = 0; it < P.pgs_iterations; ++it) {
+    bool changed = false;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float lo, hi;
+      if (k == 0) { lo = 0.f; hi = hiL; }
+      else if (k == 1) { lo = 0.f; hi = hiR; }
+      else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
+      const float nl = fminf(fmaxf(r[k], lo), hi);
+      const float delta = nl - lam[k];
+      changed = changed || (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+      lam[k] = nl;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) r[m] += G[m][k] * delta;
+    }
+#ifdef UPKIE_PGS_STATS
+    if (!changed) { upkie_pgs_stats(it + 1); break; }
+    if (it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 2);
+#else
+    if (!warp_any(changed)) break;
+#endif
+  }
+}
+
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
                               AnyFn warp_any, SyncFn phase_sync = SyncFn(), const float* wext = nullptr) {
@@ -683,28 +723,7 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
       for (int l = 0; l < 6; ++l) W[k][l] = -jdi[k] * W[k][l];
       W[k][k] += 1.f - (k < 2 ? cfmrow * jdi[k] : 0.f);
     }
-    for (int it = 0; it < P.pgs_iterations; ++it) {
-      bool changed = false;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        float sum = rhs[k];
-#pragma unroll
-        for (int l = 0; l < 6; ++l) sum += W[k][l] * lam[l];
-        float lo, hi;
-        if (k == 0) { lo = 0.f; hi = hiL; }
-        else if (k == 1) { lo = 0.f; hi = hiR; }
-        else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
-        const float nl = fminf(fmaxf(sum, lo), hi);
-        changed = changed || (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
-        lam[k] = nl;
-      }
-#ifdef UPKIE_PGS_STATS
-      if (!changed) { upkie_pgs_stats(it + 1); break; }
-      if (it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 2);
-#else
-      if (!warp_any(changed)) break;
-#endif
-    }
+    pgs_solve(P, W, rhs, lam, mu, hiL, hiR, pgs_atol, warp_any);
     S.lam_n[0] = lam[0];
     S.lam_n[1] = lam[1];
     // apply the total wheel impulses

@@ -468,26 +468,39 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
     const float hiL = actL ? 1e10f : 0.f, hiR = actR ? 1e10f : 0.f;
     // Projected Gauss-Seidel, see physics_substep() for the exit rule
     const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+    // residual-form sweep of pgs_solve() (sim_core.cuh) with the six residuals as three (left, right) pairs:
+    // r2[0] = (nL, nR), r2[1] = (t1L, t1R), r2[2] = (t2L, t2R); column k of the scaled matrix in the same pairing
+    f2 Gc[6][3];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
+      float g[6];
 #pragma unroll
-      for (int l = 0; l < 6; ++l) W[k][l] = -jdi[k] * W[k][l];
-      W[k][k] += 1.f - (k < 2 ? cfmrow * jdi[k] : 0.f);
+      for (int m = 0; m < 6; ++m) g[m] = -jdi[m] * W[m][k] + (m == k ? 1.f - (k < 2 ? cfmrow * jdi[k] : 0.f) : 0.f);
+      Gc[k][0] = mk2(g[0], g[1]);
+      Gc[k][1] = mk2(g[2], g[4]);
+      Gc[k][2] = mk2(g[3], g[5]);
     }
+    f2 r2[3] = {mk2(rhs[0], rhs[1]), mk2(rhs[2], rhs[4]), mk2(rhs[3], rhs[5])};
+#pragma unroll
+    for (int l = 0; l < 2; ++l)  // warm-started normals; frictions start from 0
+#pragma unroll
+      for (int p = 0; p < 3; ++p) r2[p] = fma2(Gc[l][p], bc2(lam[l]), r2[p]);
     for (int it = 0; it < P.pgs_iterations; ++it) {
       bool changed = false;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        float sum = rhs[k];
-#pragma unroll
-        for (int l = 0; l < 6; ++l) sum += W[k][l] * lam[l];
         float lo, hi;
         if (k == 0) { lo = 0.f; hi = hiL; }
         else if (k == 1) { lo = 0.f; hi = hiR; }
         else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
-        const float nl = fminf(fmaxf(sum, lo), hi);
-        changed = changed || (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+        const float rk = k == 0 ? r2[0].x : k == 1 ? r2[0].y : k == 2 ? r2[1].x : k == 3 ? r2[2].x : k == 4 ? r2[1].y : r2[2].y;
+        const float nl = fminf(fmaxf(rk, lo), hi);
+        const float delta = nl - lam[k];
+        changed = changed || (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
         lam[k] = nl;
+        const f2 d2 = bc2(delta);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) r2[p] = fma2(Gc[k][p], d2, r2[p]);
       }
 #ifdef UPKIE_PGS_STATS
       if (!changed) { upkie_pgs_stats(it + 1); break; }
