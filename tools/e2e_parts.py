@@ -51,7 +51,7 @@ def main():
     configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": "2", "UPKIE_B200_HOST_KERNEL_STREAMS": "1"})
     configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": "3", "UPKIE_B200_HOST_KERNEL_STREAMS": "2"})
     configs.append({"compact": "", "UPKIE_B200_ZERO_COPY": "0", "UPKIE_B200_HOST_CHUNKS": "4"})
-    for cfg in configs:
+    for cfg in (configs if "--host" in sys.argv or "--kernel" not in sys.argv else []):
         for k in ("UPKIE_B200_ZERO_COPY", "UPKIE_B200_HOST_BLOCK", "UPKIE_B200_HOST_BLOCKS_PER_SM", "UPKIE_B200_HOST_CHUNKS",
                   "UPKIE_B200_HOST_KERNEL_STREAMS"):
             os.environ.pop(k, None)

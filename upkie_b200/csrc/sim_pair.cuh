@@ -17,6 +17,8 @@
 // remain available with -DUPKIE_PAIRED_LEGS=0.
 #pragma once
 
+#include <type_traits>
+
 namespace upkie_b200 {
 
 UPKIE_HD f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
@@ -465,7 +467,6 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
       }
     }
     const float cfmrow = P.cfm;  // m_cfm = cfm * jacDiagABInv
-    const float hiL = actL ? 1e10f : 0.f, hiR = actR ? 1e10f : 0.f;
     // Projected Gauss-Seidel, see physics_substep() for the exit rule
     const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
     // residual-form sweep of pgs_solve() (sim_core.cuh) with the six residuals as three (left, right) pairs:
@@ -480,31 +481,55 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
       Gc[k][1] = mk2(g[2], g[4]);
       Gc[k][2] = mk2(g[3], g[5]);
     }
+    // a wheel out of contact: zero its normal row and right-hand side, so that its residual stays 0 and the
+    // normal update is a single max(r, 0) (its friction bounds are then +-mu * 0)
+    if (!actL) {
+      rhs[0] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Gc[k][0].x = 0.f;
+    }
+    if (!actR) {
+      rhs[1] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Gc[k][0].y = 0.f;
+    }
     f2 r2[3] = {mk2(rhs[0], rhs[1]), mk2(rhs[2], rhs[4]), mk2(rhs[3], rhs[5])};
 #pragma unroll
     for (int l = 0; l < 2; ++l)  // warm-started normals; frictions start from 0
 #pragma unroll
       for (int p = 0; p < 3; ++p) r2[p] = fma2(Gc[l][p], bc2(lam[l]), r2[p]);
-    for (int it = 0; it < P.pgs_iterations; ++it) {
+    // One sweep = six row updates in Bullet's order: clamp the row's residual, push the change into all six
+    // residuals (three FFMA2). The exit test costs as much as a third of a sweep, so it runs on every second
+    // sweep only; robots standing on both wheels use all pgs_iterations sweeps anyway (their two lateral
+    // friction rows are nearly redundant and converge slowly), flying or rolling ones leave after a few.
+    auto sweep = [&](auto with_test) -> bool {
       bool changed = false;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        float lo, hi;
-        if (k == 0) { lo = 0.f; hi = hiL; }
-        else if (k == 1) { lo = 0.f; hi = hiR; }
-        else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
         const float rk = k == 0 ? r2[0].x : k == 1 ? r2[0].y : k == 2 ? r2[1].x : k == 3 ? r2[2].x : k == 4 ? r2[1].y : r2[2].y;
-        const float nl = fminf(fmaxf(rk, lo), hi);
+        float nl;
+        if (k < 2) {
+          nl = fmaxf(rk, 0.f);
+        } else {
+          const float hi = mu * lam[(k < 4) ? 0 : 1];
+          nl = fminf(fmaxf(rk, -hi), hi);
+        }
         const float delta = nl - lam[k];
-        changed = changed || (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
-        lam[k] = nl;
         const f2 d2 = bc2(delta);
 #pragma unroll
         for (int p = 0; p < 3; ++p) r2[p] = fma2(Gc[k][p], d2, r2[p]);
+        if (decltype(with_test)::value) changed = changed | (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+        lam[k] = nl;
       }
+      return changed;
+    };
+    for (int it = 0; it < P.pgs_iterations; it += 2) {
+      sweep(std::false_type());
+      if (it + 1 >= P.pgs_iterations) break;
+      const bool changed = sweep(std::true_type());
 #ifdef UPKIE_PGS_STATS
-      if (!changed) { upkie_pgs_stats(it + 1); break; }
-      if (it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 2);
+      if (!changed) { upkie_pgs_stats(it + 2); break; }
+      if (it + 2 >= P.pgs_iterations) upkie_pgs_stats(it + 3);
 #else
       if (!warp_any(changed)) break;
 #endif
