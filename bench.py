@@ -262,6 +262,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host buffers and the stepping thread on the GPU's NUMA node (the e2e path is PCIe-bound)
+    from upkie_b200.numa import bind_to_gpu_node, gpu_numa_node
+
+    previous_affinity = bind_to_gpu_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -285,6 +289,10 @@ def main():
         return
 
     units, t_ms, kernel_ms, e2e, launches, clocks, config, n_per_gpu = result
+    if previous_affinity is not None:
+        os.sched_setaffinity(0, previous_affinity)  # the CPU baseline below uses every host core
+    config["host_numa"] = (f"stepping thread and pinned buffers on NUMA node {gpu_numa_node(local_rank)} of the GPU"
+                           if previous_affinity is not None else "no NUMA binding (single node or unknown topology)")
     total_units = units * world
     value = total_units / (t_ms * 1e-3)
     b_alg = B_ALG[args.workload]

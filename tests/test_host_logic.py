@@ -263,3 +263,13 @@ def test_external_force_rows(model):
         model.external_force_rows({"torso": ExternalForce([0, 0, 1]), "imu": ExternalForce([0, 0, 1], local=True)}, n=1)
     with pytest.raises(ValueError):
         ExternalForce([1.0, 2.0])
+
+
+def test_numa_cpulist_parser_and_fallbacks():
+    from upkie_b200 import numa
+
+    assert numa._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert numa._parse_cpulist("") == []
+    # no GPU here: unknown topology -> nothing is bound, nothing raises
+    assert numa.gpu_numa_node(0) is None or isinstance(numa.gpu_numa_node(0), int)
+    assert numa.bind_to_gpu_node(0) is None or isinstance(numa.bind_to_gpu_node(0), list)
