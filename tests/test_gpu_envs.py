@@ -131,8 +131,17 @@ def test_host_buffer_api_equals_device_api(model, torch, n):
     o2, r2, t2, u2 = s2.step_servos_host(pinned)  # zero-copy
     assert s2.launches - l0 == 1
     o3, r3, t3, u3 = s3.step_servos_host(a.copy())  # pageable action: staged
+    # the pinned and the pageable route run the same TILE=1 kernel: bit-exact
+    assert np.array_equal(o2, o3) and np.array_equal(t2, t3)
+    # device buffers run the TILE=0 instantiation, compiled separately: same arithmetic, but the compiler is
+    # free to contract / schedule it differently, so equality holds to round-off (amplified by the contact
+    # rows' 1/h sensitivity on velocities), not bit for bit
+    ref = o1.cpu().numpy()
     for o, r, t, u in ((o2, r2, t2, u2), (o3, r3, t3, u3)):
-        assert np.array_equal(o1.cpu().numpy(), o)  # same kernel: bit-exact
+        d = np.abs(ref - o)
+        assert d[:, :, 0].max() < 1e-5 and d[:, :, 2].max() < 1e-4, (d[:, :, 0].max(), d[:, :, 2].max())
+        assert d[:, :, 1].max() < 2e-2 and np.median(d[:, :, 1]) < 1e-5, (d[:, :, 1].max(), np.median(d[:, :, 1]))
+        assert np.array_equal(d[:, :, 3:], np.zeros_like(d[:, :, 3:]))
         assert np.array_equal(t1.cpu().numpy(), t) and np.array_equal(r1.cpu().numpy(), r)
         assert np.array_equal(u1.cpu().numpy(), u)
     # compact transport: only position / velocity / torque rows cross PCIe
@@ -144,21 +153,23 @@ def test_host_buffer_api_equals_device_api(model, torch, n):
     c4, ct4 = s4.step_servos_host_compact(p4)
     c5, ct5 = s5.step_servos_host_compact(a.copy())  # pageable: staged through the handle's pinned buffers
     for c, ct in ((c4, ct4), (c5, ct5)):
-        assert c.shape == (n, 6, 3) and np.array_equal(c, o1.cpu().numpy()[:, :, :3]) and np.array_equal(ct, t1.cpu().numpy())
+        assert c.shape == (n, 6, 3) and np.array_equal(c, o2[:, :, :3]) and np.array_equal(ct, t2)  # TILE=1 both
     g = np.random.default_rng(3).uniform(-3, 3, (n, 2)).astype(np.float32)
     o1, _, t1, _ = s1.step_gyropod(torch.from_numpy(g).cuda())
     pg = s2.host_action_buffer(2)
     pg[:] = g
     o2, _, t2, _ = s2.step_gyropod_host(pg)
     o3, _, t3, _ = s3.step_gyropod_host(g)
-    assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(t1.cpu().numpy(), t2)
-    assert np.array_equal(o1.cpu().numpy(), o3) and np.array_equal(t1.cpu().numpy(), t3)
+    assert np.array_equal(o2, o3) and np.array_equal(t2, t3)
+    assert np.abs(o1.cpu().numpy() - o2).max() < 2e-2 and np.median(np.abs(o1.cpu().numpy() - o2)) < 1e-5
+    assert np.array_equal(t1.cpu().numpy(), t2)
     p = np.random.default_rng(4).uniform(-3, 3, (n, 1)).astype(np.float32)
     o1, _, t1, _ = s1.step_pendulum(torch.from_numpy(p).cuda())
     pp = s2.host_action_buffer(1)
     pp[:] = p
     o2, _, t2, _ = s2.step_gyropod_host(pp)
-    assert np.array_equal(o1.cpu().numpy(), o2) and np.array_equal(t1.cpu().numpy(), t2)
+    assert np.abs(o1.cpu().numpy() - o2).max() < 2e-2 and np.median(np.abs(o1.cpu().numpy() - o2)) < 1e-5
+    assert np.array_equal(t1.cpu().numpy(), t2)
 
 
 def test_vector_env_api_and_reference_semantics(model, torch):

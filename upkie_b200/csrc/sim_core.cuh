@@ -524,7 +524,9 @@ UPKIE_HD void pgs_solve(const SimParams& P, const float G[6][6], const float rhs
 #pragma unroll
     for (int l = 0; l < 2; ++l) r[k] += G[k][l] * lam[l];  // warm-started normals; frictions start from 0
   }
+  // the exit test runs on every second sweep (as in the paired build, sim_pair.cuh)
   for (int it = 0; it < P.pgs_iterations; ++it) {
+    const bool test = (it & 1) != 0;
     bool changed = false;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -534,11 +536,12 @@ UPKIE_HD void pgs_solve(const SimParams& P, const float G[6][6], const float rhs
       else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
       const float nl = fminf(fmaxf(r[k], lo), hi);
       const float delta = nl - lam[k];
-      changed = changed || (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+      if (test) changed = changed | (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
       lam[k] = nl;
 #pragma unroll
       for (int m = 0; m < 6; ++m) r[m] += G[m][k] * delta;
     }
+    if (!test) continue;
 #ifdef UPKIE_PGS_STATS
     if (!changed) { upkie_pgs_stats(it + 1); break; }
     if (it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 2);

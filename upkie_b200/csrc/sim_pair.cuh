@@ -413,32 +413,46 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
         Vw[5] = fma2(lc.ox[k], w, Vw[5]);
       }
     }
-    // Delassus matrix W = J M^-1 J^T: three impulse responses, each for the (left, right) column pair
+    // Delassus matrix W = J M^-1 J^T without walking back down the legs. With the up-pass quantities of a unit
+    // impulse along direction d on a wheel (per-joint u_k(d), force left on the base ptop(d)) and the base
+    // response a0(d) = -IA0^-1 ptop(d), the articulated-body recursions telescope to
+    //   same wheel:   W[e][d] = sum_k u_k(e) u_k(d) / D_k - ptop(e) . a0(d)
+    //   other wheel:  W[e][d] =                            - ptop_other(e) . a0(d)
+    // (g_k = p_k(e)^T a_k(d) obeys g_k = g_{k-1} - u_k(e) u_k(d) / D_k). Three packed up-passes and three
+    // two-right-hand-side base solves; W is symmetric, so each (e <= d) pair is computed once.
     float W[6][6];
+    {
+      f2 uu_[3][3], pt_[3][6];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      f2 u[3], da0[6];
-      legs_impulse_up(P, lc, J[d], u, da0);
+      for (int d = 0; d < 3; ++d) {
+        legs_impulse_up(P, lc, J[d], uu_[d], pt_[d]);
+        f2 da0[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) da0[i] = neg2(da0[i]);
-      ldl6_solve2(IA0, da0);  // lane x: base response to the left column, lane y: to the right column
-      f2 a_own[6], a_cross[6], dq[3];
-      legs_impulse_down<false>(P, lc, u, da0, a_own, dq);    // (left wheel | left col, right wheel | right col)
-      legs_impulse_down<true>(P, lc, u, da0, a_cross, dq);   // (right wheel | left col, left wheel | right col)
+        for (int i = 0; i < 6; ++i) da0[i] = neg2(pt_[d][i]);
+        ldl6_solve2(IA0, da0);  // lane x: base response to the left column, lane y: to the right column
 #pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        f2 wo = bc2(0.f), wc = bc2(0.f);
+        for (int e = 0; e <= d; ++e) {
+          f2 wo = bc2(0.f), wc = bc2(0.f);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          wo = fma2(J[e][i], a_own[i], wo);
-          wc = fma2(swp2(J[e][i]), a_cross[i], wc);
+          for (int k = 0; k < 3; ++k) wo = fma2(mul2(uu_[e][k], lc.invD[k]), uu_[d][k], wo);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            wo = fma2(neg2(pt_[e][i]), da0[i], wo);
+            wc = fma2(neg2(swp2(pt_[e][i])), da0[i], wc);
+          }
+          W[row_of(0, e)][row_of(0, d)] = wo.x;
+          W[row_of(1, e)][row_of(1, d)] = wo.y;
+          W[row_of(1, e)][row_of(0, d)] = wc.x;  // right wheel row e, left wheel column d
+          W[row_of(0, e)][row_of(1, d)] = wc.y;  // left wheel row e, right wheel column d
+          if (e != d) {
+            W[row_of(0, d)][row_of(0, e)] = wo.x;
+            W[row_of(1, d)][row_of(1, e)] = wo.y;
+            W[row_of(0, d)][row_of(1, e)] = wc.x;
+            W[row_of(1, d)][row_of(0, e)] = wc.y;
+          }
         }
-        W[row_of(0, e)][row_of(0, d)] = wo.x;
-        W[row_of(1, e)][row_of(1, d)] = wo.y;
-        W[row_of(1, e)][row_of(0, d)] = wc.x;
-        W[row_of(0, e)][row_of(1, d)] = wc.y;
+        phase_sync();  // 3, 4, 5
       }
-      phase_sync();  // 3, 4, 5
     }
     // right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
     float rhs[6], jdi[6], lam[6];
