@@ -46,14 +46,15 @@ def main():
     # host path as shipped: zero-copy persistent kernel (block, blocks/SM) and the staged pipeline (chunks)
     import time
     configs = []
-    for c in (2, 3, 4):
-        configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "0", "UPKIE_B200_HOST_CHUNKS": str(c)})
-    configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": "2", "UPKIE_B200_HOST_KERNEL_STREAMS": "1"})
-    configs.append({"compact": "1", "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_CHUNKS": "3", "UPKIE_B200_HOST_KERNEL_STREAMS": "2"})
-    configs.append({"compact": "", "UPKIE_B200_ZERO_COPY": "0", "UPKIE_B200_HOST_CHUNKS": "4"})
+    for split, k in (("", 1), ("0.4,0.4,0.2", 2), ("0.45,0.35,0.2", 2), ("0.6,0.4", 1), ("0.6,0.4", 2), ("0.4,0.35,0.25", 2),
+                     ("0.35,0.3,0.2,0.15", 2), ("0.5,0.3,0.2", 2), ("0.5,0.3,0.2", 1), ("0.3,0.3,0.25,0.15", 2)):
+        c = {"compact": "1", "UPKIE_B200_ZERO_COPY": "2", "UPKIE_B200_HOST_KERNEL_STREAMS": str(k)}
+        if split:
+            c["UPKIE_B200_HOST_SPLIT"] = split
+        configs.append(c)
     for cfg in (configs if "--host" in sys.argv or "--kernel" not in sys.argv else []):
         for k in ("UPKIE_B200_ZERO_COPY", "UPKIE_B200_HOST_BLOCK", "UPKIE_B200_HOST_BLOCKS_PER_SM", "UPKIE_B200_HOST_CHUNKS",
-                  "UPKIE_B200_HOST_KERNEL_STREAMS"):
+                  "UPKIE_B200_HOST_KERNEL_STREAMS", "UPKIE_B200_HOST_SPLIT"):
             os.environ.pop(k, None)
         os.environ.update({k: v for k, v in cfg.items() if k != "compact"})
         sim = UpkieSim(n, model=m, config=_abi.default_sim_config())

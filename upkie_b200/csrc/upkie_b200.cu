@@ -75,7 +75,9 @@ struct Handle {
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
   cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t host_events[64] = {};
-  int host_kernel_streams = 1;   // hybrid host step: kernels of successive chunks alternate over this many streams
+  int host_kernel_streams = 1;
+  double host_split[8] = {};
+  int host_split_n = 0;   // hybrid host step: kernels of successive chunks alternate over this many streams
 };
 constexpr int kHostStreams = 3;  // H2D, kernel and D2H of different chunks overlap
 constexpr uint32_t kMagic = 0x55504B42u;  // "UPKB"
@@ -309,16 +311,33 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
 
   int pipeline = h->zero_copy;
   if (pipeline == 2 && mode != MODE_SERVOS) pipeline = 1;  // tiny rows: nothing to stream
-  const int want = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
-  int per = (h->n + want - 1) / want;
-  per = (per + 255) / 256 * 256;
-  const int chunks = (h->n + per - 1) / per;
-  auto chunk_count = [&](int c) { return (c * per + per <= h->n) ? per : h->n - c * per; };
+  // chunk boundaries (multiples of 256 envs). Default: host_chunks equal chunks; UPKIE_B200_HOST_SPLIT gives the
+  // fractions explicitly (a small last chunk shortens the exposed tail: last kernel + its write drain).
+  int start[65];
+  int chunks = 0;
+  start[0] = 0;
+  if (h->host_split_n > 0 && h->n >= 4 * 8192) {
+    double acc = 0.0;
+    for (int c = 0; c < h->host_split_n && chunks < 64; ++c) {
+      acc += h->host_split[c];
+      int end = c + 1 == h->host_split_n ? h->n : int(acc * h->n + 0.5);
+      end = (end + 255) / 256 * 256;
+      if (end > h->n) end = h->n;
+      if (end > start[chunks]) start[++chunks] = end;
+    }
+    if (start[chunks] < h->n) start[++chunks] = h->n;
+  } else {
+    const int want = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
+    int per = (h->n + want - 1) / want;
+    per = (per + 255) / 256 * 256;
+    for (int i0 = 0; i0 < h->n && chunks < 64; i0 += per) start[++chunks] = (i0 + per < h->n) ? i0 + per : h->n;
+  }
+  auto chunk_count = [&](int c) { return start[c + 1] - start[c]; };
 
   if (pipeline == 2) {
     cudaStream_t sc = h->host_streams[0];
     for (int c = 0; c < chunks; ++c) {
-      const size_t i0 = size_t(c) * per;
+      const size_t i0 = size_t(start[c]);
       CUDA_TRY(cudaMemcpyAsync(h->d_act + i0 * act_dim, src_act + i0 * act_dim, size_t(chunk_count(c)) * act_dim * sizeof(float),
                                cudaMemcpyHostToDevice, sc));
       CUDA_TRY(cudaEventRecord(h->host_events[c], sc));
@@ -326,7 +345,7 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
     for (int c = 0; c < chunks; ++c) {
       cudaStream_t sk = h->host_streams[1 + (c % h->host_kernel_streams)];
       CUDA_TRY(cudaStreamWaitEvent(sk, h->host_events[c], 0));
-      rc = step_range(h, mode, c * per, chunk_count(c), h->d_act, mapped(dst_obs), mapped(dst_rew), mapped(dst_term),
+      rc = step_range(h, mode, start[c], chunk_count(c), h->d_act, mapped(dst_obs), mapped(dst_rew), mapped(dst_term),
                       mapped(dst_trunc), sk, /*tile=*/true, /*persistent=*/false, compact);
       if (rc) return rc;
     }
@@ -339,7 +358,7 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
     CUDA_TRY(cudaStreamSynchronize(s));
   } else {
     for (int c = 0; c < chunks; ++c) {
-      const int i0 = c * per;
+      const int i0 = start[c];
       const int cnt = chunk_count(c);
       cudaStream_t s = h->host_streams[c % kHostStreams];
       CUDA_TRY(cudaMemcpyAsync(h->d_act + size_t(i0) * act_dim, src_act + size_t(i0) * act_dim,
@@ -416,6 +435,17 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
     if (v >= 1 && v <= 8) h->host_blocks_per_sm = v;
   }
   if (const char* b = std::getenv("UPKIE_B200_ZERO_COPY")) h->zero_copy = std::atoi(b);  // developer knob: 0, 1, 2
+  if (const char* b = std::getenv("UPKIE_B200_HOST_SPLIT")) {  // developer knob: "0.4,0.4,0.2"
+    h->host_split_n = 0;
+    const char* p = b;
+    while (*p && h->host_split_n < 8) {
+      char* end = nullptr;
+      const double v = std::strtod(p, &end);
+      if (end == p) break;
+      if (v > 0.0) h->host_split[h->host_split_n++] = v;
+      p = (*end == ',') ? end + 1 : end;
+    }
+  }
   if (const char* b = std::getenv("UPKIE_B200_HOST_KERNEL_STREAMS")) {  // developer knob
     const int v = std::atoi(b);
     if (v >= 1 && v <= 2) h->host_kernel_streams = v;
