@@ -24,9 +24,14 @@ namespace upkie_b200 {
 UPKIE_HD f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
 UPKIE_HD f2 bc2(float a) { return mk2(a, a); }          // broadcast
 UPKIE_HD f2 swp2(f2 v) { return mk2(v.y, v.x); }       // lane swap (free: .LO_HI operand modifier)
-UPKIE_HD f2 neg2(f2 v) { return mk2(-v.x, -v.y); }     // free: operand negation
-
 #if defined(__CUDA_ARCH__)
+// FFMA2 / FMUL2 / FADD2 take no negate modifier on a packed register operand (checked in SASS: a scalar
+// negation of each lane costs two FADDs), so a packed negation is ONE multiply by (-1, -1) -- exact -- and the
+// hot paths below carry pre-negated copies instead (noz, ninvD, negated LDL factors, p' = -p in the up-pass).
+UPKIE_HD f2 neg2(f2 v) {
+  const float2 r = __fmul2_rn(make_float2(v.x, v.y), make_float2(-1.f, -1.f));
+  return mk2(r.x, r.y);
+}
 UPKIE_HD f2 fma2(f2 a, f2 b, f2 c) {
   const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
   return mk2(r.x, r.y);
@@ -40,6 +45,7 @@ UPKIE_HD f2 add2(f2 a, f2 b) {
   return mk2(r.x, r.y);
 }
 #else
+UPKIE_HD f2 neg2(f2 v) { return mk2(-v.x, -v.y); }
 UPKIE_HD f2 fma2(f2 a, f2 b, f2 c) { return mk2(a.x * b.x + c.x, a.y * b.y + c.y); }
 UPKIE_HD f2 mul2(f2 a, f2 b) { return mk2(a.x * b.x, a.y * b.y); }
 UPKIE_HD f2 add2(f2 a, f2 b) { return mk2(a.x + b.x, a.y + b.y); }
@@ -53,27 +59,28 @@ UPKIE_HD void cross3_2(const f2 a[3], const f2 b[3], f2 c[3]) {
 }
 
 // S^T x for S = s * [0 1 0 | -oz 0 ox], both legs
-UPKIE_HD f2 sdot2(f2 s, f2 ox, f2 oz, const f2 x[6]) { return mul2(s, fma2(ox, x[5], fma2(neg2(oz), x[3], x[1]))); }
+UPKIE_HD f2 sdot2(f2 s, f2 ox, f2 noz, const f2 x[6]) { return mul2(s, fma2(ox, x[5], fma2(noz, x[3], x[1]))); }
 
 struct LegCache2 {
-  f2 ox[3], oz[3];
+  f2 ox[3], oz[3], noz[3];  // joint origins (x, z) in the base frame, and -z
   f2 U[3][6];
-  f2 invD[3];
+  f2 invD[3], ninvD[3];     // 1 / D and -1 / D
 };
 
-// two right-hand sides at once against the scalar LDL^T factors of ldl6()
-UPKIE_HD void ldl6_solve2(const float A[21], f2 x[6]) {
+// two right-hand sides at once against the scalar LDL^T factors of ldl6(); nA = -A (negated once per substep,
+// the packed FMA has no negate modifier)
+UPKIE_HD void ldl6_solve2(const float A[21], const float nA[21], f2 x[6]) {
 #pragma unroll
   for (int i = 1; i < 6; ++i) {
 #pragma unroll
-    for (int k = 0; k < i; ++k) x[i] = fma2(bc2(-A[SI(k, i)]), x[k], x[i]);
+    for (int k = 0; k < i; ++k) x[i] = fma2(bc2(nA[SI(k, i)]), x[k], x[i]);
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) x[i] = mul2(x[i], bc2(A[SI(i, i)]));
 #pragma unroll
   for (int i = 4; i >= 0; --i) {
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) x[i] = fma2(bc2(-A[SI(i, k)]), x[k], x[i]);
+    for (int k = i + 1; k < 6; ++k) x[i] = fma2(bc2(nA[SI(i, k)]), x[k], x[i]);
   }
 }
 
@@ -97,6 +104,7 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
       oz = oz_n;
       lc.ox[k] = ox;
       lc.oz[k] = oz;
+      lc.noz[k] = neg2(oz);
       phi = fma2(s, mk2(q[k], q[k + 3]), phi);
       if (k < 2 || !P.wheel_symmetric) {
         float sx, cx, sy, cy;
@@ -109,7 +117,7 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
       sphi[k] = sp;
       const f2 w = mul2(s, mk2(qd[k], qd[k + 3]));
       Vc[1] = add2(Vc[1], w);
-      Vc[3] = fma2(neg2(oz), w, Vc[3]);
+      Vc[3] = fma2(lc.noz[k], w, Vc[3]);
       Vc[5] = fma2(ox, w, Vc[5]);
 #pragma unroll
       for (int i = 0; i < 6; ++i) V[k][i] = Vc[i];
@@ -119,7 +127,7 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
 #pragma unroll
   for (int k = 2; k >= 0; --k) {
     const f2 s = P.sgn2[k];
-    const f2 ox = lc.ox[k], oz = lc.oz[k];
+    const f2 ox = lc.ox[k], oz = lc.oz[k], noz = lc.noz[k];
     const f2 scale = eps ? mk2(1.f + eps[k], 1.f + eps[k + 3]) : bc2(1.f);
     const f2 m = mul2(P.mass2[k], scale);
     f2 C[3], Ib[6];
@@ -219,22 +227,24 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
     // U = IA S, D = S^T U, u = tau - S^T pA
     f2 U[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) U[r] = mul2(s, fma2(ox, IA[SI(r, 5)], fma2(neg2(oz), IA[SI(r, 3)], IA[SI(r, 1)])));
-    const f2 D = sdot2(s, ox, oz, U);
+    for (int r = 0; r < 6; ++r) U[r] = mul2(s, fma2(ox, IA[SI(r, 5)], fma2(noz, IA[SI(r, 3)], IA[SI(r, 1)])));
+    const f2 D = sdot2(s, ox, noz, U);
     const f2 invD = mk2(1.f / D.x, 1.f / D.y);
-    const f2 u = sub2(mk2(tau[k], tau[k + 3]), sdot2(s, ox, oz, pA));
+    const f2 u = sub2(mk2(tau[k], tau[k + 3]), sdot2(s, ox, noz, pA));
 #pragma unroll
     for (int r = 0; r < 6; ++r) lc.U[k][r] = U[r];
     lc.invD[k] = invD;
     uu[k] = u;
     // Ia = IA - U U^T / D ; pa = pA + Ia c + U u / D
-    f2 Ud[6];
+    const f2 ninvD = neg2(invD);
+    lc.ninvD[k] = ninvD;
+    f2 nUd[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) Ud[r] = mul2(U[r], invD);
+    for (int r = 0; r < 6; ++r) nUd[r] = mul2(U[r], ninvD);
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
 #pragma unroll
-      for (int c2 = r; c2 < 6; ++c2) IA[SI(r, c2)] = fma2(neg2(Ud[r]), U[c2], IA[SI(r, c2)]);
+      for (int c2 = r; c2 < 6; ++c2) IA[SI(r, c2)] = fma2(nUd[r], U[c2], IA[SI(r, c2)]);
     }
     const f2 ud = mul2(u, invD);
 #pragma unroll
@@ -267,31 +277,33 @@ UPKIE_HD void legs_pass3(const SimParams& P, const LegCache2& lc, const f2 cc[3]
       a[i] = add2(a[i], cc[k][i]);
       dot = fma2(lc.U[k][i], a[i], dot);
     }
-    const f2 dd = mul2(sub2(uu[k], dot), lc.invD[k]);
+    const f2 dd = fma2(dot, lc.ninvD[k], mul2(uu[k], lc.invD[k]));  // (u - U.a) / D
     qdd[k] = dd.x;
     qdd[k + 3] = dd.y;
     const f2 w = mul2(P.sgn2[k], dd);
     a[1] = add2(a[1], w);
-    a[3] = fma2(neg2(lc.oz[k]), w, a[3]);
+    a[3] = fma2(lc.noz[k], w, a[3]);
     a[5] = fma2(lc.ox[k], w, a[5]);
   }
 }
 
 // lane x: impulse f.x on the LEFT wheel up the left leg; lane y: f.y on the RIGHT wheel up the right leg
-UPKIE_HD void legs_impulse_up(const SimParams& P, const LegCache2& lc, const f2 f[6], f2 uu[3], f2 ptop[6]) {
-  f2 p[6];
+// Carries q = -p (so q starts as +f): u_k = -S^T p = S^T q, q <- q - U u / D. Returns nptop = -ptop, the force the
+// base feels with its sign flipped, i.e. the right-hand side of IA0 a0 = -ptop as is.
+UPKIE_HD void legs_impulse_up(const SimParams& P, const LegCache2& lc, const f2 f[6], f2 uu[3], f2 nptop[6]) {
+  f2 q[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) p[i] = neg2(f[i]);
+  for (int i = 0; i < 6; ++i) q[i] = f[i];
 #pragma unroll
   for (int k = 2; k >= 0; --k) {
-    const f2 u = neg2(sdot2(P.sgn2[k], lc.ox[k], lc.oz[k], p));
+    const f2 u = sdot2(P.sgn2[k], lc.ox[k], lc.noz[k], q);
     uu[k] = u;
-    const f2 ud = mul2(u, lc.invD[k]);
+    const f2 nud = mul2(u, lc.ninvD[k]);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) p[i] = fma2(lc.U[k][i], ud, p[i]);
+    for (int i = 0; i < 6; ++i) q[i] = fma2(lc.U[k][i], nud, q[i]);
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i) ptop[i] = p[i];
+  for (int i = 0; i < 6; ++i) nptop[i] = q[i];
 }
 
 // Velocity changes down the legs. SWAP = false: lane x walks the left leg, lane y the right leg (with the
@@ -308,11 +320,12 @@ UPKIE_HD void legs_impulse_down(const SimParams& P, const LegCache2& lc, const f
 #pragma unroll
     for (int i = 0; i < 6; ++i) dot = fma2(SWAP ? swp2(lc.U[k][i]) : lc.U[k][i], aw[i], dot);
     const f2 invD = SWAP ? swp2(lc.invD[k]) : lc.invD[k];
-    const f2 dd = SWAP ? mul2(neg2(dot), invD) : mul2(sub2(uu[k], dot), invD);
+    const f2 ninvD = SWAP ? swp2(lc.ninvD[k]) : lc.ninvD[k];
+    const f2 dd = SWAP ? mul2(dot, ninvD) : fma2(dot, ninvD, mul2(uu[k], invD));
     dqd[k] = dd;
     const f2 w = mul2(SWAP ? swp2(P.sgn2[k]) : P.sgn2[k], dd);
     aw[1] = add2(aw[1], w);
-    aw[3] = fma2(neg2(SWAP ? swp2(lc.oz[k]) : lc.oz[k]), w, aw[3]);
+    aw[3] = fma2(SWAP ? swp2(lc.noz[k]) : lc.noz[k], w, aw[3]);
     aw[5] = fma2(SWAP ? swp2(lc.ox[k]) : lc.ox[k], w, aw[5]);
   }
 }
@@ -336,6 +349,9 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   legs_pass12(P, S.q, S.qd, tau, V0, eps, lc, cc, uu, IA0, pA0);
   phase_sync();  // 1
   ldl6(IA0);
+  float nIA0[21];  // negated factors for the packed solves (ldl6_solve2)
+#pragma unroll
+  for (int i = 0; i < 21; ++i) nIA0[i] = -IA0[i];
   float a0[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) a0[i] = wext ? wext[i] - pA0[i] : -pA0[i];
@@ -409,7 +425,7 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
       for (int k = 0; k < 3; ++k) {
         const f2 w = mul2(P.sgn2[k], mk2(S.qd[k], S.qd[k + 3]));
         Vw[1] = add2(Vw[1], w);
-        Vw[3] = fma2(neg2(lc.oz[k]), w, Vw[3]);
+        Vw[3] = fma2(lc.noz[k], w, Vw[3]);
         Vw[5] = fma2(lc.ox[k], w, Vw[5]);
       }
     }
@@ -425,11 +441,11 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
       f2 uu_[3][3], pt_[3][6];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        legs_impulse_up(P, lc, J[d], uu_[d], pt_[d]);
+        legs_impulse_up(P, lc, J[d], uu_[d], pt_[d]);  // pt_ = -ptop
         f2 da0[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) da0[i] = neg2(pt_[d][i]);
-        ldl6_solve2(IA0, da0);  // lane x: base response to the left column, lane y: to the right column
+        for (int i = 0; i < 6; ++i) da0[i] = pt_[d][i];
+        ldl6_solve2(IA0, nIA0, da0);  // a0(d) = -IA0^-1 ptop(d); lane x: left column, lane y: right column
 #pragma unroll
         for (int e = 0; e <= d; ++e) {
           f2 wo = bc2(0.f), wc = bc2(0.f);
@@ -437,8 +453,8 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
           for (int k = 0; k < 3; ++k) wo = fma2(mul2(uu_[e][k], lc.invD[k]), uu_[d][k], wo);
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
-            wo = fma2(neg2(pt_[e][i]), da0[i], wo);
-            wc = fma2(neg2(swp2(pt_[e][i])), da0[i], wc);
+            wo = fma2(pt_[e][i], da0[i], wo);        // -ptop(e) . a0(d)
+            wc = fma2(swp2(pt_[e][i]), da0[i], wc);  // -ptop_other(e) . a0(d)
           }
           W[row_of(0, e)][row_of(0, d)] = wo.x;
           W[row_of(1, e)][row_of(1, d)] = wo.y;
@@ -557,11 +573,11 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
 #pragma unroll
       for (int i = 0; i < 6; ++i) F[i] = fma2(ln, J[0][i], fma2(l1, J[1][i], mul2(l2, J[2][i])));
     }
-    f2 u[3], ptop[6];
-    legs_impulse_up(P, lc, F, u, ptop);
+    f2 u[3], nptop[6];
+    legs_impulse_up(P, lc, F, u, nptop);
     float da0[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) da0[i] = -(ptop[i].x + ptop[i].y);
+    for (int i = 0; i < 6; ++i) da0[i] = nptop[i].x + nptop[i].y;
     ldl6_solve(IA0, da0);
     f2 da2[6], aw[6], dq[3];
 #pragma unroll
