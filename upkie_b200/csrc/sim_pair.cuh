@@ -7,8 +7,8 @@
 // three-register scalar FFMA saturates at 0.59 inst/cycle/scheduler on B200, FFMA2
 // moves two FMAs per lane per instruction at the same issue cost). The two legs of
 // the robot run the same arithmetic on different data, so every per-leg scalar of
-// sim_core.cuh becomes an f2 = (left, right). SASS provides for free what the
-// pairing needs: per-operand negation, broadcast of a scalar register to both lanes
+// sim_core.cuh becomes an f2 = (left, right). SASS provides for free most of what the
+// pairing needs (not the negation of a register pair, see neg2): broadcast of a scalar register to both lanes
 // (`R.F32`), lane swap (`R.F32x2.LO_HI`, used for the cross-leg impulse responses)
 // and 64-bit constant-bank operands (the per-leg model constants are stored as
 // adjacent pairs in SimParams).
