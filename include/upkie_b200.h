@@ -354,6 +354,16 @@ int upkie_b200_get_state(void* handle, float* state /* [N][UPKIE_STATE_DIM] */, 
 int upkie_b200_set_state(void* handle, const float* state, void* stream);
 int upkie_b200_error_flags(void* handle, uint32_t* flags /* [N] */, void* stream);
 
+/* Checkpoint / resume of what get_state does not carry: per-env episode counters (keys of the on-device reset
+ * sampler), tick counters (keys of the noise generator), pending next-step auto-resets and sticky error flags.
+ * Device pointers, any of them may be NULL. Together with get_state / set_state, the randomisation and
+ * external-force tensors the caller owns, and the seed / env_offset it passed, this is the complete simulator
+ * state: a restored handle continues bit for bit (the reference has no counterpart). */
+int upkie_b200_get_counters(void* handle, uint32_t* episode /* [N] */, uint32_t* tick /* [N] */,
+                            uint8_t* pending_reset /* [N] */, uint32_t* error_flags /* [N] */, void* stream);
+int upkie_b200_set_counters(void* handle, const uint32_t* episode, const uint32_t* tick,
+                            const uint8_t* pending_reset, const uint32_t* error_flags, void* stream);
+
 /* Replaces PyBulletBackend.set_external_forces (pybullet_backend.py:603-625):
  * force[N][UPKIE_NB][3] (device pointer, newtons) acts at the centre of mass of
  * body b of env i on every substep of every following step, until overwritten;

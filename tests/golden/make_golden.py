@@ -118,6 +118,28 @@ def main():
         })
     out["robot_state_samples"] = samples
 
+    # msgpack wire format: the reference's own serialize() with the Packer settings of
+    # upkie/envs/backends/spine/spine_interface.py:46 (msgpack.Packer(default=serialize, use_bin_type=True))
+    import msgpack
+
+    spec = importlib.util.spec_from_file_location(
+        "upkie_serialize", os.path.join(REF, "upkie/envs/backends/spine/serialize.py"))
+    ser = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ser)
+    packer = msgpack.Packer(default=ser.serialize, use_bin_type=True)
+    joint_names = ("left_hip", "left_knee", "left_wheel", "right_hip", "right_knee", "right_wheel")
+    keys = ("position", "velocity", "feedforward_torque", "kp_scale", "kd_scale", "maximum_torque")
+    a = np.zeros((6, 6))
+    a[:, 0] = [0.1, -0.2, np.nan, 0.3, -0.4, np.nan]
+    a[:, 1] = [0.0, 0.5, -7.0, 0.25, 0.0, 7.0]
+    a[:, 2] = [0.0, 0.0, 0.125, 0.0, 0.0, -0.125]
+    a[:, 3] = 1.0
+    a[:, 4] = [1.0, 1.0, 0.5, 1.0, 1.0, 0.5]
+    a[:, 5] = [16.0, 16.0, 1.7, 16.0, 16.0, 1.7]
+    action = {"servo": {name: {key: float(a[j, k]) for k, key in enumerate(keys)} for j, name in enumerate(joint_names)}}
+    nested = {"imu": {"linear_acceleration": np.array([0.5, -1.5, 9.81])}, "n": 3, "flag": True, "name": "upkie"}
+    out["wire"] = {"action_hex": packer.pack(action).hex(), "nested_hex": packer.pack(nested).hex()}
+
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT)

@@ -562,3 +562,48 @@ def test_external_forces_and_imu_uncertainty(model, oracle_lib, torch):
         assert np.abs(d_.std(axis=0) / sig - 1).max() < 0.1
     assert abs(np.corrcoef(dacc[:, 0], draw[:, 0])[0, 1]) < 0.12  # independent draws for the raw acceleration
     assert np.array_equal(sa.spine_obs().cpu().numpy(), pa)  # same tick, same draw
+
+
+def test_checkpoint_resume_is_bit_exact(model, torch, tmp_path):
+    """state_dict / load_state_dict: a fresh handle restored from a checkpoint continues bit for bit, with fused
+    auto-resets (episode counters), torque noise (tick counters), randomisation and external forces in play."""
+    n = 2048
+    cfg = _abi.default_sim_config()
+    cfg.servos_fall_termination = 1
+    cfg.min_base_height = 0.15
+    cfg.rand_pitch = 0.3
+    for j in range(6):
+        cfg.torque_control_noise[j] = 0.05
+    cfg.noise_seed = 11
+    rng = np.random.default_rng(5)
+    act = np.zeros((n, 6, 6), dtype=np.float32)
+    act[:, :, 0] = np.nan
+    act[:, :, 2] = rng.uniform(-1, 1, (n, 6)) * model.tau_max
+    act[:, :, 5] = model.tau_max
+    a = torch.from_numpy(act).cuda()
+
+    def fresh():
+        return _sim(n, model, cfg)
+
+    s1 = fresh()
+    s1.set_randomization(torch.from_numpy(rng.uniform(0.5, 1.2, n).astype(np.float32)).cuda(),
+                         torch.from_numpy(rng.uniform(-0.2, 0.2, (n, 6)).astype(np.float32)).cuda())
+    ext = np.zeros((n, 7, 3), dtype=np.float32)
+    ext[:, 0, 0] = 3.0
+    s1.set_external_forces(torch.from_numpy(ext).cuda(), 0)
+    s1.set_autoreset(1, 77, 0)
+    s1.reset(seed=77)
+    resets = 0
+    for _ in range(150):
+        resets += int(s1.step_servos(a)[2].sum().item())
+    assert resets > 50  # the checkpoint is taken in the middle of resets
+    path = tmp_path / "ckpt.pt"
+    torch.save(s1.state_dict(), path)
+    ref = [tuple(x.clone() for x in s1.step_servos(a)) for _ in range(40)]
+    s2 = fresh()
+    s2.load_state_dict(torch.load(path))
+    for k in range(40):
+        out = s2.step_servos(a)
+        for x, y in zip(out, ref[k]):
+            assert torch.equal(x, y), k
+    assert torch.equal(s1.get_state(), s2.get_state())

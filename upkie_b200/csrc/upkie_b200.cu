@@ -660,6 +660,34 @@ int upkie_b200_error_flags(void* handle, uint32_t* flags, void* stream) {
   return UPKIE_B200_OK;
 }
 
+int upkie_b200_get_counters(void* handle, uint32_t* episode, uint32_t* tick, uint8_t* pending_reset,
+                            uint32_t* error_flags, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "get_counters: invalid handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = size_t(h->n);
+  if (episode) CUDA_TRY(cudaMemcpyAsync(episode, h->episode, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  if (tick) CUDA_TRY(cudaMemcpyAsync(tick, h->tick, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  if (pending_reset) CUDA_TRY(cudaMemcpyAsync(pending_reset, h->done_prev, n, cudaMemcpyDeviceToDevice, s));
+  if (error_flags) CUDA_TRY(cudaMemcpyAsync(error_flags, h->err, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  return UPKIE_B200_OK;
+}
+
+int upkie_b200_set_counters(void* handle, const uint32_t* episode, const uint32_t* tick, const uint8_t* pending_reset,
+                            const uint32_t* error_flags, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "set_counters: invalid handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = size_t(h->n);
+  if (episode) CUDA_TRY(cudaMemcpyAsync(h->episode, episode, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  if (tick) CUDA_TRY(cudaMemcpyAsync(h->tick, tick, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  if (pending_reset) CUDA_TRY(cudaMemcpyAsync(h->done_prev, pending_reset, n, cudaMemcpyDeviceToDevice, s));
+  if (error_flags) CUDA_TRY(cudaMemcpyAsync(h->err, error_flags, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  return UPKIE_B200_OK;
+}
+
 // ---- MPC ---------------------------------------------------------------------------------
 
 int upkie_b200_mpc_create(const UpkieMpcConfig* config, int n_robots, int device, void** mpc) {

@@ -91,6 +91,7 @@ class UpkieSim:
     # ------------------------------------------------------------------
     def set_autoreset(self, mode: int, seed: int = 0, env_offset: int = 0) -> None:
         check(lib().upkie_b200_set_autoreset(self._h, int(mode), int(seed), int(env_offset)))
+        self._autoreset = (int(mode), int(seed), int(env_offset))
 
     def set_randomization(self, friction: Optional[torch.Tensor] = None, inertia_eps: Optional[torch.Tensor] = None):
         """Per-env floor friction [N] and ``randomize_inertias`` epsilons [N, 6]
@@ -101,6 +102,7 @@ class UpkieSim:
             self._check_tensor(inertia_eps, (self.n, 6), name="inertia_eps")
         check(lib().upkie_b200_set_randomization(self._h, _ptr(friction), _ptr(inertia_eps), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
+        self._randomization = (None if friction is None else friction.clone(), None if inertia_eps is None else inertia_eps.clone())
 
     def set_external_forces(self, force: Optional[torch.Tensor] = None, local_mask: int = 0) -> None:
         """``force[N, 7, 3]`` newtons at the centres of mass of the 7 bodies, applied on every substep of
@@ -110,6 +112,7 @@ class UpkieSim:
             self._check_tensor(force, (self.n, _abi.NB, 3), name="force")
         check(lib().upkie_b200_set_external_forces(self._h, _ptr(force), int(local_mask), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
+        self._external = (None if force is None else force.clone(), int(local_mask))
 
     def reset(
         self,
@@ -277,6 +280,38 @@ class UpkieSim:
     def set_state(self, state: torch.Tensor) -> None:
         self._check_tensor(state, (self.n, _abi.STATE_DIM), name="state")
         check(lib().upkie_b200_set_state(self._h, _ptr(state), self._stream()))
+
+    # checkpoint / resume ------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        """Everything a handle needs to continue bit for bit (``torch.save``-able): robot state, episode / tick
+        counters, pending auto-resets, error flags, randomisation, external forces, auto-reset keys. The model and
+        the configuration are construction arguments and are not included."""
+        i32, u8 = torch.int32, torch.uint8
+        episode = torch.empty(self.n, dtype=i32, device=self.device)
+        tick = torch.empty(self.n, dtype=i32, device=self.device)
+        pending = torch.empty(self.n, dtype=u8, device=self.device)
+        flags = torch.empty(self.n, dtype=i32, device=self.device)
+        check(lib().upkie_b200_get_counters(self._h, _ptr(episode), _ptr(tick), _ptr(pending), _ptr(flags), self._stream()))
+        friction, eps = getattr(self, "_randomization", (None, None))
+        force, local_mask = getattr(self, "_external", (None, 0))
+        return {
+            "state": self.get_state(), "episode": episode, "tick": tick, "pending_reset": pending, "error_flags": flags,
+            "friction": friction, "inertia_eps": eps, "external_force": force, "external_local_mask": local_mask,
+            "autoreset": getattr(self, "_autoreset", (AUTORESET_DISABLED, 0, 0)),
+        }
+
+    def load_state_dict(self, sd: dict) -> None:
+        dev = self.device
+        self.set_state(sd["state"].to(dev))
+        check(lib().upkie_b200_set_counters(
+            self._h, _ptr(sd["episode"].to(dev)), _ptr(sd["tick"].to(dev)), _ptr(sd["pending_reset"].to(dev)),
+            _ptr(sd["error_flags"].to(dev)), self._stream()))
+        torch.cuda.current_stream(dev).synchronize()
+        self.set_randomization(None if sd["friction"] is None else sd["friction"].to(dev),
+                               None if sd["inertia_eps"] is None else sd["inertia_eps"].to(dev))
+        self.set_external_forces(None if sd["external_force"] is None else sd["external_force"].to(dev),
+                                 sd["external_local_mask"])
+        self.set_autoreset(*sd["autoreset"])
 
     def error_flags(self) -> torch.Tensor:
         out = torch.empty(self.n, dtype=torch.int32, device=self.device)
