@@ -34,6 +34,8 @@ sys.path.insert(0, ROOT)
 
 # algorithmic bytes per env-step (DESIGN.md "Roofline")
 B_ALG = {"servos": 542 + 284 + 3 * 4 * 2, "pendulum": 346 + 3 * 4 * 2 + 16, "mpc": 157}
+# compact rollout records: observation rows 72 B instead of 120 B, no reward (4 B) / truncated (1 B) stores
+B_ALG_SERVOS_COMPACT = B_ALG["servos"] - 48 - 5
 N_ACTION_BUFFERS = 16
 ROLLOUT_T = 32
 
@@ -268,7 +270,14 @@ def main():
     previous_affinity = bind_to_gpu_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # The rollout all-gather runs on NCCL's own stream while the next rollout simulates. The step kernel
+        # occupies every SM (255 registers x 224 threads leave no room for a second block), so the collective's
+        # CTAs only get SMs when a simulation block retires. Measured on 2 GPUs (tools/run_2gpu_variants.sh): a
+        # high-priority NCCL stream or fewer CTAs (NCCL_MAX_CTAS) make it worse, the default is best.
+        pg_options = None
+        if os.environ.get("UPKIE_BENCH_NCCL_PRIORITY", "0") == "1":
+            pg_options = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_options)
 
     model = Model.standard_upkie()
     peaks, peaks_kind = read_peaks()
@@ -295,7 +304,7 @@ def main():
                            if previous_affinity is not None else "no NUMA binding (single node or unknown topology)")
     total_units = units * world
     value = total_units / (t_ms * 1e-3)
-    b_alg = B_ALG[args.workload]
+    b_alg = B_ALG_SERVOS_COMPACT if config.get("rollout_record", "").startswith("compact") else B_ALG[args.workload]
     achieved = b_alg * n_per_gpu / (kernel_ms * 1e-3) / 1e9  # GB/s per GPU, dominant kernel
     line = {
         "metric": "env-steps/sec" if args.workload != "mpc" else "qp-solves/sec",
@@ -385,8 +394,15 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
             a[:, :, 5] = tau
             a[:, :, 2] = (torch.rand((n, 6), device=dev, generator=gen) * 2 - 1) * tau
             acts.append(a.contiguous())
-        step = env.sim.step_servos
-        obs_bytes = 30 * 4
+        # rollout records: "compact" = position / velocity / torque rows + terminated (73 B/env/step); the constants
+        # of the reference (temperature, voltage, reward, truncated) are not written nor gathered. "full" = 126 B.
+        compact_rollout = os.environ.get("UPKIE_BENCH_ROLLOUT", "compact") == "compact"
+        if compact_rollout:
+            def step(a, obs=None, reward=None, terminated=None, truncated=None):
+                return env.sim.step_servos_compact(a, obs=obs, terminated=terminated)
+        else:
+            step = env.sim.step_servos
+        obs_bytes = (18 if compact_rollout else 30) * 4
         act_bytes = 36 * 4
     else:
         init = RobotState(randomization=RobotStateRandomization(pitch=0.1))
@@ -395,16 +411,26 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         acts = [((torch.rand((n, 1), device=dev, generator=gen) * 2 - 1) * 3.0).contiguous()
                 for _ in range(N_ACTION_BUFFERS)]
         step = env.sim.step_pendulum
+        compact_rollout = False
         obs_bytes = 4 * 4
         act_bytes = 4
     env.sim.set_autoreset(1, 2025, rank * n)
     env.sim.reset(seed=2025, env_offset=rank * n)
 
     # rollout buffer gathered over NVLink once per T steps
-    from upkie_b200.sharding import RolloutBuffer
+    from upkie_b200.sharding import PeerRolloutBuffer, RolloutBuffer
 
-    # two buffers: the all-gather of rollout r (communication stream, NVLink) overlaps the simulation of r + 1
-    rollouts = [RolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev) for _ in range(2)]
+    # two buffers: the gather of rollout r (NVLink) overlaps the simulation of r + 1. "peer": symmetric-memory
+    # buffers, every rank pushes its slot to the peers with the copy engines (no SM); "nccl": all_gather_into_tensor
+    gather_mode = os.environ.get("UPKIE_BENCH_GATHER", "peer") if world > 1 else "none"
+    if gather_mode == "peer":
+        try:
+            rollouts = [PeerRolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
+        except Exception as exc:  # symmetric memory unavailable on this box: fall back to NCCL's collective
+            print(f"bench.py: symmetric-memory rollout buffer unavailable ({exc!r}); using NCCL all-gather", file=sys.stderr)
+            gather_mode = "nccl"
+    if gather_mode != "peer":
+        rollouts = [RolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
     works = [None, None]
 
     for k in range(W):
@@ -427,17 +453,27 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
             # the kernel writes observation / reward / masks straight into the rollout slot of this step
             cur = (k // ROLLOUT_T) % 2
             if k % ROLLOUT_T == 0 and works[cur] is not None:
-                works[cur].wait()  # the gather that last read this buffer must be done before it is overwritten
+                # the gather that last read this buffer must be done before it is overwritten
+                if gather_mode == "peer":
+                    rollouts[cur].wait()
+                else:
+                    works[cur].wait()
                 works[cur] = None
             so, sr, ste, stru = rollouts[cur].slot(k)
             step(acts[k % N_ACTION_BUFFERS], obs=so, reward=sr, terminated=ste, truncated=stru)
             events[k + 1].record()
             if world > 1 and (k + 1) % ROLLOUT_T == 0:
-                # one NCCL all-gather of the [T, n, 126 B] buffer per rollout, asynchronous
-                _, works[cur] = rollouts[cur].gather_raw(async_op=True)
-        for w_ in works:
+                # one gather of the [T, n, 126 B] buffer per rollout, asynchronous
+                if gather_mode == "peer":
+                    works[cur] = rollouts[cur].push()
+                else:
+                    _, works[cur] = rollouts[cur].gather_raw(async_op=True)
+        for i_, w_ in enumerate(works):
             if w_ is not None:
-                w_.wait()
+                if gather_mode == "peer":
+                    rollouts[i_].wait()
+                else:
+                    w_.wait()
         end.record()  # after the last step / all-gather queued on this stream
         torch.cuda.synchronize()
         if profiling:
@@ -493,8 +529,13 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         ),
         "envs_per_gpu": n,
         "global_envs": n * world,
+        "rollout_record": ("compact 73 B/env/step (position, velocity, torque rows + terminated; the reference's constants "
+                           "temperature, voltage, reward, truncated are not stored)" if compact_rollout
+                           else f"{obs_bytes + 6} B/env/step"),
         "substeps_per_step": 5,
-        "parallelism": f"env-index sharded x{world}" + (", NCCL all-gather of [32] rollout buffer" if world > 1 else ""),
+        "parallelism": f"env-index sharded x{world}" + (
+            ("; rollout buffer [32] pushed to the peers' symmetric-memory buffers by the copy engines over NVLink"
+             if gather_mode == "peer" else "; NCCL all-gather of the [32] rollout buffer") if world > 1 else ""),
         "l2": f"{N_ACTION_BUFFERS} rotating action buffers ({N_ACTION_BUFFERS * n * act_bytes / 1e6:.0f} MB"
               " vs 126 MB L2); robot state stays resident by design",
     }

@@ -317,6 +317,11 @@ int upkie_b200_step_gyropod(void* handle, const float* action /* [N][act_dim] */
                             int act_dim, float* obs, float* reward,
                             uint8_t* terminated, uint8_t* truncated, void* stream);
 
+/* UpkieServos step, device buffers, compact observation rows obs[N][6][3] (position, velocity, torque; see
+ * upkie_b200_step_servos_host_compact for what is left out and why). What a rollout buffer gathered across
+ * GPUs should carry: 73 B instead of 126 B per env and step over NVLink. */
+int upkie_b200_step_servos_compact(void* handle, const float* action, float* obs, uint8_t* terminated, void* stream);
+
 /* Same calls with HOST buffers and a stream synchronisation inside the call
  * (the `e2e` path of bench.py). When every buffer is pinned and mapped
  * (cudaHostAlloc / cudaHostRegister(..Mapped), torch pin_memory) the step is

@@ -152,6 +152,10 @@ def test_host_buffer_api_equals_device_api(model, torch, n):
     p4[:] = a
     c4, ct4 = s4.step_servos_host_compact(p4)
     c5, ct5 = s5.step_servos_host_compact(a.copy())  # pageable: staged through the handle's pinned buffers
+    s6 = _sim(n, model)
+    s6.set_state(st)
+    c6, ct6 = s6.step_servos_compact(torch.from_numpy(a).cuda())  # device buffers, same TILE=1 kernel
+    assert np.array_equal(c6.cpu().numpy(), c4) and np.array_equal(ct6.cpu().numpy(), ct4)
     for c, ct in ((c4, ct4), (c5, ct5)):
         assert c.shape == (n, 6, 3) and np.array_equal(c, o2[:, :, :3]) and np.array_equal(ct, t2)  # TILE=1 both
     g = np.random.default_rng(3).uniform(-3, 3, (n, 2)).astype(np.float32)

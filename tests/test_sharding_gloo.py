@@ -59,6 +59,17 @@ def _worker(rank, world, port, n_global, T, obs_dim, out_dir):
             assert torch.equal(full["truncated"][t], ((gidx.long() + t) % 11 == 0).to(torch.uint8))
         raw = buf.gather_raw()
         assert raw.shape == (world, buf.nbytes) and torch.equal(raw[rank], buf.raw)
+        # compact records (observation rows + terminated only: 73 B/env/step for UpkieServos' 18 floats)
+        cb = RolloutBuffer(T, cnt, obs_dim, "cpu", compact=True)
+        assert cb.rec == 4 * obs_dim + 1 and cb.nbytes < buf.nbytes
+        for t in range(T):
+            o, r, te, tr = cb.slot(t)
+            assert r is None and tr is None
+            o.copy_(idx[:, None] * 10.0 + torch.arange(obs_dim)[None, :] + 1000.0 * t)
+            te.copy_(((idx.long() + t) % 7 == 0).to(torch.uint8))
+        cfull = cb.gather()
+        assert set(cfull) == {"obs", "terminated"}
+        assert torch.equal(cfull["obs"], full["obs"]) and torch.equal(cfull["terminated"], full["terminated"])
         # scalar statistics reduce across ranks (mask counts)
         c = buf.terminated.sum().to(torch.float64).reshape(1)
         dist.all_reduce(c)
@@ -91,6 +102,7 @@ def test_rollout_buffer_single_process_roundtrip():
     for t in range(T):
         assert torch.equal(full["obs"][t], ref[t][0]) and torch.equal(full["terminated"][t], ref[t][1])
     assert buf.rec == 4 * d + 6 and RolloutBuffer(1, 1, 30, "cpu").rec == 126  # 126 B/env/step
+    assert RolloutBuffer(1, 1, 18, "cpu", compact=True).rec == 73
     assert buf.nbytes >= T * n * buf.rec
     # slots are views of the one byte buffer that gets gathered
     o, r, te, tr = buf.slot(1)

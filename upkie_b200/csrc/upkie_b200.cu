@@ -555,6 +555,15 @@ int upkie_b200_step_servos(void* handle, const float* action, float* obs, float*
   return step_any(h, MODE_SERVOS, action, obs, reward, terminated, truncated, static_cast<cudaStream_t>(stream));
 }
 
+int upkie_b200_step_servos_compact(void* handle, const float* action, float* obs, uint8_t* terminated, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  if (!action || !obs || !terminated) return fail(UPKIE_B200_EINVAL, "step_servos_compact: null buffer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return step_range(h, MODE_SERVOS, 0, h->n, action, obs, nullptr, terminated, nullptr, static_cast<cudaStream_t>(stream),
+                    /*tile=*/true, /*persistent=*/false, /*compact=*/true);
+}
+
 int upkie_b200_step_gyropod(void* handle, const float* action, int act_dim, float* obs, float* reward,
                             uint8_t* terminated, uint8_t* truncated, void* stream) {
   Handle* h = as_handle(handle);

@@ -38,13 +38,17 @@ class RolloutBuffer:
     every rank.
     """
 
-    def __init__(self, horizon: int, n_local: int, obs_dim: int, device, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, horizon: int, n_local: int, obs_dim: int, device, group: Optional[dist.ProcessGroup] = None,
+                 compact: bool = False):
         self.T, self.n, self.obs_dim = int(horizon), int(n_local), int(obs_dim)
-        self.rec = 4 * self.obs_dim + 6
+        # compact records carry observation rows and `terminated` only: reward (0.0) and truncated (False) are
+        # constants of the reference (upkie_env.py:197,230) and stay out of the gather
+        self.compact = bool(compact)
+        self.rec = 4 * self.obs_dim + (1 if self.compact else 6)
         self.group = group
         self.device = torch.device(device)
         T, n, d = self.T, self.n, self.obs_dim
-        self._sizes = [T * n * d * 4, T * n * 4, T * n, T * n]
+        self._sizes = [T * n * d * 4, 0 if self.compact else T * n * 4, T * n, 0 if self.compact else T * n]
         total = sum(self._sizes)
         self.nbytes = (total + 15) // 16 * 16
         self.raw = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
@@ -57,6 +61,8 @@ class RolloutBuffer:
         o2 = o1 + T * n * 4
         o3 = o2 + T * n
         obs = raw[o0:o1].view(torch.float32).view(T, n, d)
+        if self.compact:
+            return obs, None, raw[o1:o1 + T * n].view(T, n), None
         rew = raw[o1:o2].view(torch.float32).view(T, n)
         term = raw[o2:o3].view(T, n)
         trunc = raw[o3:o3 + T * n].view(T, n)
@@ -65,25 +71,32 @@ class RolloutBuffer:
     def slot(self, t: int):
         """Output tensors of time step ``t`` (modulo the horizon)."""
         k = t % self.T
+        if self.compact:
+            return self.obs[k], None, self.terminated[k], None
         return self.obs[k], self.reward[k], self.terminated[k], self.truncated[k]
 
     def record(self, t: int, obs: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor, truncated: torch.Tensor):
         """Copy-in variant of ``slot`` for producers that own their output tensors."""
         o, r, te, tr = self.slot(t)
         o.copy_(obs.reshape(self.n, self.obs_dim))
-        r.copy_(reward)
         te.copy_(terminated)
-        tr.copy_(truncated)
+        if not self.compact:
+            r.copy_(reward)
+            tr.copy_(truncated)
 
     def gather(self) -> Dict[str, torch.Tensor]:
         """``{"obs": [T, N, obs_dim], "reward": [T, N], "terminated": [T, N], "truncated": [T, N]}``
         over all ranks (``N = world_size * n``; equal shards)."""
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            if self.compact:
+                return {"obs": self.obs, "terminated": self.terminated}
             return {"obs": self.obs, "reward": self.reward, "terminated": self.terminated, "truncated": self.truncated}
         world = dist.get_world_size(self.group)
         out = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(out, self.raw, group=self.group)
         parts = [self._views(out[r * self.nbytes:(r + 1) * self.nbytes], self.n) for r in range(world)]
+        if self.compact:
+            return {"obs": torch.cat([p[0] for p in parts], dim=1), "terminated": torch.cat([p[2] for p in parts], dim=1)}
         return {
             "obs": torch.cat([p[0] for p in parts], dim=1),
             "reward": torch.cat([p[1] for p in parts], dim=1),
@@ -106,3 +119,68 @@ class RolloutBuffer:
         work = dist.all_gather_into_tensor(self._gathered, self.raw, group=self.group, async_op=async_op)
         out = self._gathered.view(world, self.nbytes)
         return (out, work) if async_op else out
+
+
+class PeerRolloutBuffer(RolloutBuffer):
+    """Rollout buffer in symmetric memory (one node, NVLink / NVSwitch): every rank holds the FULL
+    ``[world, nbytes]`` gathered buffer; its step kernels write the rank's own slot in place, and ``push()``
+    copies that slot into the same slot of every peer's buffer with the copy engines (peer-to-peer
+    ``cudaMemcpyAsync`` over NVLink) on a side stream.
+
+    Why not NCCL's all-gather here: the step kernel occupies every SM (255 registers x 224 threads leave no
+    room for another block), so a collective implemented as SM kernels only advances when simulation blocks
+    retire and slows the simulation it is meant to overlap (2 GPUs: 74-89 % weak-scaling efficiency). Copy
+    engines need no SM.
+    """
+
+    def __init__(self, horizon: int, n_local: int, obs_dim: int, device, group: Optional[dist.ProcessGroup] = None,
+                 compact: bool = False):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.T, self.n, self.obs_dim = int(horizon), int(n_local), int(obs_dim)
+        self.compact = bool(compact)
+        self.rec = 4 * self.obs_dim + (1 if self.compact else 6)
+        self.group = group if group is not None else dist.group.WORLD
+        self.device = torch.device(device)
+        T, n, d = self.T, self.n, self.obs_dim
+        self._sizes = [T * n * d * 4, 0 if self.compact else T * n * 4, T * n, 0 if self.compact else T * n]
+        self.nbytes = (sum(self._sizes) + 255) // 256 * 256
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.all = symm_mem.empty(self.world * self.nbytes, dtype=torch.uint8, device=self.device)
+        self.all.zero_()
+        self._hdl = symm_mem.rendezvous(self.all, self.group)
+        self.raw = self.all[self.rank * self.nbytes:(self.rank + 1) * self.nbytes]
+        self.obs, self.reward, self.terminated, self.truncated = self._views(self.raw, n)
+        self._peers = [
+            self._hdl.get_buffer(p, (self.world * self.nbytes,), torch.uint8, 0)[self.rank * self.nbytes:(self.rank + 1) * self.nbytes]
+            for p in range(self.world)
+        ]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._done = None
+
+    def push(self) -> "torch.cuda.Event":
+        """Start pushing this rank's slot to every peer (asynchronous, side stream). The returned event fires when
+        this rank's copies are done AND every peer's copies into this rank's buffer are done (cross-rank barrier
+        on the side stream): after it, ``gathered()`` is complete and the slot may be rewritten."""
+        cur = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(cur)
+        with torch.cuda.stream(self._copy_stream):
+            for p in range(self.world):
+                if p != self.rank:
+                    self._peers[p].copy_(self.raw, non_blocking=True)
+            self._hdl.barrier(channel=0)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._done = ev
+        return ev
+
+    def wait(self) -> None:
+        """Make the current stream wait for the last ``push()``."""
+        if self._done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done)
+            self._done = None
+
+    def gathered(self) -> torch.Tensor:
+        """``[world, nbytes]`` bytes, rank-major (same layout as ``RolloutBuffer.gather_raw``)."""
+        return self.all.view(self.world, self.nbytes)

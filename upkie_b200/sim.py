@@ -160,6 +160,23 @@ class UpkieSim:
         )
         return obs, reward, terminated, truncated
 
+    def step_servos_compact(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, terminated=None):
+        """Device buffers, compact rows: ``obs[N, 6, 3]`` (position, velocity, torque) and ``terminated``; the
+        constants of the reference (temperature, voltage, reward, truncated) are not written. What a rollout
+        buffer gathered across GPUs carries (``RolloutBuffer(..., compact=True)``)."""
+        self._check_tensor(action, (self.n, 6, 6), name="action")
+        if obs is None:
+            if getattr(self, "obs_servos_compact", None) is None:
+                self.obs_servos_compact = torch.empty((self.n, 6, 3), dtype=torch.float32, device=self.device)
+            obs = self.obs_servos_compact
+        elif obs.numel() != self.n * 18 or obs.dtype != torch.float32 or not obs.is_contiguous() or obs.data_ptr() % 16:
+            raise UpkieRuntimeError("obs: expected contiguous 16-byte aligned float32 [N, 6, 3]")
+        terminated = self.terminated if terminated is None else terminated
+        if terminated is not self.terminated:
+            self._check_tensor(terminated, (self.n,), torch.uint8, "terminated")
+        check(lib().upkie_b200_step_servos_compact(self._h, _ptr(action), _ptr(obs), _ptr(terminated), self._stream()))
+        return obs, terminated
+
     def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
                      truncated=None):
         self._check_tensor(action, (self.n, 2), name="action")
