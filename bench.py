@@ -422,7 +422,10 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
 
     # two buffers: the gather of rollout r (NVLink) overlaps the simulation of r + 1. "peer": symmetric-memory
     # buffers, every rank pushes its slot to the peers with the copy engines (no SM); "nccl": all_gather_into_tensor
-    gather_mode = os.environ.get("UPKIE_BENCH_GATHER", "peer") if world > 1 else "none"
+    # Measured (tools/run_2gpu_variants.sh, tools/run_8gpu.sh): 2 GPUs peer 96 % vs nccl 84 % weak-scaling efficiency;
+    # 8 GPUs nccl 64 %, the first (unstaggered, one-stream) peer push collapsed there -> nccl stays the default
+    # beyond 2 GPUs until the staggered push is validated at 8.
+    gather_mode = os.environ.get("UPKIE_BENCH_GATHER", "peer" if world == 2 else "nccl") if world > 1 else "none"
     if gather_mode == "peer":
         try:
             rollouts = [PeerRolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]

@@ -156,22 +156,30 @@ class PeerRolloutBuffer(RolloutBuffer):
             self._hdl.get_buffer(p, (self.world * self.nbytes,), torch.uint8, 0)[self.rank * self.nbytes:(self.rank + 1) * self.nbytes]
             for p in range(self.world)
         ]
-        self._copy_stream = torch.cuda.Stream(device=self.device)
+        # several side streams so that the pushes to different peers run on different copy engines at once
+        self._copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(min(4, max(1, self.world - 1)))]
         self._done = None
 
     def push(self) -> "torch.cuda.Event":
-        """Start pushing this rank's slot to every peer (asynchronous, side stream). The returned event fires when
-        this rank's copies are done AND every peer's copies into this rank's buffer are done (cross-rank barrier
-        on the side stream): after it, ``gathered()`` is complete and the slot may be rewritten."""
+        """Start pushing this rank's slot to every peer (asynchronous, side streams). Destinations are visited in
+        ring order (rank + 1, rank + 2, ...): at any moment every GPU receives from one sender instead of all
+        ranks converging on peer 0, then peer 1, ... The returned event fires when this rank's copies are done AND
+        every peer's copies into this rank's buffer are done (cross-rank barrier on a side stream): after it,
+        ``gathered()`` is complete and the slot may be rewritten."""
         cur = torch.cuda.current_stream(self.device)
-        self._copy_stream.wait_stream(cur)
-        with torch.cuda.stream(self._copy_stream):
-            for p in range(self.world):
-                if p != self.rank:
-                    self._peers[p].copy_(self.raw, non_blocking=True)
+        for s_ in self._copy_streams:
+            s_.wait_stream(cur)
+        for i in range(1, self.world):
+            p = (self.rank + i) % self.world
+            with torch.cuda.stream(self._copy_streams[(i - 1) % len(self._copy_streams)]):
+                self._peers[p].copy_(self.raw, non_blocking=True)
+        main = self._copy_streams[0]
+        for s_ in self._copy_streams[1:]:
+            main.wait_stream(s_)
+        with torch.cuda.stream(main):
             self._hdl.barrier(channel=0)
             ev = torch.cuda.Event()
-            ev.record(self._copy_stream)
+            ev.record(main)
         self._done = ev
         return ev
 
