@@ -342,7 +342,7 @@ def main():
         sm_mhz = clocks.get("sm_mhz") or 1700.0
         # warp instructions per env-step of the servos workload, ncu smsp__inst_executed.sum / warps
         # (profiles/r01_ncu_summary.md, paired f32x2 legs, end of round 1); 78.5 % of them FFMA(2)/FMUL(2)/FADD(2)
-        instr_per_env_step = 15_136
+        instr_per_env_step = 13_921
         sched_cycles = 148 * 4 * sm_mhz * 1e6  # issue slots per second (one warp instruction each)
         ipc = instr_per_env_step * (n_per_gpu / 32.0) / (kernel_ms * 1e-3) / sched_cycles
         line["roofline"]["fp32_issue"] = {
