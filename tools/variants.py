@@ -17,23 +17,23 @@ VARIANTS = {
     "paired_s1": [],
     "paired_s0": ["-DUPKIE_PHASE_SYNC_LEVEL=0"],
     "scalar_s1": ["-DUPKIE_PAIRED_LEGS=0"],
-    "paired_s1_r168": ["-DUPKIE_MAX_THREADS=384", "-DUPKIE_MIN_BLOCKS=1"],
-    "paired_s1_r128": ["-DUPKIE_MAX_THREADS=512", "-DUPKIE_MIN_BLOCKS=1"],
+    "paired_s1_r128": ["-DUPKIE_MAX_THREADS=512", "-DUPKIE_MIN_BLOCKS=1"],  # run with UPKIE_B200_BLOCK=448
 }
+SOURCES = ["upkie_b200.cu", "step_device.cu", "step_host.cu"]
 
 
 def build():
     os.makedirs(OUT, exist_ok=True)
     procs = []
     for name, flags in VARIANTS.items():
-        cmd = BASE + flags + ["-Xptxas", "-v", "-o", os.path.join(OUT, f"lib_{name}.so"), os.path.join(CSRC, "upkie_b200.cu")]
+        cmd = BASE + flags + ["-Xptxas", "-v", "-o", os.path.join(OUT, f"lib_{name}.so")] + [os.path.join(CSRC, s) for s in SOURCES]
         procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for name, p in procs:
         out, _ = p.communicate()
         lines = out.splitlines()
         info = ""
         for i, l in enumerate(lines):
-            if "k_stepILi0ELi1E" in l:
+            if "k_stepILi0ELi1ELi0ELi0E" in l:
                 info = " | ".join(x.strip() for x in lines[i + 1:i + 3])
         print(f"{name:16s} rc={p.returncode} {info}")
 
