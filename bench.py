@@ -329,7 +329,10 @@ def main():
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full,
+            # profiles/r01_ncu_summary.md): below the algorithmic bytes because the 12 MB of robot state stay in the
+            # 126 MB L2 between launches (reads = actions + state + randomisation, writes almost nil)
+            "traffic": 22_959_360 if (args.workload == "servos" and n_per_gpu == 65536) else None,
             "peak_kind": f"{peaks_kind} (MEASURED_PEAKS.json hbm_gbs)" if peaks_kind == "measured" else "fallback 6650 GB/s",
             "algorithmic_bytes_per_unit": b_alg,
             "kernel_ms": kernel_ms,
