@@ -26,7 +26,6 @@ available.
 """
 
 import math
-import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 from typing import List, Optional
 
