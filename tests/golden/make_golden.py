@@ -140,6 +140,56 @@ def main():
     nested = {"imu": {"linear_acceleration": np.array([0.5, -1.5, 9.81])}, "n": 3, "flag": True, "name": "upkie"}
     out["wire"] = {"action_hex": packer.pack(action).hex(), "nested_hex": packer.pack(nested).hex()}
 
+    # upkie.model.Model / KinematicTree (upkie/model/model.py:57-110, kinematic_tree.py:52-143) on a URDF written by
+    # upkie_b200.urdf.write_urdf (the real upkie_description is absent): what the reference parses out of it
+    # (wheel radius / base, wheeledness, base -> IMU rotation, joint order and limits) pins upkie_b200's own loader.
+    import tempfile
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from upkie_b200.model import Model as B200Model
+    from upkie_b200.urdf import write_urdf
+
+    stub = types.ModuleType("upkie_description")
+    stub.URDF_PATH = ""
+    sys.modules["upkie_description"] = stub
+    model_pkg = types.ModuleType("upkie.model")
+    model_pkg.__path__ = [os.path.join(REF, "upkie", "model")]
+    sys.modules["upkie.model"] = model_pkg
+
+    def load_model_module(name):
+        spec = importlib.util.spec_from_file_location(f"upkie.model.{name}", os.path.join(REF, "upkie", "model", f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[f"upkie.model.{name}"] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    for name in ("se3", "joint_limit", "joint", "collision_geometry", "link", "kinematic_tree"):
+        load_model_module(name)
+    ref_model_mod = load_model_module("model")
+    urdf_cases = []
+    for split, flip in ((True, False), (False, False), (True, True)):
+        m = B200Model.standard_upkie()
+        if flip:  # a right-wheeled variant (Cookie-style): wheel axes reversed
+            m.joint_axis = m.joint_axis.copy()
+            m.joint_axis[[2, 5]] *= -1.0
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "robot.urdf")
+            write_urdf(m, path, split_fixed_links=split)
+            text = open(path).read()
+            rm = ref_model_mod.Model(path)
+            urdf_cases.append({
+                "urdf": text,
+                "wheel_radius": rm.wheel_radius,
+                "wheel_base": rm.wheel_base,
+                "left_wheeled": rm.left_wheeled,
+                "rotation_base_to_imu": np.asarray(rm.rotation_base_to_imu).tolist(),
+                "joint_names": [j.name for j in rm.joints],
+                "joint_limits": [[j.limit.lower, j.limit.upper, j.limit.velocity, j.limit.effort] for j in rm.joints],
+                "upper_leg_joints": [j.name for j in rm.upper_leg_joints],
+                "wheel_joints": [j.name for j in rm.wheel_joints],
+            })
+    out["urdf_model"] = urdf_cases
+
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT)

@@ -82,3 +82,30 @@ def test_backend_adapter_follows_the_backend_contract(model):
     with pytest.raises(AssertionError):
         backend.step({"servo": {"left_hip": dict(servo_action, velocity=float("nan"))}})
     backend.close()
+
+
+def test_loader_agrees_with_the_reference_model_parser(tmp_path):
+    """tests/golden/reference_vectors.json["urdf_model"]: URDFs parsed by the reference's own
+    upkie.model.Model / KinematicTree (imported in the build container, model.py:57-110). Our loader must read the
+    same wheel radius / base, wheeledness, base -> IMU rotation, joint order and limits out of the same files."""
+    import json
+    import os
+
+    from upkie_b200.model import Model
+
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))["urdf_model"]
+    assert len(golden) == 3 and {c["left_wheeled"] for c in golden} == {True, False}
+    for k, case in enumerate(golden):
+        path = tmp_path / f"robot_{k}.urdf"
+        path.write_text(case["urdf"])
+        m = Model.from_urdf(str(path))
+        assert m.wheel_radius == pytest.approx(case["wheel_radius"], abs=1e-12)
+        assert m.wheel_base == pytest.approx(case["wheel_base"], abs=1e-12)
+        assert m.left_wheeled == case["left_wheeled"]
+        assert np.allclose(m.rotation_base_to_imu, np.asarray(case["rotation_base_to_imu"]), atol=1e-12)
+        assert [j.name for j in m.joints] == case["joint_names"]
+        lim = np.asarray(case["joint_limits"])
+        assert np.array_equal(m.q_lower, lim[:, 0]) and np.array_equal(m.q_upper, lim[:, 1])
+        assert np.array_equal(m.qd_max, lim[:, 2]) and np.array_equal(m.tau_max, lim[:, 3])
+        assert [j.name for j in m.upper_leg_joints] == case["upper_leg_joints"]
+        assert [j.name for j in m.wheel_joints] == case["wheel_joints"]
