@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _abi
+from .base_velocity import base_velocity_tick
 from .exceptions import UpkieException, UpkieRuntimeError
 from .gym_compat import VectorEnv, batch_space, spaces
 from .model import Model, default_model
@@ -486,15 +487,10 @@ class B200VectorEnv(VectorEnv):
             # (x, y) dead-reckon the commanded velocity along the post-step yaw
             if self._spine is None:
                 self._spine = self.sim.spine_obs()
-            linear_velocity = action[:, 0].contiguous()
-            ground_velocity = self.mpc_balancer.step_spine(linear_velocity, self._spine, self.dt)
-            gyro_action = torch.stack([ground_velocity, action[:, 1]], dim=1).contiguous()
-            obs6, rew, term, trunc = self.sim.step_gyropod(gyro_action)
-            self._spine = self.sim.spine_obs()
-            yaw = obs6[:, 2]
-            self._xy[:, 0] += linear_velocity * torch.cos(yaw) * self.dt
-            self._xy[:, 1] += linear_velocity * torch.sin(yaw) * self.dt
-            obs = torch.cat([self._xy, yaw[:, None]], dim=1)
+            obs, rew, term, trunc, self._spine = base_velocity_tick(
+                action, self._spine, self._xy, self.dt, self.mpc_balancer.step_spine, self.sim.step_gyropod,
+                self.sim.spine_obs,
+            )
         else:
             obs, rew, term, trunc = self.sim.step_pendulum(action)
         return obs, rew, term, trunc, {"spine_observation": SpineObservations(self.sim)}

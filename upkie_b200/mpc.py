@@ -103,17 +103,9 @@ class BatchedMPCBalancer:
     def step_spine(self, target_ground_velocity: torch.Tensor, spine_obs: torch.Tensor, dt: float):
         """``MPCBalancer.step(target, spine_observation, dt)`` with the flat
         ``[N, 62]`` spine observation (``mpc_balancer.py:253-258``)."""
-        A = _abi
-        x0 = torch.stack(
-            [
-                spine_obs[:, A.SP_ODOM_POS],
-                spine_obs[:, A.SP_PITCH],
-                spine_obs[:, A.SP_ODOM_VEL],
-                spine_obs[:, A.SP_BASE_ANGVEL + 1],
-            ],
-            dim=1,
-        ).contiguous()
-        contact = (spine_obs[:, A.SP_CONTACT] > 0.5).to(torch.uint8)
+        from .base_velocity import mpc_inputs_from_spine
+
+        x0, contact = mpc_inputs_from_spine(spine_obs)
         return self.step_tensors(x0, target_ground_velocity.contiguous(), contact, dt)
 
     def step(self, x0: np.ndarray, v_target: np.ndarray, floor_contact: np.ndarray, dt: float) -> np.ndarray:
