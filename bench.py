@@ -429,13 +429,15 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     # 8 GPUs nccl 64 %, the first (unstaggered, one-stream) peer push collapsed there -> nccl stays the default
     # beyond 2 GPUs until the staggered push is validated at 8.
     gather_mode = os.environ.get("UPKIE_BENCH_GATHER", "peer" if world == 2 else "nccl") if world > 1 else "none"
-    if gather_mode == "peer":
+    if gather_mode in ("peer", "multicast"):
         try:
             rollouts = [PeerRolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
+            if gather_mode == "multicast" and not (servos and compact_rollout and rollouts[0].multicast_supported):
+                raise RuntimeError("NVSwitch multicast needs the compact servos records and multicast-capable symmetric memory")
         except Exception as exc:  # symmetric memory unavailable on this box: fall back to NCCL's collective
             print(f"bench.py: symmetric-memory rollout buffer unavailable ({exc!r}); using NCCL all-gather", file=sys.stderr)
             gather_mode = "nccl"
-    if gather_mode != "peer":
+    if gather_mode not in ("peer", "multicast"):
         rollouts = [RolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
     works = [None, None]
 
@@ -460,23 +462,34 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
             cur = (k // ROLLOUT_T) % 2
             if k % ROLLOUT_T == 0 and works[cur] is not None:
                 # the gather that last read this buffer must be done before it is overwritten
-                if gather_mode == "peer":
+                if gather_mode == "multicast":
+                    pass  # stream order: publish() already ran on this stream
+                elif gather_mode == "peer":
                     rollouts[cur].wait()
                 else:
                     works[cur].wait()
                 works[cur] = None
-            so, sr, ste, stru = rollouts[cur].slot(k)
-            step(acts[k % N_ACTION_BUFFERS], obs=so, reward=sr, terminated=ste, truncated=stru)
+            if gather_mode == "multicast":
+                # EXPERIMENTAL (UPKIE_BENCH_GATHER=multicast): the kernel's rows go to the NVSwitch multicast address
+                # of this rank's slot and land in every GPU's buffer; a barrier per rollout replaces the gather
+                env.sim.step_servos_multicast(acts[k % N_ACTION_BUFFERS], *rollouts[cur].multicast_slot(k))
+            else:
+                so, sr, ste, stru = rollouts[cur].slot(k)
+                step(acts[k % N_ACTION_BUFFERS], obs=so, reward=sr, terminated=ste, truncated=stru)
             events[k + 1].record()
             if world > 1 and (k + 1) % ROLLOUT_T == 0:
                 # one gather of the [T, n, 126 B] buffer per rollout, asynchronous
-                if gather_mode == "peer":
+                if gather_mode == "multicast":
+                    rollouts[cur].publish()
+                elif gather_mode == "peer":
                     works[cur] = rollouts[cur].push()
                 else:
                     _, works[cur] = rollouts[cur].gather_raw(async_op=True)
         for i_, w_ in enumerate(works):
             if w_ is not None:
-                if gather_mode == "peer":
+                if gather_mode == "multicast":
+                    pass
+                elif gather_mode == "peer":
                     rollouts[i_].wait()
                 else:
                     w_.wait()
@@ -541,7 +554,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         "substeps_per_step": 5,
         "parallelism": f"env-index sharded x{world}" + (
             ("; rollout buffer [32] pushed to the peers' symmetric-memory buffers by the copy engines over NVLink"
-             if gather_mode == "peer" else "; NCCL all-gather of the [32] rollout buffer") if world > 1 else ""),
+             if gather_mode == "peer" else
+             "; rollout rows stored to the NVSwitch multicast address of the symmetric buffer (experimental)"
+             if gather_mode == "multicast" else "; NCCL all-gather of the [32] rollout buffer") if world > 1 else ""),
         "l2": f"{N_ACTION_BUFFERS} rotating action buffers ({N_ACTION_BUFFERS * n * act_bytes / 1e6:.0f} MB"
               " vs 126 MB L2); robot state stays resident by design",
     }

@@ -322,6 +322,14 @@ int upkie_b200_step_gyropod(void* handle, const float* action /* [N][act_dim] */
  * GPUs should carry: 73 B instead of 126 B per env and step over NVLink. */
 int upkie_b200_step_servos_compact(void* handle, const float* action, float* obs, uint8_t* terminated, void* stream);
 
+/* Same step, but obs_mc / terminated_mc are NVSwitch MULTICAST addresses (CUmulticastObject mapping of a buffer
+ * that exists at the same offset on every GPU of the node, e.g. torch.distributed._symmetric_memory's
+ * multicast_ptr + offset): rows leave through multimem.st and land in every GPU's buffer, which is the per-step
+ * all-gather of the rollout with no collective kernel. n_envs must be a multiple of 32. The caller synchronises the
+ * ranks (a barrier per rollout) before reading. EXPERIMENTAL in round 1: compiled and unit-sized, not yet run on a
+ * multi-GPU box. */
+int upkie_b200_step_servos_multicast(void* handle, const float* action, float* obs_mc, uint8_t* terminated_mc, void* stream);
+
 /* Same calls with HOST buffers and a stream synchronisation inside the call
  * (the `e2e` path of bench.py). When every buffer is pinned and mapped
  * (cudaHostAlloc / cudaHostRegister(..Mapped), torch pin_memory) the step is

@@ -90,5 +90,6 @@ struct StepArgs {
 
 cudaError_t launch_step_device(const StepArgs& a);  // step_device.cu
 cudaError_t launch_step_host(const StepArgs& a);    // step_host.cu
+cudaError_t launch_step_multicast(const StepArgs& a);  // step_multicast.cu: TILE=2, UpkieServos, compact rows
 
 }  // namespace upkie_b200

@@ -12,6 +12,17 @@
 namespace upkie_b200 {
 namespace {
 
+// NVSwitch multicast stores (TILE=2): one store to the multicast address of a symmetric buffer is replicated by the
+// switch into the same offset of every GPU's buffer -- the rollout "all-gather" without any collective kernel or copy.
+__device__ __forceinline__ void mc_store4(float4* addr, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void mc_store_u32(uint32_t* addr, uint32_t v) {
+  asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
 // ---- one env tick of the robot `tid` --------------------------------------------------
 // `tile4` is this warp's staging tile (TILE=1): on entry it holds the warp's 32 action rows when
 // `full` (prefetched by the caller), and it is reused to transpose the observation rows on the way out.
@@ -164,7 +175,10 @@ __device__ __forceinline__ void step_env(
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int idx = k * 32 + lane;
-          if (idx < 32 * 18 / 4) op[idx] = tile4[idx];
+          if (idx < 32 * 18 / 4) {
+            if (TILE == 2) mc_store4(op + idx, tile4[idx]);
+            else op[idx] = tile4[idx];
+          }
         }
       } else if (live) {
         float2* op = reinterpret_cast<float2*>(obs + size_t(i) * 18);
@@ -207,9 +221,19 @@ __device__ __forceinline__ void step_env(
     // upkie_pendulum.py:17 _PENDULUM_OBS_INDICES = [1, 0, 4, 3]
     reinterpret_cast<float4*>(obs)[i] = make_float4(o6[1], o6[0], o6[4], o6[3]);
   }
+  if (TILE == 2) {
+    // the host only launches this variant on full, aligned warps (n % 32 == 0): the warp's 32 `terminated` bytes go
+    // out as eight multicast words built from the ballot (multimem.st has no byte form)
+    const unsigned m = __ballot_sync(0xffffffffu, term);
+    if (lane < 8) {
+      const unsigned nib = (m >> (4 * lane)) & 0xFu;
+      const uint32_t word = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+      mc_store_u32(reinterpret_cast<uint32_t*>(terminated + wb) + lane, word);
+    }
+  }
   if (!live) return;
   if (reward) reward[i] = 0.0f;  // upkie_env.py:230
-  terminated[i] = term ? 1 : 0;
+  if (TILE != 2) terminated[i] = term ? 1 : 0;
   if (truncated) truncated[i] = 0;
   if (e) err[i] |= e;
   if (AUTORESET == AUTORESET_NEXT_STEP) done_prev[i] = term ? 1 : 0;
@@ -279,7 +303,7 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
       cp_async_wait<0>();
     }
     __syncwarp();
-    step_env<MODE, AUTORESET, NOISE, 1>(P, i0 + t * blockDim.x + threadIdx.x, n, n_pad, state, action, obs, reward,
+    step_env<MODE, AUTORESET, NOISE, TILE>(P, i0 + t * blockDim.x + threadIdx.x, n, n_pad, state, action, obs, reward,
                                         terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick, seed,
                                         env_offset, ext, ext_local, buf[it & 1], warp_full(t), (coalesce & 2) != 0);
     __syncwarp();  // the tile is free again before the next prefetch lands in it

@@ -1,0 +1,9 @@
+// SPDX-License-Identifier: Apache-2.0
+// NVSwitch-multicast instantiations of the env-step kernel (TILE=2): the TILE=1 tile path whose compact observation
+// rows and `terminated` words leave through multimem.st to the multicast address of a symmetric rollout buffer, so
+// that every GPU's buffer receives them without a collective. UpkieServos only. See kernel_common.cuh.
+#include "step_kernel.cuh"
+
+namespace upkie_b200 {
+cudaError_t launch_step_multicast(const StepArgs& a) { return launch_step_mode<2, MODE_SERVOS>(a); }
+}  // namespace upkie_b200

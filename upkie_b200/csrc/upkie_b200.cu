@@ -208,7 +208,8 @@ int pick_block(const Handle* h, int cnt) {
 // envs [i0, i0 + cnt): all buffers are indexed by the env index of the handle. `tile` selects the
 // shared-memory-tile instantiation (host buffers), see kernel_common.cuh.
 int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float* obs, float* reward, uint8_t* term,
-               uint8_t* trunc, cudaStream_t s, bool tile = false, bool persistent = true, bool compact = false) {
+               uint8_t* trunc, cudaStream_t s, bool tile = false, bool persistent = true, bool compact = false,
+               bool multicast = false) {
   StepArgs a;
   a.P = &h->P;
   a.mode = mode;
@@ -237,7 +238,7 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
   a.seed = h->seed;
   a.env_offset = h->env_offset;
   a.stream = s;
-  CUDA_TRY(tile ? launch_step_host(a) : launch_step_device(a));
+  CUDA_TRY(multicast ? launch_step_multicast(a) : (tile ? launch_step_host(a) : launch_step_device(a)));
   h->step_launches += 1;
   return UPKIE_B200_OK;
 }
@@ -562,6 +563,19 @@ int upkie_b200_step_servos_compact(void* handle, const float* action, float* obs
   CUDA_TRY(cudaSetDevice(h->device));
   return step_range(h, MODE_SERVOS, 0, h->n, action, obs, nullptr, terminated, nullptr, static_cast<cudaStream_t>(stream),
                     /*tile=*/true, /*persistent=*/false, /*compact=*/true);
+}
+
+int upkie_b200_step_servos_multicast(void* handle, const float* action, float* obs_mc, uint8_t* terminated_mc, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  if (!action || !obs_mc || !terminated_mc) return fail(UPKIE_B200_EINVAL, "step_servos_multicast: null buffer");
+  if (h->n % 32 != 0) return fail(UPKIE_B200_EINVAL, "step_servos_multicast: the number of envs must be a multiple of 32");
+  if (((reinterpret_cast<uintptr_t>(action) | reinterpret_cast<uintptr_t>(obs_mc)) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(terminated_mc) & 3) != 0)
+    return fail(UPKIE_B200_EINVAL, "step_servos_multicast: action / obs rows must be 16-byte, terminated 4-byte aligned");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return step_range(h, MODE_SERVOS, 0, h->n, action, obs_mc, nullptr, terminated_mc, nullptr, static_cast<cudaStream_t>(stream),
+                    /*tile=*/true, /*persistent=*/false, /*compact=*/true, /*multicast=*/true);
 }
 
 int upkie_b200_step_gyropod(void* handle, const float* action, int act_dim, float* obs, float* reward,

@@ -183,6 +183,27 @@ class PeerRolloutBuffer(RolloutBuffer):
         self._done = ev
         return ev
 
+    # ---- NVSwitch multicast (EXPERIMENTAL in round 1: not yet run on a multi-GPU box) -------------------------
+    @property
+    def multicast_supported(self) -> bool:
+        return bool(getattr(self._hdl, "has_multicast_support", False)) and int(self._hdl.multicast_ptr) != 0
+
+    def multicast_slot(self, t: int):
+        """``(obs_ptr, terminated_ptr)``: multicast addresses of this rank's slot at time step ``t`` (compact
+        records only). Stores to them (``UpkieSim.step_servos_multicast``) land in EVERY rank's buffer."""
+        if not self.compact:
+            raise ValueError("multicast slots carry compact records")
+        k = t % self.T
+        base = int(self._hdl.multicast_ptr) + self.rank * self.nbytes
+        obs_off = k * self.n * self.obs_dim * 4
+        term_off = self.T * self.n * self.obs_dim * 4 + k * self.n
+        return base + obs_off, base + term_off
+
+    def publish(self) -> None:
+        """After the last multicast step of a rollout: cross-rank barrier on the current stream; once it has
+        passed, ``gathered()`` holds every rank's records on every rank."""
+        self._hdl.barrier(channel=1)
+
     def wait(self) -> None:
         """Make the current stream wait for the last ``push()``."""
         if self._done is not None:

@@ -177,6 +177,13 @@ class UpkieSim:
         check(lib().upkie_b200_step_servos_compact(self._h, _ptr(action), _ptr(obs), _ptr(terminated), self._stream()))
         return obs, terminated
 
+    def step_servos_multicast(self, action: torch.Tensor, obs_mc_ptr: int, terminated_mc_ptr: int) -> None:
+        """EXPERIMENTAL (round 1: compiled, not yet run on a multi-GPU box). Compact rows and ``terminated`` go to
+        NVSwitch multicast addresses (``PeerRolloutBuffer.multicast_slot``): every GPU of the node receives them."""
+        self._check_tensor(action, (self.n, 6, 6), name="action")
+        check(lib().upkie_b200_step_servos_multicast(
+            self._h, _ptr(action), C.c_void_p(int(obs_mc_ptr)), C.c_void_p(int(terminated_mc_ptr)), self._stream()))
+
     def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
                      truncated=None):
         self._check_tensor(action, (self.n, 2), name="action")
