@@ -425,7 +425,8 @@ int upkie_b200_observers_step(void* observers, const float* spine_obs, float* ou
  * call = one controller cycle of period config.dt. `obs` rows in `obs_layout`
  * supply base_orientation.pitch, floor_contact.contact and
  * wheel_odometry.position; target[N][2] = (target_ground_velocity,
- * target_yaw_velocity) of the "bullet" action key, NULL = zeros; action[N][6][6]
+ * target_yaw_velocity) of the "bullet" action key; NULL = the key is absent: ground target 0 for this cycle, the yaw
+ * target keeps its last value (WheelBalancer.cpp:37-42); action[N][6][6]
  * is updated in place: wheel entries overwritten, leg kp/kd scales set. */
 int upkie_b200_default_wheel_balancer_config(UpkieWheelBalancerConfig* config);
 int upkie_b200_wheel_balancer_create(const UpkieWheelBalancerConfig* config, int n_robots, int device, void** balancer);

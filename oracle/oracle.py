@@ -21,6 +21,58 @@ _LIB_PATH = os.path.join(_HERE, "libupkie_oracle.so")
 _lib = None
 
 
+REF_SPINE_PATH = os.path.join(_HERE, "_ref", "libupkie_ref_spine.so")
+
+
+def build_ref(reference: str = "/root/reference") -> str:
+    """Compile the reference's own spine observers / controllers in place into ``oracle/_ref/`` (``make ref``) when
+    the reference tree is present; returns the library path or "" (GPU box, fresh clone without the reference)."""
+    if os.path.isdir(os.path.join(reference, "upkie", "cpp", "observers")):
+        subprocess.check_call(["make", "-C", _HERE, "ref", f"REF={reference}"])
+    return REF_SPINE_PATH if os.path.exists(REF_SPINE_PATH) else ""
+
+
+class RefSpine:
+    """ctypes wrapper of oracle/_ref/libupkie_ref_spine.so: the REFERENCE'S observer and controller pipelines
+    (oracle/ref_spine_shim.cpp). Test infrastructure; raises FileNotFoundError when the library was not built."""
+
+    def __init__(self, observer_config, balancer_config, spine_frequency: int):
+        if not os.path.exists(REF_SPINE_PATH):
+            raise FileNotFoundError(REF_SPINE_PATH)
+        L = C.CDLL(REF_SPINE_PATH)
+        L.ref_spine_create.restype = C.c_void_p
+        L.ref_spine_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+        L.ref_spine_destroy.argtypes = [C.c_void_p]
+        L.ref_spine_reset.argtypes = [C.c_void_p]
+        L.ref_spine_observers_step.argtypes = [C.c_void_p, _dp, _dp]
+        L.ref_spine_controllers_step.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        self._L = L
+        self._h = L.ref_spine_create(C.byref(observer_config), C.byref(balancer_config) if balancer_config is not None else None,
+                                     int(spine_frequency))
+
+    def __del__(self):
+        try:
+            self._L.ref_spine_destroy(self._h)
+        except Exception:
+            pass
+
+    def reset(self):
+        self._L.ref_spine_reset(self._h)
+
+    def observers_step(self, spine_row):
+        s = np.ascontiguousarray(spine_row, dtype=np.float64).reshape(_abi.SPINE_DIM)
+        out = np.zeros(_abi.OBSV_DIM)
+        self._L.ref_spine_observers_step(self._h, _d(s), _d(out))
+        return out
+
+    def controllers_step(self, obs3, target2, action):
+        o = np.ascontiguousarray(obs3, dtype=np.float64).reshape(3)
+        t = None if target2 is None else np.ascontiguousarray(target2, dtype=np.float64).reshape(2)
+        a = np.ascontiguousarray(action, dtype=np.float64).reshape(36).copy()
+        self._L.ref_spine_controllers_step(self._h, _d(o), _d(t) if t is not None else None, _d(a))
+        return a.reshape(6, 6)
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with g++ (``oracle/Makefile``)."""
     src = os.path.join(_HERE, "upkie_oracle.cpp")

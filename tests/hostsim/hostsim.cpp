@@ -134,8 +134,8 @@ void hostsim_wheel_balancer_step(const UpkieWheelBalancerConfig* c, int n, float
                                      float(c->stiff_yaw_velocity), float(c->wheel_radius)};
   for (int i = 0; i < n; ++i) {
     WheelBalancerState<float> s{state[4 * i], state[4 * i + 1], state[4 * i + 2], state[4 * i + 3]};
-    wheel_balancer_read(P, s, obs[3 * i], obs[3 * i + 2], obs[3 * i + 1] != 0.f, target ? target[2 * i] : 0.f,
-                        target ? target[2 * i + 1] : 0.f);
+    wheel_balancer_read(P, s, obs[3 * i], obs[3 * i + 2], obs[3 * i + 1] != 0.f, target != nullptr,
+                        target ? target[2 * i] : 0.f, target ? target[2 * i + 1] : 0.f);
     wheel_balancer_write(P, s, action + size_t(i) * UPKIE_ACT_DIM, std::nanf(""));
     state[4 * i] = s.ground_velocity; state[4 * i + 1] = s.integral_velocity;
     state[4 * i + 2] = s.target_ground_position; state[4 * i + 3] = s.target_yaw_velocity;

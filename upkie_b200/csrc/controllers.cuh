@@ -45,7 +45,7 @@ __global__ void k_wheel_balancer_step(const __grid_constant__ WheelBalancerParam
   WheelBalancerState<float> s{state[i], state[size_t(n) + i], state[size_t(2) * n + i], state[size_t(3) * n + i]};
   const float* o = obs + size_t(i) * obs_stride;
   const float tgv = target ? target[2 * i] : 0.f, tyv = target ? target[2 * i + 1] : 0.f;
-  wheel_balancer_read(P, s, o[pitch_off], o[odom_off], o[contact_off] != 0.f, tgv, tyv);
+  wheel_balancer_read(P, s, o[pitch_off], o[odom_off], o[contact_off] != 0.f, target != nullptr, tgv, tyv);
   float a[UPKIE_ACT_DIM];
   for (int k = 0; k < UPKIE_ACT_DIM; ++k) a[k] = action[size_t(i) * UPKIE_ACT_DIM + k];
   wheel_balancer_write(P, s, a, __int_as_float(0x7fc00000));

@@ -35,8 +35,11 @@ UPKIE_HD T wb_clamp(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 // WheelBalancer::read (WheelBalancer.cpp:35-88)
 template <typename T>
 UPKIE_HD void wheel_balancer_read(const WheelBalancerParams<T>& P, WheelBalancerState<T>& s, T pitch, T ground_position,
-                                  bool floor_contact, T target_ground_velocity, T target_yaw_velocity) {
-  s.target_yaw_velocity = target_yaw_velocity;
+                                  bool floor_contact, bool has_target, T target_ground_velocity, T target_yaw_velocity) {
+  // without a "bullet" action key the ground-velocity target is 0 for this cycle and the yaw-velocity target keeps
+  // its last value (WheelBalancer.cpp:37-42: only the local is re-initialised)
+  if (has_target) s.target_yaw_velocity = target_yaw_velocity;
+  else target_ground_velocity = T(0);
   const T dt = P.dt;
   if ((pitch < 0 ? -pitch : pitch) > P.fall_pitch) {
     s.ground_velocity = T(0);
