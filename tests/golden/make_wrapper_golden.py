@@ -261,6 +261,25 @@ def main():
         out["cases"].append(case)
         print(kind, "seed", seed, "steps", steps, "terminated at", [i for i, x in enumerate(case["terminated"]) if x][:3])
 
+    # spaces and neutral action of the reference's classes (upkie_servos.py:173-286, upkie_gyropod.py:118-160,
+    # upkie_pendulum.py:87-102): what B200VectorEnv's single_*_space must equal
+    def box(b):
+        return {"low": np.asarray(b.low, dtype=float).tolist(), "high": np.asarray(b.high, dtype=float).tolist(),
+                "shape": list(b.shape), "dtype": str(np.dtype(b.dtype))}
+
+    servos = UpkieServos(backend=OracleBackend(), frequency=200.0, frequency_checks=False, init_state=None,
+                         regulate_frequency=False, model=ref_model)
+    gyro = UpkieGyropod(servos)
+    pend = UpkiePendulum(servos)
+    out["spaces"] = {
+        "servos_action": {j: {k: box(v) for k, v in servos.action_space[j].items()} for j in servos.action_space},
+        "servos_observation": {j: {k: box(v) for k, v in servos.observation_space[j].items()} for j in servos.observation_space},
+        "neutral_action": {j: {k: (None if (isinstance(v, float) and v != v) else float(v)) for k, v in d.items()}
+                           for j, d in servos.get_neutral_action().items()},
+        "gyropod_action": box(gyro.action_space), "gyropod_observation": box(gyro.observation_space),
+        "pendulum_action": box(pend.action_space), "pendulum_observation": box(pend.observation_space),
+    }
+
     with open(OUT, "w") as f:
         json.dump(out, f)
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KB")

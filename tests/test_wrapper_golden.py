@@ -111,3 +111,34 @@ def test_kernel_arithmetic_follows_the_reference_wrappers(cases, model, index):
     assert (fell_at is None) == (golden_fall is None)
     if golden_fall is not None:
         assert abs(fell_at - golden_fall) <= 1
+
+
+def test_spaces_and_neutral_action_equal_the_reference_classes(model):
+    """single_action_space / single_observation_space of B200VectorEnv against the spaces the reference's own
+    UpkieServos / UpkieGyropod / UpkiePendulum instances reported in the build container (bounds, shapes, dtypes)."""
+    from upkie_b200.envs import make_gyropod_spaces, make_pendulum_spaces, make_servo_spaces
+
+    g = json.load(open(GOLDEN))["spaces"]
+
+    def same(box, ref):
+        assert list(box.shape) == ref["shape"] and str(np.dtype(box.dtype)) == ref["dtype"]
+        assert np.array_equal(np.asarray(box.low, dtype=float), np.asarray(ref["low"]))
+        assert np.array_equal(np.asarray(box.high, dtype=float), np.asarray(ref["high"]))
+
+    act, obs, neutral, _, _ = make_servo_spaces(model)
+    assert list(act.spaces if hasattr(act, "spaces") else act) == list(g["servos_action"])  # joint order
+    for joint in g["servos_action"]:
+        assert list(act[joint].spaces if hasattr(act[joint], "spaces") else act[joint]) == list(g["servos_action"][joint])
+        for key, ref in g["servos_action"][joint].items():
+            same(act[joint][key], ref)
+        for key, ref in g["servos_observation"][joint].items():
+            same(obs[joint][key], ref)
+        for key, ref in g["neutral_action"][joint].items():
+            mine = float(neutral[joint][key])
+            assert (mine != mine) if ref is None else (mine == ref), (joint, key)
+    ga, go = make_gyropod_spaces()
+    same(ga, g["gyropod_action"])
+    same(go, g["gyropod_observation"])
+    pa, po = make_pendulum_spaces()
+    same(pa, g["pendulum_action"])
+    same(po, g["pendulum_observation"])
