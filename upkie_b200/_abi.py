@@ -10,6 +10,8 @@ action keys ``upkie/envs/upkie_servos.py:98-105``, observation keys
 
 import ctypes as C
 
+import numpy as np
+
 ABI_VERSION = 1
 
 NJ = 6
@@ -201,9 +203,8 @@ def default_observer_config(model, spine_frequency: float = 1000.0) -> UpkieObse
     sign = 1.0 if model.left_wheeled else -1.0
     c.signed_radius[0] = sign * model.wheel_radius
     c.signed_radius[1] = -sign * model.wheel_radius
-    R = [float(x) for x in __import__("numpy").asarray(model.rotation_base_to_imu, dtype=float).reshape(9)]
-    for k in range(9):
-        c.rotation_base_to_imu[k] = R[k]
+    for k, x in enumerate(np.asarray(model.rotation_base_to_imu, dtype=float).reshape(9)):
+        c.rotation_base_to_imu[k] = float(x)
     return c
 
 
