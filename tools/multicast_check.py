@@ -1,0 +1,66 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Round-2 validation of the experimental NVSwitch-multicast rollout path (not run in round 1: no GPU budget left).
+
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 tools/multicast_check.py
+
+Every rank steps two identical simulators for T ticks: one writes compact rows into a plain local buffer
+(upkie_b200_step_servos_compact), the other stores them to the multicast address of its slot in a symmetric buffer
+(upkie_b200_step_servos_multicast). After publish() (cross-rank barrier) every rank must hold, for EVERY rank r, slot r
+bit-identical to what rank r computed locally (exchanged with a plain all_gather for the comparison)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from upkie_b200 import _abi  # noqa: E402
+from upkie_b200.model import Model  # noqa: E402
+from upkie_b200.sharding import PeerRolloutBuffer, RolloutBuffer  # noqa: E402
+from upkie_b200.sim import UpkieSim  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n, T = 4096, 8
+    model = Model.standard_upkie()
+    cfg = _abi.default_sim_config()
+    sims = [UpkieSim(n, model=model, config=cfg, device=local) for _ in range(2)]
+    for s in sims:
+        s.set_autoreset(0, 0, rank * n)
+        s.reset(seed=100 + rank, env_offset=rank * n)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5 + rank)
+    tau = torch.tensor(model.tau_max, dtype=torch.float32, device=dev)
+    local_buf = RolloutBuffer(T, n, 18, dev, compact=True)
+    peer = PeerRolloutBuffer(T, n, 18, dev, compact=True)
+    if not peer.multicast_supported:
+        print(f"rank {rank}: symmetric memory reports no multicast support on this box", flush=True)
+        dist.destroy_process_group()
+        return
+    for t in range(T):
+        a = torch.zeros((n, 6, 6), device=dev)
+        a[:, :, 0] = float("nan")
+        a[:, :, 5] = tau
+        a[:, :, 2] = (torch.rand((n, 6), device=dev, generator=gen) * 2 - 1) * tau
+        o, _, te, _ = local_buf.slot(t)
+        sims[0].step_servos_compact(a, obs=o, terminated=te)
+        sims[1].step_servos_multicast(a, *peer.multicast_slot(t))
+    peer.publish()
+    torch.cuda.synchronize()
+    expect = local_buf.gather_raw()  # [world, nbytes] through NCCL, for the comparison only
+    got = peer.gathered()
+    nb = local_buf.nbytes
+    ok = all(torch.equal(got[r, :nb], expect[r, :nb]) for r in range(world))
+    print(f"rank {rank}: multicast rollout {'MATCHES' if ok else 'DIFFERS FROM'} the NCCL-gathered reference "
+          f"({world} ranks x {nb} bytes)", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
