@@ -149,7 +149,7 @@ def test_randomization_update_and_bounds():
     assert r.roll == 0.1 and r.pitch == 0.2 and np.array_equal(r.linear_velocity, [0.5, 0.0, 0.25])
     rng = np.random.default_rng(1)
     for _ in range(50):
-        q = r.sample_orientation(rng)
+        q = r.sample_orientation_quat(rng)
         assert abs(np.linalg.norm(q) - 1) < 1e-12
         om = r.sample_angular_velocity(rng)
         assert om[0] == 0.0 and abs(om[1]) <= 0.3 and om[2] == 0.0

@@ -1,0 +1,65 @@
+# SPDX-License-Identifier: Apache-2.0
+"""Runs the REFERENCE'S OWN unit tests against this package's mirrors of the reference's host-side types.
+
+Where the reference tree is present (the build container), its test files for the types we mirror are loaded as they
+are and executed with ``upkie.utils.robot_state`` / ``robot_state_randomization`` / ``external_force`` aliased to
+``upkie_b200``'s classes: a user switching packages keeps the behaviour those tests specify. Skipped elsewhere (the
+GPU box and fresh clones have no /root/reference; nothing else in the suite depends on it)."""
+import importlib.util
+import os
+import sys
+import types
+import unittest
+
+import pytest
+
+REF_TESTS = os.path.join(os.environ.get("UPKIE_REFERENCE", "/root/reference"), "tests")
+
+CASES = [
+    ("utils/test_robot_state.py", "robot state and its randomisation"),
+    ("utils/test_external_force.py", "ExternalForce validation"),
+]
+
+
+@pytest.fixture()
+def aliased_upkie():
+    import upkie_b200.model as b200_model
+    import upkie_b200.robot_state as b200_state
+
+    saved = {k: v for k, v in sys.modules.items() if k == "upkie" or k.startswith("upkie.")}
+    for k in saved:
+        del sys.modules[k]
+    pkg = types.ModuleType("upkie")
+    pkg.__path__ = []
+    utils = types.ModuleType("upkie.utils")
+    utils.__path__ = []
+    rs = types.ModuleType("upkie.utils.robot_state")
+    rs.RobotState = b200_state.RobotState
+    rsr = types.ModuleType("upkie.utils.robot_state_randomization")
+    rsr.RobotStateRandomization = b200_state.RobotStateRandomization
+    ef = types.ModuleType("upkie.utils.external_force")
+    ef.ExternalForce = b200_model.ExternalForce
+    sys.modules.update({"upkie": pkg, "upkie.utils": utils, "upkie.utils.robot_state": rs,
+                        "upkie.utils.robot_state_randomization": rsr, "upkie.utils.external_force": ef})
+    try:
+        yield
+    finally:
+        for k in [k for k in sys.modules if k == "upkie" or k.startswith("upkie.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+@pytest.mark.parametrize("rel,what", CASES)
+def test_reference_unit_tests_pass_on_our_mirrors(aliased_upkie, rel, what):
+    path = os.path.join(REF_TESTS, rel)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present on this machine")
+    spec = importlib.util.spec_from_file_location("reference_test_" + os.path.basename(rel)[:-3], path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+    assert suite.countTestCases() > 0
+    result = unittest.TestResult()
+    suite.run(result)
+    problems = [f"{t}: {tb.splitlines()[-1]}" for t, tb in result.failures + result.errors]
+    assert not problems, f"{what}: {problems}"

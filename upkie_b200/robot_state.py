@@ -52,6 +52,15 @@ def _as_quat_wxyz(orientation) -> np.ndarray:
     return q / np.linalg.norm(q)
 
 
+def _rotation_from_quat_wxyz(q: np.ndarray):
+    try:
+        from scipy.spatial.transform import Rotation
+
+        return Rotation.from_quat([q[1], q[2], q[3], q[0]])
+    except ImportError:  # pragma: no cover
+        return q
+
+
 class RobotStateRandomization:
     """Domain randomisation of the initial state
     (``robot_state_randomization.py:14-189``)."""
@@ -94,11 +103,15 @@ class RobotStateRandomization:
         if v_z is not None:
             self.linear_velocity[2] = v_z
 
-    def sample_orientation(self, np_random: np.random.Generator) -> np.ndarray:
+    def sample_orientation_quat(self, np_random: np.random.Generator) -> np.ndarray:
         """Quaternion (w, x, y, z) of the sampled rotation (``:135-150``)."""
         yaw_pitch_roll_bounds = np.array([0.0, self.pitch, self.roll])
         ypr = np_random.uniform(low=-yaw_pitch_roll_bounds, high=+yaw_pitch_roll_bounds, size=3)
         return quat_from_euler_zyx(ypr[0], ypr[1], ypr[2])
+
+    def sample_orientation(self, np_random: np.random.Generator):
+        """As in the reference: a scipy ``Rotation`` (the (w, x, y, z) quaternion when scipy is missing)."""
+        return _rotation_from_quat_wxyz(self.sample_orientation_quat(np_random))
 
     def sample_position(self, np_random: np.random.Generator) -> np.ndarray:
         return np_random.uniform(
@@ -170,9 +183,13 @@ class RobotState:
     def sample_linear_velocity(self, np_random):
         return self.linear_velocity_base_to_world_in_world + self.randomization.sample_linear_velocity(np_random)
 
-    def sample_orientation(self, np_random) -> np.ndarray:
+    def sample_orientation_quat(self, np_random) -> np.ndarray:
         # rotation_base_to_world * rotation_rand_to_base
-        return _quat_mul(self.orientation_quat_wxyz, self.randomization.sample_orientation(np_random))
+        return _quat_mul(self.orientation_quat_wxyz, self.randomization.sample_orientation_quat(np_random))
+
+    def sample_orientation(self, np_random):
+        """As in the reference (``robot_state.py:150-163``): a scipy ``Rotation``."""
+        return _rotation_from_quat_wxyz(self.sample_orientation_quat(np_random))
 
     def sample_position(self, np_random):
         return self.position_base_in_world + self.randomization.sample_position(np_random)
@@ -182,7 +199,7 @@ class RobotState:
         velocity, orientation, position."""
         sampled_angular_velocity = self.sample_angular_velocity(np_random)
         sampled_linear_velocity = self.sample_linear_velocity(np_random)
-        sampled_orientation = self.sample_orientation(np_random)
+        sampled_orientation = self.sample_orientation_quat(np_random)
         sampled_position = self.sample_position(np_random)
         return RobotState(
             angular_velocity_base_in_base=sampled_angular_velocity,
