@@ -63,3 +63,55 @@ def test_reference_unit_tests_pass_on_our_mirrors(aliased_upkie, rel, what):
     suite.run(result)
     problems = [f"{t}: {tb.splitlines()[-1]}" for t, tb in result.failures + result.errors]
     assert not problems, f"{what}: {problems}"
+
+
+def test_reference_pybullet_backend_suite_passes_on_our_physics(tmp_path):
+    """tests/envs/backends/test_pybullet_backend.py of the reference (its tests of the REAL PyBullet backend: step
+    returns a dict, pitch 0 after a step, the robot falls within 100 un-actuated steps, also from a yawed start)
+    executed unmodified with ``pybullet`` replaced by the stand-in whose physics is oracle/ and ``upkie_description``
+    pointing at a URDF written by upkie_b200: what the reference expects of Bullet at that level holds for the
+    restated physics."""
+    path = os.path.join(REF_TESTS, "envs", "backends", "test_pybullet_backend.py")
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present on this machine")
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_backend_golden as bg
+    import make_wrapper_golden as wg
+    from upkie_b200.model import Model
+    from upkie_b200.urdf import write_urdf
+
+    saved = {k: v for k, v in sys.modules.items()
+             if k.split(".")[0] in ("upkie", "gymnasium", "pybullet", "pybullet_data", "loop_rate_limiters", "upkie_description")}
+    try:
+        wg.install_fake_gymnasium()
+        wg.load_reference()
+        for name, rel in (("upkie.utils.joystick", "upkie/utils/joystick.py"),
+                          ("upkie.utils.point_contact", "upkie/utils/point_contact.py")):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(wg.REF, rel))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+        urdf = str(tmp_path / "robot.urdf")
+        write_urdf(Model.standard_upkie(), urdf, split_fixed_links=False)
+        sys.modules["upkie_description"].URDF_PATH = urdf
+        pb, data = bg.make_fake_pybullet(Model.from_urdf(urdf), urdf)
+        sys.modules["pybullet"], sys.modules["pybullet_data"] = pb, data
+        spec = importlib.util.spec_from_file_location(
+            "upkie.envs.backends.pybullet_backend", os.path.join(wg.REF, "upkie/envs/backends/pybullet_backend.py"))
+        backend_mod = importlib.util.module_from_spec(spec)
+        sys.modules["upkie.envs.backends.pybullet_backend"] = backend_mod
+        spec.loader.exec_module(backend_mod)
+        spec = importlib.util.spec_from_file_location("reference_test_pybullet_backend", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+        assert suite.countTestCases() >= 4
+        result = unittest.TestResult()
+        suite.run(result)
+        problems = [f"{t}: {tb.splitlines()[-1]}" for t, tb in result.failures + result.errors]
+        assert not problems, problems
+    finally:
+        for k in [k for k in sys.modules
+                  if k.split(".")[0] in ("upkie", "gymnasium", "pybullet", "pybullet_data", "loop_rate_limiters", "upkie_description")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
