@@ -294,6 +294,7 @@ UPKIE_HD void leg_pass12(const SimParams& P, const float q[6], const float qd[6]
     }
     // momentum, bias force p = V x* (I V) - damping wrench
     float p[6];
+    float spin_damp = 0.f;  // damping moment about the body's own y axis (closed-form wheel leaf below)
     {
       const float* om = &V[k][0];
       const float* v = &V[k][3];
@@ -322,6 +323,7 @@ UPKIE_HD void leg_pass12(const SimParams& P, const float q[6], const float qd[6]
       p[3] = a3[0] + F[0];
       p[4] = a3[1] + F[1];
       p[5] = a3[2] + F[2];
+      spin_damp = nC[1] * ga;
     }
     if (k == 2) {
 #pragma unroll
@@ -347,33 +349,54 @@ UPKIE_HD void leg_pass12(const SimParams& P, const float q[6], const float qd[6]
       cc[k][5] = (om[1] * oz + v[0]) * w;
     }
     // U = IA S, D = S^T U, u = tau - S^T pA
-    float U[6];
+    float U[6], invD, u;
+    if (k == 2 && P.wheel_symmetric) {
+      // closed-form leaf (see legs_pass12 in sim_pair.cuh): U = (0, s Iyy, 0 | 0), D = Iyy, S^T pA = s * damping_y
+      const float Iyy = Ib[1];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) U[r] = s * (IA[SI(r, 1)] - oz * IA[SI(r, 3)] + ox * IA[SI(r, 5)]);
-    const float D = sdot(s, ox, oz, U);
-    const float invD = 1.f / D;
-    const float u = tau[j] - sdot(s, ox, oz, pA);
+      for (int r = 0; r < 6; ++r) U[r] = 0.f;
+      U[1] = s * Iyy;
+      invD = 1.f / Iyy;
+      u = tau[j] - s * spin_damp;
+      IA[SI(1, 1)] -= Iyy;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        float acc = pA[r];
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2) {
+          if (c2 != 1) acc += IA[SI(r, c2)] * cc[k][c2];
+        }
+        p[r] = acc;
+      }
+      p[1] += s * u;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) U[r] = s * (IA[SI(r, 1)] - oz * IA[SI(r, 3)] + ox * IA[SI(r, 5)]);
+      const float D = sdot(s, ox, oz, U);
+      invD = 1.f / D;
+      u = tau[j] - sdot(s, ox, oz, pA);
+      // Ia = IA - U U^T / D ; pa = pA + Ia c + U u / D
+      float Ud[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Ud[r] = U[r] * invD;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+#pragma unroll
+        for (int c2 = r; c2 < 6; ++c2) IA[SI(r, c2)] -= Ud[r] * U[c2];
+      }
+      const float ud = u * invD;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        float acc = pA[r] + U[r] * ud;
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2) acc += IA[SI(r, c2)] * cc[k][c2];
+        p[r] = acc;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < 6; ++r) lc.U[k][r] = U[r];
     lc.invD[k] = invD;
     uu[k] = u;
-    // Ia = IA - U U^T / D ; pa = pA + Ia c + U u / D
-    float Ud[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) Ud[r] = U[r] * invD;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-#pragma unroll
-      for (int c2 = r; c2 < 6; ++c2) IA[SI(r, c2)] -= Ud[r] * U[c2];
-    }
-    const float ud = u * invD;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      float acc = pA[r] + U[r] * ud;
-#pragma unroll
-      for (int c2 = 0; c2 < 6; ++c2) acc += IA[SI(r, c2)] * cc[k][c2];
-      p[r] = acc;
-    }
 #pragma unroll
     for (int r = 0; r < 6; ++r) pA[r] = p[r];
   }

@@ -169,6 +169,7 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
     }
     // momentum, bias force p = V x* (I V) - damping wrench
     f2 p[6];
+    f2 spin_damp = bc2(0.f);  // damping moment about the body's own y axis (closed-form wheel leaf below)
     {
       const f2* om = &V[k][0];
       const f2* v = &V[k][3];
@@ -200,6 +201,7 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
       p[3] = add2(a3[0], F[0]);
       p[4] = add2(a3[1], F[1]);
       p[5] = add2(a3[2], F[2]);
+      spin_damp = mul2(nC[1], ga);
     }
     if (k == 2) {
 #pragma unroll
@@ -225,35 +227,62 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
       cc[k][5] = mul2(fma2(om[1], oz, v[0]), w);
     }
     // U = IA S, D = S^T U, u = tau - S^T pA
-    f2 U[6];
+    f2 U[6], invD, u;
+    if (k == 2 && P.wheel_symmetric) {
+      // The wheel is a leaf whose centre of mass lies on its joint axis, with Ixx = Izz: spinning it moves no
+      // mass, so U = (0, s Iyy, 0 | 0, 0, 0), D = Iyy, and S^T pA is the damping moment about the axis alone
+      // (the gyroscopic term om x Ic om has no y component). Taking these closed forms instead of S^T IA S
+      // about the base origin avoids the m |o|^2 / Iyy ~ 150x cancellation that otherwise dominates the fp32
+      // error of the wheel rates ("fp32 budget").
+      const f2 Iyy = Ib[1];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) U[r] = mul2(s, fma2(ox, IA[SI(r, 5)], fma2(noz, IA[SI(r, 3)], IA[SI(r, 1)])));
-    const f2 D = sdot2(s, ox, noz, U);
-    const f2 invD = mk2(1.f / D.x, 1.f / D.y);
-    const f2 u = sub2(mk2(tau[k], tau[k + 3]), sdot2(s, ox, noz, pA));
+      for (int r = 0; r < 6; ++r) U[r] = bc2(0.f);
+      U[1] = mul2(s, Iyy);
+      invD = mk2(1.f / Iyy.x, 1.f / Iyy.y);
+      u = sub2(mk2(tau[k], tau[k + 3]), mul2(s, spin_damp));
+      lc.ninvD[k] = neg2(invD);
+      // Ia = IA - U U^T / D: the rotor stops resisting rotation about its own axis; pa = pA + Ia c + S u
+      IA[SI(1, 1)] = sub2(IA[SI(1, 1)], Iyy);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        f2 acc = pA[r];
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2) {
+          if (c2 != 1) acc = fma2(IA[SI(r, c2)], cc[k][c2], acc);  // cc[k][1] = 0
+        }
+        p[r] = acc;
+      }
+      p[1] = fma2(s, u, p[1]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) U[r] = mul2(s, fma2(ox, IA[SI(r, 5)], fma2(noz, IA[SI(r, 3)], IA[SI(r, 1)])));
+      const f2 D = sdot2(s, ox, noz, U);
+      invD = mk2(1.f / D.x, 1.f / D.y);
+      u = sub2(mk2(tau[k], tau[k + 3]), sdot2(s, ox, noz, pA));
+      // Ia = IA - U U^T / D ; pa = pA + Ia c + U u / D
+      const f2 ninvD = neg2(invD);
+      lc.ninvD[k] = ninvD;
+      f2 nUd[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) nUd[r] = mul2(U[r], ninvD);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+#pragma unroll
+        for (int c2 = r; c2 < 6; ++c2) IA[SI(r, c2)] = fma2(nUd[r], U[c2], IA[SI(r, c2)]);
+      }
+      const f2 ud = mul2(u, invD);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        f2 acc = fma2(U[r], ud, pA[r]);
+#pragma unroll
+        for (int c2 = 0; c2 < 6; ++c2) acc = fma2(IA[SI(r, c2)], cc[k][c2], acc);
+        p[r] = acc;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < 6; ++r) lc.U[k][r] = U[r];
     lc.invD[k] = invD;
     uu[k] = u;
-    // Ia = IA - U U^T / D ; pa = pA + Ia c + U u / D
-    const f2 ninvD = neg2(invD);
-    lc.ninvD[k] = ninvD;
-    f2 nUd[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) nUd[r] = mul2(U[r], ninvD);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-#pragma unroll
-      for (int c2 = r; c2 < 6; ++c2) IA[SI(r, c2)] = fma2(nUd[r], U[c2], IA[SI(r, c2)]);
-    }
-    const f2 ud = mul2(u, invD);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      f2 acc = fma2(U[r], ud, pA[r]);
-#pragma unroll
-      for (int c2 = 0; c2 < 6; ++c2) acc = fma2(IA[SI(r, c2)], cc[k][c2], acc);
-      p[r] = acc;
-    }
 #pragma unroll
     for (int r = 0; r < 6; ++r) pA[r] = p[r];
   }
