@@ -205,6 +205,16 @@ typedef struct UpkieSimConfig {
    * warmstarting_factor x the previous substep's value while the contact persists (Bullet: 0.85), friction rows
    * at 0. Default 0 = cold start: the fixed point is the same and the sweep count did not drop in measurements */
   double warmstarting_factor;
+  /* Bullet's joint-limit constraints: PyBullet's URDF importer attaches a btMultiBodyJointLimitConstraint to every
+   * revolute joint that declares limits (hips and knees; the wheels are continuous). While a joint sits at or
+   * beyond a bound, one unilateral row along that joint joins the contact rows in the PGS solve (solved before the
+   * contact normals, in alternating order from sweep to sweep), with Baumgarte factor joint_limit_erp and the
+   * impulse capped at joint_limit_max_impulse. 0 = no limit rows (round-1 default: the rows exist in the oracle and
+   * in the kernels' arithmetic, CPU-validated against each other, but have not run on a GPU yet) */
+  int32_t joint_limits;
+  int32_t reserved_joint_limits; /* keeps the doubles below 8-byte aligned without implicit padding */
+  double joint_limit_erp;         /* btContactSolverInfo::m_erp = 0.2 */
+  double joint_limit_max_impulse; /* btMultiBodyConstraint::m_maxAppliedImpulse = 100 */
   /* RobotStateRandomization bounds used by the on-device sampler
    * (upkie/utils/robot_state_randomization.py:135-189) */
   double init_position[3];     /* nominal position_base_in_world (0, 0, 0.6) */

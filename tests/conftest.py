@@ -84,3 +84,15 @@ def mpc_kkt_residual(P, q, U, bound):
     r[lower] = np.maximum(-g[lower], 0.0)  # at the lower bound only up
     primal = max(0.0, float(np.max(np.abs(U)) - bound))
     return max(float(r.max()), primal)
+
+
+def at_joint_bounds(model, n, seed):
+    """Random states with about a third of the hips and knees at or slightly beyond a bound."""
+    rng = np.random.default_rng(seed)
+    st = random_states(n, seed=seed + 1).astype(np.float32)
+    st[: n // 2, 2] = rng.uniform(0.45, 0.62, n // 2)  # half of them on or near the ground
+    for j in (0, 1, 3, 4):
+        sel = rng.random(n) < 0.35
+        bound = np.where(rng.random(n) < 0.5, model.joints[j].limit.lower, model.joints[j].limit.upper)
+        st[sel, 13 + j] = (bound + np.sign(bound) * rng.uniform(-0.01, 0.03, n))[sel]
+    return st

@@ -12,7 +12,7 @@ steady contact agrees to ~1e-5.
 import numpy as np
 import pytest
 
-from conftest import mpc_kkt_residual, random_servo_actions, random_states
+from conftest import at_joint_bounds, mpc_kkt_residual, random_servo_actions, random_states
 from hostsim_wrap import HostSim, mpc_step, philox
 from upkie_b200 import _abi
 
@@ -110,10 +110,15 @@ def test_fp32_error_budget_against_textbook_fp32(model, oracle_lib):
     hs.set_state(st)
     o64.set_state(st.astype(np.float64))
     o32.set_state(st.astype(np.float64))
-    hs.step_servos(act)
+    hp = HostSim(model, cfg, n)  # the paired (f32x2) substep the device runs, reached through the extras entry point
+    hp.set_state(st)
+    hp.step_servos_ext(act, np.zeros((n, 7, 3), dtype=np.float32))
+    hs.step_servos(act)  # the scalar-leg substep
     o64.step_servos(act.astype(np.float64))
     o32.step_servos(act.astype(np.float64))
     ref = o64.get_state()[:, 19:25]
+    ep = np.abs(hp.state[:, 19:25].astype(np.float64) - ref).max(axis=1)
+    assert np.median(ep) < 2.5e-5, np.median(ep)
     ek = np.abs(hs.state[:, 19:25].astype(np.float64) - ref).max(axis=1)
     et = np.abs(o32.get_state()[:, 19:25] - ref).max(axis=1)
     assert np.median(ek) < 2.5e-5, np.median(ek)
@@ -122,6 +127,75 @@ def test_fp32_error_budget_against_textbook_fp32(model, oracle_lib):
     # wheels (joints 2 and 5) are no worse than the other joints any more
     per_joint = np.median(np.abs(hs.state[:, 19:25].astype(np.float64) - ref), axis=0)
     assert per_joint[[2, 5]].max() < 2.0 * per_joint[[0, 1, 3, 4]].max()
+
+
+def test_joint_limit_rows(model, oracle_lib):
+    """btMultiBodyJointLimitConstraint rows (config.joint_limits = 1): the kernels' slow path
+    (limit_contact_solve, sim_pair.cuh: limit rows + contact rows of a robot in one scalar PGS) against the
+    oracle's restatement, three ticks with a third of the robots on a bound, in flight and on the ground."""
+    n = 2048
+    cfg = _abi.default_sim_config()
+    cfg.joint_limits = 1
+    hs, osim = HostSim(model, cfg, n), oracle_lib.OracleSim(model, cfg, n, threads=4)
+    free = HostSim(model, _abi.default_sim_config(), n)
+    st = at_joint_bounds(model, n, seed=5)
+    act = random_servo_actions(n, model, seed=12).astype(np.float32)
+    zero = np.zeros((n, 7, 3), dtype=np.float32)
+    hs.set_state(st)
+    free.set_state(st)
+    osim.set_state(st.astype(np.float64))
+    lo = np.array([j.limit.lower for j in model.joints])[[0, 1, 3, 4]]
+    hi = np.array([j.limit.upper for j in model.joints])[[0, 1, 3, 4]]
+    for tick in range(3):
+        hs.step_servos_ext(act, zero)  # the paired substep, as the "extras" kernels run it
+        free.step_servos_ext(act, zero)
+        osim.step_servos(act.astype(np.float64))
+        a, b = hs.state.astype(np.float64), osim.get_state()
+        d = np.abs(a[:, :25] - b[:, :25])
+        assert d[:, :7].max() < 2e-5 and d[:, 13:19].max() < 2e-4
+        assert np.median(d[:, 19:25].max(axis=1)) < 5e-5 and np.percentile(d[:, 19:25].max(axis=1), 99) < 2e-3
+        assert d[:, 19:25].max() < 0.4  # touchdown outliers as in test_random_states_one_tick
+        assert np.array_equal(a[:, 40], b[:, 40])  # contact flags
+        q = b[:, 13:19][:, [0, 1, 3, 4]]
+        assert ((q < lo) | (q > hi)).any(axis=1).mean() > 0.1  # the rows are exercised on every tick
+        assert np.abs(a[:, 19:25] - free.state[:, 19:25]).max() > 5.0  # and they matter
+        osim.set_state(hs.state.astype(np.float64))
+        free.set_state(hs.state)
+    # robots away from their bounds take the packed solver: bit-identical with and without the flag
+    st2 = random_states(256, seed=3).astype(np.float32)
+    h1, h0 = HostSim(model, cfg, 256), HostSim(model, _abi.default_sim_config(), 256)
+    h1.set_state(st2)
+    h0.set_state(st2)
+    z = np.zeros((256, 7, 3), dtype=np.float32)
+    h1.step_servos_ext(act[:256], z)
+    h0.step_servos_ext(act[:256], z)
+    inside = np.all((st2[:, 13:19][:, [0, 1, 3, 4]] > lo + 0.2) & (st2[:, 13:19][:, [0, 1, 3, 4]] < hi - 0.2), axis=1)
+    assert inside.sum() > 100 and np.array_equal(h1.state[inside], h0.state[inside])
+
+
+def test_joint_limit_stops_a_swinging_knee(model, oracle_lib):
+    """What the rows do, on the oracle: a knee swinging at 3 rad/s towards its upper bound in free flight passes
+    it by less than 2 mrad and comes back, where without the rows it keeps going."""
+    out = {}
+    for flag in (0, 1):
+        cfg = _abi.default_sim_config()
+        cfg.joint_limits = flag
+        osim = oracle_lib.OracleSim(model, cfg, 1)
+        st = osim.get_state().copy()
+        st[0, 2] = 2.0
+        st[0, 14], st[0, 20] = 2.45, 3.0
+        osim.set_state(st)
+        act = np.zeros((1, 6, 6))
+        act[:, :, 0] = np.nan
+        act[:, :, 5] = 16.0
+        traj = []
+        for _ in range(40):
+            osim.step_servos(act)
+            traj.append(osim.get_state()[0, [14, 20]].copy())
+        out[flag] = np.array(traj)
+    upper = model.joints[1].limit.upper
+    assert out[0][-1, 0] > upper + 0.3
+    assert out[1][:, 0].max() < upper + 2e-3 and out[1][-1, 1] < 0.0
 
 
 def test_clamps_match_get_spine_action(model, oracle_lib):

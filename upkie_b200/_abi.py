@@ -111,6 +111,10 @@ class UpkieSimConfig(C.Structure):
         ("min_base_height", C.c_double),
         ("pgs_tolerance", C.c_double),
         ("warmstarting_factor", C.c_double),
+        ("joint_limits", C.c_int32),
+        ("reserved_joint_limits", C.c_int32),
+        ("joint_limit_erp", C.c_double),
+        ("joint_limit_max_impulse", C.c_double),
         ("init_position", C.c_double * 3),
         ("init_quat", C.c_double * 4),
         ("rand_roll", C.c_double),
@@ -250,6 +254,9 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.min_base_height = 0.0
     c.pgs_tolerance = 1e-5
     c.warmstarting_factor = 0.0  # measured: no fewer sweeps (friction rows dominate); Bullet's value would be 0.85
+    c.joint_limits = 0  # limit rows are CPU-validated only so far; 1 = Bullet's behaviour
+    c.joint_limit_erp = 0.2
+    c.joint_limit_max_impulse = 100.0
     c.init_position[0], c.init_position[1], c.init_position[2] = 0.0, 0.0, 0.6
     c.init_quat[0], c.init_quat[1], c.init_quat[2], c.init_quat[3] = 1.0, 0.0, 0.0, 0.0
     c.rand_roll = c.rand_pitch = c.rand_x = c.rand_z = 0.0

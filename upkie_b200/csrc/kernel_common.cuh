@@ -66,7 +66,7 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
 // One launch of the env-step kernel over the envs [i0, i0 + cnt) of a handle.
 struct StepArgs {
   const SimParams* P;
-  int mode, autoreset, noise;  // noise: the "extras" instantiation (torque noise models, external forces)
+  int mode, autoreset, noise;  // noise: 1 = the "extras" instantiation (torque noise models, external forces), 2 = extras + joint-limit rows
   int i0, cnt, n_pad, block;
   int compact_obs;      // TILE=1, servos: observation rows [6][3] (position, velocity, torque) instead of [6][5]
   int grid;             // TILE=1: number of persistent blocks (0 = one block per tile)
@@ -91,5 +91,7 @@ struct StepArgs {
 cudaError_t launch_step_device(const StepArgs& a);  // step_device.cu
 cudaError_t launch_step_host(const StepArgs& a);    // step_host.cu
 cudaError_t launch_step_multicast(const StepArgs& a);  // step_multicast.cu: TILE=2, UpkieServos, compact rows
+cudaError_t launch_step_device_limits(const StepArgs& a);  // step_device_limits.cu: NOISE=2 (joint-limit rows), TILE=0
+cudaError_t launch_step_host_limits(const StepArgs& a);    // step_host_limits.cu: NOISE=2, TILE=1
 
 }  // namespace upkie_b200

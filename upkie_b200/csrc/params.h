@@ -44,6 +44,10 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->min_base_height = 0.0;
   c->pgs_tolerance = 1e-5;
   c->warmstarting_factor = 0.0;  // off by default (Bullet's m_warmstartingFactor is 0.85)
+  c->joint_limits = 0;  // limit rows off by default in round 1 (CPU-validated only)
+  c->reserved_joint_limits = 0;
+  c->joint_limit_erp = 0.2;
+  c->joint_limit_max_impulse = 100.0;
   c->init_position[0] = 0.0; c->init_position[1] = 0.0; c->init_position[2] = 0.6;  // upkie_env.py:87-90
   c->init_quat[0] = 1.0; c->init_quat[1] = 0.0; c->init_quat[2] = 0.0; c->init_quat[3] = 0.0;
   c->rand_roll = c->rand_pitch = c->rand_x = c->rand_z = 0.0;
@@ -150,6 +154,9 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.pgs_iterations = c.pgs_iterations;
   P.pgs_rtol = float(c.pgs_tolerance);
   P.warm = float(c.warmstarting_factor);
+  P.joint_limits = c.joint_limits ? 1 : 0;
+  P.limit_erp = float(c.joint_limit_erp);
+  P.limit_max_impulse = float(c.joint_limit_max_impulse);
   P.skip_action_clamps = c.skip_action_clamps;
   P.gravity = float(c.gravity);
   P.kp = float(c.torque_control_kp);

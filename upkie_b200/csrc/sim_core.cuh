@@ -91,6 +91,10 @@ struct SimParams {
   // init-state sampling (RobotStateRandomization)
   float init_pos[3], init_quat[4];
   float rand_roll, rand_pitch, rand_x, rand_z, rand_omega_x, rand_omega_y, rand_linvel[3];
+  // joint-limit rows (btMultiBodyJointLimitConstraint; "extras" instantiations only). Kept at the end of the
+  // struct so that the constant-bank offsets of everything above stay where the GPU-validated kernels read them.
+  int joint_limits;
+  float limit_erp, limit_max_impulse;
 };
 
 // per-robot state in registers
@@ -815,10 +819,11 @@ namespace upkie_b200 {
 // `wext`: external wrench on the base (moment about the base origin, force; base coordinates) or null
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu, AnyFn warp_any,
-                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr) {
+                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr, bool limits = false) {
 #if UPKIE_PAIRED_LEGS
-  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext);
+  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext, limits);
 #else
+  (void)limits;  // the scalar-leg build has no joint-limit rows
   physics_substep(P, S, tau, eps, mu, warp_any, phase_sync, wext);
 #endif
 }
@@ -1046,7 +1051,8 @@ UPKIE_HD void gaussian8(uint64_t seed, const NoiseCtx& nz, uint32_t slot, float 
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPKIE_ACT_DIM], bool zero_torque,
                             const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync = SyncFn(),
-                            const NoiseCtx* nz = nullptr, int sub = 0, const ExtForces* ext = nullptr) {
+                            const NoiseCtx* nz = nullptr, int sub = 0, const ExtForces* ext = nullptr,
+                            bool limits = false) {
   float tau[6];
   float noise[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (P.any_ctrl_noise && nz) {
@@ -1068,9 +1074,9 @@ UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPK
     external_generalized_forces(P, S, *ext, tau_add, wbase);
 #pragma unroll
     for (int j = 0; j < 6; ++j) tau[j] += tau_add[j];
-    substep(P, S, tau, eps, mu, warp_any, phase_sync, wbase);
+    substep(P, S, tau, eps, mu, warp_any, phase_sync, wbase, limits);
   } else {
-    substep(P, S, tau, eps, mu, warp_any, phase_sync);
+    substep(P, S, tau, eps, mu, warp_any, phase_sync, nullptr, limits);
   }
 }
 

@@ -359,12 +359,218 @@ UPKIE_HD void legs_impulse_down(const SimParams& P, const LegCache2& lc, const f
   }
 }
 
+// ---- joint-limit rows: the slow path ------------------------------------------------------------------------------
+// PyBullet's URDF importer hangs a btMultiBodyJointLimitConstraint on every revolute joint with limits (hips and
+// knees). While such a joint sits at or beyond a bound, one unilateral row along its coordinate joins the contact rows
+// of the substep's PGS solve. That is rare (position commands are clamped to the limits upstream), so a robot with
+// an active limit row solves ALL of its rows here - scalar, looped, local-memory arrays - and stays out of the packed
+// six-row solver below, whose registers and instruction count are what the roofline is quoted on.
+// Restated from Bullet 3.24 (third-party, absent from the reference tree): rows only while
+// `penetration <= 0`, rhs = (-penetration * erp / h - rel_vel) / W_kk, impulse in [0, m_maxAppliedImpulse], limit rows
+// before the contact normals and walked backwards on even sweeps, forwards on odd ones.
+struct LimitRows {
+  int n;
+  int joint[4];
+  float dir[4], pen[4];
+};
+
+UPKIE_HD float lane(const f2& v, int leg) { return leg == 0 ? v.x : v.y; }
+
+UPKIE_HD int active_joint_limits(const SimParams& P, const float q[6], LimitRows& L) {
+  L.n = 0;
+  for (int j = 0; j < 6; ++j) {
+    // wheels carry infinite bounds: both tests fail for them
+    const float pen_lo = q[j] - P.q_lower[j], pen_hi = P.q_upper[j] - q[j];
+    if (pen_lo <= 0.f && L.n < 4) { L.joint[L.n] = j; L.dir[L.n] = 1.f; L.pen[L.n] = pen_lo; ++L.n; }
+    if (pen_hi <= 0.f && L.n < 4) { L.joint[L.n] = j; L.dir[L.n] = -1.f; L.pen[L.n] = pen_hi; ++L.n; }
+  }
+  return L.n;
+}
+
+// Velocity change for spatial impulses fw[side] on the two wheels (about the base origin, base coordinates) plus
+// generalized impulses g[j] on the joint coordinates: da0 (base), dqd (joints), aw[side] (wheel bodies).
+UPKIE_HD void impulse_response_generic(const SimParams& P, const LegCache2& lc, const float IA0[21], const float fw[2][6],
+                                       const float g[6], float da0[6], float dqd[6], float aw[2][6]) {
+  float u[6];
+  for (int i = 0; i < 6; ++i) da0[i] = 0.f;
+  for (int leg = 0; leg < 2; ++leg) {
+    float q[6];  // q = -p
+    for (int i = 0; i < 6; ++i) q[i] = fw[leg][i];
+    for (int k = 2; k >= 0; --k) {
+      const float s = lane(P.sgn2[k], leg), ox = lane(lc.ox[k], leg), oz = lane(lc.oz[k], leg);
+      const float uj = s * (q[1] - oz * q[3] + ox * q[5]) + g[3 * leg + k];
+      u[3 * leg + k] = uj;
+      const float c = uj * lane(lc.invD[k], leg);
+      for (int i = 0; i < 6; ++i) q[i] -= lane(lc.U[k][i], leg) * c;
+    }
+    for (int i = 0; i < 6; ++i) da0[i] += q[i];
+  }
+  ldl6_solve(IA0, da0);
+  for (int leg = 0; leg < 2; ++leg) {
+    float a[6];
+    for (int i = 0; i < 6; ++i) a[i] = da0[i];
+    for (int k = 0; k < 3; ++k) {
+      float dot = 0.f;
+      for (int i = 0; i < 6; ++i) dot += lane(lc.U[k][i], leg) * a[i];
+      const float dd = (u[3 * leg + k] - dot) * lane(lc.invD[k], leg);
+      dqd[3 * leg + k] = dd;
+      const float w = lane(P.sgn2[k], leg) * dd;
+      a[1] += w;
+      a[3] -= lane(lc.oz[k], leg) * w;
+      a[5] += lane(lc.ox[k], leg) * w;
+    }
+    for (int i = 0; i < 6; ++i) aw[leg][i] = a[i];
+  }
+}
+
+// All constraint rows of one robot with at least one active joint limit: limit rows, then nL nR, then t1 t2 per wheel
+// in contact. Updates the velocities and the cached normal impulses of S.
+UPKIE_HD void limit_contact_solve(const SimParams& P, RobotState& S, const LegCache2& lc, const float IA0[21],
+                                  const float R[9], const float zb[3], float inv_n, const f2 Pc[3], const f2& dist,
+                                  bool actL, bool actR, float mu, const LimitRows& L, const float lam_prev[2]) {
+  constexpr int kMaxRows = 10;
+  int kind[kMaxRows], side[kMaxRows], joint[kMaxRows], partner[kMaxRows];  // kind 0 normal, 1 friction, 2 limit
+  float dirj[kMaxRows], J[kMaxRows][6];
+  int n = 0;
+  for (int l = 0; l < L.n; ++l) {
+    kind[n] = 2; side[n] = -1; joint[n] = L.joint[l]; dirj[n] = L.dir[l]; partner[n] = -1;
+    for (int i = 0; i < 6; ++i) J[n][i] = 0.f;
+    ++n;
+  }
+  const int nlimit = n;
+  const float t1[3] = {zb[2] * inv_n, 0.f, -zb[0] * inv_n};
+  float t2[3];
+  cross3(zb, t1, t2);
+  const bool act[2] = {actL, actR};
+  int normal_of[2] = {-1, -1};
+  auto add_contact_row = [&](int sd, int d) {
+    const float sw = lane(P.sgn2[2], sd);
+    const float pc[3] = {lane(Pc[0], sd), lane(Pc[1], sd), lane(Pc[2], sd)};
+    float dir[3];
+    for (int i = 0; i < 3; ++i) dir[i] = d == 0 ? zb[i] : sw * (d == 1 ? t1[i] : t2[i]);
+    cross3(pc, dir, &J[n][0]);
+    J[n][3] = dir[0]; J[n][4] = dir[1]; J[n][5] = dir[2];
+    kind[n] = d == 0 ? 0 : 1; side[n] = sd; joint[n] = -1; dirj[n] = 0.f;
+    partner[n] = d == 0 ? -1 : normal_of[sd];
+    if (d == 0) normal_of[sd] = n;
+    ++n;
+  };
+  for (int sd = 0; sd < 2; ++sd)
+    if (act[sd]) add_contact_row(sd, 0);
+  for (int sd = 0; sd < 2; ++sd)
+    if (act[sd]) { add_contact_row(sd, 1); add_contact_row(sd, 2); }
+
+  // wheel spatial velocities at the predicted generalized velocity
+  float Vw[2][6];
+  {
+    float Vb[6];
+    rot_tmul(R, S.angvel, &Vb[0]);
+    rot_tmul(R, S.linvel, &Vb[3]);
+    for (int sd = 0; sd < 2; ++sd) {
+      for (int i = 0; i < 6; ++i) Vw[sd][i] = Vb[i];
+      for (int k = 0; k < 3; ++k) {
+        const float w = lane(P.sgn2[k], sd) * S.qd[3 * sd + k];
+        Vw[sd][1] += w;
+        Vw[sd][3] -= lane(lc.oz[k], sd) * w;
+        Vw[sd][5] += lane(lc.ox[k], sd) * w;
+      }
+    }
+  }
+  // Delassus matrix, one generic response per row
+  float W[kMaxRows][kMaxRows];
+  for (int l = 0; l < n; ++l) {
+    float fw[2][6], g[6], da0[6], dqd[6], aw[2][6];
+    for (int i = 0; i < 6; ++i) { fw[0][i] = 0.f; fw[1][i] = 0.f; g[i] = 0.f; }
+    if (kind[l] == 2) g[joint[l]] = dirj[l];
+    else for (int i = 0; i < 6; ++i) fw[side[l]][i] = J[l][i];
+    impulse_response_generic(P, lc, IA0, fw, g, da0, dqd, aw);
+    for (int k = 0; k < n; ++k) {
+      float wkl;
+      if (kind[k] == 2) {
+        wkl = dirj[k] * dqd[joint[k]];
+      } else {
+        wkl = 0.f;
+        for (int i = 0; i < 6; ++i) wkl += J[k][i] * aw[side[k]][i];
+      }
+      W[k][l] = wkl;
+    }
+  }
+  float rhs[kMaxRows], jdi[kMaxRows], cfmrow[kMaxRows], lam[kMaxRows];
+  for (int k = 0; k < n; ++k) {
+    lam[k] = 0.f;
+    if (kind[k] == 2) {
+      const float rel = dirj[k] * S.qd[joint[k]];
+      jdi[k] = W[k][k] > 1.1920929e-7f ? 1.f / W[k][k] : 0.f;
+      rhs[k] = (-L.pen[k] * P.limit_erp * P.inv_h - rel) * jdi[k];
+      cfmrow[k] = 0.f;
+      continue;
+    }
+    float rel = 0.f;
+    for (int i = 0; i < 6; ++i) rel += J[k][i] * Vw[side[k]][i];
+    if (kind[k] == 0) {
+      lam[k] = P.warm * lam_prev[side[k]];
+      const float pen = lane(dist, side[k]);
+      jdi[k] = 1.f / (W[k][k] + P.cfm);
+      float pos_err = 0.f, vel_err = -rel;
+      if (pen > 0.f) vel_err -= pen * P.inv_h;
+      else pos_err = -pen * P.erp * P.inv_h;
+      rhs[k] = (pos_err + vel_err) * jdi[k];
+      cfmrow[k] = P.cfm * jdi[k];
+    } else {
+      jdi[k] = W[k][k] > 0.f ? 1.f / W[k][k] : 0.f;
+      rhs[k] = -rel * jdi[k];
+      cfmrow[k] = 0.f;
+    }
+  }
+  const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+  for (int it = 0; it < P.pgs_iterations; ++it) {
+    bool changed = false;
+    for (int pos = 0; pos < n; ++pos) {
+      const int k = pos < nlimit ? ((it & 1) ? pos : nlimit - 1 - pos) : pos;
+      float jdv = 0.f;
+      for (int l = 0; l < n; ++l) jdv += W[k][l] * lam[l];
+      const float sum = lam[k] + (rhs[k] - lam[k] * cfmrow[k] - jdv * jdi[k]);
+      float lo, hi;
+      if (kind[k] == 0) { lo = 0.f; hi = 1e10f; }
+      else if (kind[k] == 2) { lo = 0.f; hi = P.limit_max_impulse; }
+      else { hi = mu * lam[partner[k]]; lo = -hi; }
+      const float nl = fminf(fmaxf(sum, lo), hi);
+      changed = changed | (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+      lam[k] = nl;
+    }
+    if (!changed) break;  // per robot here (the packed solver votes per warp)
+  }
+  // apply the total impulse
+  float fw[2][6], g[6], da0[6], dqd[6], aw[2][6];
+  for (int i = 0; i < 6; ++i) { fw[0][i] = 0.f; fw[1][i] = 0.f; g[i] = 0.f; }
+  S.lam_n[0] = 0.f;
+  S.lam_n[1] = 0.f;
+  for (int k = 0; k < n; ++k) {
+    if (kind[k] == 2) {
+      g[joint[k]] += dirj[k] * lam[k];
+    } else {
+      for (int i = 0; i < 6; ++i) fw[side[k]][i] += J[k][i] * lam[k];
+      if (kind[k] == 0) S.lam_n[side[k]] = lam[k];
+    }
+  }
+  impulse_response_generic(P, lc, IA0, fw, g, da0, dqd, aw);
+  float dw[3], dv[3];
+  rot_mul(R, &da0[0], dw);
+  rot_mul(R, &da0[3], dv);
+  for (int i = 0; i < 3; ++i) {
+    S.angvel[i] = clampf(S.angvel[i] + dw[i], -P.vmax, P.vmax);
+    S.linvel[i] = clampf(S.linvel[i] + dv[i], -P.vmax, P.vmax);
+  }
+  for (int j = 0; j < 6; ++j) S.qd[j] = clampf(S.qd[j] + dqd[j], -P.vmax, P.vmax);
+}
+
 // row / column index of (side, direction) in Bullet's order: nL nR t1L t2L t1R t2R
 UPKIE_HD constexpr int row_of(int side, int d) { return d == 0 ? side : 2 + 2 * side + (d - 1); }
 
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
-                                     AnyFn warp_any, SyncFn phase_sync = SyncFn(), const float* wext = nullptr) {
+                                     AnyFn warp_any, SyncFn phase_sync = SyncFn(), const float* wext = nullptr,
+                                     bool limits = false) {
   float R[9];
   quat_to_rot(S.quat, R);
   float V0[6];
@@ -414,9 +620,16 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   const float dB0 = -zb[0] * inv_n * P.wheel_radius, dB2 = -zb[2] * inv_n * P.wheel_radius;
   const f2 Pc[3] = {add2(lc.ox[2], bc2(dB0)), P.oy2[2], add2(lc.oz[2], bc2(dB2))};
   const f2 dist = fma2(bc2(zb[0]), Pc[0], fma2(bc2(zb[1]), Pc[1], fma2(bc2(zb[2]), Pc[2], bc2(S.pos[2]))));
-  const bool actL = rim_ok && (dist.x < P.breaking_threshold);
-  const bool actR = rim_ok && (dist.y < P.breaking_threshold);
-  S.contact = (actL || actR) ? 1.f : 0.f;
+  const bool inL = rim_ok && (dist.x < P.breaking_threshold);
+  const bool inR = rim_ok && (dist.y < P.breaking_threshold);
+  S.contact = (inL || inR) ? 1.f : 0.f;
+  // a robot with an active joint-limit row leaves the packed solver alone (its contact rows are switched off
+  // there, which makes that solve a no-op for it) and solves all of its rows in limit_contact_solve() below
+  LimitRows lim;
+  lim.n = 0;
+  const bool slow = limits && active_joint_limits(P, S.q, lim) > 0;
+  const float lam_prev[2] = {S.lam_n[0], S.lam_n[1]};
+  const bool actL = inL && !slow, actR = inR && !slow;
   phase_sync();  // 2
 
   if (!warp_any(actL || actR)) {
@@ -624,6 +837,7 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
     }
     phase_sync();  // 6
   }
+  if (slow) limit_contact_solve(P, S, lc, IA0, R, zb, inv_n, Pc, dist, inL, inR, mu, lim, lam_prev);
 
   // -- position integration with the new velocities (as physics_substep)
 #pragma unroll

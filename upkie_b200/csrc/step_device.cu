@@ -3,5 +3,8 @@
 #include "step_kernel.cuh"
 
 namespace upkie_b200 {
-cudaError_t launch_step_device(const StepArgs& a) { return launch_step_kernels<0>(a); }
+cudaError_t launch_step_device(const StepArgs& a) {
+  if (a.noise == 2) return launch_step_device_limits(a);  // step_device_limits.cu
+  return launch_step_kernels<0>(a);
+}
 }  // namespace upkie_b200

@@ -1,0 +1,8 @@
+// SPDX-License-Identifier: Apache-2.0
+// TILE=0 instantiations with joint-limit rows (NOISE=2: extras + limits), see kernel_common.cuh.
+#define UPKIE_STEP_LIMITS_TU 1
+#include "step_kernel.cuh"
+
+namespace upkie_b200 {
+cudaError_t launch_step_device_limits(const StepArgs& a) { return launch_step_kernels<0>(a); }
+}  // namespace upkie_b200

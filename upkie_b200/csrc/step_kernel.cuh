@@ -4,10 +4,18 @@
 //   k_step<MODE, AUTORESET, NOISE, TILE>   one 5 ms env tick: action front-end, 5 x (moteus torque law,
 //       articulated-body dynamics, wheel-ground contact solve, semi-implicit integration), observation,
 //       termination; optional fused auto-reset; optional torque noise models.
-// Included by step_device.cu (TILE=0) and step_host.cu (TILE=1) only, see kernel_common.cuh.
+//       NOISE: 0 plain, 1 "extras" (noise models, external forces), 2 extras + joint-limit rows.
+// Included by step_device.cu (TILE=0), step_host.cu (TILE=1), step_multicast.cu (TILE=2) and the two *_limits.cu
+// units (NOISE=2), see kernel_common.cuh.
 #pragma once
 
 #include "kernel_common.cuh"
+
+// 1 in step_device_limits.cu / step_host_limits.cu: that translation unit holds the NOISE=2 instantiations only
+// (separate units so that the build stays parallel and the other units' kernels are untouched)
+#ifndef UPKIE_STEP_LIMITS_TU
+#define UPKIE_STEP_LIMITS_TU 0
+#endif
 
 namespace upkie_b200 {
 namespace {
@@ -110,7 +118,7 @@ __device__ __forceinline__ void step_env(
 #endif
     if (sub < nsub) {
       servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
-                    (NOISE && ext) ? &xf : nullptr);
+                    (NOISE && ext) ? &xf : nullptr, NOISE == 2);
     } else {
 #pragma unroll
       for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
@@ -324,11 +332,15 @@ cudaError_t launch_step_mode(const StepArgs& a) {
   k_step<MODE, AR, NZ, TILE><<<grid, a.block, smem, a.stream>>>(                                                 \
       *a.P, a.i0, a.i0 + a.cnt, a.n_pad, a.state, a.action, a.obs, a.reward, a.terminated, a.truncated, a.eps,   \
       a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, a.ext, a.ext_local, coalesce)
+#if UPKIE_STEP_LIMITS_TU
+#define LAUNCH(AR) LAUNCH_N(AR, 2)
+#else
 #define LAUNCH(AR)                \
   do {                            \
     if (a.noise) LAUNCH_N(AR, 1); \
     else LAUNCH_N(AR, 0);         \
   } while (0)
+#endif
   if (a.autoreset == AUTORESET_NEXT_STEP) LAUNCH(AUTORESET_NEXT_STEP);
   else if (a.autoreset == AUTORESET_SAME_STEP) LAUNCH(AUTORESET_SAME_STEP);
   else LAUNCH(AUTORESET_DISABLED);

@@ -5,5 +5,8 @@
 #include "step_kernel.cuh"
 
 namespace upkie_b200 {
-cudaError_t launch_step_multicast(const StepArgs& a) { return launch_step_mode<2, MODE_SERVOS>(a); }
+cudaError_t launch_step_multicast(const StepArgs& a) {
+  if (a.noise == 2) return cudaErrorNotSupported;  // no joint-limit instantiation of the multicast variant
+  return launch_step_mode<2, MODE_SERVOS>(a);
+}
 }  // namespace upkie_b200

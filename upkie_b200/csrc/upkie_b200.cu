@@ -214,7 +214,7 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
   a.P = &h->P;
   a.mode = mode;
   a.autoreset = h->autoreset;
-  a.noise = (h->P.any_ctrl_noise || h->P.any_meas_noise || h->ext) ? 1 : 0;
+  a.noise = h->P.joint_limits ? 2 : ((h->P.any_ctrl_noise || h->P.any_meas_noise || h->ext) ? 1 : 0);  // "extras" kernels
   a.ext = h->ext;
   a.ext_local = h->ext_local;
   a.i0 = i0;

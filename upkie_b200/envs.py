@@ -218,6 +218,7 @@ def make_config(
     max_yaw_velocity: float = 1.0,
     init_state: Optional[RobotState] = None,
     noise_seed: int = 0,
+    joint_limits: bool = False,
 ) -> _abi.UpkieSimConfig:
     """Split of the keyword arguments the reference's factories forward to the
     backend, the servo env and the wrappers (``upkie/envs/entry_points.py:41-61,99-109``)."""
@@ -237,6 +238,9 @@ def make_config(
             cfg.torque_control_noise[j] = float(getattr(props, "torque_control_noise", 0.0))
             cfg.torque_measurement_noise[j] = float(getattr(props, "torque_measurement_noise", 0.0))
     cfg.noise_seed = int(noise_seed) & 0xFFFFFFFFFFFFFFFF
+    # Bullet's joint-limit constraint rows on hips and knees (include/upkie_b200.h: joint_limits). Off by default
+    # until the "extras + limits" kernels have run on a GPU
+    cfg.joint_limits = 1 if joint_limits else 0
     cfg.max_gain_scale = max_gain_scale
     cfg.fall_pitch = fall_pitch
     cfg.leg_gain_scale = leg_gain_scale
@@ -276,6 +280,7 @@ class B200VectorEnv(VectorEnv):
         leg_length: float = 0.58,
         max_ground_accel: float = 10.0,
         noise_seed: int = 0,
+        joint_limits: bool = False,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")
@@ -296,6 +301,7 @@ class B200VectorEnv(VectorEnv):
             config = make_config(
                 frequency, nb_substeps, torque_control_kp, torque_control_kd, joint_properties, max_gain_scale,
                 fall_pitch, leg_gain_scale, max_ground_velocity, max_yaw_velocity, self.init_state, noise_seed,
+                joint_limits,
             )
         self.config = config
         (
