@@ -115,3 +115,67 @@ def test_reference_pybullet_backend_suite_passes_on_our_physics(tmp_path):
                   if k.split(".")[0] in ("upkie", "gymnasium", "pybullet", "pybullet_data", "loop_rate_limiters", "upkie_description")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_reference_model_suite_passes_on_urdfs_written_by_upkie_b200(tmp_path):
+    """tests/model/test_model.py, test_kinematic_tree.py and test_se3.py of the reference, unmodified, run with the
+    reference's OWN ``upkie.model`` package while ``upkie_description.URDF_PATH`` / ``cookie_description.URDF_PATH``
+    point at URDFs written by ``upkie_b200.urdf.write_urdf`` (left- and right-wheeled stand-ins): wheel radius 0.05,
+    wheel base 0.3048, base -> IMU rotation, torso at (0, 0, -0.1), frame names, tire cylinders, left / right
+    wheeledness - every constant the reference pins on its model comes out of our file through its parser."""
+    if not os.path.exists(os.path.join(REF_TESTS, "model", "test_model.py")):
+        pytest.skip("reference tree not present on this machine")
+    from upkie_b200.model import Model
+    from upkie_b200.urdf import write_urdf
+
+    ref_root = os.path.dirname(REF_TESTS)
+    saved = {k: v for k, v in sys.modules.items()
+             if k.split(".")[0] in ("upkie", "upkie_description", "cookie_description")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        upkie_urdf, cookie_urdf = str(tmp_path / "upkie.urdf"), str(tmp_path / "cookie.urdf")
+        write_urdf(Model.standard_upkie(), upkie_urdf, split_fixed_links=True)
+        right = Model.standard_upkie()
+        right.joint_axis = right.joint_axis.copy()
+        right.joint_axis[[2, 5]] *= -1.0  # wheel axes reversed: a right-wheeled (Cookie-style) robot
+        write_urdf(right, cookie_urdf, split_fixed_links=True)
+        for name, path in (("upkie_description", upkie_urdf), ("cookie_description", cookie_urdf)):
+            stub = types.ModuleType(name)
+            stub.URDF_PATH = path
+            sys.modules[name] = stub
+        pkg = types.ModuleType("upkie")
+        pkg.__path__ = [os.path.join(ref_root, "upkie")]
+        sys.modules["upkie"] = pkg
+
+        def load(name, rel):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(ref_root, rel))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            return mod
+
+        load("upkie.exceptions", "upkie/exceptions.py")
+        utils = types.ModuleType("upkie.utils")
+        utils.__path__ = [os.path.join(ref_root, "upkie", "utils")]
+        sys.modules["upkie.utils"] = utils
+        model_pkg = types.ModuleType("upkie.model")
+        model_pkg.__path__ = [os.path.join(ref_root, "upkie", "model")]
+        sys.modules["upkie.model"] = model_pkg
+        for leaf in ("se3", "joint_limit", "joint", "collision_geometry", "link", "kinematic_tree", "model"):
+            load(f"upkie.model.{leaf}", f"upkie/model/{leaf}.py")
+        model_pkg.Model = sys.modules["upkie.model.model"].Model
+        total = 0
+        for rel in ("model/test_model.py", "model/test_kinematic_tree.py", "model/test_se3.py"):
+            mod = load("reference_test_" + os.path.basename(rel)[:-3], os.path.join("tests", rel))
+            suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+            total += suite.countTestCases()
+            result = unittest.TestResult()
+            suite.run(result)
+            problems = [f"{t}: {tb.splitlines()[-1]}" for t, tb in result.failures + result.errors]
+            assert not problems, (rel, problems)
+        assert total >= 30
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("upkie", "upkie_description", "cookie_description")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -274,6 +274,24 @@ def write_urdf(model, path: str, split_fixed_links: bool = True) -> None:
                        f'length="0.02"/></geometry></collision></link>')
             out.append(f'<joint name="{side}_wheel_tire_fix" type="fixed"><parent link="{names[b]}"/>'
                        f'<child link="{side}_wheel_tire"/></joint>')
+            if split_fixed_links:
+                # massless frames of the real description (tests/model/test_model.py:32-45): the wheel centre and
+                # the ground contact point below it at the zero configuration
+                down = Rj_full(model, b).T @ np.array([0.0, 0.0, -float(model.wheel_radius)])
+                out.append(f'<link name="{side}_wheel_center"/>')
+                out.append(f'<joint name="{side}_wheel_center_fix" type="fixed"><parent link="{side}_wheel_tire"/>'
+                           f'<child link="{side}_wheel_center"/></joint>')
+                out.append(f'<link name="{side}_contact"/>')
+                out.append(f'<joint name="{side}_contact_fix" type="fixed"><parent link="{side}_wheel_tire"/>'
+                           f'<child link="{side}_contact"/><origin xyz="{down[0]:.17g} {down[1]:.17g} {down[2]:.17g}" '
+                           f'rpy="0 0 0"/></joint>')
+        if split_fixed_links and b in (1, 4):
+            # the hip actuator's stator: a massless frame fixed to the torso at the hip joint
+            side = "left" if b == 1 else "right"
+            out.append(f'<link name="{side}_hip_qdd100_stator"/>')
+            out.append(f'<joint name="{side}_hip_qdd100_stator_fix" type="fixed"><parent link="torso"/>'
+                       f'<child link="{side}_hip_qdd100_stator"/><origin xyz="{po[0]:.17g} {po[1]:.17g} {po[2]:.17g}" '
+                       f'rpy="0 0 0"/></joint>')
     out.append("</robot>")
     with open(path, "w") as f:
         f.write("\n".join(out))
