@@ -18,6 +18,7 @@ REF_TESTS = os.path.join(os.environ.get("UPKIE_REFERENCE", "/root/reference"), "
 CASES = [
     ("utils/test_robot_state.py", "robot state and its randomisation"),
     ("utils/test_external_force.py", "ExternalForce validation"),
+    ("utils/test_rotations.py", "rotation_matrix_from_rpy of the URDF loader"),
 ]
 
 
@@ -39,8 +40,13 @@ def aliased_upkie():
     rsr.RobotStateRandomization = b200_state.RobotStateRandomization
     ef = types.ModuleType("upkie.utils.external_force")
     ef.ExternalForce = b200_model.ExternalForce
+    import upkie_b200.urdf as b200_urdf
+
+    rot = types.ModuleType("upkie.utils.rotations")
+    rot.rotation_matrix_from_rpy = b200_urdf.rotation_matrix_from_rpy
     sys.modules.update({"upkie": pkg, "upkie.utils": utils, "upkie.utils.robot_state": rs,
-                        "upkie.utils.robot_state_randomization": rsr, "upkie.utils.external_force": ef})
+                        "upkie.utils.robot_state_randomization": rsr, "upkie.utils.external_force": ef,
+                        "upkie.utils.rotations": rot})
     try:
         yield
     finally:
