@@ -396,6 +396,55 @@ def test_two_second_closed_loop_stays_on_the_oracle(model, oracle_lib):
     assert np.abs(oo[:, 0]).max() < 0.5  # nobody fell: the comparison above is about balancing robots
 
 
+def test_wheel_contact_points_follow_the_collision_pass(model, oracle_lib):
+    """Host-side contact query of the Backend adapter (``PyBulletBackend.get_contact_points``): a contact point is
+    reported exactly when the oracle's collision pass saw one, it lies on the tire under the wheel centre, and for
+    a robot at rest the two normal forces carry its weight."""
+    from upkie_b200.model import wheel_contact_points
+
+    n = 512
+    cfg = _abi.default_sim_config()
+    osim = oracle_lib.OracleSim(model, cfg, n, threads=4)
+    st = random_states(n, seed=21)
+    st[:, 7:13] *= 0.05  # slow base motion: the contact flag of the last substep then describes the final pose
+    st[:, 19:25] *= 0.05
+    osim.set_state(st.astype(np.float64))
+    act = np.zeros((n, 6, 6))
+    act[:, :, 0] = np.nan
+    act[:, :, 5] = 1.0
+    osim.step_servos(act)
+    rows = osim.get_state()
+    h = cfg.dt / cfg.nb_substeps
+    agree = 0
+    for i in range(n):
+        pts = wheel_contact_points(model, rows[i], h)
+        # the flag belongs to the collision pass at the START of the last substep: skip robots within 2 mm of the
+        # threshold at the end of it
+        near = [abs(p[2] - 0.02) < 2e-3 for _, p, _ in wheel_contact_points(model, rows[i], h, breaking_threshold=1e9)]
+        if any(near):
+            continue
+        assert (len(pts) > 0) == (rows[i, _abi.ST_CONTACT] > 0.5), i
+        agree += 1
+        for side, p, force in pts:
+            assert p[2] < 0.02 and force >= 0.0
+    assert agree > 0.9 * n
+    # a robot standing still on its wheels
+    osim1 = oracle_lib.OracleSim(model, cfg, 1)
+    init = np.zeros((1, _abi.INIT_DIM))
+    init[:, 2], init[:, 3] = 0.6, 1.0
+    osim1.reset(init)
+    hold = np.zeros((1, 6, 6))
+    hold[:, :, 3], hold[:, :, 4], hold[:, :, 5] = 1.0, 1.0, np.asarray(model.tau_max)
+    for _ in range(40):
+        osim1.step_servos(hold)
+    pts = wheel_contact_points(model, osim1.get_state()[0], h)
+    assert [s for s, _, _ in pts] == [0, 1]
+    total = sum(f for _, _, f in pts)
+    assert abs(total - float(np.sum(model.mass)) * cfg.gravity) < 0.15 * float(np.sum(model.mass)) * cfg.gravity
+    (_, pl, _), (_, pr, _) = pts
+    assert abs(pl[2]) < 5e-3 and abs(pr[2]) < 5e-3 and abs((pl[1] - pr[1]) - model.wheel_base) < 1e-3
+
+
 # ---- counter-based RNG ------------------------------------------------------------------------
 
 def test_philox4x32_10_known_answers():

@@ -19,6 +19,7 @@ CASES = [
     ("utils/test_robot_state.py", "robot state and its randomisation"),
     ("utils/test_external_force.py", "ExternalForce validation"),
     ("utils/test_rotations.py", "rotation_matrix_from_rpy of the URDF loader"),
+    ("utils/test_point_contact.py", "PointContact of Backend.get_contact_points"),
 ]
 
 
@@ -44,9 +45,11 @@ def aliased_upkie():
 
     rot = types.ModuleType("upkie.utils.rotations")
     rot.rotation_matrix_from_rpy = b200_urdf.rotation_matrix_from_rpy
+    pc = types.ModuleType("upkie.utils.point_contact")
+    pc.PointContact = b200_model.PointContact
     sys.modules.update({"upkie": pkg, "upkie.utils": utils, "upkie.utils.robot_state": rs,
                         "upkie.utils.robot_state_randomization": rsr, "upkie.utils.external_force": ef,
-                        "upkie.utils.rotations": rot})
+                        "upkie.utils.rotations": rot, "upkie.utils.point_contact": pc})
     try:
         yield
     finally:

@@ -43,3 +43,25 @@ def test_joint_limit_rows_on_device(model, oracle_lib):
         assert np.abs(g[:, 19:25] - plain.get_state().cpu().numpy()[:, 19:25]).max() > 5.0  # the rows matter
         osim.set_state(g)
         plain.set_state(sim.get_state())
+
+
+def test_backend_contact_points_on_device(model):
+    """``B200Backend.get_contact_points`` (``PyBulletBackend.get_contact_points``, pybullet_backend.py:660-716) for
+    a robot standing on its wheels: two tire contacts that carry its weight, filtered by link name."""
+    from upkie_b200.backend import B200Backend
+    from upkie_b200.robot_state import RobotState
+
+    backend = B200Backend(dt=1.0 / 200.0)
+    backend.reset(RobotState(position_base_in_world=np.array([0.0, 0.0, 0.6])))
+    hold = {"servo": {name: {"position": 0.0, "velocity": 0.0, "maximum_torque": float(model.tau_max[j])}
+                      for j, name in enumerate(_abi.JOINT_NAMES)}}
+    for _ in range(40):
+        backend.step(hold)
+    contacts = backend.get_contact_points()
+    assert [c.link_name for c in contacts] == ["left_wheel_tire", "right_wheel_tire"]
+    weight = float(np.sum(model.mass)) * 9.81
+    assert abs(sum(c.force_in_world[2] for c in contacts) - weight) < 0.15 * weight
+    assert all(abs(c.position_contact_in_world[2]) < 5e-3 for c in contacts)
+    assert len(backend.get_contact_points("left_wheel_tire")) == 1
+    assert backend.get_contact_points("imu") == [] and backend.get_contact_points("no_such_link") == []
+    backend.close()

@@ -3,7 +3,8 @@
 
 ``B200Backend`` implements the reference's backend interface
 (``upkie/envs/backends/backend.py:11-50``: ``reset(init_state) -> dict``,
-``step(action: dict) -> dict``, ``get_spine_observation() -> dict``, ``close()``)
+``step(action: dict) -> dict``, ``get_spine_observation() -> dict``, ``close()``, plus
+``PyBulletBackend``'s ``randomize_inertias``, ``set_external_forces`` and ``get_contact_points``)
 with one env of the vectorised simulation, so that the reference's own
 ``UpkieServos`` / ``UpkieGyropod`` / ``UpkiePendulum`` / ``UpkieBaseVelocity``
 run unmodified on top of it (``UpkieServos(backend=B200Backend(dt=1/200))``).
@@ -17,14 +18,14 @@ absent from the dictionary receive no torque; unknown joints are ignored;
 ``step({})`` is legal.
 """
 
-from typing import Dict, Optional
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
 
 from . import _abi
 from .envs import make_config, spine_row_to_dict
-from .model import Model, default_model
+from .model import Model, PointContact, default_model, wheel_contact_points
 from .robot_state import RobotState
 from .sim import UpkieSim
 
@@ -84,6 +85,26 @@ class B200Backend(_Base):
         self._external_forces.update(external_forces)
         rows, mask = self._sim.model.external_force_rows(self._external_forces, 1)
         self._sim.set_external_forces(torch.from_numpy(rows).to(self._sim.device), mask)
+
+    def get_contact_points(self, link_name: Optional[str] = None) -> List[PointContact]:
+        """``PyBulletBackend.get_contact_points`` (``pybullet_backend.py:660-716``): the contacts of the robot, or
+        of one link of it, as of the last simulation substep. The simulated contacts are the two tire-ground
+        points, reported on ``left_wheel_tire`` / ``right_wheel_tire``. ``force_in_world``
+        holds the normal force of the last substep; its friction components are not reported yet (the state row
+        keeps the normal impulses only), which is a documented difference from the reference."""
+        names = ("left_wheel_tire", "right_wheel_tire")
+        if link_name is not None and link_name not in names:
+            return []  # a link without simulated contacts, or one the robot does not have (the reference: [] too)
+        row = self._sim.get_state()[0].cpu().numpy()
+        h = self.__dt / self._sim.config.nb_substeps
+        contacts = wheel_contact_points(
+            self._sim.model, row, h, breaking_threshold=self._sim.config.contact_breaking_threshold
+        )
+        return [
+            PointContact(names[side], position, np.array([0.0, 0.0, force]))
+            for side, position, force in contacts
+            if link_name is None or names[side] == link_name
+        ]
 
     def reset(self, init_state: RobotState) -> dict:
         row = torch.from_numpy(init_state.to_row().astype(np.float32)).reshape(1, _abi.INIT_DIM).to(self._sim.device)

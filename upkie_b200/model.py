@@ -338,3 +338,58 @@ def default_model(urdf_path: Optional[str] = None) -> Model:
         return Model.from_urdf(upkie_description.URDF_PATH)
     except ImportError:
         return Model.standard_upkie()
+
+@dataclass(eq=False)
+class PointContact:
+    """Same constructor, attributes and ``repr`` as ``upkie.utils.point_contact.PointContact``
+    (``upkie/utils/point_contact.py:8-55``): one contact seen from the robot's side."""
+
+    link_name: str
+    position_contact_in_world: np.ndarray
+    force_in_world: np.ndarray
+
+    def __repr__(self) -> str:
+        fields = (
+            f"link_name='{self.link_name}'",
+            f"position_contact_in_world={np.asarray(self.position_contact_in_world).tolist()}",
+            f"force_in_world={np.asarray(self.force_in_world).tolist()}",
+        )
+        return "PointContact(" + ", ".join(fields) + ")"
+
+
+def wheel_contact_points(model, state_row, substep_dt: float, breaking_threshold: float = 0.02):
+    """Contact points of the two tires for one robot, from a simulator state row (``UPKIE_ST_*`` layout).
+
+    Restates the collision pass of the step kernel on the host (``physics_substep_paired``, sim_pair.cuh: the
+    lowest point of the tire circle against the plane z = 0, a contact while it is closer than Bullet's contact
+    breaking threshold) and reads the normal impulses the last substep applied (``UPKIE_ST_CONTACT_IMPULSE``).
+    Returns ``[(side, position_in_world[3], normal_force), ...]``; ``side`` is 0 (left) or 1 (right)."""
+    row = np.asarray(state_row, dtype=float)
+    pos = row[_abi.ST_POS:_abi.ST_POS + 3]
+    w, x, y, z = row[_abi.ST_QUAT:_abi.ST_QUAT + 4]
+    R = np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)],
+    ])
+    q = row[_abi.ST_Q:_abi.ST_Q + 6]
+    zb = R.T @ np.array([0.0, 0.0, 1.0])  # world up in base coordinates
+    out = []
+    for side in (0, 1):
+        origin, phi = np.zeros(3), 0.0
+        for k in range(3):  # hip, knee, wheel: every joint turns about +-y of the base
+            j = 3 * side + k
+            c, s = np.cos(phi), np.sin(phi)
+            origin = origin + np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]]) @ np.asarray(model.joint_origin[j], dtype=float)
+            phi += float(model.joint_axis[j][1]) * q[j]
+        n_xz = np.hypot(zb[0], zb[2])
+        if n_xz <= 1e-6:  # wheel lying flat: no rim contact
+            continue
+        down = np.array([-zb[0], 0.0, -zb[2]]) / n_xz  # in the wheel plane, towards the ground
+        p_base = origin + float(model.wheel_radius) * down
+        p_world = pos + R @ p_base
+        if p_world[2] >= breaking_threshold:
+            continue
+        impulse = float(row[_abi.ST_CONTACT_IMPULSE + side])
+        out.append((side, p_world, impulse / substep_dt))
+    return out
