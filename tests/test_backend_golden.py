@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from hostsim_wrap import HostSim
-from upkie_b200 import _abi, wire
+from upkie_b200 import _abi
 from upkie_b200.model import Model
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "backend_runs.json")

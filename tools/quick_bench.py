@@ -1,4 +1,4 @@
-import sys, time, torch, numpy as np
+import sys, torch, numpy as np
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from upkie_b200.model import Model
 from upkie_b200 import _abi
