@@ -16,6 +16,7 @@ using namespace upkie_b200;
 
 struct HostSim {
   SimParams P;
+  int scalar_legs = 0;  // 1: step with the scalar-leg substep instead of the paired one the kernels run
 };
 
 static bool any_fn(bool p) { return p; }
@@ -42,6 +43,8 @@ void hostsim_reset(void* hv, int n, float* state, const float* init, const float
   }
 }
 
+void hostsim_set_scalar_legs(void* hv, int on) { static_cast<HostSim*>(hv)->scalar_legs = on ? 1 : 0; }
+
 void hostsim_step_servos(void* hv, int n, float* state, const float* action, float* obs, const float* eps,
                          const float* mu, uint32_t* err) {
   HostSim* h = static_cast<HostSim*>(hv);
@@ -50,7 +53,10 @@ void hostsim_step_servos(void* hv, int n, float* state, const float* action, flo
     state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
     float a[UPKIE_ACT_DIM];
     std::memcpy(a, action + size_t(i) * UPKIE_ACT_DIM, sizeof(a));
-    const uint32_t e = step_servo_action(h->P, S, a, eps ? eps + size_t(i) * 6 : nullptr, mu ? mu[i] : h->P.friction, any_fn);
+    const float* e6 = eps ? eps + size_t(i) * 6 : nullptr;
+    const float mui = mu ? mu[i] : h->P.friction;
+    const uint32_t e = h->scalar_legs ? step_servo_action<true>(h->P, S, a, e6, mui, any_fn)
+                                      : step_servo_action<false>(h->P, S, a, e6, mui, any_fn);
     if (err) err[i] = e;
     for (int j = 0; j < 6; ++j) {
       float* o = obs + size_t(i) * UPKIE_OBS_DIM + j * 5;
@@ -70,7 +76,8 @@ void hostsim_step_gyropod(void* hv, int n, float* state, const float* action, in
     const float a0 = action[size_t(i) * act_dim];
     const float a1 = act_dim > 1 ? action[size_t(i) * act_dim + 1] : 0.f;
     gyropod_action(h->P, S, a0, a1, a);
-    step_servo_action(h->P, S, a, nullptr, h->P.friction, any_fn);
+    if (h->scalar_legs) step_servo_action<true>(h->P, S, a, nullptr, h->P.friction, any_fn);
+    else step_servo_action<false>(h->P, S, a, nullptr, h->P.friction, any_fn);
     S.yaw += a1 * h->P.dt;
     S.yaw_vel = a1;
     gyropod_obs(h->P, S, obs6 + size_t(i) * 6);

@@ -37,6 +37,7 @@ def lib():
         build()
         L = C.CDLL(_LIB)
         L.hostsim_create.restype = C.c_void_p
+        L.hostsim_set_scalar_legs.argtypes = [C.c_void_p, C.c_int]
         L.hostsim_create.argtypes = [C.POINTER(_abi.UpkieModel), C.POINTER(_abi.UpkieSimConfig)]
         L.hostsim_destroy.argtypes = [C.c_void_p]
         L.hostsim_reset.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp]
@@ -65,12 +66,15 @@ def _f(a):
 class HostSim:
     """fp32 kernel arithmetic, one robot after the other, on the CPU."""
 
-    def __init__(self, model, config, n):
+    def __init__(self, model, config, n, scalar_legs=False):
+        """``scalar_legs=False``: ``step_servos`` / ``step_gyropod`` run the substep the kernels run (f32x2-paired
+        legs, sim_pair.cuh); ``True``: the scalar-leg variant of sim_core.cuh (``UPKIE_PAIRED_LEGS=0`` builds)."""
         self.n = n
         self._m = model.to_struct()
         self._c = config
         self._h = lib().hostsim_create(C.byref(self._m), C.byref(config))
         assert self._h, "hostsim_create failed (model not supported by the kernels)"
+        lib().hostsim_set_scalar_legs(self._h, 1 if scalar_legs else 0)
         self.state = np.zeros((n, _abi.STATE_DIM), dtype=np.float32)
         self.state[:, 2] = config.init_position[2]
         self.state[:, 3] = 1.0

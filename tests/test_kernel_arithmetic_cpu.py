@@ -1,6 +1,6 @@
 # SPDX-License-Identifier: Apache-2.0
-"""The kernels' per-robot arithmetic (sim_core.cuh / mpc_core.cuh compiled for the
-host, fp32) against the fp64 oracle. Runs without a GPU; the `-m gpu` tests repeat
+"""The kernels' per-robot arithmetic (sim_core.cuh / sim_pair.cuh / mpc_core.cuh compiled for the
+host, fp32: `HostSim` steps with the same f32x2-paired substep functions the device runs) against the fp64 oracle. Runs without a GPU; the `-m gpu` tests repeat
 the comparisons through the C ABI on the device.
 
 Tolerances (DESIGN.md "Parity"): the fp32 common-frame formulation carries ~1e-5
@@ -113,12 +113,18 @@ def test_fp32_error_budget_against_textbook_fp32(model, oracle_lib):
     hp = HostSim(model, cfg, n)  # the paired (f32x2) substep the device runs, reached through the extras entry point
     hp.set_state(st)
     hp.step_servos_ext(act, np.zeros((n, 7, 3), dtype=np.float32))
-    hs.step_servos(act)  # the scalar-leg substep
+    hs.step_servos(act)  # the same substep through the plain entry point
+    assert np.array_equal(hs.state[:, :25], hp.state[:, :25])
+    hsc = HostSim(model, cfg, n, scalar_legs=True)  # the scalar-leg variant (UPKIE_PAIRED_LEGS=0 builds)
+    hsc.set_state(st)
+    hsc.step_servos(act)
     o64.step_servos(act.astype(np.float64))
     o32.step_servos(act.astype(np.float64))
     ref = o64.get_state()[:, 19:25]
     ep = np.abs(hp.state[:, 19:25].astype(np.float64) - ref).max(axis=1)
     assert np.median(ep) < 2.5e-5, np.median(ep)
+    esc = np.abs(hsc.state[:, 19:25].astype(np.float64) - ref).max(axis=1)
+    assert np.median(esc) < 2.5e-5, np.median(esc)
     ek = np.abs(hs.state[:, 19:25].astype(np.float64) - ref).max(axis=1)
     et = np.abs(o32.get_state()[:, 19:25] - ref).max(axis=1)
     assert np.median(ek) < 2.5e-5, np.median(ek)

@@ -1085,7 +1085,9 @@ UPKIE_HD uint32_t state_sanity(const RobotState& S) {
   return (fabsf(chk) <= 3.0e38f) ? 0u : UPKIE_ERR_NAN_STATE;
 }
 
-template <typename AnyFn>
+// Host-side test entry (tests/hostsim): one env tick from a servo action. SCALAR_LEGS = false runs the substep the
+// kernels run (substep(): the f32x2-paired legs unless UPKIE_PAIRED_LEGS is 0), true the scalar-leg variant.
+template <bool SCALAR_LEGS = false, typename AnyFn>
 UPKIE_HD uint32_t step_servo_action(const SimParams& P, RobotState& S, float a[UPKIE_ACT_DIM], const float* eps, float mu,
                                     AnyFn warp_any) {
   uint32_t err = 0;
@@ -1112,7 +1114,8 @@ UPKIE_HD uint32_t step_servo_action(const SimParams& P, RobotState& S, float a[U
                             aj[UPKIE_ACT_MAXIMUM_TORQUE]);
       S.torque[j] = tau[j];
     }
-    physics_substep(P, S, tau, eps, mu, warp_any);
+    if (SCALAR_LEGS) physics_substep(P, S, tau, eps, mu, warp_any);
+    else substep(P, S, tau, eps, mu, warp_any);
   }
   observe_update(P, S);
   const float chk = S.quat[0] + S.quat[1] + S.quat[2] + S.quat[3] + S.pos[2] + S.linvel[0];
