@@ -105,6 +105,23 @@ void hostsim_spine_obs(void* hv, int n, const float* state, float* out) {
   }
 }
 
+// the spine observation as k_spine_obs assembles it: measurement noise on the torques and ImuUncertainty on the IMU
+// block, drawn for env tick `tick` (the same draw as the step that produced the state)
+void hostsim_spine_obs_with_uncertainty(void* hv, int n, const float* state, uint32_t tick, uint64_t env_offset,
+                                        float* out) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    const NoiseCtx nz{env_offset + uint64_t(i), tick};
+    float tq[6];
+    measured_torques(h->P, S, &nz, tq);
+    float* o = out + size_t(i) * UPKIE_SPINE_DIM;
+    spine_observation(h->P, S, o, tq);
+    apply_imu_uncertainty(h->P, nz, o);
+  }
+}
+
 void hostsim_sample_init(void* hv, int n, uint64_t seed, uint64_t env_offset, uint64_t episode, float* init) {
   HostSim* h = static_cast<HostSim*>(hv);
   for (int i = 0; i < n; ++i) sample_init_state(h->P, seed, env_offset + i, episode, init + size_t(i) * UPKIE_INIT_DIM);

@@ -140,6 +140,13 @@ class HostSim:
         lib().hostsim_spine_obs(self._h, self.n, _f(self.state), _f(out))
         return out
 
+    def spine_obs_with_uncertainty(self, tick, env_offset=0):
+        """``k_spine_obs``: torque measurement noise and ImuUncertainty included (draws of env tick ``tick``)."""
+        out = np.empty((self.n, _abi.SPINE_DIM), dtype=np.float32)
+        lib().hostsim_spine_obs_with_uncertainty(
+            self._h, self.n, _f(self.state), C.c_uint32(tick), C.c_uint64(env_offset), _f(out))
+        return out
+
     def sample_init(self, seed, env_offset=0, episode=1):
         out = np.empty((self.n, _abi.INIT_DIM), dtype=np.float32)
         lib().hostsim_sample_init(self._h, self.n, seed, env_offset, episode, _f(out))

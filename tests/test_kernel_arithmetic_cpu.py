@@ -451,6 +451,48 @@ def test_wheel_contact_points_follow_the_collision_pass(model, oracle_lib):
     assert abs(pl[2]) < 5e-3 and abs(pr[2]) < 5e-3 and abs((pl[1] - pr[1]) - model.wheel_base) < 1e-3
 
 
+def test_imu_uncertainty_known_answers(model):
+    """ImuUncertainty on the spine observation (`apply_imu_uncertainty`, as `k_spine_obs` calls it) against the
+    reference's own cases (upkie/cpp/interfaces/tests/ImuUncertaintyTest.cpp:23-41): no bias and no noise leaves the
+    observation alone; a pure bias is added exactly, to the filtered and raw accelerations and the angular velocity,
+    and to nothing else; white noise has the configured standard deviation and independent raw / filtered draws."""
+    n = 4096
+    st = random_states(n, seed=41).astype(np.float32)
+
+    def spine(cfg, tick=7):
+        hs = HostSim(model, cfg, n)
+        hs.set_state(st)
+        return hs.spine_obs(), hs.spine_obs_with_uncertainty(tick)
+
+    plain, same = spine(_abi.default_sim_config())
+    assert np.array_equal(plain, same)  # NoBiasNoNoise
+    cfg = _abi.default_sim_config()
+    acc_bias, gyro_bias = (0.1, -0.2, 0.3), (-0.01, 0.02, 0.03)
+    for k in range(3):
+        cfg.imu_accelerometer_bias[k], cfg.imu_gyroscope_bias[k] = acc_bias[k], gyro_bias[k]
+    plain, biased = spine(cfg)
+    d = biased.astype(np.float64) - plain
+    s_acc, s_raw, s_gyr = _abi.SP_IMU_LINACC, _abi.SP_IMU_RAWACC, _abi.SP_IMU_ANGVEL
+    assert np.abs(d[:, s_acc:s_acc + 3] - acc_bias).max() < 2e-6  # PureBias (fp32 round-off of the sum)
+    assert np.abs(d[:, s_raw:s_raw + 3] - acc_bias).max() < 2e-6
+    assert np.abs(d[:, s_gyr:s_gyr + 3] - gyro_bias).max() < 2e-6
+    other = np.ones(_abi.SPINE_DIM, dtype=bool)
+    for s0 in (s_acc, s_raw, s_gyr):
+        other[s0:s0 + 3] = False
+    assert np.array_equal(biased[:, other], plain[:, other])
+    cfg = _abi.default_sim_config()
+    cfg.imu_accelerometer_noise, cfg.imu_gyroscope_noise, cfg.noise_seed = 0.5, 0.05, 3
+    plain, noisy = spine(cfg)
+    d = noisy.astype(np.float64) - plain
+    assert abs(d[:, s_acc:s_acc + 3].std() / 0.5 - 1) < 0.03 and abs(d[:, s_gyr:s_gyr + 3].std() / 0.05 - 1) < 0.03
+    assert abs(d[:, s_raw:s_raw + 3].std() / 0.5 - 1) < 0.03 and abs(d[:, s_acc:s_acc + 3].mean()) < 0.02
+    assert abs(np.corrcoef(d[:, s_acc], d[:, s_raw])[0, 1]) < 0.05  # raw and filtered: independent draws
+    _, again = spine(cfg)
+    assert np.array_equal(again, noisy)  # counter-based: repeatable
+    _, later = spine(cfg, tick=8)
+    assert not np.array_equal(later[:, s_acc], noisy[:, s_acc])
+
+
 # ---- counter-based RNG ------------------------------------------------------------------------
 
 def test_philox4x32_10_known_answers():
