@@ -45,6 +45,7 @@ def lib():
         L.hostsim_step_gyropod.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_int, fp, u8p]
         L.hostsim_substep.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.hostsim_spine_obs.argtypes = [C.c_void_p, C.c_int, fp, fp]
+        L.hostsim_spine_obs_with_uncertainty.argtypes = [C.c_void_p, C.c_int, fp, C.c_uint32, C.c_uint64, fp]
         L.hostsim_sample_init.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, fp]
         L.hostsim_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
         L.hostsim_step_servos_ext.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, C.c_uint32, fp]
@@ -144,7 +145,7 @@ class HostSim:
         """``k_spine_obs``: torque measurement noise and ImuUncertainty included (draws of env tick ``tick``)."""
         out = np.empty((self.n, _abi.SPINE_DIM), dtype=np.float32)
         lib().hostsim_spine_obs_with_uncertainty(
-            self._h, self.n, _f(self.state), C.c_uint32(tick), C.c_uint64(env_offset), _f(out))
+            self._h, self.n, _f(self.state), tick, env_offset, _f(out))
         return out
 
     def sample_init(self, seed, env_offset=0, episode=1):
