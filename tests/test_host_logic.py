@@ -273,3 +273,36 @@ def test_numa_cpulist_parser_and_fallbacks():
     # no GPU here: unknown topology -> nothing is bound, nothing raises
     assert numa.gpu_numa_node(0) is None or isinstance(numa.gpu_numa_node(0), int)
     assert numa.bind_to_gpu_node(0) is None or isinstance(numa.bind_to_gpu_node(0), list)
+
+
+def test_env_ids_and_cookie_model(tmp_path, monkeypatch):
+    """``<Robot>-B200-<Action>`` ids (upkie/envs/__init__.py:24-44) and the Cookie factory's model loading
+    (entry_points.py:295-336): optional ``cookie_description``, right-wheeled model out of its URDF."""
+    import sys
+    import types
+
+    import upkie_b200
+    from upkie_b200.model import Model
+    from upkie_b200.urdf import write_urdf
+
+    assert set(upkie_b200.ENV_IDS) == {
+        f"{robot}-B200-{name}" for robot in ("Upkie", "Cookie")
+        for name in ("Servos", "Gyropod", "Pendulum", "BaseVelocity")
+    }
+    assert upkie_b200.ENV_IDS["Cookie-B200-BaseVelocity"] == "base_velocity"
+    with pytest.raises(upkie_b200.UpkieException):
+        upkie_b200.make_vec("Upkie-B200-Nope", 4)
+    monkeypatch.setitem(sys.modules, "cookie_description", None)  # import raises ImportError
+    with pytest.raises(upkie_b200.MissingOptionalDependency):
+        upkie_b200.get_cookie_model()
+    right = Model.standard_upkie()
+    right.joint_axis = right.joint_axis.copy()
+    right.joint_axis[[2, 5]] *= -1.0
+    path = str(tmp_path / "cookie.urdf")
+    write_urdf(right, path)
+    stub = types.ModuleType("cookie_description")
+    stub.URDF_PATH = path
+    monkeypatch.setitem(sys.modules, "cookie_description", stub)
+    cookie = upkie_b200.get_cookie_model()
+    assert cookie.left_wheeled is False and Model.standard_upkie().left_wheeled is True
+    assert cookie.wheel_radius == pytest.approx(0.05) and cookie.wheel_base == pytest.approx(0.3048, abs=1e-6)
