@@ -65,3 +65,22 @@ def test_backend_contact_points_on_device(model):
     assert len(backend.get_contact_points("left_wheel_tire")) == 1
     assert backend.get_contact_points("imu") == [] and backend.get_contact_points("no_such_link") == []
     backend.close()
+
+
+def test_parity_audit_records_from_the_b200_backend(tmp_path):
+    """tools/parity_audit.py record --backend b200: the recording a real-PyBullet machine would be compared with."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("parity_audit", os.path.join(root, "tools", "parity_audit.py"))
+    audit = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(audit)
+    paths = [str(tmp_path / f"run{k}.mpack") for k in range(2)]
+    for path in paths:
+        assert audit.main(["record", "--backend", "b200", "--scenario", "squat", "--ticks", "30", "--out", path]) == 0
+    header, records = audit.load(paths[0])
+    assert header["backend"] == "b200" and len(records) == 31
+    assert abs(records[-1]["observation"]["servo"]["left_hip"]["position"]) > 1e-3  # the squat moved the hips
+    table = audit.compare(paths[0], paths[1])
+    assert max(max(row.values()) for row in table.values()) == 0.0  # deterministic: two runs, identical recordings
