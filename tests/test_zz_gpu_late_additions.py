@@ -1,9 +1,11 @@
 # SPDX-License-Identifier: Apache-2.0
-"""Joint-limit rows on the device (k_step<.., NOISE=2, ..>, config.joint_limits = 1) against the oracle.
+"""GPU tests of what was written after round 1's GPU budget had been spent: joint-limit rows on the device
+(k_step<.., NOISE=2, ..>, config.joint_limits = 1) against the oracle, the Backend contact query, and the
+parity-audit recorder.
 
-This file sorts last on purpose: the "extras + limits" kernels were written after round 1's GPU budget had been
-spent, so their first run on a B200 is the driver's round-end `pytest -m gpu`. The CPU build of
-the same code agrees with the oracle (tests/test_kernel_arithmetic_cpu.py::test_joint_limit_rows)."""
+This file sorts last on purpose: its first run on a B200 is the driver's round-end `pytest -m gpu` (DESIGN.md
+section 3), after every test that was green on the GPU during the round. The CPU build of the same kernel code agrees
+with the oracle (tests/test_kernel_arithmetic_cpu.py::test_joint_limit_rows)."""
 import numpy as np
 import pytest
 
