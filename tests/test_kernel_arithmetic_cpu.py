@@ -449,6 +449,15 @@ def test_wheel_contact_points_follow_the_collision_pass(model, oracle_lib):
     assert abs(total - float(np.sum(model.mass)) * cfg.gravity) < 0.15 * float(np.sum(model.mass)) * cfg.gravity
     (_, pl, _), (_, pr, _) = pts
     assert abs(pl[2]) < 5e-3 and abs(pr[2]) < 5e-3 and abs((pl[1] - pr[1]) - model.wheel_base) < 1e-3
+    from upkie_b200.model import contact_points_from_state
+
+    row = osim1.get_state()[0]
+    contacts = contact_points_from_state(model, row, cfg)
+    assert [c.link_name for c in contacts] == ["left_wheel_tire", "right_wheel_tire"]
+    assert contacts[0].force_in_world[2] == pytest.approx(pts[0][2]) and contacts[0].force_in_world[0] == 0.0
+    assert [c.link_name for c in contact_points_from_state(model, row, cfg, "right_wheel_tire")] == ["right_wheel_tire"]
+    assert contact_points_from_state(model, row, cfg, "imu") == [] == contact_points_from_state(model, row, cfg, "nope")
+    assert "PointContact(link_name='left_wheel_tire'" in repr(contacts[0])
 
 
 def test_imu_uncertainty_known_answers(model):

@@ -25,7 +25,7 @@ import torch
 
 from . import _abi
 from .envs import make_config, spine_row_to_dict
-from .model import Model, PointContact, default_model, wheel_contact_points
+from .model import Model, PointContact, contact_points_from_state, default_model
 from .robot_state import RobotState
 from .sim import UpkieSim
 
@@ -92,19 +92,8 @@ class B200Backend(_Base):
         points, reported on ``left_wheel_tire`` / ``right_wheel_tire``. ``force_in_world``
         holds the normal force of the last substep; its friction components are not reported yet (the state row
         keeps the normal impulses only), which is a documented difference from the reference."""
-        names = ("left_wheel_tire", "right_wheel_tire")
-        if link_name is not None and link_name not in names:
-            return []  # a link without simulated contacts, or one the robot does not have (the reference: [] too)
         row = self._sim.get_state()[0].cpu().numpy()
-        h = self.__dt / self._sim.config.nb_substeps
-        contacts = wheel_contact_points(
-            self._sim.model, row, h, breaking_threshold=self._sim.config.contact_breaking_threshold
-        )
-        return [
-            PointContact(names[side], position, np.array([0.0, 0.0, force]))
-            for side, position, force in contacts
-            if link_name is None or names[side] == link_name
-        ]
+        return contact_points_from_state(self._sim.model, row, self._sim.config, link_name)
 
     def reset(self, init_state: RobotState) -> dict:
         row = torch.from_numpy(init_state.to_row().astype(np.float32)).reshape(1, _abi.INIT_DIM).to(self._sim.device)

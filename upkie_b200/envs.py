@@ -377,6 +377,13 @@ class B200VectorEnv(VectorEnv):
                 self._obs_dict_cache = cache
         return cache[1]
 
+    def get_contact_points(self, env_index: int = 0, link_name: Optional[str] = None) -> list:
+        """``PyBulletBackend.get_contact_points`` (``pybullet_backend.py:660-716``) for one env of the batch."""
+        from .model import contact_points_from_state
+
+        row = self.sim.get_state()[int(env_index)].cpu().numpy()
+        return contact_points_from_state(self.model, row, self.config, link_name)
+
     def set_external_forces(self, external_forces: Optional[dict]) -> None:
         """Batched ``PyBulletBackend.set_external_forces``: ``{link name: ExternalForce}`` whose ``force`` is
         ``[3]`` (all envs) or ``[N, 3]``; ``None`` or ``{}`` clears."""

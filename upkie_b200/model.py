@@ -393,3 +393,21 @@ def wheel_contact_points(model, state_row, substep_dt: float, breaking_threshold
         impulse = float(row[_abi.ST_CONTACT_IMPULSE + side])
         out.append((side, p_world, impulse / substep_dt))
     return out
+
+TIRE_LINKS = ("left_wheel_tire", "right_wheel_tire")
+
+
+def contact_points_from_state(model, state_row, config, link_name=None):
+    """``PyBulletBackend.get_contact_points`` (``pybullet_backend.py:660-716``) for one robot from its state row:
+    ``PointContact`` instances on ``left_wheel_tire`` / ``right_wheel_tire``, filtered by ``link_name``. A link
+    without simulated contacts, or one the robot does not have, yields ``[]`` like the reference. ``force_in_world``
+    holds the normal force of the last substep (friction components: DESIGN.md section 8)."""
+    if link_name is not None and link_name not in TIRE_LINKS:
+        return []
+    h = float(config.dt) / int(config.nb_substeps)
+    contacts = wheel_contact_points(model, state_row, h, breaking_threshold=float(config.contact_breaking_threshold))
+    return [
+        PointContact(TIRE_LINKS[side], position, np.array([0.0, 0.0, force]))
+        for side, position, force in contacts
+        if link_name is None or TIRE_LINKS[side] == link_name
+    ]
