@@ -306,3 +306,25 @@ def test_env_ids_and_cookie_model(tmp_path, monkeypatch):
     cookie = upkie_b200.get_cookie_model()
     assert cookie.left_wheeled is False and Model.standard_upkie().left_wheeled is True
     assert cookie.wheel_radius == pytest.approx(0.05) and cookie.wheel_base == pytest.approx(0.3048, abs=1e-6)
+
+
+def test_header_is_c99_and_struct_sizes_match_ctypes(tmp_path):
+    """include/upkie_b200.h compiles as plain C99 (the boundary is a C ABI), and every struct a caller fills has the
+    size its ctypes mirror has (field-by-field agreement of the defaults is test_c_default_configs_equal_python_mirrors)."""
+    import ctypes as C
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = ("UpkieModel", "UpkieSimConfig", "UpkieMpcConfig", "UpkieObserverConfig", "UpkieWheelBalancerConfig")
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "upkie_b200.h"\nint main(void) {\n'
+        + "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names)
+        + "  return 0;\n}\n"
+    )
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                           "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n in names:
+        assert int(out[n]) == C.sizeof(getattr(_abi, n)), n
