@@ -345,3 +345,72 @@ def test_energy_and_momentum_conservation_rate(model, oracle_lib):
         assert np.allclose(e1["linear_momentum"][:2], e0["linear_momentum"][:2], atol=2e-2 * h / 1e-3 * 0.1)
     # first-order integrator: the energy error shrinks ~linearly with the step
     assert drift[1] < 0.2 * drift[0]
+
+
+def test_resting_contact_is_the_implicit_spring_of_the_tire(model, oracle_lib):
+    """What Bullet documents for a URDF `<contact><stiffness/><damping/>` pair: the normal row acts as an implicit
+    spring-damper (cfm = 1 / (h k + d) / h, erp = h k / (h k + d)). At rest each tire therefore sinks by F / k with
+    F half of the weight - an analytic pin of the contact-row restatement (the kernels' arithmetic repeats it)."""
+    from hostsim_wrap import HostSim
+    from upkie_b200.model import wheel_contact_points
+
+    cfg = _abi.default_sim_config()
+    init = np.zeros((1, _abi.INIT_DIM))
+    init[:, 2], init[:, 3] = 0.6, 1.0
+    hold = np.zeros((1, 6, 6))
+    hold[:, :, 3], hold[:, :, 4], hold[:, :, 5] = 1.0, 1.0, np.asarray(model.tau_max)
+    h = cfg.dt / cfg.nb_substeps
+    weight = float(np.sum(model.mass)) * cfg.gravity
+    osim = oracle_lib.OracleSim(model, cfg, 1)
+    osim.reset(init)
+    hs = HostSim(model, cfg, 1)
+    hs.reset(init.astype(np.float32))
+    for _ in range(60):
+        osim.step_servos(hold)
+        hs.step_servos(hold.astype(np.float32))
+    for row, tol in ((osim.get_state()[0], 2e-3), (hs.state[0], 5e-3)):
+        points = wheel_contact_points(model, row, h)
+        assert [side for side, _, _ in points] == [0, 1]
+        for _, position, force in points:
+            assert force == pytest.approx(weight / 2, rel=0.01)  # the robot leans 0.03 rad by now: not exactly half
+            assert -position[2] == pytest.approx(force / cfg.contact_stiffness, rel=tol)
+
+
+def test_lateral_push_obeys_coulomb_friction(model, oracle_lib):
+    """Analytic pin of the friction rows: a lateral force on the two wheels of a standing robot is held by friction
+    while it is below mu W (stick) and accelerates the robot by (F - mu W) / M above it (slip) - for the oracle and
+    for the kernels' arithmetic."""
+    from hostsim_wrap import HostSim
+    from upkie_b200.model import ExternalForce
+
+    cfg = _abi.default_sim_config()
+    mass = float(np.sum(model.mass))
+    weight = mass * cfg.gravity
+    init = np.zeros((1, _abi.INIT_DIM))
+    init[:, 2], init[:, 3] = 0.6, 1.0
+    hold = np.zeros((1, 6, 6))
+    hold[:, :, 3], hold[:, :, 4], hold[:, :, 5] = 1.0, 1.0, np.asarray(model.tau_max)
+    for push in (0.75 * cfg.friction * weight, 1.35 * cfg.friction * weight, 1.7 * cfg.friction * weight):
+        rows, mask = model.external_force_rows(
+            {"left_wheel_tire": ExternalForce([0.0, push / 2, 0.0]), "right_wheel_tire": ExternalForce([0.0, push / 2, 0.0])}, 1)
+        osim = oracle_lib.OracleSim(model, cfg, 1)
+        osim.reset(init)
+        hs = HostSim(model, cfg, 1)
+        hs.reset(init.astype(np.float32))
+        for _ in range(40):  # settle on the wheels
+            osim.step_servos(hold)
+            hs.step_servos(hold.astype(np.float32))
+        osim.set_external_forces(rows.astype(np.float64), mask)
+        vo, vk = [], []
+        for _ in range(20):
+            osim.step_servos(hold)
+            hs.step_servos_ext(hold.astype(np.float32), rows, mask)
+            vo.append(osim.get_state()[0, 8])
+            vk.append(float(hs.state[0, 8]))
+        expected = max(0.0, push - cfg.friction * weight) / mass
+        for v in (np.array(vo), np.array(vk)):
+            accel = (v[-1] - v[4]) / (15 * cfg.dt)
+            if expected == 0.0:
+                assert abs(v[-1]) < 5e-3 and abs(accel) < 0.5  # stick (a slow creep of the compliant contact is allowed)
+            else:
+                assert accel == pytest.approx(expected, rel=0.06)  # slip: damping and the leaning robot cost a few %
