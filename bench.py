@@ -552,6 +552,8 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
                            "temperature, voltage, reward, truncated are not stored)" if compact_rollout
                            else f"{obs_bytes + 6} B/env/step"),
         "substeps_per_step": 5,
+        "joint_limit_rows": bool(getattr(env.config, "joint_limits", 0)),  # Bullet's hip / knee limit constraints: off
+        # by default in round 1; on this torque workload they would be active on ~20 % of the robot-ticks
         "parallelism": f"env-index sharded x{world}" + (
             ("; rollout buffer [32] pushed to the peers' symmetric-memory buffers by the copy engines over NVLink"
              if gather_mode == "peer" else
