@@ -210,7 +210,9 @@ typedef struct UpkieSimConfig {
    * beyond a bound, one unilateral row along that joint joins the contact rows in the PGS solve (solved before the
    * contact normals, in alternating order from sweep to sweep), with Baumgarte factor joint_limit_erp and the
    * impulse capped at joint_limit_max_impulse. 0 = no limit rows (round-1 default: the rows exist in the oracle and
-   * in the kernels' arithmetic, CPU-validated against each other, but have not run on a GPU yet) */
+   * in the kernels' arithmetic, CPU-validated against each other, but have not run on a GPU yet);
+   * 1 = rows on, robots with an active limit row solve their rows in a scalar slow path; 2 = rows on, every robot
+   * runs the packed ten-row solver (four limit slots + six contact rows). Same results to round-off. */
   int32_t joint_limits;
   int32_t reserved_joint_limits; /* keeps the doubles below 8-byte aligned without implicit padding */
   double joint_limit_erp;         /* btContactSolverInfo::m_erp = 0.2 */

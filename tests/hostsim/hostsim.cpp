@@ -139,7 +139,7 @@ void hostsim_step_servos_ext(void* hv, int n, float* state, const float* action,
     clamp_servo_action(h->P, a);
     const ExtForces X{ext + size_t(i) * 21, 1, local_mask};
     for (int sub = 0; sub < h->P.nb_substeps; ++sub)
-      servo_substep(h->P, S, a, false, nullptr, h->P.friction, any_fn, NoSync(), nullptr, sub, &X, h->P.joint_limits != 0);
+      servo_substep(h->P, S, a, false, nullptr, h->P.friction, any_fn, NoSync(), nullptr, sub, &X, h->P.joint_limits);
     observe_update(h->P, S);
     for (int j = 0; j < 6; ++j) {
       float* o = obs + size_t(i) * UPKIE_OBS_DIM + j * 5;

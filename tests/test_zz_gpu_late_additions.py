@@ -15,14 +15,16 @@ from upkie_b200 import _abi
 pytestmark = pytest.mark.gpu
 
 
-def test_joint_limit_rows_on_device(model, oracle_lib):
+@pytest.mark.parametrize("solver", [1, 2])
+def test_joint_limit_rows_on_device(model, oracle_lib, solver):
+    """solver 1: scalar slow path for the robots with an active limit row; 2: packed ten-row solver for all."""
     import torch
 
     from upkie_b200.sim import UpkieSim
 
     n = 2048
     cfg = _abi.default_sim_config()
-    cfg.joint_limits = 1
+    cfg.joint_limits = solver
     sim = UpkieSim(n, model=model, config=cfg)
     plain = UpkieSim(n, model=model, config=_abi.default_sim_config())
     osim = oracle_lib.OracleSim(model, cfg, n, threads=8)

@@ -154,7 +154,7 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.pgs_iterations = c.pgs_iterations;
   P.pgs_rtol = float(c.pgs_tolerance);
   P.warm = float(c.warmstarting_factor);
-  P.joint_limits = c.joint_limits ? 1 : 0;
+  P.joint_limits = c.joint_limits < 0 ? 0 : (c.joint_limits > 2 ? 2 : c.joint_limits);
   P.limit_erp = float(c.joint_limit_erp);
   P.limit_max_impulse = float(c.joint_limit_max_impulse);
   P.skip_action_clamps = c.skip_action_clamps;

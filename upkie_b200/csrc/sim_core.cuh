@@ -93,7 +93,7 @@ struct SimParams {
   float rand_roll, rand_pitch, rand_x, rand_z, rand_omega_x, rand_omega_y, rand_linvel[3];
   // joint-limit rows (btMultiBodyJointLimitConstraint; "extras" instantiations only). Kept at the end of the
   // struct so that the constant-bank offsets of everything above stay where the GPU-validated kernels read them.
-  int joint_limits;
+  int joint_limits;        // 0 off, 1 scalar slow path, 2 packed ten-row solver (sim_pair.cuh)
   float limit_erp, limit_max_impulse;
 };
 
@@ -819,7 +819,7 @@ namespace upkie_b200 {
 // `wext`: external wrench on the base (moment about the base origin, force; base coordinates) or null
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu, AnyFn warp_any,
-                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr, bool limits = false) {
+                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr, int limits = 0) {
 #if UPKIE_PAIRED_LEGS
   physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext, limits);
 #else
@@ -1052,7 +1052,7 @@ template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPKIE_ACT_DIM], bool zero_torque,
                             const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync = SyncFn(),
                             const NoiseCtx* nz = nullptr, int sub = 0, const ExtForces* ext = nullptr,
-                            bool limits = false) {
+                            int limits = 0) {
   float tau[6];
   float noise[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (P.any_ctrl_noise && nz) {
