@@ -1069,14 +1069,25 @@ UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPK
     tau[j] = zero_torque ? 0.f : t;
     if (!zero_torque) S.torque[j] = t;
   }
-  if (ext && !zero_torque) {  // the substep of a reset runs without external forces (pybullet_backend.py:227-228)
+  if (limits != 0) {
+    // joint-limit instantiations: ONE inlined copy of the substep (its code is twice as long there), the external
+    // wrench passed through a nullable pointer
+    float tau_add[6], wbase[6];
+    const bool forced = ext && !zero_torque;
+    if (forced) {
+      external_generalized_forces(P, S, *ext, tau_add, wbase);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) tau[j] += tau_add[j];
+    }
+    substep(P, S, tau, eps, mu, warp_any, phase_sync, forced ? wbase : nullptr, limits);
+  } else if (ext && !zero_torque) {  // the substep of a reset runs without external forces (pybullet_backend.py:227-228)
     float tau_add[6], wbase[6];
     external_generalized_forces(P, S, *ext, tau_add, wbase);
 #pragma unroll
     for (int j = 0; j < 6; ++j) tau[j] += tau_add[j];
-    substep(P, S, tau, eps, mu, warp_any, phase_sync, wbase, limits);
+    substep(P, S, tau, eps, mu, warp_any, phase_sync, wbase, 0);
   } else {
-    substep(P, S, tau, eps, mu, warp_any, phase_sync, nullptr, limits);
+    substep(P, S, tau, eps, mu, warp_any, phase_sync, nullptr, 0);
   }
 }
 

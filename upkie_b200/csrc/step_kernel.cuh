@@ -118,7 +118,7 @@ __device__ __forceinline__ void step_env(
 #endif
     if (sub < nsub) {
       servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
-                    (NOISE && ext) ? &xf : nullptr, NOISE == 2 ? P.joint_limits : 0);
+                    (NOISE && ext) ? &xf : nullptr, NOISE == 2 ? (P.joint_limits == 2 ? 2 : 1) : 0);
     } else {
 #pragma unroll
       for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
