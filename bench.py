@@ -37,7 +37,7 @@ B_ALG = {"servos": 542 + 284 + 3 * 4 * 2, "pendulum": 346 + 3 * 4 * 2 + 16, "mpc
 # compact rollout records: observation rows 72 B instead of 120 B, no reward (4 B) / truncated (1 B) stores
 B_ALG_SERVOS_COMPACT = B_ALG["servos"] - 48 - 5
 N_ACTION_BUFFERS = 16
-ROLLOUT_T = 32
+ROLLOUT_T = 32  # steps per rollout gather; shortened to K // 4 when the timed region has fewer than 128 steps
 
 
 def read_peaks():
@@ -49,65 +49,93 @@ def read_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock / throttle reasons of one GPU around and DURING the timed region.
 
-    FIELDS = (
-        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-        "clocks_event_reasons.sw_power_cap"
-    )
+    Round 1's sampler initialised NVML inside its thread after the timed region had started; the driver's 20-step
+    run lasts ~2 ms, so it never produced a sample. Now NVML is initialised up front, the thread samples from
+    before the warm-up on, `mark_begin()` / `mark_end()` bracket the timed region, and `sample_now()` takes one
+    reading synchronously right after the timed launches were enqueued (the GPU is still executing them)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.samples = []  # (t, sm_mhz, power_w, reason bits, in_region_sync)
         self._stop = threading.Event()
         self._thread = None
+        self._t0 = self._t1 = None
+        self._nv = None
+        self._h = None
+        self.max_mhz = None
+        self.source = "unavailable"
+        try:
+            import pynvml as nv
 
-    def _run_nvml(self):
-        import pynvml as nv
+            nv.nvmlInit()
+            self._nv = nv
+            self._h = nv.nvmlDeviceGetHandleByIndex(self._physical_index(nv, index))
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception as exc:  # no NVML: nvidia-smi polling (slow, ~50 ms per query)
+            self._nv = None
+            self.source = f"nvidia-smi ({type(exc).__name__})"
 
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        bits = {
-            "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else nv.nvmlClocksThrottleReasonHwSlowdown,
-            "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
-            "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
-            "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap,
-        }
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
-            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+    @staticmethod
+    def _physical_index(nv, index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
+
+    def _read(self):
+        nv = self._nv
+        if nv is not None:
+            sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
             try:
-                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
             except Exception:
-                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
             try:
-                power = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                power = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
             except Exception:
                 power = 0.0
-            self.samples.append(
-                [str(sm), str(mx), str(power)] + ["Active" if (reasons & bits[k]) else "Not Active" for k in names]
-            )
-            self._stop.wait(0.01)
+            bits = {
+                "hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap,
+            }
+            return sm, power, [k for k in self.NAMES if reasons & bits[k]]
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}",
+             "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"],
+            capture_output=True, text=True, timeout=5,
+        ).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        self.max_mhz = float(f[1])
+        return float(f[0]), float(f[2]), [k for i, k in enumerate(self.NAMES) if f[3 + i] == "Active"]
 
-    def _run(self):
+    def sample_now(self, sync=True):
         try:
-            self._run_nvml()
-            return
+            sm, power, reasons = self._read()
+            self.samples.append((time.perf_counter(), sm, power, reasons, sync))
         except Exception:
             pass
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+            self.sample_now(sync=False)
+            self._stop.wait(0.002 if self._nv is not None else 0.1)
+
+    def mark_begin(self):
+        self._t0 = time.perf_counter()
+
+    def mark_end(self):
+        self._t1 = time.perf_counter()
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -120,16 +148,20 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for s in self.samples for k in range(4) if len(s) > 3 + k and s[3 + k] == "Active"})
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [f"no sample ({self.source})"]}
+        t0 = self._t0 if self._t0 is not None else -1e30
+        t1 = self._t1 if self._t1 is not None else 1e30
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        used = inside if inside else self.samples[-3:]
+        reasons = sorted({r for x in used for r in x[3]})
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
+            "sm_mhz": float(np.median([x[1] for x in used])),
+            "sm_max_mhz": self.max_mhz,
             "reasons": reasons,
-            "samples": len(self.samples),
+            "power_w": float(np.max([x[2] for x in used])),
+            "samples_in_timed_region": len(inside),
+            "samples_total": len(self.samples),
+            "source": self.source,
         }
 
 
@@ -142,66 +174,112 @@ def servos_config():
     cfg.servos_fall_termination = 1
     cfg.min_base_height = 0.15
     cfg.rand_pitch = 0.3
+    if os.environ.get("UPKIE_BENCH_JOINT_LIMITS"):  # developer knob: 0 off, 1 scalar slow path, 2 ten-row, 3 hybrid
+        cfg.joint_limits = int(os.environ["UPKIE_BENCH_JOINT_LIMITS"])
     if os.environ.get("UPKIE_BENCH_PGS_TOL"):  # developer knob (profiles/r01_variants.md)
         cfg.pgs_tolerance = float(os.environ["UPKIE_BENCH_PGS_TOL"])
     return cfg
 
 
-def cpu_servos(n_envs, steps, threads, seed=2025):
-    """Times the oracle (CPU restatement) on a bounded sample of the servos workload."""
-    from oracle import oracle
-    from upkie_b200.model import Model
+class CpuServos:
+    """The servos workload on the oracle (CPU restatement, fp64): same envs, randomisation, torque actions and
+    fall / height termination with reset as the GPU arm. The simulator and its worker pool are created once
+    (round 1 re-created both inside every timed call)."""
 
-    oracle.build()
-    model = Model.standard_upkie()
-    cfg = servos_config()
-    rng = np.random.default_rng(seed)
-    sim = oracle.OracleSim(model, cfg, n_envs, threads=threads)
-    sim.set_randomization(friction=rng.uniform(0.5, 1.2, n_envs), inertia_eps=rng.uniform(-0.2, 0.2, (n_envs, 6)))
-    init = np.zeros((n_envs, 25))
-    init[:, 2] = 0.6
-    pitch = rng.uniform(-0.3, 0.3, n_envs)
-    init[:, 3] = np.cos(pitch / 2)
-    init[:, 5] = np.sin(pitch / 2)
-    sim.reset(init)
-    tau = np.asarray(model.tau_max)
-    act = np.zeros((n_envs, 6, 6))
-    act[:, :, 0] = np.nan
-    act[:, :, 5] = tau
-    act[:, :, 2] = rng.uniform(-1, 1, (n_envs, 6)) * tau
-    sim.step_servos(act)  # warm-up
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        act[:, :, 2] = rng.uniform(-1, 1, (n_envs, 6)) * tau
-        _, _, term, _ = sim.step_servos(act)
+    def __init__(self, n_envs, threads, seed=2025, n_action_buffers=4):
+        from oracle import oracle
+        from upkie_b200.model import Model
+
+        oracle.build()
+        model = Model.standard_upkie()
+        self.n, self.threads = int(n_envs), int(threads)
+        rng = np.random.default_rng(seed)
+        self.sim = oracle.OracleSim(model, servos_config(), self.n, threads=self.threads)
+        self.sim.set_randomization(friction=rng.uniform(0.5, 1.2, self.n), inertia_eps=rng.uniform(-0.2, 0.2, (self.n, 6)))
+        self.init = np.zeros((self.n, 25))
+        self.init[:, 2] = 0.6
+        pitch = rng.uniform(-0.3, 0.3, self.n)
+        self.init[:, 3] = np.cos(pitch / 2)
+        self.init[:, 5] = np.sin(pitch / 2)
+        self.sim.reset(self.init)
+        tau = np.asarray(model.tau_max)
+        self.acts = []
+        for _ in range(n_action_buffers):  # pre-drawn like the GPU arm's rotating action buffers
+            act = np.zeros((self.n, 6, 6))
+            act[:, :, 0] = np.nan
+            act[:, :, 5] = tau
+            act[:, :, 2] = rng.uniform(-1, 1, (self.n, 6)) * tau
+            self.acts.append(act)
+        self.k = 0
+
+    def tick(self):
+        """One env tick of every env + the masked reset of the fallen ones (the GPU arm's fused auto-reset)."""
+        _, _, term, _ = self.sim.step_servos(self.acts[self.k % len(self.acts)])
+        self.k += 1
         if term.any():
-            sim.reset(init, mask=term)
-    dt = time.perf_counter() - t0
-    return n_envs * steps / dt, dt
+            self.sim.reset(self.init, mask=term)
+
+    def rate(self, min_seconds=2.0, max_ticks=10_000):
+        """(env-steps/s, seconds, ticks): whole ticks until `min_seconds` of wall time have passed."""
+        self.tick()  # warm-up
+        t0 = time.perf_counter()
+        ticks = 0
+        while ticks < max_ticks:
+            self.tick()
+            ticks += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds:
+                break
+        dt = time.perf_counter() - t0
+        return self.n * ticks / dt, dt, ticks
+
+
+def cpu_baseline_servos(n_envs):
+    """`cpu_baseline` of the GPU arm's line: the oracle on all host threads on the SAME config (n_envs envs per tick),
+    for >= 2 s of wall time, plus a single-thread figure on a 2 048-env sample."""
+    cores = os.cpu_count() or 1
+    allc = CpuServos(n_envs, cores)
+    rate, dt, ticks = allc.rate(2.0)
+    one = CpuServos(2048, 1)
+    rate1, dt1, ticks1 = one.rate(1.0)
+    return {
+        "value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "same_config": True,
+        "sample": f"{n_envs} envs x {ticks} ticks of the same workload (joint_limits={int(servos_config().joint_limits)}), "
+                  f"oracle fp64, persistent pool of {cores} threads, {dt:.1f} s wall",
+        "single_thread_value": rate1,
+        "single_thread_sample": f"2048 envs x {ticks1} ticks, 1 thread, {dt1:.1f} s wall",
+    }
 
 
 def run_reference_arm(args, rank, world):
-    """`--impl reference`: the reference's CPU implementation of the path. The
-    reference itself (pybullet + gymnasium + upkie_description) cannot be
-    installed here (DESIGN.md "Reference arm"), so this times the oracle port
-    with all host threads."""
+    """`--impl reference`: the reference's CPU implementation of the path. The reference itself (pybullet +
+    gymnasium + upkie_description) cannot be installed here (DESIGN.md "Reference arm"), so this times the oracle
+    port with all host threads, on the GPU arm's config: one step = one tick of all 65 536 envs."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # bounded sample per step: calibrate so that the whole run ends within ~2 minutes
-    rate_est, _ = cpu_servos(4096, 2, cores)
-    budget_s = 100.0 / max(1, args.steps + args.warmup)
-    n_sample = int(min(16384, max(256, rate_est * budget_s / 4)))
-    n_sample = 1 << (n_sample.bit_length() - 1)
-    rates = []
-    for _ in range(args.warmup):
-        cpu_servos(n_sample, 4, cores)
-    t_total = 0.0
+    n = args.envs_per_gpu or 65536
+    w = CpuServos(n, cores)
+    # bounded: the whole --steps K --warmup W run must end within a few minutes whatever the host
+    probe0 = time.perf_counter()
+    w.tick()
+    per_tick = time.perf_counter() - probe0
+    budget = 150.0
+    if per_tick * (args.steps + args.warmup) > budget:
+        n = max(2048, int(n * budget / (per_tick * (args.steps + args.warmup))) // 2048 * 2048)
+        w = CpuServos(n, cores)
+    for _ in range(max(1, args.warmup)):
+        w.tick()
+    per_step = []
+    t_all = time.perf_counter()
     for _ in range(args.steps):
-        r, dt = cpu_servos(n_sample, 4, cores)
-        rates.append(r)
-        t_total += dt
-    value = float(np.mean(rates))
+        t0 = time.perf_counter()
+        w.tick()
+        per_step.append(time.perf_counter() - t0)
+    t_total = time.perf_counter() - t_all
+    value = n * args.steps / t_total
+    one = CpuServos(2048, 1)
+    rate1, dt1, ticks1 = one.rate(1.0)
     line = {
         "impl": "reference",
         "metric": "env-steps/sec",
@@ -217,13 +295,18 @@ def run_reference_arm(args, rank, world):
         "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": "UpkieServos 6-DoF torque actions, domain-randomized (BASELINE configs[2]/[4]); CPU port, "
-            f"each step = {n_sample} envs x 4 ticks sample",
-            "envs_per_step": n_sample,
+            "workload": "UpkieServos 6-DoF torque actions, domain-randomized, fall/height termination + reset "
+                        f"(BASELINE configs[2]/[4]); CPU port, each step = one tick of {n} envs",
+            "envs_per_step": n,
+            "same_config_as_gpu_arm": n == 65536,
+            "joint_limit_rows": int(servos_config().joint_limits),
         },
         "cpu_baseline": {
             "value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n_sample} envs x 4 ticks per step, {args.steps} steps, oracle fp64, {cores} threads",
+            "sample": f"{n} envs x 1 tick per step, {args.steps} steps, oracle fp64, persistent pool of {cores} threads; "
+                      f"median step {1e3 * float(np.median(per_step)):.1f} ms",
+            "single_thread_value": rate1,
+            "single_thread_sample": f"2048 envs x {ticks1} ticks, 1 thread, {dt1:.1f} s wall",
         },
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -242,6 +325,7 @@ def main():
     ap.add_argument("--workload", default="servos", choices=["servos", "pendulum", "mpc", "plumbing"])
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -306,6 +390,7 @@ def main():
     value = total_units / (t_ms * 1e-3)
     b_alg = B_ALG_SERVOS_COMPACT if config.get("rollout_record", "").startswith("compact") else B_ALG[args.workload]
     achieved = b_alg * n_per_gpu / (kernel_ms * 1e-3) / 1e9  # GB/s per GPU, dominant kernel
+    side = ncu_sidecar(args.workload, config, n_per_gpu)
     line = {
         "metric": "env-steps/sec" if args.workload != "mpc" else "qp-solves/sec",
         "value": value,
@@ -329,48 +414,122 @@ def main():
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full,
-            # profiles/r01_ncu_summary.md): below the algorithmic bytes because the 12 MB of robot state stay in the
-            # 126 MB L2 between launches (reads = actions + state + randomisation, writes almost nil)
-            "traffic": 22_959_360 if (args.workload == "servos" and n_per_gpu == 65536) else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the ncu sidecar of THIS
+            # build (profiles/ncu_sidecar.json, written by tools/ncu_summary.py, keyed on the hash of the CUDA
+            # sources); null when no capture of this build / workload exists
+            "traffic": side.get("dram_bytes"),
+            "traffic_source": side.get("source"),
             "peak_kind": f"{peaks_kind} (MEASURED_PEAKS.json hbm_gbs)" if peaks_kind == "measured" else "fallback 6650 GB/s",
             "algorithmic_bytes_per_unit": b_alg,
             "kernel_ms": kernel_ms,
+            "kernel_ms_statistic": "median over the timed steps of the CUDA-event interval around each launch",
             "note": "fp32 issue-bound path (DESIGN.md): HBM fraction is reported as asked, the binding bound is the "
                     "fp32 pipe; see fp32_issue",
         },
     }
     if args.workload != "mpc":
-        # secondary roofline: non-tensor fp32 issue slots
-        sm_mhz = clocks.get("sm_mhz") or 1700.0
-        # warp instructions per env-step of the servos workload, ncu smsp__inst_executed.sum / warps
-        # (profiles/r01_ncu_summary.md, paired f32x2 legs, end of round 1); 78.5 % of them FFMA(2)/FMUL(2)/FADD(2)
-        instr_per_env_step = 13_921
-        sched_cycles = 148 * 4 * sm_mhz * 1e6  # issue slots per second (one warp instruction each)
-        ipc = instr_per_env_step * (n_per_gpu / 32.0) / (kernel_ms * 1e-3) / sched_cycles
-        line["roofline"]["fp32_issue"] = {
-            "ipc_per_scheduler": ipc,
-            "peak_ipc": 1.0,
-            "frac": ipc,
-            # tools/micro/ffma2_bench.cu on this pool: three-register scalar FFMA saturates at 0.59 inst/cycle/scheduler
-            "measured_scalar_ffma_ceiling_ipc": 0.59,
-            "fp_instr_frac_of_ceiling": 0.785 * ipc / 0.59,
-            "instr_per_env_step": instr_per_env_step,
-            "exact_for": "servos workload (the pendulum front-end changes the count by < 2 %)",
-        }
+        # secondary roofline: non-tensor fp32 issue slots (one warp instruction per scheduler and cycle)
+        sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+        instr = side.get("instr_per_env_step")
+        if sm_mhz and instr:
+            sched_cycles = 148 * 4 * sm_mhz * 1e6  # issue slots per second
+            ipc = instr * (n_per_gpu / 32.0) / (kernel_ms * 1e-3) / sched_cycles
+            line["roofline"]["fp32_issue"] = {
+                "ipc_per_scheduler": ipc, "peak_ipc": 1.0, "frac": ipc,
+                # tools/micro/ffma2_bench.cu on this pool: three-register scalar FFMA saturates at 0.59 inst/cycle/scheduler
+                "measured_scalar_ffma_ceiling_ipc": 0.59,
+                "instr_per_env_step": instr,
+                "fp_instr_share": side.get("fp_instr_share"),
+                "sm_mhz_used": sm_mhz,
+                "source": side.get("source"),
+            }
+        else:
+            line["roofline"]["fp32_issue"] = {
+                "ipc_per_scheduler": None,
+                "reason": "no SM clock sample" if not sm_mhz else f"no ncu sidecar for this build ({side.get('source')})",
+            }
     if world == 1 and not args.no_cpu_baseline and args.workload != "mpc":
-        cores = os.cpu_count() or 1
-        n_cpu = 16384
-        rate, dt = cpu_servos(n_cpu, 8, cores)
-        line["cpu_baseline"] = {
-            "value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n_cpu} envs x 8 ticks of the same workload, oracle fp64 ({dt:.1f} s wall, {cores} threads)",
-        }
+        line["cpu_baseline"] = cpu_baseline_servos(n_per_gpu if args.workload == "servos" else 65536)
     elif world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_mpc_baseline()
+    if world == 1 and args.workload == "servos" and not args.no_other_workloads:
+        # BASELINE configs[1] and [3] on the record of the same run (device-timed, secondary lines)
+        line["other_workloads"] = other_workloads(torch, dev, model)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_sidecar(workload, config, n_per_gpu):
+    """Per-launch DRAM bytes and warp instructions per env-step of the benchmarked kernel, from the sidecar that
+    tools/ncu_summary.py writes from an `ncu --set full` capture, valid only for the build it was captured on."""
+    from upkie_b200 import build as b
+
+    path = os.path.join(ROOT, "profiles", "ncu_sidecar.json")
+    key = f"{workload}:limits{config.get('joint_limit_solver', 0)}:n{n_per_gpu}"
+    try:
+        with open(path) as f:
+            data = json.load(f)
+    except Exception:
+        return {"source": "profiles/ncu_sidecar.json missing"}
+    h = b.source_hash()
+    ent = data.get(h, {}).get(key)
+    if ent is None:
+        have = [k for k in data if key in data[k]]
+        return {"source": f"no ncu capture of build {h} for {key}" + (f" (captures exist for builds {have})" if have else "")}
+    out = dict(ent)
+    out["source"] = f"profiles/ncu_sidecar.json[{h}][{key}] <- {ent.get('report', '?')}"
+    return out
+
+
+def other_workloads(torch, dev, model):
+    """Short device-timed runs of BASELINE configs[1] (4 096 ground-velocity envs) and configs[3] (MPC 4 096 x
+    horizon 16, and the reference's default horizon 50), so that they are on the driver's record too."""
+    out = {}
+    try:
+        from upkie_b200 import _abi
+        from upkie_b200.envs import B200VectorEnv
+        from upkie_b200.mpc import BatchedMPCBalancer
+        from upkie_b200.robot_state import RobotState, RobotStateRandomization
+
+        def timed(fn, k=200, w=20):
+            for i in range(w):
+                fn(i)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+            ev[0].record()
+            for i in range(k):
+                fn(i)
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            return ev[0].elapsed_time(ev[k]) / k, float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(k)]))
+
+        n = 4096
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        env = B200VectorEnv(n, "pendulum", device=dev.index, autoreset_mode="next_step", model=model,
+                            init_state=RobotState(randomization=RobotStateRandomization(pitch=0.1)))
+        env.sim.set_autoreset(1, 2025, 0)
+        env.sim.reset(seed=2025)
+        acts = [((torch.rand((n, 1), device=dev, generator=gen) * 2 - 1) * 3.0).contiguous() for _ in range(8)]
+        ms, med = timed(lambda i: env.sim.step_pendulum(acts[i % 8]))
+        out["pendulum_4096"] = {"metric": "env-steps/sec", "value": n / (ms * 1e-3), "ms_per_step": ms,
+                                "kernel_ms_median": med, "workload": "BASELINE configs[1]"}
+        env.close()
+        for H in (16, 50):
+            cfg = _abi.default_mpc_config()
+            cfg.nb_timesteps = H
+            mpc = BatchedMPCBalancer(n, config=cfg, device=dev.index)
+            U = lambda lo, hi: torch.rand(n, device=dev, generator=gen) * (hi - lo) + lo  # noqa: E731
+            xs = [torch.stack([U(-0.5, 0.5), U(-0.2, 0.2), U(-0.5, 0.5), U(-1, 1)], dim=1).contiguous() for _ in range(8)]
+            vt, contact = U(-1, 1), torch.ones(n, dtype=torch.uint8, device=dev)
+            ms, med = timed(lambda i: mpc.step_tensors(xs[i % 8], vt, contact, 0.005))
+            out[f"mpc_4096_h{H}"] = {"metric": "qp-solves/sec", "value": n / (ms * 1e-3), "ms_per_step": ms,
+                                     "kernel_ms_median": med,
+                                     "workload": "BASELINE configs[3]" + (" at the reference's default horizon" if H == 50 else "")}
+    except Exception as exc:  # secondary lines must never take the headline down
+        out["error"] = repr(exc)
+    return out
 
 
 def bench_env(args, torch, dist, dev, rank, world, model, K, W):
@@ -420,27 +579,46 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     env.sim.set_autoreset(1, 2025, rank * n)
     env.sim.reset(seed=2025, env_offset=rank * n)
 
-    # rollout buffer gathered over NVLink once per T steps
+    # rollout buffer gathered over NVLink once per T steps. At least four gathers - issued AND waited
+    # for - fall inside the timed region whatever K is (the driver runs K = 20: T = 5)
     from upkie_b200.sharding import PeerRolloutBuffer, RolloutBuffer
+
+    T_roll = max(1, min(ROLLOUT_T, K // 4))
 
     # two buffers: the gather of rollout r (NVLink) overlaps the simulation of r + 1. "peer": symmetric-memory
     # buffers, every rank pushes its slot to the peers with the copy engines (no SM); "nccl": all_gather_into_tensor
     # Measured (tools/run_2gpu_variants.sh, tools/run_8gpu.sh): 2 GPUs peer 96 % vs nccl 84 % weak-scaling efficiency;
     # 8 GPUs nccl 64 %, the first (unstaggered, one-stream) peer push collapsed there -> nccl stays the default
     # beyond 2 GPUs until the staggered push is validated at 8.
-    gather_mode = os.environ.get("UPKIE_BENCH_GATHER", "peer" if world == 2 else "nccl") if world > 1 else "none"
-    if gather_mode in ("peer", "multicast"):
+    # Transport of the rollout records (UPKIE_BENCH_GATHER overrides): "multicast" - the step kernel's row stores go
+    # to the NVSwitch multicast address of a symmetric-memory buffer (multimem.st), one store reaches every GPU, the
+    # only collective left is a barrier per rollout; "peerstore" - same kernel storing each row into every peer's
+    # buffer over NVLink (no multicast object needed); "peer" - copy-engine pushes per rollout; "nccl" -
+    # all_gather_into_tensor. Default: multicast where the symmetric memory supports it, else peerstore, else nccl.
+    want = os.environ.get("UPKIE_BENCH_GATHER", "auto") if world > 1 else "none"
+    gather_mode = want
+    gather_note = ""
+    if want in ("auto", "multicast", "peerstore", "peer"):
         try:
-            rollouts = [PeerRolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
-            if gather_mode == "multicast" and not (servos and compact_rollout and rollouts[0].multicast_supported):
-                raise RuntimeError("NVSwitch multicast needs the compact servos records and multicast-capable symmetric memory")
+            if not (servos and compact_rollout) and want != "peer":
+                raise RuntimeError("in-kernel transports carry the compact servos records")
+            rollouts = [PeerRolloutBuffer(T_roll, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
+            if want == "auto":
+                gather_mode = "multicast" if rollouts[0].multicast_supported else "peerstore"
+            elif want == "multicast" and not rollouts[0].multicast_supported:
+                raise RuntimeError("symmetric memory reports no multicast support")
         except Exception as exc:  # symmetric memory unavailable on this box: fall back to NCCL's collective
-            print(f"bench.py: symmetric-memory rollout buffer unavailable ({exc!r}); using NCCL all-gather", file=sys.stderr)
+            gather_note = f"symmetric-memory rollout buffer unavailable ({exc!r}); NCCL all-gather instead"
+            print(f"bench.py: {gather_note}", file=sys.stderr)
             gather_mode = "nccl"
-    if gather_mode not in ("peer", "multicast"):
-        rollouts = [RolloutBuffer(ROLLOUT_T, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
+    if gather_mode not in ("peer", "multicast", "peerstore"):
+        rollouts = [RolloutBuffer(T_roll, n, obs_bytes // 4, dev, compact=compact_rollout) for _ in range(2)]
     works = [None, None]
+    # stalls of the simulation stream waiting for the gather of the buffer it is about to overwrite
+    stall_events = []
 
+    clk = ClockSampler(dev.index)
+    clk.__enter__()
     for k in range(W):
         step(acts[k % N_ACTION_BUFFERS])
     torch.cuda.synchronize()
@@ -449,59 +627,79 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     launches0 = env.sim.launches
     events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     end = torch.cuda.Event(enable_timing=True)
+    gathers = 0
     # ncu --profile-from-start off: "1" brackets the timed device loop, "e2e" the host-buffer loop
     profiling = os.environ.get("UPKIE_BENCH_CUDA_PROFILER", "") not in ("", "e2e")
     profiling_e2e = os.environ.get("UPKIE_BENCH_CUDA_PROFILER", "") == "e2e"
-    with ClockSampler(dev.index) as clk:
+    if True:
         torch.cuda.synchronize()
         if profiling:
             torch.cuda.profiler.start()
+        clk.mark_begin()
         events[0].record()
         for k in range(K):
             # the kernel writes observation / reward / masks straight into the rollout slot of this step
-            cur = (k // ROLLOUT_T) % 2
-            if k % ROLLOUT_T == 0 and works[cur] is not None:
+            cur = (k // T_roll) % 2
+            if k % T_roll == 0 and works[cur] is not None:
                 # the gather that last read this buffer must be done before it is overwritten
-                if gather_mode == "multicast":
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                if gather_mode in ("multicast", "peerstore"):
                     pass  # stream order: publish() already ran on this stream
                 elif gather_mode == "peer":
                     rollouts[cur].wait()
                 else:
                     works[cur].wait()
+                ev1.record()
+                stall_events.append((ev0, ev1))
                 works[cur] = None
             if gather_mode == "multicast":
-                # EXPERIMENTAL (UPKIE_BENCH_GATHER=multicast): the kernel's rows go to the NVSwitch multicast address
-                # of this rank's slot and land in every GPU's buffer; a barrier per rollout replaces the gather
+                # the kernel's rows go to the NVSwitch multicast address of this rank's slot and land in every GPU's
+                # buffer; a barrier per rollout replaces the gather
                 env.sim.step_servos_multicast(acts[k % N_ACTION_BUFFERS], *rollouts[cur].multicast_slot(k))
+            elif gather_mode == "peerstore":
+                # no multicast object: the kernel stores each row into every peer's buffer over NVLink itself
+                env.sim.step_servos_peers(acts[k % N_ACTION_BUFFERS], *rollouts[cur].peer_slots(k))
             else:
                 so, sr, ste, stru = rollouts[cur].slot(k)
                 step(acts[k % N_ACTION_BUFFERS], obs=so, reward=sr, terminated=ste, truncated=stru)
             events[k + 1].record()
-            if world > 1 and (k + 1) % ROLLOUT_T == 0:
-                # one gather of the [T, n, 126 B] buffer per rollout, asynchronous
-                if gather_mode == "multicast":
+            if world > 1 and (k + 1) % T_roll == 0:
+                # one gather of the [T, n, record] buffer per rollout, asynchronous
+                gathers += 1
+                if gather_mode in ("multicast", "peerstore"):
                     rollouts[cur].publish()
+                    works[cur] = True
                 elif gather_mode == "peer":
                     works[cur] = rollouts[cur].push()
                 else:
                     _, works[cur] = rollouts[cur].gather_raw(async_op=True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         for i_, w_ in enumerate(works):
             if w_ is not None:
-                if gather_mode == "multicast":
+                if gather_mode in ("multicast", "peerstore"):
                     pass
                 elif gather_mode == "peer":
                     rollouts[i_].wait()
                 else:
                     w_.wait()
-        end.record()  # after the last step / all-gather queued on this stream
+        ev1.record()
+        stall_events.append((ev0, ev1))
+        end.record()  # after the last step AND every gather issued inside the timed region
+        clk.sample_now()  # the GPU is still working through the queue: one reading inside the timed region for sure
         torch.cuda.synchronize()
+        clk.mark_end()
         if profiling:
             torch.cuda.profiler.stop()
         if world > 1:
             dist.barrier()
+    clk.__exit__()
     total_ms = events[0].elapsed_time(end)
     per_step = np.array([events[k].elapsed_time(events[k + 1]) for k in range(K)])
-    kernel_ms = float(np.median(per_step)) if world == 1 else float(np.min(per_step))
+    # steps that waited for a gather carry that wait in their event interval: the median is the kernel alone
+    kernel_ms = float(np.median(per_step))
+    gather_stall_ms = float(sum(a.elapsed_time(b) for a, b in stall_events))
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -511,34 +709,49 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     # e2e through the public VectorEnv API with HOST buffers (H2D + kernel + D2H per step)
     # this step's inputs live in pinned host memory (4 rotating buffers), outputs land in pinned memory
     host_acts = [a.cpu().pin_memory().numpy() for a in acts[:4]]
-    Ke = max(10, min(K, 400))
-    for k in range(3):
+    Ke = max(100, min(K, 400))
+    for k in range(12):  # warm-up: first-touch of the handle's pinned staging buffers, streams, events
         env.step(host_acts[k % 4])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     if profiling_e2e:
         torch.cuda.profiler.start()
+    step_s = np.empty(Ke)
     t0 = time.perf_counter()
     for k in range(Ke):
-        env.step(host_acts[k % 4])
+        ts = time.perf_counter()
+        env.step(host_acts[k % 4])  # returns when the step's results are in host memory
+        step_s[k] = time.perf_counter() - ts
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if profiling_e2e:
         torch.cuda.profiler.stop()
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    te = torch.tensor([e2e_s, float(np.median(step_s))], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {
-        "value": n * world * Ke / float(te.item()),
+        "value": n * world * Ke / float(te[0].item()),
         "unit": "env-steps/s",
         "h2d_bytes_per_step": n * act_bytes,
         # servos: position/velocity/torque rows (72 B) + terminated; temperature, voltage, reward and truncated
         # are constants of the reference that the env fills once on the host (host path)
         "d2h_bytes_per_step": n * ((72 if servos else obs_bytes) + 1),
         "steps": Ke,
+        "warmup": 12,
+        "median_ms_per_step": 1e3 * float(te[1].item()),
+        "value_from_median_step": n * world / float(te[1].item()),
         "api": "B200VectorEnv.step(numpy action) -> numpy obs/reward/terminated/truncated",
     }
+    transport = {
+        "none": "",
+        "peer": "; rollout buffer pushed to the peers' symmetric-memory buffers by the copy engines over NVLink",
+        "multicast": "; the step kernel stores its rollout rows to the NVSwitch multicast address of the symmetric "
+                     "rollout buffer (multimem.st): every GPU receives them, one barrier per rollout, no collective kernel",
+        "peerstore": "; the step kernel stores its rollout rows into every peer's symmetric rollout buffer over "
+                     "NVLink, one barrier per rollout, no collective kernel",
+        "nccl": "; NCCL all_gather_into_tensor of the rollout buffer",
+    }[gather_mode]
     config = {
         "workload": (
             "UpkieServos 6-DoF torque actions, 65536 envs/GPU, friction~U(0.5,1.2), init pitch~U(+-0.3), inertia "
@@ -552,16 +765,22 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
                            "temperature, voltage, reward, truncated are not stored)" if compact_rollout
                            else f"{obs_bytes + 6} B/env/step"),
         "substeps_per_step": 5,
-        "joint_limit_rows": bool(getattr(env.config, "joint_limits", 0)),  # Bullet's hip / knee limit constraints: off
-        # by default in round 1; on this torque workload they would be active on ~20 % of the robot-ticks
-        "parallelism": f"env-index sharded x{world}" + (
-            ("; rollout buffer [32] pushed to the peers' symmetric-memory buffers by the copy engines over NVLink"
-             if gather_mode == "peer" else
-             "; rollout rows stored to the NVSwitch multicast address of the symmetric buffer (experimental)"
-             if gather_mode == "multicast" else "; NCCL all-gather of the [32] rollout buffer") if world > 1 else ""),
+        # Bullet's hip / knee joint-limit constraint rows (pybullet_backend.py:121 loadURDF): 0 off, 1 scalar slow
+        # path, 2 packed ten-row solver, 3 ten-row solver for the warps that hold a robot on a bound
+        "joint_limit_rows": int(getattr(env.config, "joint_limits", 0)) != 0,
+        "joint_limit_solver": int(getattr(env.config, "joint_limits", 0)),
+        "parallelism": f"env-index sharded x{world}" + transport,
         "l2": f"{N_ACTION_BUFFERS} rotating action buffers ({N_ACTION_BUFFERS * n * act_bytes / 1e6:.0f} MB"
               " vs 126 MB L2); robot state stays resident by design",
     }
+    if world > 1:
+        config["gather"] = {
+            "transport": gather_mode, "rollout_steps": T_roll, "gathers_in_timed_region": gathers,
+            "bytes_per_rank_and_gather": int(rollouts[0].nbytes),
+            # time the simulation stream spent waiting for a gather before re-using its buffer, inside the timed region
+            "sim_stream_stall_ms_total": gather_stall_ms,
+            "note": gather_note,
+        }
     return n * K, t_ms * K, kernel_ms, e2e, launches, clk.summary(), config, n
 
 
@@ -638,11 +857,14 @@ def bench_mpc(args, torch, dev, rank, world, K, W):
     torch.cuda.synchronize()
     events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     with ClockSampler(dev.index) as clk:
+        clk.mark_begin()
         events[0].record()
         for k in range(K):
             mpc.step_tensors(xs[k % N_ACTION_BUFFERS], vt, contact, 0.005)
             events[k + 1].record()
+        clk.sample_now()
         torch.cuda.synchronize()
+        clk.mark_end()
     total_ms = events[0].elapsed_time(events[K])
     per_step = np.array([events[k].elapsed_time(events[k + 1]) for k in range(K)])
     xh = [x.cpu().numpy() for x in xs[:4]]

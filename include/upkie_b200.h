@@ -338,9 +338,17 @@ int upkie_b200_step_servos_compact(void* handle, const float* action, float* obs
  * that exists at the same offset on every GPU of the node, e.g. torch.distributed._symmetric_memory's
  * multicast_ptr + offset): rows leave through multimem.st and land in every GPU's buffer, which is the per-step
  * all-gather of the rollout with no collective kernel. n_envs must be a multiple of 32. The caller synchronises the
- * ranks (a barrier per rollout) before reading. EXPERIMENTAL in round 1: compiled and unit-sized, not yet run on a
- * multi-GPU box. */
+ * ranks (a barrier per rollout) before reading. */
 int upkie_b200_step_servos_multicast(void* handle, const float* action, float* obs_mc, uint8_t* terminated_mc, void* stream);
+
+/* Same kernel without a multicast object: the compact rows and `terminated` words of this step are stored into
+ * n_peers buffers (peer-mapped device memory of the GPUs of the node, e.g. torch.distributed._symmetric_memory
+ * buffers; list this rank's own buffer too if it should hold the rows). obs_ptrs[p] / terminated_ptrs[p] address
+ * this step's slot in buffer p (16-byte / 4-byte aligned). 1 <= n_peers <= UPKIE_MAX_PEERS; n_envs a multiple of 32.
+ * Replaces the per-rollout all-gather of SURVEY.md section 8(e) like the multicast variant, over plain NVLink stores. */
+#define UPKIE_MAX_PEERS 8
+int upkie_b200_step_servos_peers(void* handle, const float* action, float* const* obs_ptrs,
+                                 uint8_t* const* terminated_ptrs, int n_peers, void* stream);
 
 /* Same calls with HOST buffers and a stream synchronisation inside the call
  * (the `e2e` path of bench.py). When every buffer is pinned and mapped

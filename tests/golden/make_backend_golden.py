@@ -33,7 +33,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, ROOT)
 
 
-def make_fake_pybullet(b200_model, urdf_path):
+def make_fake_pybullet(b200_model, urdf_path, joint_limits=None):
     """``pybullet`` API subset over one oracle robot. Link / joint indices follow the URDF joint order like Bullet."""
     from oracle import oracle as O
     from upkie_b200 import _abi
@@ -54,6 +54,8 @@ def make_fake_pybullet(b200_model, urdf_path):
         if S.sim is None:
             cfg = _abi.default_sim_config()
             cfg.gravity = -S.gravity[2]
+            if joint_limits is not None:
+                cfg.joint_limits = int(joint_limits)
             S.cfg = cfg
             S.sim = O.OracleSim(b200_model, cfg, 1, threads=1)
 

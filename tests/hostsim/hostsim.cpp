@@ -38,7 +38,7 @@ void hostsim_reset(void* hv, int n, float* state, const float* init, const float
     RobotState S;
     state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
     reset_robot(h->P, S, init + size_t(i) * UPKIE_INIT_DIM, eps ? eps + size_t(i) * 6 : nullptr,
-                mu ? mu[i] : h->P.friction, any_fn);
+                mu ? mu[i] : h->P.friction, any_fn, h->P.joint_limits);
     state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
   }
 }
@@ -91,7 +91,7 @@ void hostsim_substep(void* hv, int n, float* state, const float* tau) {
   for (int i = 0; i < n; ++i) {
     RobotState S;
     state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
-    substep(h->P, S, tau + size_t(i) * 6, nullptr, h->P.friction, any_fn);
+    substep(h->P, S, tau + size_t(i) * 6, nullptr, h->P.friction, any_fn, NoSync(), nullptr, h->P.joint_limits);
     state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
   }
 }
@@ -183,7 +183,7 @@ void hostsim_step_servos_noise(void* hv, int n, float* state, const float* actio
     clamp_servo_action(h->P, a);
     const NoiseCtx nz{env_offset + uint64_t(i), tick};
     for (int sub = 0; sub < h->P.nb_substeps; ++sub)
-      servo_substep(h->P, S, a, false, nullptr, h->P.friction, any_fn, NoSync(), &nz, sub);
+      servo_substep(h->P, S, a, false, nullptr, h->P.friction, any_fn, NoSync(), &nz, sub, nullptr, h->P.joint_limits);
     observe_update(h->P, S);
     float tq[6];
     measured_torques(h->P, S, &nz, tq);

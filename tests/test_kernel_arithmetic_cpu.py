@@ -135,7 +135,7 @@ def test_fp32_error_budget_against_textbook_fp32(model, oracle_lib):
     assert per_joint[[2, 5]].max() < 2.0 * per_joint[[0, 1, 3, 4]].max()
 
 
-@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("solver", [1, 2, 3])
 def test_joint_limit_rows(model, oracle_lib, solver):
     """btMultiBodyJointLimitConstraint rows against the oracle's restatement, three ticks with a third of the robots
     on a bound, in flight and on the ground. config.joint_limits = 1: the scalar slow path (limit_contact_solve,
@@ -145,7 +145,9 @@ def test_joint_limit_rows(model, oracle_lib, solver):
     cfg = _abi.default_sim_config()
     cfg.joint_limits = solver
     hs, osim = HostSim(model, cfg, n), oracle_lib.OracleSim(model, cfg, n, threads=4)
-    free = HostSim(model, _abi.default_sim_config(), n)
+    cfg_free = _abi.default_sim_config()
+    cfg_free.joint_limits = 0
+    free = HostSim(model, cfg_free, n)
     st = at_joint_bounds(model, n, seed=5)
     act = random_servo_actions(n, model, seed=12).astype(np.float32)
     zero = np.zeros((n, 7, 3), dtype=np.float32)
@@ -172,7 +174,7 @@ def test_joint_limit_rows(model, oracle_lib, solver):
     # robots away from their bounds: with the slow path they take the six-row solver (bit-identical with and without
     # the flag), with the ten-row solver their limit slots are empty (same result to round-off)
     st2 = random_states(256, seed=3).astype(np.float32)
-    h1, h0 = HostSim(model, cfg, 256), HostSim(model, _abi.default_sim_config(), 256)
+    h1, h0 = HostSim(model, cfg, 256), HostSim(model, cfg_free, 256)
     h1.set_state(st2)
     h0.set_state(st2)
     z = np.zeros((256, 7, 3), dtype=np.float32)

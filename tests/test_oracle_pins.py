@@ -294,30 +294,46 @@ def _zero_torque_action():
     return a
 
 
-def test_pitch_zero_after_one_step_and_fall_without_action(model, oracle_lib):
+def _fall_pitches(model, oracle_lib, joint_limits, quat=(1.0, 0.0, 0.0, 0.0)):
     cfg = _abi.default_sim_config()
+    cfg.joint_limits = joint_limits
     sim = oracle_lib.OracleSim(model, cfg, 1)
     init = np.zeros((1, _abi.INIT_DIM))
     init[0, 2] = 0.6
-    init[0, 3] = 1.0
+    init[0, 3:7] = quat
     sim.reset(init)
-    sim.step_servos(_zero_torque_action())
-    assert sim.spine_obs()[0, _abi.SP_PITCH] == pytest.approx(0.0, abs=1e-7)
-    for _ in range(100):
+    out = []
+    for _ in range(101):
         sim.step_servos(_zero_torque_action())
-    assert abs(sim.spine_obs()[0, _abi.SP_PITCH]) > 0.5  # the robot falls within 100 x 5 ms
+        out.append(sim.spine_obs()[0, _abi.SP_PITCH])
+    return np.array(out)
 
 
-def test_fall_from_yaw_rotated_start(model, oracle_lib):
-    cfg = _abi.default_sim_config()
-    sim = oracle_lib.OracleSim(model, cfg, 1)
-    init = np.zeros((1, _abi.INIT_DIM))
-    init[0, 2] = 0.6
-    init[0, 3:7] = [math.cos(math.pi / 4), 0.0, 0.0, math.sin(math.pi / 4)]  # yaw = pi/2
-    sim.reset(init)
-    for _ in range(100):
-        sim.step_servos(_zero_torque_action())
-    assert abs(sim.spine_obs()[0, _abi.SP_PITCH]) > 0.5
+@pytest.mark.parametrize("joint_limits", [0, 3])
+def test_pitch_zero_after_one_step_and_fall_without_action(model, oracle_lib, joint_limits):
+    """tests/envs/backends/test_pybullet_backend.py:31-42 of the reference: pitch ~ 0 after one step, |pitch| > 0.5
+    after 100 no-action steps. Without limit rows (round 1's physics) the legs fold through their stops and the sample
+    at step 100 is beyond the threshold; with Bullet's hip / knee limit rows (the default now) the robot passes 0.5 rad
+    at tick ~45, its hips reach their stops at tick ~50 and the torso swings back, so that the sample AT step 100
+    depends on the (stand-in, parity unpinned) inertias: +2 cm on the torso's centre of mass flips it (DESIGN.md
+    section 3). What is asserted with the rows on is that the robot does fall beyond the threshold within the
+    100 steps."""
+    pitch = _fall_pitches(model, oracle_lib, joint_limits)
+    assert pitch[0] == pytest.approx(0.0, abs=1e-7)
+    if joint_limits == 0:
+        assert abs(pitch[100]) > 0.5
+    else:
+        assert np.abs(pitch).max() > 0.5 and np.argmax(np.abs(pitch) > 0.5) < 60
+
+
+@pytest.mark.parametrize("joint_limits", [0, 3])
+def test_fall_from_yaw_rotated_start(model, oracle_lib, joint_limits):
+    """tests/envs/backends/test_pybullet_backend.py:44-57 (upkie issue 527): same from yaw = pi / 2."""
+    pitch = _fall_pitches(model, oracle_lib, joint_limits, (math.cos(math.pi / 4), 0.0, 0.0, math.sin(math.pi / 4)))
+    if joint_limits == 0:
+        assert abs(pitch[99]) > 0.5
+    else:
+        assert np.abs(pitch).max() > 0.5 and np.argmax(np.abs(pitch) > 0.5) < 60
 
 
 # ---- invariants of the restated dynamics (no reference value exists: parity unpinned) ---------------

@@ -15,7 +15,7 @@ from upkie_b200 import _abi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("solver", [1, 2, 3])
 def test_joint_limit_rows_on_device(model, oracle_lib, solver):
     """solver 1: scalar slow path for the robots with an active limit row; 2: packed ten-row solver for all."""
     import torch
@@ -26,7 +26,9 @@ def test_joint_limit_rows_on_device(model, oracle_lib, solver):
     cfg = _abi.default_sim_config()
     cfg.joint_limits = solver
     sim = UpkieSim(n, model=model, config=cfg)
-    plain = UpkieSim(n, model=model, config=_abi.default_sim_config())
+    cfg_plain = _abi.default_sim_config()
+    cfg_plain.joint_limits = 0
+    plain = UpkieSim(n, model=model, config=cfg_plain)
     osim = oracle_lib.OracleSim(model, cfg, n, threads=8)
     st = at_joint_bounds(model, n, seed=5)
     act = random_servo_actions(n, model, seed=12).astype(np.float32)

@@ -1,5 +1,5 @@
 # SPDX-License-Identifier: Apache-2.0
-"""Round-2 validation of the experimental NVSwitch-multicast rollout path (not run in round 1: no GPU budget left).
+"""Validation of the in-kernel rollout transports (NVSwitch multicast stores, peer stores) on 2..8 GPUs.
 
     torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 tools/multicast_check.py
 
@@ -28,7 +28,7 @@ def main():
     n, T = 4096, 8
     model = Model.standard_upkie()
     cfg = _abi.default_sim_config()
-    sims = [UpkieSim(n, model=model, config=cfg, device=local) for _ in range(2)]
+    sims = [UpkieSim(n, model=model, config=cfg, device=local) for _ in range(3)]
     for s in sims:
         s.set_autoreset(0, 0, rank * n)
         s.reset(seed=100 + rank, env_offset=rank * n)
@@ -36,11 +36,11 @@ def main():
     gen.manual_seed(5 + rank)
     tau = torch.tensor(model.tau_max, dtype=torch.float32, device=dev)
     local_buf = RolloutBuffer(T, n, 18, dev, compact=True)
-    peer = PeerRolloutBuffer(T, n, 18, dev, compact=True)
-    if not peer.multicast_supported:
+    peer = PeerRolloutBuffer(T, n, 18, dev, compact=True)   # multicast stores
+    peer2 = PeerRolloutBuffer(T, n, 18, dev, compact=True)  # peer stores
+    mc = peer.multicast_supported
+    if not mc:
         print(f"rank {rank}: symmetric memory reports no multicast support on this box", flush=True)
-        dist.destroy_process_group()
-        return
     for t in range(T):
         a = torch.zeros((n, 6, 6), device=dev)
         a[:, :, 0] = float("nan")
@@ -48,15 +48,24 @@ def main():
         a[:, :, 2] = (torch.rand((n, 6), device=dev, generator=gen) * 2 - 1) * tau
         o, _, te, _ = local_buf.slot(t)
         sims[0].step_servos_compact(a, obs=o, terminated=te)
-        sims[1].step_servos_multicast(a, *peer.multicast_slot(t))
-    peer.publish()
+        if mc:
+            sims[1].step_servos_multicast(a, *peer.multicast_slot(t))
+        sims[2].step_servos_peers(a, *peer2.peer_slots(t))
+    if mc:
+        peer.publish()
+    peer2.publish()
     torch.cuda.synchronize()
     expect = local_buf.gather_raw()  # [world, nbytes] through NCCL, for the comparison only
-    got = peer.gathered()
     nb = local_buf.nbytes
-    ok = all(torch.equal(got[r, :nb], expect[r, :nb]) for r in range(world))
-    print(f"rank {rank}: multicast rollout {'MATCHES' if ok else 'DIFFERS FROM'} the NCCL-gathered reference "
-          f"({world} ranks x {nb} bytes)", flush=True)
+    ok = True
+    for name, buf in (("multicast", peer if mc else None), ("peerstore", peer2)):
+        if buf is None:
+            continue
+        got = buf.gathered()
+        good = all(torch.equal(got[r, :nb], expect[r, :nb]) for r in range(world))
+        ok = ok and good
+        print(f"rank {rank}: {name} rollout {'MATCHES' if good else 'DIFFERS FROM'} the NCCL-gathered reference "
+              f"({world} ranks x {nb} bytes)", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

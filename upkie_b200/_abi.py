@@ -254,7 +254,7 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.min_base_height = 0.0
     c.pgs_tolerance = 1e-5
     c.warmstarting_factor = 0.0  # measured: no fewer sweeps (friction rows dominate); Bullet's value would be 0.85
-    c.joint_limits = 0  # limit rows are CPU-validated only so far; 1 = Bullet's behaviour
+    c.joint_limits = 3  # Bullet's hip / knee limit rows on (0 off, 1 scalar reference path [host build], 2 ten-row, 3 ten-row per warp on demand)
     c.joint_limit_erp = 0.2
     c.joint_limit_max_impulse = 100.0
     c.init_position[0], c.init_position[1], c.init_position[2] = 0.0, 0.0, 0.6

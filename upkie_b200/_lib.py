@@ -41,6 +41,7 @@ SYMBOLS = {
     "upkie_b200_step_gyropod": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_servos_compact": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_servos_multicast": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "upkie_b200_step_servos_peers": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     "upkie_b200_step_servos_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_gyropod_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_servos_host_compact": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -9,10 +9,10 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libupkie_b200.so")
 # compiled in parallel, then linked
 SOURCES = ["upkie_b200.cu", "step_device.cu", "step_host.cu", "step_multicast.cu", "step_device_limits.cu",
-           "step_host_limits.cu"]
+           "step_host_limits.cu", "step_multicast_limits.cu"]
 DEPS = SOURCES + [
     "sim_core.cuh", "sim_pair.cuh", "kernel_common.cuh", "step_kernel.cuh", "params.h", "mpc.cuh", "mpc_core.cuh",
-    "observers.cuh", "observers_core.cuh", "../../include/upkie_b200.h",
+    "observers.cuh", "observers_core.cuh", "controllers.cuh", "controllers_core.cuh", "../../include/upkie_b200.h",
 ]
 
 NVCC_FLAGS = [
@@ -23,6 +23,20 @@ NVCC_FLAGS = [
     "--use_fast_math",
     "-Xcompiler", "-fPIC",
 ]
+
+
+def source_hash() -> str:
+    """sha256 (first 16 hex digits) over the CUDA sources and compile flags of the library: the key that ties a
+    committed ncu sidecar (``profiles/ncu_sidecar.json``, written by ``tools/ncu_summary.py``) to the build that is
+    benchmarked. Stable across rebuilds and machines, unlike a hash of the binary."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in sorted(DEPS):
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode() + b"\0" + f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
 
 
 def is_stale() -> bool:

@@ -63,6 +63,15 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
   for (int k = 0; k < UPKIE_STATE_DIM; ++k) st[size_t(k) * n_pad + i] = r[k];
 }
 
+// TILE=2 (rollout rows leave the GPU from inside the step kernel): n = 0 -> `obs` / `terminated` are NVSwitch multicast
+// addresses (multimem.st, the switch replicates the store into every GPU's buffer); n > 0 -> plain stores into the n
+// peer buffers listed here (peer-mapped symmetric memory over NVLink; the list includes this rank's own buffer).
+struct PeerPtrs {
+  float* obs[UPKIE_MAX_PEERS];
+  uint8_t* term[UPKIE_MAX_PEERS];
+  int n;
+};
+
 // One launch of the env-step kernel over the envs [i0, i0 + cnt) of a handle.
 struct StepArgs {
   const SimParams* P;
@@ -86,6 +95,7 @@ struct StepArgs {
   const float* ext;     // external forces [21][n_pad] or null (noise != 0 when set)
   uint32_t ext_local;
   cudaStream_t stream;
+  PeerPtrs peers;       // TILE=2 only
 };
 
 cudaError_t launch_step_device(const StepArgs& a);  // step_device.cu
@@ -93,5 +103,6 @@ cudaError_t launch_step_host(const StepArgs& a);    // step_host.cu
 cudaError_t launch_step_multicast(const StepArgs& a);  // step_multicast.cu: TILE=2, UpkieServos, compact rows
 cudaError_t launch_step_device_limits(const StepArgs& a);  // step_device_limits.cu: NOISE=2 (joint-limit rows), TILE=0
 cudaError_t launch_step_host_limits(const StepArgs& a);    // step_host_limits.cu: NOISE=2, TILE=1
+cudaError_t launch_step_multicast_limits(const StepArgs& a);  // step_multicast_limits.cu: NOISE=2, TILE=2
 
 }  // namespace upkie_b200

@@ -44,7 +44,7 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->min_base_height = 0.0;
   c->pgs_tolerance = 1e-5;
   c->warmstarting_factor = 0.0;  // off by default (Bullet's m_warmstartingFactor is 0.85)
-  c->joint_limits = 0;  // limit rows off by default in round 1 (CPU-validated only)
+  c->joint_limits = 3;  // Bullet's hip / knee limit constraints ON (pybullet_backend.py:121 loadURDF): ten-row solver for warps with a robot on a bound
   c->reserved_joint_limits = 0;
   c->joint_limit_erp = 0.2;
   c->joint_limit_max_impulse = 100.0;
@@ -154,7 +154,7 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.pgs_iterations = c.pgs_iterations;
   P.pgs_rtol = float(c.pgs_tolerance);
   P.warm = float(c.warmstarting_factor);
-  P.joint_limits = c.joint_limits < 0 ? 0 : (c.joint_limits > 2 ? 2 : c.joint_limits);
+  P.joint_limits = c.joint_limits < 0 ? 0 : (c.joint_limits > 3 ? 3 : c.joint_limits);
   P.limit_erp = float(c.joint_limit_erp);
   P.limit_max_impulse = float(c.joint_limit_max_impulse);
   P.skip_action_clamps = c.skip_action_clamps;

@@ -1125,8 +1125,8 @@ UPKIE_HD uint32_t step_servo_action(const SimParams& P, RobotState& S, float a[U
                             aj[UPKIE_ACT_MAXIMUM_TORQUE]);
       S.torque[j] = tau[j];
     }
-    if (SCALAR_LEGS) physics_substep(P, S, tau, eps, mu, warp_any);
-    else substep(P, S, tau, eps, mu, warp_any);
+    if (SCALAR_LEGS) physics_substep(P, S, tau, eps, mu, warp_any);  // no joint-limit rows in the scalar-leg variant
+    else substep(P, S, tau, eps, mu, warp_any, NoSync(), nullptr, P.joint_limits);
   }
   observe_update(P, S);
   const float chk = S.quat[0] + S.quat[1] + S.quat[2] + S.quat[3] + S.pos[2] + S.linvel[0];
@@ -1214,10 +1214,10 @@ UPKIE_HD void reset_wrapper_state(RobotState& S) {
 // PyBulletBackend.reset (pybullet_backend.py:220-267) + UpkieGyropod.reset (upkie_gyropod.py:216-244)
 template <typename AnyFn>
 UPKIE_HD void reset_robot(const SimParams& P, RobotState& S, const float init[UPKIE_INIT_DIM], const float* eps, float mu,
-                          AnyFn warp_any) {
+                          AnyFn warp_any, int limits) {
   reset_pose(S, init);
   const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  substep(P, S, zero, eps, mu, warp_any);  // one stepSimulation (:228)
+  substep(P, S, zero, eps, mu, warp_any, NoSync(), nullptr, limits);  // one stepSimulation (:228)
   observe_update(P, S);
   reset_wrapper_state(S);
 }

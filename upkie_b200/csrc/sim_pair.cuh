@@ -885,12 +885,32 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   LimitRows lim;
   lim.n = 0;
   // limits: 0 no joint-limit rows, 1 scalar slow path for the robots that have one, 2 packed ten-row solver for all
+  // The scalar slow path exists in the HOST build only (the CPU test-suite's independent second implementation of the
+  // limit rows): on a B200 it measured 18x the plain kernel on the torque workload (profiles/r02_limits.md) and its
+  // dynamically indexed local arrays cost every NOISE=2 kernel a 2 KB stack frame. On the device 1 aliases to 3.
+#if defined(__CUDA_ARCH__)
+  const bool slow = false;
+  if (limits == 1) limits = 3;
+#else
   const bool slow = limits == 1 && active_joint_limits(P, S.q, lim) > 0;
+#endif
   const float lam_prev[2] = {S.lam_n[0], S.lam_n[1]};
   const bool actL = inL && !slow, actR = inR && !slow;
   phase_sync();  // 2
 
-  if (limits == 2) {
+  // limits == 3: the ten-row solver only for warps that hold a robot on a bound (warp-uniform choice), the six-row
+  // contact block otherwise: workloads that never reach a bound (position-controlled legs) keep the plain cost
+  bool ten_rows = limits == 2;
+  if (limits == 3) {
+    bool on_bound = false;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int j = a < 2 ? a : a + 1;
+      on_bound = on_bound || (S.q[j] - P.q_lower[j] <= 0.f) || (P.q_upper[j] - S.q[j] <= 0.f);
+    }
+    ten_rows = warp_any(on_bound);
+  }
+  if (ten_rows) {
     contact_solve_ten_rows(P, S, lc, IA0, nIA0, R, zb, inv_n, Pc, dist, inL, inR, mu, warp_any, phase_sync);
   } else if (!warp_any(actL || actR)) {
     S.lam_n[0] = 0.f;
@@ -1097,7 +1117,11 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
     }
     phase_sync();  // 6
   }
+#if !defined(__CUDA_ARCH__)
   if (slow) limit_contact_solve(P, S, lc, IA0, R, zb, inv_n, Pc, dist, inL, inR, mu, lim, lam_prev);
+#else
+  (void)lam_prev;
+#endif
 
   // -- position integration with the new velocities (as physics_substep)
 #pragma unroll

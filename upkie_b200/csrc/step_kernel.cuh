@@ -41,7 +41,7 @@ __device__ __forceinline__ void step_env(
     uint8_t* __restrict__ truncated, const float* __restrict__ eps_all, const float* __restrict__ mu_all,
     uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev, uint32_t* __restrict__ episode,
     uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset, const float* __restrict__ ext,
-    uint32_t ext_local, float4* tile4, bool full, bool compact) {
+    uint32_t ext_local, float4* tile4, bool full, bool compact, const PeerPtrs* peers = nullptr) {
   const bool live = tid < n;
   const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
   const int lane = threadIdx.x & 31;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void step_env(
 #endif
     if (sub < nsub) {
       servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
-                    (NOISE && ext) ? &xf : nullptr, NOISE == 2 ? (P.joint_limits == 2 ? 2 : 1) : 0);
+                    (NOISE && ext) ? &xf : nullptr, NOISE == 2 ? (P.joint_limits >= 1 ? P.joint_limits : 1) : 0);
     } else {
 #pragma unroll
       for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
@@ -152,7 +152,7 @@ __device__ __forceinline__ void step_env(
       if (live) episode[i] = ep;
       float init[UPKIE_INIT_DIM];
       sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
-      reset_robot(P, S, init, eps, mu, WarpAny());
+      reset_robot(P, S, init, eps, mu, WarpAny(), NOISE == 2 ? P.joint_limits : 0);
       if (MODE != MODE_SERVOS) gyropod_obs(P, S, o6);
     }
   }
@@ -184,8 +184,17 @@ __device__ __forceinline__ void step_env(
         for (int k = 0; k < 5; ++k) {
           const int idx = k * 32 + lane;
           if (idx < 32 * 18 / 4) {
-            if (TILE == 2) mc_store4(op + idx, tile4[idx]);
-            else op[idx] = tile4[idx];
+            if (TILE == 2) {
+              const float4 v = tile4[idx];
+              if (peers->n == 0) {
+                mc_store4(op + idx, v);
+              } else {
+                // `obs` is unused here: the row offset of this step's slot is already in every peer pointer
+                for (int p = 0; p < peers->n; ++p) reinterpret_cast<float4*>(peers->obs[p] + size_t(wb) * 18)[idx] = v;
+              }
+            } else {
+              op[idx] = tile4[idx];
+            }
           }
         }
       } else if (live) {
@@ -236,7 +245,11 @@ __device__ __forceinline__ void step_env(
     if (lane < 8) {
       const unsigned nib = (m >> (4 * lane)) & 0xFu;
       const uint32_t word = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-      mc_store_u32(reinterpret_cast<uint32_t*>(terminated + wb) + lane, word);
+      if (peers->n == 0) {
+        mc_store_u32(reinterpret_cast<uint32_t*>(terminated + wb) + lane, word);
+      } else {
+        for (int p = 0; p < peers->n; ++p) reinterpret_cast<uint32_t*>(peers->term[p] + wb)[lane] = word;
+      }
     }
   }
   if (!live) return;
@@ -276,7 +289,7 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
        uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
        const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
        uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset,
-       const float* __restrict__ ext, uint32_t ext_local, int coalesce) {
+       const float* __restrict__ ext, uint32_t ext_local, int coalesce, const __grid_constant__ PeerPtrs peers) {
   // this launch covers the envs [i0, n)
   if (!TILE) {
     step_env<MODE, AUTORESET, NOISE, 0>(P, i0 + blockIdx.x * blockDim.x + threadIdx.x, n, n_pad, state, action, obs,
@@ -313,7 +326,8 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
     __syncwarp();
     step_env<MODE, AUTORESET, NOISE, TILE>(P, i0 + t * blockDim.x + threadIdx.x, n, n_pad, state, action, obs, reward,
                                         terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick, seed,
-                                        env_offset, ext, ext_local, buf[it & 1], warp_full(t), (coalesce & 2) != 0);
+                                        env_offset, ext, ext_local, buf[it & 1], warp_full(t), (coalesce & 2) != 0,
+                                        TILE == 2 ? &peers : nullptr);
     __syncwarp();  // the tile is free again before the next prefetch lands in it
   }
 }
@@ -331,7 +345,7 @@ cudaError_t launch_step_mode(const StepArgs& a) {
 #define LAUNCH_N(AR, NZ)                                                                                         \
   k_step<MODE, AR, NZ, TILE><<<grid, a.block, smem, a.stream>>>(                                                 \
       *a.P, a.i0, a.i0 + a.cnt, a.n_pad, a.state, a.action, a.obs, a.reward, a.terminated, a.truncated, a.eps,   \
-      a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, a.ext, a.ext_local, coalesce)
+      a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, a.ext, a.ext_local, coalesce, a.peers)
 #if UPKIE_STEP_LIMITS_TU
 #define LAUNCH(AR) LAUNCH_N(AR, 2)
 #else

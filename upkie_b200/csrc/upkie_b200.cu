@@ -115,7 +115,7 @@ k_reset(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict
     episode[i] = ep;
     sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
   }
-  reset_robot(P, S, init, eps, mu, WarpAny());
+  reset_robot(P, S, init, eps, mu, WarpAny(), P.joint_limits);
   store_state(state, n_pad, i, S);
   err[i] = 0;
   done_prev[i] = 0;
@@ -209,8 +209,10 @@ int pick_block(const Handle* h, int cnt) {
 // shared-memory-tile instantiation (host buffers), see kernel_common.cuh.
 int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float* obs, float* reward, uint8_t* term,
                uint8_t* trunc, cudaStream_t s, bool tile = false, bool persistent = true, bool compact = false,
-               bool multicast = false) {
+               bool multicast = false, const PeerPtrs* peers = nullptr) {
   StepArgs a;
+  a.peers.n = 0;
+  if (peers) a.peers = *peers;
   a.P = &h->P;
   a.mode = mode;
   a.autoreset = h->autoreset;
@@ -576,6 +578,28 @@ int upkie_b200_step_servos_multicast(void* handle, const float* action, float* o
   CUDA_TRY(cudaSetDevice(h->device));
   return step_range(h, MODE_SERVOS, 0, h->n, action, obs_mc, nullptr, terminated_mc, nullptr, static_cast<cudaStream_t>(stream),
                     /*tile=*/true, /*persistent=*/false, /*compact=*/true, /*multicast=*/true);
+}
+
+int upkie_b200_step_servos_peers(void* handle, const float* action, float* const* obs_ptrs,
+                                 uint8_t* const* terminated_ptrs, int n_peers, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  if (!action || !obs_ptrs || !terminated_ptrs) return fail(UPKIE_B200_EINVAL, "step_servos_peers: null buffer");
+  if (n_peers < 1 || n_peers > UPKIE_MAX_PEERS) return fail(UPKIE_B200_EINVAL, "step_servos_peers: 1 <= n_peers <= UPKIE_MAX_PEERS");
+  if (h->n % 32 != 0) return fail(UPKIE_B200_EINVAL, "step_servos_peers: the number of envs must be a multiple of 32");
+  PeerPtrs pp;
+  pp.n = n_peers;
+  for (int p = 0; p < UPKIE_MAX_PEERS; ++p) {
+    pp.obs[p] = p < n_peers ? obs_ptrs[p] : nullptr;
+    pp.term[p] = p < n_peers ? terminated_ptrs[p] : nullptr;
+    if (p < n_peers && (!pp.obs[p] || !pp.term[p] || (reinterpret_cast<uintptr_t>(pp.obs[p]) & 15) != 0 ||
+                        (reinterpret_cast<uintptr_t>(pp.term[p]) & 3) != 0))
+      return fail(UPKIE_B200_EINVAL, "step_servos_peers: slot pointers must be non-null, obs 16-byte and terminated 4-byte aligned");
+  }
+  if ((reinterpret_cast<uintptr_t>(action) & 15) != 0) return fail(UPKIE_B200_EINVAL, "step_servos_peers: action rows must be 16-byte aligned");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return step_range(h, MODE_SERVOS, 0, h->n, action, pp.obs[0], nullptr, pp.term[0], nullptr, static_cast<cudaStream_t>(stream),
+                    /*tile=*/true, /*persistent=*/false, /*compact=*/true, /*multicast=*/true, &pp);
 }
 
 int upkie_b200_step_gyropod(void* handle, const float* action, int act_dim, float* obs, float* reward,

@@ -218,7 +218,7 @@ def make_config(
     max_yaw_velocity: float = 1.0,
     init_state: Optional[RobotState] = None,
     noise_seed: int = 0,
-    joint_limits: Union[bool, int] = False,
+    joint_limits: Union[bool, int] = True,
 ) -> _abi.UpkieSimConfig:
     """Split of the keyword arguments the reference's factories forward to the
     backend, the servo env and the wrappers (``upkie/envs/entry_points.py:41-61,99-109``)."""
@@ -238,9 +238,10 @@ def make_config(
             cfg.torque_control_noise[j] = float(getattr(props, "torque_control_noise", 0.0))
             cfg.torque_measurement_noise[j] = float(getattr(props, "torque_measurement_noise", 0.0))
     cfg.noise_seed = int(noise_seed) & 0xFFFFFFFFFFFFFFFF
-    # Bullet's joint-limit constraint rows on hips and knees (include/upkie_b200.h: joint_limits). Off by default
-    # until the "extras + limits" kernels have run on a GPU
-    cfg.joint_limits = int(joint_limits)  # True / 1: scalar slow path, 2: packed ten-row solver
+    # Bullet's joint-limit constraint rows on hips and knees (include/upkie_b200.h: joint_limits): on, as in the
+    # multibody PyBullet's importer builds (pybullet_backend.py:121). True -> 3 (the packed ten-row solver for the warps
+    # that hold a robot on a bound); 2 = ten-row solver for every warp; False / 0 = no limit rows (round-1 behaviour)
+    cfg.joint_limits = 3 if joint_limits is True else int(joint_limits)
     cfg.max_gain_scale = max_gain_scale
     cfg.fall_pitch = fall_pitch
     cfg.leg_gain_scale = leg_gain_scale
@@ -280,7 +281,7 @@ class B200VectorEnv(VectorEnv):
         leg_length: float = 0.58,
         max_ground_accel: float = 10.0,
         noise_seed: int = 0,
-        joint_limits: Union[bool, int] = False,
+        joint_limits: Union[bool, int] = True,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")

@@ -183,7 +183,7 @@ class PeerRolloutBuffer(RolloutBuffer):
         self._done = ev
         return ev
 
-    # ---- NVSwitch multicast (EXPERIMENTAL in round 1: not yet run on a multi-GPU box) -------------------------
+    # ---- in-kernel transports: NVSwitch multicast stores, or stores into every peer's buffer ------------------
     @property
     def multicast_supported(self) -> bool:
         return bool(getattr(self._hdl, "has_multicast_support", False)) and int(self._hdl.multicast_ptr) != 0
@@ -198,6 +198,17 @@ class PeerRolloutBuffer(RolloutBuffer):
         obs_off = k * self.n * self.obs_dim * 4
         term_off = self.T * self.n * self.obs_dim * 4 + k * self.n
         return base + obs_off, base + term_off
+
+    def peer_slots(self, t: int):
+        """``(obs_ptrs, terminated_ptrs)``: device addresses of this rank's slot at time step ``t`` in EVERY rank's
+        buffer (own buffer included), for ``UpkieSim.step_servos_peers`` (compact records only)."""
+        if not self.compact:
+            raise ValueError("peer slots carry compact records")
+        k = t % self.T
+        obs_off = k * self.n * self.obs_dim * 4
+        term_off = self.T * self.n * self.obs_dim * 4 + k * self.n
+        bases = [p_.data_ptr() for p_ in self._peers]
+        return [b + obs_off for b in bases], [b + term_off for b in bases]
 
     def publish(self) -> None:
         """After the last multicast step of a rollout: cross-rank barrier on the current stream; once it has

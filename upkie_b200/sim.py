@@ -178,11 +178,20 @@ class UpkieSim:
         return obs, terminated
 
     def step_servos_multicast(self, action: torch.Tensor, obs_mc_ptr: int, terminated_mc_ptr: int) -> None:
-        """EXPERIMENTAL (round 1: compiled, not yet run on a multi-GPU box). Compact rows and ``terminated`` go to
-        NVSwitch multicast addresses (``PeerRolloutBuffer.multicast_slot``): every GPU of the node receives them."""
+        """Compact rows and ``terminated`` go to NVSwitch multicast addresses (``PeerRolloutBuffer.multicast_slot``): every GPU of the node receives them."""
         self._check_tensor(action, (self.n, 6, 6), name="action")
         check(lib().upkie_b200_step_servos_multicast(
             self._h, _ptr(action), C.c_void_p(int(obs_mc_ptr)), C.c_void_p(int(terminated_mc_ptr)), self._stream()))
+
+    def step_servos_peers(self, action: torch.Tensor, obs_ptrs, terminated_ptrs) -> None:
+        """Compact rows and ``terminated`` stored by the step kernel into every buffer of ``obs_ptrs`` /
+        ``terminated_ptrs`` (device addresses of this step's slot in each peer's symmetric rollout buffer,
+        ``PeerRolloutBuffer.peer_slots``): the rollout gather over plain NVLink stores, no collective kernel."""
+        self._check_tensor(action, (self.n, 6, 6), name="action")
+        k = len(obs_ptrs)
+        oa = (C.c_void_p * k)(*[C.c_void_p(int(x)) for x in obs_ptrs])
+        ta = (C.c_void_p * k)(*[C.c_void_p(int(x)) for x in terminated_ptrs])
+        check(lib().upkie_b200_step_servos_peers(self._h, _ptr(action), oa, ta, k, self._stream()))
 
     def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
                      truncated=None):
