@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UPKIE_B200_ABI_VERSION 1
+#define UPKIE_B200_ABI_VERSION 2
 
 #define UPKIE_NJ 6 /* actuated joints */
 #define UPKIE_NB 7 /* moving bodies: base lump + 2 x (upper leg, lower leg, wheel) */
@@ -209,10 +209,12 @@ typedef struct UpkieSimConfig {
    * revolute joint that declares limits (hips and knees; the wheels are continuous). While a joint sits at or
    * beyond a bound, one unilateral row along that joint joins the contact rows in the PGS solve (solved before the
    * contact normals, in alternating order from sweep to sweep), with Baumgarte factor joint_limit_erp and the
-   * impulse capped at joint_limit_max_impulse. 0 = no limit rows (round-1 default: the rows exist in the oracle and
-   * in the kernels' arithmetic, CPU-validated against each other, but have not run on a GPU yet);
-   * 1 = rows on, robots with an active limit row solve their rows in a scalar slow path; 2 = rows on, every robot
-   * runs the packed ten-row solver (four limit slots + six contact rows). Same results to round-off. */
+   * impulse capped at joint_limit_max_impulse. 0 = no limit rows (round 1's physics); 2 = rows on, every robot runs
+   * the packed ten-row solver (four limit slots + six contact rows); 3 (default) = rows on, the ten-row solver for
+   * the warps that hold a robot on a bound and the six-row contact solver for the others; 1 = the scalar reference
+   * implementation of the rows, which exists in the HOST build of the kernel arithmetic only (tests): on the device
+   * it is an alias of 3 (measured 18x slower than the plain kernel on a B200).
+   * Same results to round-off in all three. */
   int32_t joint_limits;
   int32_t reserved_joint_limits; /* keeps the doubles below 8-byte aligned without implicit padding */
   double joint_limit_erp;         /* btContactSolverInfo::m_erp = 0.2 */
@@ -224,6 +226,13 @@ typedef struct UpkieSimConfig {
   double rand_roll, rand_pitch, rand_x, rand_z;
   double rand_omega_x, rand_omega_y;
   double rand_linear_velocity[3];
+  /* nominal joint configuration and base velocities of the initial state (RobotState.joint_configuration,
+   * angular_velocity_base_in_base, linear_velocity_base_to_world_in_world; upkie/utils/robot_state.py:175-196):
+   * sample_state keeps the joint configuration and ADDS the random velocity parts to the nominal ones, and so does the
+   * on-device sampler of the fused auto-reset */
+  double init_joint_configuration[6];
+  double init_angular_velocity[3];
+  double init_linear_velocity[3];
 } UpkieSimConfig;
 
 /* MPCBalancer parameters (upkie/controllers/mpc_balancer.py:168-181) */

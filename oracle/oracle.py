@@ -351,8 +351,10 @@ def sample_init_state(config, np_random):
     out = np.zeros(_abi.INIT_DIM)
     out[_abi.INIT_POS:_abi.INIT_POS + 3] = np.array(list(c.init_position)) + pos
     out[_abi.INIT_QUAT:_abi.INIT_QUAT + 4] = q
-    out[_abi.INIT_LINVEL:_abi.INIT_LINVEL + 3] = v
-    out[_abi.INIT_ANGVEL:_abi.INIT_ANGVEL + 3] = om
+    # nominal + random part; the joint configuration is kept, joint velocities are not set by the reset
+    out[_abi.INIT_LINVEL:_abi.INIT_LINVEL + 3] = np.array(list(c.init_linear_velocity)) + v
+    out[_abi.INIT_ANGVEL:_abi.INIT_ANGVEL + 3] = np.array(list(c.init_angular_velocity)) + om
+    out[_abi.INIT_Q:_abi.INIT_Q + 6] = np.array(list(c.init_joint_configuration))
     return out
 
 

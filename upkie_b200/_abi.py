@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 NJ = 6
 NB = 7
@@ -124,6 +124,9 @@ class UpkieSimConfig(C.Structure):
         ("rand_omega_x", C.c_double),
         ("rand_omega_y", C.c_double),
         ("rand_linear_velocity", C.c_double * 3),
+        ("init_joint_configuration", C.c_double * 6),
+        ("init_angular_velocity", C.c_double * 3),
+        ("init_linear_velocity", C.c_double * 3),
     ]
 
 
@@ -263,6 +266,10 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.rand_omega_x = c.rand_omega_y = 0.0
     for k in range(3):
         c.rand_linear_velocity[k] = 0.0
+        c.init_angular_velocity[k] = 0.0
+        c.init_linear_velocity[k] = 0.0
+    for j in range(NJ):
+        c.init_joint_configuration[j] = 0.0
     return c
 
 

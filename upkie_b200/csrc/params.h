@@ -53,6 +53,8 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->rand_roll = c->rand_pitch = c->rand_x = c->rand_z = 0.0;
   c->rand_omega_x = c->rand_omega_y = 0.0;
   for (int k = 0; k < 3; ++k) c->rand_linear_velocity[k] = 0.0;
+  for (int j = 0; j < UPKIE_NJ; ++j) c->init_joint_configuration[j] = 0.0;
+  for (int k = 0; k < 3; ++k) c->init_angular_velocity[k] = c->init_linear_velocity[k] = 0.0;
 }
 
 inline void default_mpc_config(UpkieMpcConfig* c) {
@@ -187,6 +189,11 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.rand_omega_x = float(c.rand_omega_x);
   P.rand_omega_y = float(c.rand_omega_y);
   for (int k = 0; k < 3; ++k) P.rand_linvel[k] = float(c.rand_linear_velocity[k]);
+  for (int j = 0; j < 6; ++j) P.init_q[j] = float(c.init_joint_configuration[j]);
+  for (int k = 0; k < 3; ++k) {
+    P.init_angvel[k] = float(c.init_angular_velocity[k]);
+    P.init_linvel[k] = float(c.init_linear_velocity[k]);
+  }
   return 0;
 }
 

@@ -95,6 +95,8 @@ struct SimParams {
   // struct so that the constant-bank offsets of everything above stay where the GPU-validated kernels read them.
   int joint_limits;        // 0 off, 1 scalar slow path, 2 packed ten-row solver (sim_pair.cuh)
   float limit_erp, limit_max_impulse;
+  // nominal joint configuration / base velocities of the initial state (RobotState.sample_state keeps / adds them)
+  float init_q[6], init_angvel[3], init_linvel[3];
 };
 
 // per-robot state in registers
@@ -1329,13 +1331,14 @@ UPKIE_HD void sample_init_state(const SimParams& P, uint64_t seed, uint64_t env_
   init[UPKIE_INIT_POS + 2] = P.init_pos[2] + pz;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    init[UPKIE_INIT_LINVEL + i] = v[i];
-    init[UPKIE_INIT_ANGVEL + i] = om[i];
+    // nominal + random part (robot_state.py:113-135 sample_angular_velocity / sample_linear_velocity)
+    init[UPKIE_INIT_LINVEL + i] = P.init_linvel[i] + v[i];
+    init[UPKIE_INIT_ANGVEL + i] = P.init_angvel[i] + om[i];
   }
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    init[UPKIE_INIT_Q + j] = 0.f;
-    init[UPKIE_INIT_QD + j] = 0.f;
+    init[UPKIE_INIT_Q + j] = P.init_q[j];  // joint configuration is not randomised (robot_state.py:183)
+    init[UPKIE_INIT_QD + j] = 0.f;         // resetJointState zeroes the rates (pybullet_backend.py:262-267)
   }
 }
 

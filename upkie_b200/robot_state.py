@@ -234,3 +234,8 @@ class RobotState:
         config.rand_roll, config.rand_pitch = float(r.roll), float(r.pitch)
         config.rand_x, config.rand_z = float(r.x), float(r.z)
         config.rand_omega_x, config.rand_omega_y = float(r.omega_x), float(r.omega_y)
+        for j in range(6):
+            config.init_joint_configuration[j] = float(self.joint_configuration[j])
+        for k in range(3):
+            config.init_angular_velocity[k] = float(self.angular_velocity_base_in_base[k])
+            config.init_linear_velocity[k] = float(self.linear_velocity_base_to_world_in_world[k])
