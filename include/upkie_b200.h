@@ -298,6 +298,11 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config,
 void upkie_b200_destroy(void* handle);
 int upkie_b200_num_envs(void* handle);
 
+/* Replace the simulation configuration of a live handle (same model): the initial-state bounds and nominal values
+ * the on-device reset sampler draws from (UpkieEnv.update_init_rand, upkie/envs/upkie_env.py:244-251), noise levels,
+ * gains... Takes effect for launches enqueued after the call; the robot state is untouched. */
+int upkie_b200_set_config(void* handle, const UpkieSimConfig* config);
+
 /* Vector-env auto-reset, fused into the step kernels (the reference has no
  * auto-reset: "you are responsible for calling reset()", upkie_env.py:200-201;
  * Gymnasium vector envs do). mode 0 = disabled (reference behaviour, default),

@@ -61,6 +61,36 @@ def test_reset_matches_oracle(model, oracle_lib, torch):
     assert torch.equal(after[1::2], before[1::2])
 
 
+def test_device_reset_starts_from_the_nominal_state(model, torch):
+    """Auto-reset episodes (on-device sampler) start from the same state as ``reset()`` episodes: with the random
+    bounds at zero, a reset sampled on the device equals a reset from the RobotState row, crouched joints and nominal
+    base velocities included (round-1 advisor finding); ``update_init_rand`` reaches the device sampler."""
+    from upkie_b200.envs import B200VectorEnv
+    from upkie_b200.robot_state import RobotState, RobotStateRandomization
+
+    crouch = np.array([0.4, -0.8, 0.0, -0.4, 0.8, 0.0])
+    nominal = RobotState(joint_configuration=crouch, position_base_in_world=np.array([0.0, 0.0, 0.55]),
+                         angular_velocity_base_in_base=np.array([0.0, 0.2, 0.0]),
+                         linear_velocity_base_to_world_in_world=np.array([0.3, 0.0, 0.0]),
+                         randomization=RobotStateRandomization())
+    n = 256
+    env = B200VectorEnv(n, "servos", model=model, init_state=nominal, autoreset_mode="next_step")
+    env.sim.reset(seed=5)  # sampled on the device
+    dev_state = env.sim.get_state().cpu().numpy()
+    row = torch.from_numpy(np.tile(nominal.to_row().astype(np.float32), (n, 1))).cuda()
+    env.sim.reset(init_state=row)
+    assert np.array_equal(env.sim.get_state().cpu().numpy(), dev_state)
+    assert np.abs(dev_state[:, 13:19] - crouch).max() < 5e-3  # one substep away from the nominal configuration
+    # a fused auto-reset (next step after `terminated`) lands there too
+    env.update_init_rand(pitch=0.25)
+    env.sim.reset(seed=6)
+    st = env.sim.get_state().cpu().numpy()
+    pitch = 2 * np.arctan2(st[:, 5], st[:, 3])
+    assert 0.05 < np.abs(pitch).max() <= 0.27 and pitch.std() > 0.08  # the new bound reached the device sampler
+    assert np.abs(st[:, 13:19] - crouch).max() < 5e-3
+    env.close()
+
+
 def test_gyropod_and_pendulum_match_oracle(model, oracle_lib, torch):
     n = 1024
     cfg = _abi.default_sim_config()
@@ -385,6 +415,39 @@ def test_base_velocity_env(model, torch):
     assert np.abs(sp[:, _abi.SP_PITCH]).max() < 0.3
     obs, _ = env.reset(seed=3)
     assert not obs.any() and (env.mpc_balancer.commanded_velocity == 0).all().item()
+    env.close()
+
+
+def test_base_velocity_env_replays_the_reference_run(model, torch):
+    """tests/golden/base_velocity_run.json - 300 ticks of the reference's own UpkieBaseVelocity env (MPCBalancer in
+    front of the gyropod wrappers) on the oracle - replayed through B200VectorEnv on the GPU: same initial state and
+    actions; the observation [x, y, yaw], the MPC's commanded ground velocity (which closes the loop through the
+    simulated pitch / odometry) and `terminated` are compared tick by tick."""
+    import json
+    import os
+
+    from upkie_b200.envs import B200VectorEnv
+
+    run = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "base_velocity_run.json")))
+    n = 32  # identical copies: the batch must stay identical too
+    env = B200VectorEnv(n, "base_velocity", model=model)
+    row = torch.tensor(run["init_row"], dtype=torch.float32, device="cuda").reshape(1, -1).repeat(n, 1).contiguous()
+    env.sim.reset(init_state=row)
+    env.mpc_balancer.reset()
+    env._xy.zero_()
+    env._spine = env.sim.spine_obs()
+    worst_obs, worst_v = 0.0, 0.0
+    for t, (a, o, term, v) in enumerate(zip(run["actions"], run["obs"], run["terminated"], run["commanded_velocity"])):
+        act = torch.tensor([a], dtype=torch.float32, device="cuda").repeat(n, 1).contiguous()
+        obs, rew, te, tr, info = env.step(act)
+        ob = obs.cpu().numpy()
+        vc = env.mpc_balancer.commanded_velocity.cpu().numpy()
+        assert np.array_equal(ob, np.tile(ob[:1], (n, 1))) and np.array_equal(vc, np.tile(vc[:1], n))
+        worst_obs = max(worst_obs, float(np.abs(ob[0] - np.asarray(o)).max()))
+        worst_v = max(worst_v, abs(float(vc[0]) - v))
+        assert bool(te[0].item()) == term and float(rew[0].item()) == 0.0
+    assert worst_obs < 5e-5, worst_obs  # dead reckoning of the commanded velocity along the post-step yaw
+    assert worst_v < 2e-2, worst_v      # fp32 closed loop over 1.5 s against the fp64 run of the reference's classes
     env.close()
 
 

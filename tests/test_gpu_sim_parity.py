@@ -11,9 +11,31 @@ pytestmark = pytest.mark.gpu
 # Velocities carry the touchdown sensitivity of the Bullet-style contact row
 # (d v / d penetration = 1/h = 1000 1/s, times 1/r = 20 on wheel rates), so the
 # worst-case velocity tolerance is looser than the position tolerance.
+# Round 2: the worst-case caps are tied to what the fp64 -> fp32 change alone costs, measured on the same inputs with
+# the oracle instantiated in fp32 (textbook link-frame ABA): on these 2 048 states the fp32 oracle's worst joint-rate
+# error is 1.1e-3 rad/s (base twist 3.6e-5), the kernels' arithmetic compiled for the host 2.2e-3 (7.3e-5). Round 1
+# allowed 0.4 rad/s here. The measured values are appended to gpurun_out/parity_report.json when that directory exists.
 TOL_POS = 2e-5
 TOL_VEL_STEADY = 5e-4
-TOL_VEL_WORST = 2e-2
+TOL_VEL_WORST = 1e-3        # base twist, worst env
+TOL_JOINT_RATE_WORST = 2e-2  # joint rates, worst env (touchdown sensitivity x 1/r on wheel rates)
+
+
+def _report(name, **values):
+    import json
+    import os
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(root):
+        return
+    path = os.path.join(root, "parity_report.json")
+    try:
+        data = json.load(open(path)) if os.path.exists(path) else {}
+    except Exception:
+        data = {}
+    data[name] = {k: float(v) for k, v in values.items()}
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1)
 
 
 def _mk(n, model, cfg=None):
@@ -48,7 +70,18 @@ def test_one_tick_servos_matches_oracle(model, oracle_lib):
     assert dpos < TOL_POS and dq < 2e-4, (dpos, dq)
     assert np.median(dvel.max(axis=1)) < TOL_VEL_STEADY
     assert np.median(dqd.max(axis=1)) < TOL_VEL_STEADY
-    assert dvel.max() < TOL_VEL_WORST and dqd.max() < 20 * TOL_VEL_WORST, (dvel.max(), dqd.max())
+    # the same tick on the oracle in fp32: what single precision alone costs on these inputs
+    o32 = oracle_lib.OracleSim(model, cfg, n, use_float=True, threads=8)
+    o32.set_state(st32.astype(np.float64))
+    o32.step_servos(act32.astype(np.float64))
+    s32 = o32.get_state()
+    dvel32, dqd32 = np.abs(s32[:, 7:13] - os_[:, 7:13]).max(), np.abs(s32[:, 19:25] - os_[:, 19:25]).max()
+    _report("one_tick_servos_2048", base_twist_worst=dvel.max(), joint_rate_worst=dqd.max(),
+            joint_rate_p99=np.percentile(dqd.max(axis=1), 99), joint_rate_median=np.median(dqd.max(axis=1)),
+            fp32_oracle_base_twist_worst=dvel32, fp32_oracle_joint_rate_worst=dqd32, position_worst=dpos, joint_angle_worst=dq)
+    assert dvel.max() < TOL_VEL_WORST and dqd.max() < TOL_JOINT_RATE_WORST, (dvel.max(), dqd.max())
+    assert dqd.max() < max(10.0 * dqd32, 5e-3), (dqd.max(), dqd32)  # within an order of magnitude of fp32 itself
+    assert np.percentile(dqd.max(axis=1), 99) < 1e-3
     # observations: positions/velocities/torques as the state, constants exact
     g = gobs.cpu().numpy().astype(np.float64)
     assert np.array_equal(g[:, :, 3], np.full((n, 6), 42.0))

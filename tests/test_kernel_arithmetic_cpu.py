@@ -548,6 +548,37 @@ def test_device_sampler_statistics_and_determinism(model):
     assert np.allclose(np.linalg.norm(a[:, 3:7], axis=1), 1.0, atol=1e-6)
 
 
+def test_device_sampler_draws_around_the_nominal_state(model):
+    """Round-1 advisor finding: the on-device sampler of the fused auto-reset ignored the nominal joint configuration
+    and base velocities of the initial state. RobotState.sample_state keeps ``joint_configuration`` and ADDS the
+    random velocity parts to the nominal ones (upkie/utils/robot_state.py:175-196); so must auto-reset episodes."""
+    from upkie_b200.robot_state import RobotState, RobotStateRandomization
+
+    crouch = np.array([0.4, -0.8, 0.0, -0.4, 0.8, 0.0])
+    nominal = RobotState(
+        joint_configuration=crouch, position_base_in_world=np.array([0.1, 0.0, 0.5]),
+        angular_velocity_base_in_base=np.array([0.0, 0.3, 0.1]),
+        linear_velocity_base_to_world_in_world=np.array([0.5, 0.0, -0.2]),
+        randomization=RobotStateRandomization(pitch=0.2, omega_y=0.4, linear_velocity=np.array([0.3, 0.0, 0.0])),
+    )
+    cfg = _abi.default_sim_config()
+    nominal.apply_to_config(cfg)
+    n = 2048
+    a = HostSim(model, cfg, n).sample_init(seed=11, env_offset=0, episode=3)
+    assert np.allclose(a[:, _abi.INIT_Q:_abi.INIT_Q + 6], crouch.astype(np.float32))
+    assert (a[:, _abi.INIT_QD:_abi.INIT_QD + 6] == 0).all()
+    om, v = a[:, _abi.INIT_ANGVEL:_abi.INIT_ANGVEL + 3], a[:, _abi.INIT_LINVEL:_abi.INIT_LINVEL + 3]
+    assert np.allclose(om[:, 0], 0.0) and np.allclose(om[:, 2], 0.1) and np.abs(om[:, 1] - 0.3).max() <= 0.4 + 1e-6
+    assert om[:, 1].std() > 0.15 and abs(om[:, 1].mean() - 0.3) < 0.03
+    assert np.abs(v[:, 0] - 0.5).max() <= 0.3 + 1e-6 and np.allclose(v[:, 2], -0.2) and v[:, 0].std() > 0.1
+    assert np.allclose(a[:, 0], 0.1) and np.allclose(a[:, 2], 0.5)
+    # the same bounds through the reference-order host sampler: same ranges, same nominal values
+    rows = np.stack([nominal.sample_state(np.random.default_rng(s)).to_row() for s in range(256)])
+    assert np.allclose(rows[:, _abi.INIT_Q:_abi.INIT_Q + 6], crouch)
+    assert abs(rows[:, _abi.INIT_ANGVEL + 1].mean() - 0.3) < 0.08 and np.allclose(rows[:, _abi.INIT_ANGVEL + 2], 0.1)
+    assert abs(rows[:, _abi.INIT_LINVEL].mean() - 0.5) < 0.06
+
+
 # ---- MPC ------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("horizon", [16, 50])

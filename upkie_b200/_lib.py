@@ -35,6 +35,7 @@ SYMBOLS = {
     "upkie_b200_destroy": (None, [_vp]),
     "upkie_b200_num_envs": (C.c_int, [_vp]),
     "upkie_b200_set_autoreset": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64]),
+    "upkie_b200_set_config": (C.c_int, [_vp, C.POINTER(_abi.UpkieSimConfig)]),
     "upkie_b200_set_randomization": (C.c_int, [_vp, _vp, _vp, _vp]),
     "upkie_b200_reset": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp]),
     "upkie_b200_step_servos": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -50,6 +50,7 @@ struct Handle {
   uint32_t magic;
   int n, n_pad, device;
   SimParams P;
+  UpkieModel model;            // kept for upkie_b200_set_config
   float* state = nullptr;      // [STATE_DIM][n_pad]
   float* eps = nullptr;        // [n][6] or null
   float* mu = nullptr;         // [n] or null
@@ -422,6 +423,7 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
   int rc = make_sim_params(*model, *config, h->P, err);
   if (rc) { delete h; return fail(rc, err); }
   h->magic = kMagic;
+  h->model = *model;
   h->n = n_envs;
   h->n_pad = (n_envs + 31) / 32 * 32;
   h->device = device;
@@ -501,6 +503,19 @@ void upkie_b200_destroy(void* handle) {
 int upkie_b200_num_envs(void* handle) {
   Handle* h = as_handle(handle);
   return h ? h->n : fail(UPKIE_B200_EINVAL, "invalid handle");
+}
+
+int upkie_b200_set_config(void* handle, const UpkieSimConfig* config) {
+  Handle* h = as_handle(handle);
+  if (!h || !config) return fail(UPKIE_B200_EINVAL, "set_config: invalid argument");
+  SimParams P;
+  std::memset(&P, 0, sizeof(P));
+  std::string err;
+  int rc = make_sim_params(h->model, *config, P, err);
+  if (rc) return fail(rc, err);
+  // kernels read the parameter block by value at launch: steps already enqueued keep the old one
+  h->P = P;
+  return UPKIE_B200_OK;
 }
 
 int upkie_b200_set_autoreset(void* handle, int mode, uint64_t seed, uint64_t env_offset) {

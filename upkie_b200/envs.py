@@ -358,6 +358,9 @@ class B200VectorEnv(VectorEnv):
     def update_init_rand(self, **kwargs) -> None:
         """``UpkieEnv.update_init_rand`` (``upkie_env.py:244-251``)."""
         self.init_state.randomization.update(**kwargs)
+        # the fused auto-reset samples on the device: carry the new bounds there too
+        self.init_state.apply_to_config(self.config)
+        self.sim.set_config(self.config)
 
     def close(self, **kwargs) -> None:
         self.sim.close()

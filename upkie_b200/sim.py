@@ -93,6 +93,12 @@ class UpkieSim:
         check(lib().upkie_b200_set_autoreset(self._h, int(mode), int(seed), int(env_offset)))
         self._autoreset = (int(mode), int(seed), int(env_offset))
 
+    def set_config(self, config: _abi.UpkieSimConfig) -> None:
+        """Replace the configuration of the live handle (``upkie_b200_set_config``): initial-state bounds of the
+        on-device reset sampler, noise levels, gains. Steps enqueued afterwards use it."""
+        check(lib().upkie_b200_set_config(self._h, C.byref(config)))
+        self.config = config
+
     def set_randomization(self, friction: Optional[torch.Tensor] = None, inertia_eps: Optional[torch.Tensor] = None):
         """Per-env floor friction [N] and ``randomize_inertias`` epsilons [N, 6]
         (``pybullet_backend.py:571-601``)."""
