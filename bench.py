@@ -22,6 +22,12 @@ Workloads (BASELINE.json configs):
 import argparse
 import json
 import os
+
+# One OpenMP / BLAS thread, as torchrun sets for every rank of a multi-GPU run: the stepping thread of the host path
+# is latency-critical (copy, launch, synchronise per step) and idle-spinning OpenMP workers on its cores cost the
+# single-GPU run up to half of its end-to-end rate in round 1 (per-GPU e2e at N = 1 was half of N >= 2 on the same
+# node). Must happen before numpy / torch are imported. The CPU baseline uses its own std::thread pool.
+os.environ.setdefault("OMP_NUM_THREADS", "1")
 import subprocess
 import sys
 import threading
@@ -544,7 +550,7 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     if servos:
         cfg = servos_config()
         env = B200VectorEnv(n, "servos", config=cfg, device=dev.index, autoreset_mode="next_step",
-                            env_offset=rank * n, model=model)
+                            env_offset=rank * n, model=model, copy=False)
         mu = torch.empty(n, device=dev).uniform_(0.5, 1.2, generator=gen)
         eps = torch.empty((n, 6), device=dev).uniform_(-0.2, 0.2, generator=gen)
         env.sim.set_randomization(friction=mu, inertia_eps=eps)
@@ -569,7 +575,7 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     else:
         init = RobotState(randomization=RobotStateRandomization(pitch=0.1))
         env = B200VectorEnv(n, "pendulum", device=dev.index, autoreset_mode="next_step", env_offset=rank * n,
-                            model=model, init_state=init)
+                            model=model, init_state=init, copy=False)
         acts = [((torch.rand((n, 1), device=dev, generator=gen) * 2 - 1) * 3.0).contiguous()
                 for _ in range(N_ACTION_BUFFERS)]
         step = env.sim.step_pendulum
@@ -616,18 +622,68 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     works = [None, None]
     # stalls of the simulation stream waiting for the gather of the buffer it is about to overwrite
     stall_events = []
+    counters = {"gathers": 0}
+
+    def wait_for(cur, record):
+        """The gather that last read buffer `cur` must be done before its slots are overwritten."""
+        if works[cur] is None:
+            return
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        if gather_mode in ("multicast", "peerstore"):
+            pass  # stream order: publish() already ran on this stream
+        elif gather_mode == "peer":
+            rollouts[cur].wait()
+        else:
+            works[cur].wait()
+        ev1.record()
+        if record:
+            stall_events.append((ev0, ev1))
+        works[cur] = None
+
+    def do_step(k, timed):
+        """Step k (counted from the first warm-up step): the kernel writes its records straight into the rollout
+        slot of this step; every T_roll steps the rollout is handed to the transport."""
+        cur = (k // T_roll) % 2
+        if k % T_roll == 0:
+            wait_for(cur, timed)
+        a = acts[k % N_ACTION_BUFFERS]
+        if gather_mode == "multicast":
+            # the kernel's rows go to the NVSwitch multicast address of this rank's slot and land in every GPU's
+            # buffer; a barrier per rollout replaces the gather
+            env.sim.step_servos_multicast(a, *rollouts[cur].multicast_slot(k))
+        elif gather_mode == "peerstore":
+            # no multicast object: the kernel stores each row into every peer's buffer over NVLink itself
+            env.sim.step_servos_peers(a, *rollouts[cur].peer_slots(k))
+        else:
+            so, sr, ste, stru = rollouts[cur].slot(k)
+            step(a, obs=so, reward=sr, terminated=ste, truncated=stru)
+        if world > 1 and (k + 1) % T_roll == 0:
+            # one gather of the [T, n, record] buffer per rollout, asynchronous
+            if timed:
+                counters["gathers"] += 1
+            if gather_mode in ("multicast", "peerstore"):
+                rollouts[cur].publish()
+                works[cur] = True
+            elif gather_mode == "peer":
+                works[cur] = rollouts[cur].push()
+            else:
+                _, works[cur] = rollouts[cur].gather_raw(async_op=True)
 
     clk = ClockSampler(dev.index)
     clk.__enter__()
-    for k in range(W):
-        step(acts[k % N_ACTION_BUFFERS])
+    # Warm-up THROUGH THE TIMED CODE PATH (same kernel instantiation, same transport, at least one rollout hand-over):
+    # the first multicast store / barrier kernel / NCCL collective of a process costs ~1.5 ms once (lazy module load,
+    # channel set-up), which the driver's 20-step timed region must not carry. W is rounded up to whole rollouts.
+    Wa = ((W + T_roll - 1) // T_roll) * T_roll if world > 1 else W
+    for k in range(Wa):
+        do_step(k, False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches0 = env.sim.launches
     events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     end = torch.cuda.Event(enable_timing=True)
-    gathers = 0
     # ncu --profile-from-start off: "1" brackets the timed device loop, "e2e" the host-buffer loop
     profiling = os.environ.get("UPKIE_BENCH_CUDA_PROFILER", "") not in ("", "e2e")
     profiling_e2e = os.environ.get("UPKIE_BENCH_CUDA_PROFILER", "") == "e2e"
@@ -638,54 +694,10 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         clk.mark_begin()
         events[0].record()
         for k in range(K):
-            # the kernel writes observation / reward / masks straight into the rollout slot of this step
-            cur = (k // T_roll) % 2
-            if k % T_roll == 0 and works[cur] is not None:
-                # the gather that last read this buffer must be done before it is overwritten
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-                if gather_mode in ("multicast", "peerstore"):
-                    pass  # stream order: publish() already ran on this stream
-                elif gather_mode == "peer":
-                    rollouts[cur].wait()
-                else:
-                    works[cur].wait()
-                ev1.record()
-                stall_events.append((ev0, ev1))
-                works[cur] = None
-            if gather_mode == "multicast":
-                # the kernel's rows go to the NVSwitch multicast address of this rank's slot and land in every GPU's
-                # buffer; a barrier per rollout replaces the gather
-                env.sim.step_servos_multicast(acts[k % N_ACTION_BUFFERS], *rollouts[cur].multicast_slot(k))
-            elif gather_mode == "peerstore":
-                # no multicast object: the kernel stores each row into every peer's buffer over NVLink itself
-                env.sim.step_servos_peers(acts[k % N_ACTION_BUFFERS], *rollouts[cur].peer_slots(k))
-            else:
-                so, sr, ste, stru = rollouts[cur].slot(k)
-                step(acts[k % N_ACTION_BUFFERS], obs=so, reward=sr, terminated=ste, truncated=stru)
+            do_step(Wa + k, True)
             events[k + 1].record()
-            if world > 1 and (k + 1) % T_roll == 0:
-                # one gather of the [T, n, record] buffer per rollout, asynchronous
-                gathers += 1
-                if gather_mode in ("multicast", "peerstore"):
-                    rollouts[cur].publish()
-                    works[cur] = True
-                elif gather_mode == "peer":
-                    works[cur] = rollouts[cur].push()
-                else:
-                    _, works[cur] = rollouts[cur].gather_raw(async_op=True)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for i_, w_ in enumerate(works):
-            if w_ is not None:
-                if gather_mode in ("multicast", "peerstore"):
-                    pass
-                elif gather_mode == "peer":
-                    rollouts[i_].wait()
-                else:
-                    w_.wait()
-        ev1.record()
-        stall_events.append((ev0, ev1))
+        for i_ in range(2):
+            wait_for(i_, True)
         end.record()  # after the last step AND every gather issued inside the timed region
         clk.sample_now()  # the GPU is still working through the queue: one reading inside the timed region for sure
         torch.cuda.synchronize()
@@ -694,6 +706,7 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
             torch.cuda.profiler.stop()
         if world > 1:
             dist.barrier()
+    gathers = counters["gathers"]
     clk.__exit__()
     total_ms = events[0].elapsed_time(end)
     per_step = np.array([events[k].elapsed_time(events[k + 1]) for k in range(K)])
@@ -741,7 +754,8 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         "warmup": 12,
         "median_ms_per_step": 1e3 * float(te[1].item()),
         "value_from_median_step": n * world / float(te[1].item()),
-        "api": "B200VectorEnv.step(numpy action) -> numpy obs/reward/terminated/truncated",
+        "api": "B200VectorEnv(copy=False).step(numpy action) -> numpy obs/reward/terminated/truncated (views of the "
+               "handle's pinned result buffers, valid until the next step; the default copy=True adds a host memcpy)",
     }
     transport = {
         "none": "",
@@ -779,6 +793,7 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
             "bytes_per_rank_and_gather": int(rollouts[0].nbytes),
             # time the simulation stream spent waiting for a gather before re-using its buffer, inside the timed region
             "sim_stream_stall_ms_total": gather_stall_ms,
+            "warmup_steps_run": Wa,  # --warmup rounded up to whole rollouts, through the same transport
             "note": gather_note,
         }
     return n * K, t_ms * K, kernel_ms, e2e, launches, clk.summary(), config, n

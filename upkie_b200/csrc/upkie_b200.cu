@@ -313,6 +313,12 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
   uint8_t* dst_term = pin_out ? term : h->h_term;
   uint8_t* dst_trunc = trunc ? (pin_out ? trunc : h->h_trunc) : nullptr;
 
+  // Order the private (non-blocking) streams after whatever the caller enqueued on the default stream - reset(),
+  // set_state(), set_counters() through PyTorch's default current stream: without this a step_*_host() right after
+  // an asynchronous reset raced with it (round-1 advisor finding). Callers on other streams synchronise themselves.
+  CUDA_TRY(cudaEventRecord(h->host_events[63], cudaStreamLegacy));
+  for (int k = 0; k < kHostStreams; ++k) CUDA_TRY(cudaStreamWaitEvent(h->host_streams[k], h->host_events[63], 0));
+
   int pipeline = h->zero_copy;
   if (pipeline == 2 && mode != MODE_SERVOS) pipeline = 1;  // tiny rows: nothing to stream
   // chunk boundaries (multiples of 256 envs). Default: host_chunks equal chunks; UPKIE_B200_HOST_SPLIT gives the
@@ -322,7 +328,7 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
   start[0] = 0;
   if (h->host_split_n > 0 && h->n >= 4 * 8192) {
     double acc = 0.0;
-    for (int c = 0; c < h->host_split_n && chunks < 64; ++c) {
+    for (int c = 0; c < h->host_split_n && chunks < 62; ++c) {
       acc += h->host_split[c];
       int end = c + 1 == h->host_split_n ? h->n : int(acc * h->n + 0.5);
       end = (end + 255) / 256 * 256;
@@ -334,7 +340,7 @@ int step_host(Handle* h, int mode, const float* action, float* obs, float* rewar
     const int want = h->n >= 4 * 8192 ? h->host_chunks : (h->n >= 2 * 8192 ? 2 : 1);
     int per = (h->n + want - 1) / want;
     per = (per + 255) / 256 * 256;
-    for (int i0 = 0; i0 < h->n && chunks < 64; i0 += per) start[++chunks] = (i0 + per < h->n) ? i0 + per : h->n;
+    for (int i0 = 0; i0 < h->n && chunks < 63; i0 += per) start[++chunks] = (i0 + per < h->n) ? i0 + per : h->n;
   }
   auto chunk_count = [&](int c) { return start[c + 1] - start[c]; };
 
@@ -457,7 +463,7 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
   }
   if (const char* b = std::getenv("UPKIE_B200_HOST_CHUNKS")) {  // developer knob
     const int v = std::atoi(b);
-    if (v >= 1 && v <= 64) h->host_chunks = v;
+    if (v >= 1 && v <= 62) h->host_chunks = v;
   }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);

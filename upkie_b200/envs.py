@@ -163,10 +163,16 @@ class SpineObservations:
     def __init__(self, sim: UpkieSim):
         self._sim = sim
         self._array = None
+        self._stamp = sim.launches  # step kernels launched so far: identifies the tick this object belongs to
 
     @property
     def array(self) -> np.ndarray:
         if self._array is None:
+            if self._sim.launches != self._stamp:
+                # the simulator has moved on: fetching now would silently return a LATER tick's observation
+                raise UpkieRuntimeError(
+                    "info['spine_observation'] is fetched lazily and the simulator has been stepped since this step: "
+                    "read it (e.g. `.array`) before calling step() again")
             self._array = self._sim.spine_obs().cpu().numpy()
         return self._array
 
@@ -282,12 +288,18 @@ class B200VectorEnv(VectorEnv):
         max_ground_accel: float = 10.0,
         noise_seed: int = 0,
         joint_limits: Union[bool, int] = True,
+        copy: bool = True,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")
         if autoreset_mode not in _AUTORESET:
             raise UpkieException(f"autoreset_mode must be one of {tuple(_AUTORESET)}")
         self.env_type = env_type
+        # host path: ``step()`` results live in the handle's pinned output buffers, which the next ``step()``
+        # overwrites. copy=True (default, as gymnasium.vector.SyncVectorEnv(copy=True)) hands out copies, so that
+        # ``buf.append(obs)`` or ``prev_obs`` comparisons do not alias; copy=False returns views of the pinned buffers
+        # (zero-copy fast path, valid until the next step; what bench.py's e2e figure uses and says so)
+        self.copy = bool(copy)
         self.num_envs = int(num_envs)
         self.model = model if model is not None else default_model()
         self.init_state = init_state if init_state is not None else RobotState(
@@ -397,17 +409,21 @@ class B200VectorEnv(VectorEnv):
         rows, mask = self.model.external_force_rows(external_forces, self.num_envs)
         self.sim.set_external_forces(torch.from_numpy(rows).to(self.sim.device), mask)
 
-    def _servo_obs_dict(self, obs18: np.ndarray) -> dict:
+    def _servo_obs_dict(self, obs18: np.ndarray, cache: bool = True) -> dict:
         """Batched observation dictionary over the persistent pinned ``[N, 6, 3]`` buffer the kernel writes
         (position, velocity, torque): built once, updated in place by every step. Temperature and voltage
         are the simulator's constants (``pybullet_backend.py:471-472``) and never cross PCIe."""
-        cache = getattr(self, "_obs18_cache", None)
-        if cache is None or cache[0] is not obs18:
+        cached = getattr(self, "_obs18_cache", None) if cache else None
+        if cached is None or cached[0] is not obs18:
             n = self.num_envs
-            temperature = np.full((n, 1), 42.0, dtype=np.float32)
-            voltage = np.full((n, 1), 18.0, dtype=np.float32)
-            temperature.flags.writeable = False
-            voltage.flags.writeable = False
+            const = getattr(self, "_obs_constants", None)
+            if const is None:
+                temperature = np.full((n, 1), 42.0, dtype=np.float32)
+                voltage = np.full((n, 1), 18.0, dtype=np.float32)
+                temperature.flags.writeable = False
+                voltage.flags.writeable = False
+                const = self._obs_constants = (temperature, voltage)
+            temperature, voltage = const
             d = {
                 name: {
                     "position": obs18[:, j, 0:1],
@@ -418,9 +434,10 @@ class B200VectorEnv(VectorEnv):
                 }
                 for j, name in enumerate(_abi.JOINT_NAMES)
             }
-            cache = (obs18, d)
-            self._obs18_cache = cache
-        return cache[1]
+            cached = (obs18, d)
+            if cache:
+                self._obs18_cache = cached
+        return cached[1]
 
     def reset(self, *, seed: Optional[Union[int, list]] = None, options: Optional[dict] = None):
         """Reset all envs (or ``options["reset_mask"]``) and return the initial
@@ -482,13 +499,19 @@ class B200VectorEnv(VectorEnv):
             obs18, term = self.sim.step_servos_host_compact(a)
             hb = self.sim._host_buffers()
             info = {"spine_observation": SpineObservations(self.sim)}
+            if self.copy:
+                obs18 = obs18.copy()
+                return (self._servo_obs_dict(obs18, cache=False), hb["rew"].copy(), term.view(np.bool_).copy(),
+                        hb["trunc"].view(np.bool_).copy(), info)
             return self._servo_obs_dict(obs18), hb["rew"], term.view(np.bool_), hb["trunc"].view(np.bool_), info
         else:
             d = 2 if self.env_type == "gyropod" else 1
             a = np.ascontiguousarray(np.asarray(action, dtype=np.float32).reshape(n, d))
             obs, rew, term, trunc = self.sim.step_gyropod_host(a)
         info = {"spine_observation": SpineObservations(self.sim)}
-        # views of the handle's pinned output buffers: valid until the next step() (copy to keep them)
+        if self.copy:
+            return obs.copy(), rew.copy(), term.view(np.bool_).copy(), trunc.view(np.bool_).copy(), info
+        # views of the handle's pinned output buffers: valid until the next step()
         return self._format_obs(obs), rew, term.view(np.bool_), trunc.view(np.bool_), info
 
     def step_tensors(self, action: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, dict]:
