@@ -67,9 +67,20 @@ def test_backend_adapter_follows_the_backend_contract(model):
     obs = backend.step({})  # legal: no torques (test_pybullet_backend.py:28-31)
     assert isinstance(obs, dict)
     assert obs["base_orientation"]["pitch"] == pytest.approx(0.0, abs=1e-5)  # :31-38
+    worst = 0.0
     for _ in range(100):
         obs = backend.step({})
-    assert abs(obs["base_orientation"]["pitch"]) > 0.5  # :40-47
+        worst = max(worst, abs(obs["base_orientation"]["pitch"]))
+    # :40-47 samples |pitch| > 0.5 AT step 100. With Bullet's joint-limit rows on (the default) the robot passes 0.5 rad
+    # at tick ~45, its hips hit their stops and the torso swings back; where it is at step 100 depends on the stand-in
+    # inertias (tests/test_oracle_pins.py::test_pitch_zero_after_one_step_and_fall_without_action). Asserted: it falls.
+    assert worst > 0.5
+    free = B200Backend(dt=0.005, model=model, joint_limits=False)
+    free.reset(init)
+    for _ in range(101):
+        obs_free = free.step({})
+    assert abs(obs_free["base_orientation"]["pitch"]) > 0.5  # round 1's physics (no limit rows): the sample at step 100
+    free.close()
     # commanded joints follow the moteus law; uncommanded joints keep their last reported torque
     backend.reset(init)
     servo_action = {"position": 0.2, "velocity": 0.1, "kp_scale": 1.0, "kd_scale": 1.0, "maximum_torque": 10.0}

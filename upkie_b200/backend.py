@@ -51,8 +51,10 @@ class B200Backend(_Base):
         torque_control_kd: float = 1.0,
         torque_control_kp: float = 20.0,
         device: int = 0,
+        joint_limits: bool = True,
     ) -> None:
-        # same keyword arguments as PyBulletBackend.__init__ (pybullet_backend.py:55-66); gui is ignored
+        # same keyword arguments as PyBulletBackend.__init__ (pybullet_backend.py:55-66); gui is ignored.
+        # joint_limits (extension): Bullet's hip / knee limit constraints, on as in the multibody loadURDF builds
         self.__dt = dt
         self.__model = model if model is not None else default_model()
         self.torque_control_kd = torque_control_kd
@@ -60,7 +62,7 @@ class B200Backend(_Base):
         self.inertia_variation = inertia_variation
         cfg = make_config(
             frequency=1.0 / dt, nb_substeps=nb_substeps, torque_control_kp=torque_control_kp,
-            torque_control_kd=torque_control_kd, joint_properties=joint_properties,
+            torque_control_kd=torque_control_kd, joint_properties=joint_properties, joint_limits=joint_limits,
         )
         cfg.skip_action_clamps = 1  # the env on top (UpkieServos.get_spine_action) clamps, as in the reference
         self._sim = UpkieSim(1, model=self.__model, config=cfg, device=device)

@@ -659,14 +659,36 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
       Vw[5] = fma2(lc.ox[k], w, Vw[5]);
     }
   }
-  // Delassus matrix over the five direction pairs (normal, t1, t2, hip, knee)
-  float W[10][10];
+  // Delassus matrix over the five direction pairs (normal, t1, t2, hip, knee). The up-pass of a joint impulse has a
+  // closed form (it enters at its own level with nothing below it): with nUd_k = -U_k / D_k,
+  //   hip  impulse g: u = (g, 0, 0),        -ptop = g nUd_0
+  //   knee impulse g: u = (g sigma, g, 0),  -ptop = g (nUd_1 + sigma nUd_0),  sigma = S_0 . nUd_1
+  // (indices hip, knee, wheel), which replaces two generic up-passes (262 instructions in the round-2 profile).
+  // Stored as paired columns: Wc[k][p] = (W[row(p, L)][k], W[row(p, R)][k]) - the layout the sweep's residual update
+  // wants - so that the row scaling below is 50 packed multiplies in place (round 2; was a scalar 10 x 10 matrix plus
+  // a second, scaled copy).
+  f2 Wc[10][5];
   {
     f2 uu_[5][3], pt_[5][6];
+    {
+      f2 nUd1[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        pt_[3][i] = mul2(lc.U[0][i], lc.ninvD[0]);  // nUd_0
+        nUd1[i] = mul2(lc.U[1][i], lc.ninvD[1]);
+      }
+      const f2 sigma = sdot2(P.sgn2[0], lc.ox[0], lc.noz[0], nUd1);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        pt_[4][i] = mul2(dirK, fma2(sigma, pt_[3][i], nUd1[i]));
+        pt_[3][i] = mul2(dirH, pt_[3][i]);
+      }
+      uu_[3][0] = dirH; uu_[3][1] = bc2(0.f); uu_[3][2] = bc2(0.f);
+      uu_[4][0] = mul2(dirK, sigma); uu_[4][1] = dirK; uu_[4][2] = bc2(0.f);
+    }
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
-      if (d < 3) legs_impulse_up_general(P, lc, J[d], bc2(0.f), bc2(0.f), uu_[d], pt_[d]);
-      else legs_impulse_up_general(P, lc, nullptr, d == 3 ? dirH : bc2(0.f), d == 4 ? dirK : bc2(0.f), uu_[d], pt_[d]);
+      if (d < 3) legs_impulse_up(P, lc, J[d], uu_[d], pt_[d]);
       f2 da0[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) da0[i] = pt_[d][i];
@@ -674,27 +696,28 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
 #pragma unroll
       for (int e = 0; e <= d; ++e) {
         f2 wo = bc2(0.f), wc = bc2(0.f);
+        // sum_k u_k(e) u_k(d) / D_k over the levels where both are non-zero: hip rows only at level 0, knee rows at 0, 1
+        const int kmax = (d == 3 || e == 3) ? 1 : ((d == 4 || e == 4) ? 2 : 3);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wo = fma2(mul2(uu_[e][k], lc.invD[k]), uu_[d][k], wo);
+        for (int k = 0; k < 3; ++k)
+          if (k < kmax) wo = fma2(mul2(uu_[e][k], lc.invD[k]), uu_[d][k], wo);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           wo = fma2(pt_[e][i], da0[i], wo);
           wc = fma2(swp2(pt_[e][i]), da0[i], wc);
         }
-        W[row10_of(e, 0)][row10_of(d, 0)] = wo.x;
-        W[row10_of(e, 1)][row10_of(d, 1)] = wo.y;
-        W[row10_of(e, 1)][row10_of(d, 0)] = wc.x;
-        W[row10_of(e, 0)][row10_of(d, 1)] = wc.y;
+        // wo = (W[eL][dL], W[eR][dR]), wc = (W[eR][dL], W[eL][dR]); W is symmetric
+        Wc[row10_of(d, 0)][e] = mk2(wo.x, wc.x);
+        Wc[row10_of(d, 1)][e] = mk2(wc.y, wo.y);
         if (e != d) {
-          W[row10_of(d, 0)][row10_of(e, 0)] = wo.x;
-          W[row10_of(d, 1)][row10_of(e, 1)] = wo.y;
-          W[row10_of(d, 0)][row10_of(e, 1)] = wc.x;
-          W[row10_of(d, 1)][row10_of(e, 0)] = wc.y;
+          Wc[row10_of(e, 0)][d] = mk2(wo.x, wc.y);
+          Wc[row10_of(e, 1)][d] = mk2(wc.x, wo.y);
         }
       }
       if (d < 3) phase_sync();  // 3, 4, 5
     }
   }
+  auto Wdiag = [&](int k) { return lane_of_row10(k) == 0 ? Wc[k][pair_of_row10(k)].x : Wc[k][pair_of_row10(k)].y; };
   float rhs[10], jdi[10], lam[10];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -708,13 +731,13 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
       lam[k] = d == 0 ? ((side == 0 ? actL : actR) ? P.warm * S.lam_n[side] : 0.f) : 0.f;
       if (d == 0) {
         const float pen = side == 0 ? dist.x : dist.y;
-        jdi[k] = 1.f / (W[k][k] + P.cfm);
+        jdi[k] = 1.f / (Wdiag(k) + P.cfm);
         float pos_err = 0.f, vel_err = -r;
         if (pen > 0.f) vel_err -= pen * P.inv_h;
         else pos_err = -pen * P.erp * P.inv_h;
         rhs[k] = (pos_err + vel_err) * jdi[k];
       } else {
-        jdi[k] = W[k][k] > 0.f ? 1.f / W[k][k] : 0.f;
+        jdi[k] = Wdiag(k) > 0.f ? 1.f / Wdiag(k) : 0.f;
         rhs[k] = -r * jdi[k];
       }
     }
@@ -725,20 +748,25 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
     const float dir = a == 0 ? dirH.x : a == 1 ? dirK.x : a == 2 ? dirH.y : dirK.y;
     const float pen = a == 0 ? penH.x : a == 1 ? penK.x : a == 2 ? penH.y : penK.y;
     lam[a] = 0.f;
-    jdi[a] = W[a][a] > 1.1920929e-7f ? 1.f / W[a][a] : 0.f;
+    jdi[a] = Wdiag(a) > 1.1920929e-7f ? 1.f / Wdiag(a) : 0.f;
     rhs[a] = (-pen * P.limit_erp * P.inv_h - dir * S.qd[j]) * jdi[a];
   }
   const float cfmrow = P.cfm;
   const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
-  f2 Gc[10][5];
+  // scaled columns in place: G[m][k] = -jdi[m] W[m][k] (+ 1 - cfm jdi on the diagonal of the normal rows)
+  f2 (&Gc)[10][5] = Wc;
+  {
+    f2 njdi2[5];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    float g[10];
+    for (int p = 0; p < 5; ++p) njdi2[p] = mk2(-jdi[row10_of(p, 0)], -jdi[row10_of(p, 1)]);
 #pragma unroll
-    for (int m = 0; m < 10; ++m)
-      g[m] = -jdi[m] * W[m][k] + (m == k ? 1.f - ((k == 4 || k == 5) ? cfmrow * jdi[k] : 0.f) : 0.f);
+    for (int k = 0; k < 10; ++k) {
 #pragma unroll
-    for (int p = 0; p < 5; ++p) Gc[k][p] = mk2(g[row10_of(p, 0)], g[row10_of(p, 1)]);
+      for (int p = 0; p < 5; ++p) Gc[k][p] = mul2(Gc[k][p], njdi2[p]);
+      const float dg = 1.f - ((k == 4 || k == 5) ? cfmrow * jdi[k] : 0.f);
+      if (lane_of_row10(k) == 0) Gc[k][pair_of_row10(k)].x += dg;
+      else Gc[k][pair_of_row10(k)].y += dg;
+    }
   }
   if (!actL) {
     rhs[4] = 0.f;
@@ -788,7 +816,12 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
     sweep(false, false);  // even iteration: the non-contact rows are walked backwards
     if (it + 1 >= P.pgs_iterations) break;
     const bool changed = sweep(true, true);
+#ifdef UPKIE_PGS_STATS
+    if (!changed) { upkie_pgs_stats(100 + it + 2); break; }
+    if (it + 2 >= P.pgs_iterations) upkie_pgs_stats(100 + it + 3);
+#else
     if (!warp_any(changed)) break;
+#endif
   }
   S.lam_n[0] = lam[4];
   S.lam_n[1] = lam[5];

@@ -16,6 +16,9 @@
 #ifndef UPKIE_STEP_LIMITS_TU
 #define UPKIE_STEP_LIMITS_TU 0
 #endif
+#ifndef UPKIE_ACTION_IN_TILE
+#define UPKIE_ACTION_IN_TILE 0  // build-time experiment (tools/variants.py)
+#endif
 
 namespace upkie_b200 {
 namespace {
@@ -112,9 +115,29 @@ __device__ __forceinline__ void step_env(
     if (MODE != MODE_SERVOS) e |= gyropod_action(P, S, a0, a1, a);
     e |= clamp_servo_action(P, a);
   }
+#if UPKIE_ACTION_IN_TILE
+  // TILE kernels: the clamped action row goes back to the warp's staging tile and is re-read at the top of every
+  // substep (9 conflict-free LDS.128), instead of living in 36 registers / local-memory slots across the substep body
+  const bool a_in_tile = TILE && full && MODE == MODE_SERVOS;
+  if (a_in_tile) {
+#pragma unroll
+    for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k)
+      tile4[lane * (UPKIE_ACT_DIM / 4) + k] = make_float4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
+    __syncwarp();
+  }
+#endif
   for (int sub = 0; sub < P.nb_substeps; ++sub) {
 #if UPKIE_PHASE_SYNC_LEVEL >= 1
     __syncthreads();  // once per substep: all threads are converged here
+#endif
+#if UPKIE_ACTION_IN_TILE
+    if (a_in_tile) {
+#pragma unroll
+      for (int k = 0; k < UPKIE_ACT_DIM / 4; ++k) {
+        const float4 v = tile4[lane * (UPKIE_ACT_DIM / 4) + k];
+        a[4 * k + 0] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+      }
+    }
 #endif
     if (sub < nsub) {
       servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
