@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UPKIE_B200_ABI_VERSION 2
+#define UPKIE_B200_ABI_VERSION 3
 
 #define UPKIE_NJ 6 /* actuated joints */
 #define UPKIE_NB 7 /* moving bodies: base lump + 2 x (upper leg, lower leg, wheel) */
@@ -233,7 +233,28 @@ typedef struct UpkieSimConfig {
   double init_joint_configuration[6];
   double init_angular_velocity[3];
   double init_linear_velocity[3];
+  /* 0 (default): the timing of PyBulletBackend - an env step is nb_substeps physics steps and the observation is
+   * taken from the state after the last of them. 1: the timing of the C++ Bullet spine in simulate() mode
+   * (spines/bullet_spine.cpp --nb-substeps, upkie/cpp/spine/Spine.cpp:116-140,185-265 and
+   * upkie/cpp/interfaces/BulletInterface.cpp:228-352), UpkieServos steps only: every spine cycle reads the joint
+   * sensors and the IMU, computes the torques from THOSE readings (tau_max = min(maximum_torque, URDF effort)) and
+   * steps Bullet once at 1 / spine_frequency = dt / nb_substeps; the observation an env step returns is the one the
+   * spine assembled in its FIRST cycle of that step, i.e. with S physics steps done before it: joint sensors (and the
+   * torque commanded with them) of the state after S - 2 steps, IMU of the state after S - 1 steps, IMU acceleration
+   * differentiated over one cycle; a reset runs three cycles with the servos stopped (Bullet velocity motors holding
+   * 0 rad/s with 100 N m, restated as locked joints) and returns the observation of the third; the base angular
+   * velocity of the initial state is rotated to the world frame (BulletInterface.cpp:146-152); servo temperature
+   * reads 20.0 (BulletInterface.cpp:70). Needs joint_limits != 0 (the "extras + limits" kernels carry it). */
+  int32_t spine_mode;
+  int32_t reserved_spine_mode;
 } UpkieSimConfig;
+
+/* Spine-mode lag record of one env (upkie_b200_get_lag / set_lag, [N][UPKIE_LAG_DIM] floats): the two latest
+ * servo replies and the latest IMU reading of the spine's actuation interface. */
+#define UPKIE_LAG_REPLY1 0   /* [6][3] position, velocity, torque read / commanded in the latest cycle */
+#define UPKIE_LAG_REPLY2 18  /* the cycle before: what the next observation reports */
+#define UPKIE_LAG_IMU 36     /* orientation_imu_in_ars wxyz (4), angular velocity (3), linear acceleration (3), raw (3) */
+#define UPKIE_LAG_DIM 49
 
 /* MPCBalancer parameters (upkie/controllers/mpc_balancer.py:168-181) */
 typedef struct UpkieMpcConfig {

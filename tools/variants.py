@@ -18,10 +18,9 @@ CSRC = os.path.join(ROOT, "upkie_b200", "csrc")
 OBJ = os.path.join(ROOT, "upkie_b200", "build")
 OUT = os.path.join(ROOT, "variants")
 VARIANTS = {
-    "base": [],
-    "nosync": ["-DUPKIE_PHASE_SYNC_LEVEL=0"],
-    "atile": ["-DUPKIE_ACTION_IN_TILE=1"],
-    "nosync_atile": ["-DUPKIE_PHASE_SYNC_LEVEL=0", "-DUPKIE_ACTION_IN_TILE=1"],
+    "new_paired": [],
+    "new_scalarW": ["-DUPKIE_TENROW_PAIRED_COLS=0"],
+    "v1": ["-DUPKIE_TENROW_V1=1"],
 }
 UNIT = "step_host_limits"
 KERNEL = "k_stepILi0ELi1ELi2ELi1E"

@@ -12,7 +12,8 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+LAG_REPLY1, LAG_REPLY2, LAG_IMU, LAG_DIM = 0, 18, 36, 49  # spine-mode lag record (include/upkie_b200.h)
 
 NJ = 6
 NB = 7
@@ -127,6 +128,8 @@ class UpkieSimConfig(C.Structure):
         ("init_joint_configuration", C.c_double * 6),
         ("init_angular_velocity", C.c_double * 3),
         ("init_linear_velocity", C.c_double * 3),
+        ("spine_mode", C.c_int32),
+        ("reserved_spine_mode", C.c_int32),
     ]
 
 
@@ -270,6 +273,8 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
         c.init_linear_velocity[k] = 0.0
     for j in range(NJ):
         c.init_joint_configuration[j] = 0.0
+    c.spine_mode = 0  # 1: timing of the C++ Bullet spine in simulate() mode (include/upkie_b200.h)
+    c.reserved_spine_mode = 0
     return c
 
 

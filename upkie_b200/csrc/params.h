@@ -55,6 +55,8 @@ inline void default_sim_config(UpkieSimConfig* c) {
   for (int k = 0; k < 3; ++k) c->rand_linear_velocity[k] = 0.0;
   for (int j = 0; j < UPKIE_NJ; ++j) c->init_joint_configuration[j] = 0.0;
   for (int k = 0; k < 3; ++k) c->init_angular_velocity[k] = c->init_linear_velocity[k] = 0.0;
+  c->spine_mode = 0;
+  c->reserved_spine_mode = 0;
 }
 
 inline void default_mpc_config(UpkieMpcConfig* c) {
