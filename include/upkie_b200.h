@@ -254,7 +254,12 @@ typedef struct UpkieSimConfig {
 #define UPKIE_LAG_REPLY1 0   /* [6][3] position, velocity, torque read / commanded in the latest cycle */
 #define UPKIE_LAG_REPLY2 18  /* the cycle before: what the next observation reports */
 #define UPKIE_LAG_IMU 36     /* orientation_imu_in_ars wxyz (4), angular velocity (3), linear acceleration (3), raw (3) */
-#define UPKIE_LAG_DIM 49
+/* the observation the spine assembled last (what the env step / reset returned and get_spine_observation reports) */
+#define UPKIE_LAG_OBS_REPLY 49   /* [6][3] */
+#define UPKIE_LAG_OBS_IMU 67     /* [13] */
+#define UPKIE_LAG_OBS_BASE 80    /* "sim" ground truth at that instant: base quaternion wxyz, linear, angular velocity (world) */
+#define UPKIE_LAG_OBS_CONTACT 90
+#define UPKIE_LAG_DIM 91
 
 /* MPCBalancer parameters (upkie/controllers/mpc_balancer.py:168-181) */
 typedef struct UpkieMpcConfig {
@@ -419,6 +424,9 @@ int upkie_b200_spine_obs(void* handle, float* out, void* stream);
 int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream);
 
 int upkie_b200_get_state(void* handle, float* state /* [N][UPKIE_STATE_DIM] */, void* stream);
+/* spine mode: the lag records [N][UPKIE_LAG_DIM] (device buffers), for checkpoints and parity tests */
+int upkie_b200_get_lag(void* handle, float* lag_rows, void* stream);
+int upkie_b200_set_lag(void* handle, const float* lag_rows, void* stream);
 int upkie_b200_set_state(void* handle, const float* state, void* stream);
 int upkie_b200_error_flags(void* handle, uint32_t* flags /* [N] */, void* stream);
 

@@ -118,6 +118,8 @@ def lib():
         L.oracle_spine_obs.argtypes = [C.c_void_p, _dp]
         L.oracle_get_state.argtypes = [C.c_void_p, _dp]
         L.oracle_set_state.argtypes = [C.c_void_p, _dp]
+        L.oracle_get_lag.argtypes = [C.c_void_p, _dp]
+        L.oracle_set_lag.argtypes = [C.c_void_p, _dp]
         L.oracle_error_flags.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
         L.oracle_substep.argtypes = [C.c_void_p, _dp, C.c_double]
         L.oracle_observe.argtypes = [C.c_void_p]
@@ -243,6 +245,17 @@ class OracleSim:
         out = np.empty((self.n, _abi.STATE_DIM))
         lib().oracle_get_state(self._h, _d(out))
         return out
+
+    def get_lag(self):
+        """Spine mode: lag records ``[n, LAG_DIM]`` (the first 49 entries: replies of the last two cycles, last IMU
+        reading; the oracle keeps the assembled observation in its spine row, so the rest reads 0)."""
+        out = np.zeros((self.n, _abi.LAG_DIM))
+        lib().oracle_get_lag(self._h, _d(out))
+        return out
+
+    def set_lag(self, lag):
+        a = np.ascontiguousarray(lag, dtype=np.float64).reshape(self.n, _abi.LAG_DIM)
+        lib().oracle_set_lag(self._h, _d(a))
 
     def set_state(self, state):
         s = _f64(state, (self.n, _abi.STATE_DIM))

@@ -195,6 +195,39 @@ void hostsim_step_servos_noise(void* hv, int n, float* state, const float* actio
   }
 }
 
+// spine mode (config.spine_mode): reset = three stopped cycles, step = observation of the first cycle + nb_substeps cycles;
+// state[n][STATE_DIM] and lag[n][LAG_DIM] in / out, spine[n][SPINE_DIM] = the assembled observation row
+void hostsim_reset_spine(void* hv, int n, float* state, float* lag, const float* init, float* spine) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    SpineLag L;
+    reset_robot_spine(h->P, S, L, init + size_t(i) * UPKIE_INIT_DIM, nullptr, h->P.friction, any_fn, h->P.joint_limits);
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+    lag_to_row(L, lag + size_t(i) * UPKIE_LAG_DIM);
+    spine_observation_from_lag(h->P, L, spine + size_t(i) * UPKIE_SPINE_DIM);
+  }
+}
+void hostsim_step_servos_spine(void* hv, int n, float* state, float* lag, const float* action, float* spine) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    SpineLag L;
+    lag_from_row(lag + size_t(i) * UPKIE_LAG_DIM, L);
+    float a[UPKIE_ACT_DIM];
+    std::memcpy(a, action + size_t(i) * UPKIE_ACT_DIM, sizeof(a));
+    clamp_servo_action(h->P, a);
+    spine_assemble_observation(S, L);
+    for (int sub = 0; sub < h->P.nb_substeps; ++sub)
+      spine_cycle(h->P, S, L, a, false, nullptr, h->P.friction, any_fn, NoSync(), h->P.joint_limits);
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+    lag_to_row(L, lag + size_t(i) * UPKIE_LAG_DIM);
+    spine_observation_from_lag(h->P, L, spine + size_t(i) * UPKIE_SPINE_DIM);
+  }
+}
+
 void hostsim_philox(uint64_t clo, uint64_t chi, uint64_t key, uint32_t* out) {
   Philox4 r = philox4x32_10(clo, chi, key);
   for (int i = 0; i < 4; ++i) out[i] = r.v[i];

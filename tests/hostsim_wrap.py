@@ -52,6 +52,8 @@ def lib():
         L.hostsim_wheel_balancer_step.argtypes = [C.POINTER(_abi.UpkieWheelBalancerConfig), C.c_int, fp, fp, fp, fp]
         L.hostsim_gaussian8.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, fp]
         L.hostsim_step_servos_noise.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_uint32, C.c_uint64, fp]
+        L.hostsim_reset_spine.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp]
+        L.hostsim_step_servos_spine.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp]
         for name in ("hostsim_mpc_step_f32", "hostsim_mpc_step_f64"):
             getattr(L, name).argtypes = [
                 C.POINTER(_abi.UpkieMpcConfig), C.c_int, dp, dp, u8p, C.c_double, dp, dp, u8p, C.POINTER(C.c_int),
@@ -146,6 +148,21 @@ class HostSim:
         out = np.empty((self.n, _abi.SPINE_DIM), dtype=np.float32)
         lib().hostsim_spine_obs_with_uncertainty(
             self._h, self.n, _f(self.state), tick, env_offset, _f(out))
+        return out
+
+    def reset_spine(self, init):
+        """Spine mode: three stopped cycles from ``init[n, 25]``; returns the assembled observation rows."""
+        init = np.ascontiguousarray(init, dtype=np.float32)
+        if getattr(self, "lag", None) is None:
+            self.lag = np.zeros((self.n, _abi.LAG_DIM), dtype=np.float32)
+        out = np.empty((self.n, _abi.SPINE_DIM), dtype=np.float32)
+        lib().hostsim_reset_spine(self._h, self.n, _f(self.state), _f(self.lag), _f(init), _f(out))
+        return out
+
+    def step_servos_spine(self, action):
+        a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.n, 36)
+        out = np.empty((self.n, _abi.SPINE_DIM), dtype=np.float32)
+        lib().hostsim_step_servos_spine(self._h, self.n, _f(self.state), _f(self.lag), _f(a), _f(out))
         return out
 
     def sample_init(self, seed, env_offset=0, episode=1):

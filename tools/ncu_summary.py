@@ -11,6 +11,8 @@ import subprocess
 import sys
 
 rep, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+# optional: --sidecar servos:limits3:n65536  -> profiles/ncu_sidecar.json[source hash of this build][key], read by bench.py
+sidecar_key = sys.argv[sys.argv.index("--sidecar") + 1] if "--sidecar" in sys.argv else None
 out = []
 
 # ---- launch list -------------------------------------------------------------------
@@ -85,3 +87,34 @@ out.append("\n| warp stall reason (sampled) | share |\n|---|---:|")
 for h, c in stalls.most_common(8):
     out.append(f"| {h} | {100*c/st:.1f}% |")
 print("\n".join(out))
+
+if sidecar_key:
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from upkie_b200 import build as b
+
+    def num(key):
+        v = float(d[key].replace(",", ""))
+        unit = u[key].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+
+    fp_ops = ("FFMA2", "FMUL2", "FADD2", "FFMA", "FMUL", "FADD")
+    entry = {
+        "kernel": d.get("Kernel Name", "")[:60],
+        "dram_bytes": int(num("dram__bytes_read.sum") + num("dram__bytes_write.sum")),
+        "instr_per_env_step": tot / max(1, warps),
+        "fp_instr_share": sum(ops[o] for o in fp_ops) / max(1, tot),
+        "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+        "duration_us_under_ncu": float(d["gpu__time_duration.sum"]),
+        "report": os.path.basename(rep),
+        "captured": "one launch, `ncu --set full --clock-control none`, steady state (launch 200 of the bench loop)",
+    }
+    path = os.path.join(root, "profiles", "ncu_sidecar.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data.setdefault(b.source_hash(), {})[sidecar_key] = entry
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1)
+    print(f"\nsidecar: profiles/ncu_sidecar.json[{b.source_hash()}][{sidecar_key}] = {entry}", file=sys.stderr)

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 ABI_VERSION = 3
-LAG_REPLY1, LAG_REPLY2, LAG_IMU, LAG_DIM = 0, 18, 36, 49  # spine-mode lag record (include/upkie_b200.h)
+LAG_REPLY1, LAG_REPLY2, LAG_IMU, LAG_OBS_REPLY, LAG_OBS_IMU, LAG_OBS_BASE, LAG_OBS_CONTACT, LAG_DIM = 0, 18, 36, 49, 67, 80, 90, 91  # spine-mode lag record (include/upkie_b200.h)
 
 NJ = 6
 NB = 7

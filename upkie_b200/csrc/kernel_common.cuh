@@ -75,7 +75,7 @@ struct PeerPtrs {
 // One launch of the env-step kernel over the envs [i0, i0 + cnt) of a handle.
 struct StepArgs {
   const SimParams* P;
-  int mode, autoreset, noise;  // noise: 1 = the "extras" instantiation (torque noise models, external forces), 2 = extras + joint-limit rows
+  int mode, autoreset, noise;  // noise: 1 = the "extras" instantiation (torque noise models, external forces), 2 = extras + joint-limit rows, 3 = 2 + spine timing
   int i0, cnt, n_pad, block;
   int compact_obs;      // TILE=1, servos: observation rows [6][3] (position, velocity, torque) instead of [6][5]
   int grid;             // TILE=1: number of persistent blocks (0 = one block per tile)
@@ -96,6 +96,7 @@ struct StepArgs {
   uint32_t ext_local;
   cudaStream_t stream;
   PeerPtrs peers;       // TILE=2 only
+  float* lag;           // spine mode: [UPKIE_LAG_DIM][n_pad] lag records, else null
 };
 
 cudaError_t launch_step_device(const StepArgs& a);  // step_device.cu
@@ -104,5 +105,7 @@ cudaError_t launch_step_multicast(const StepArgs& a);  // step_multicast.cu: TIL
 cudaError_t launch_step_device_limits(const StepArgs& a);  // step_device_limits.cu: NOISE=2 (joint-limit rows), TILE=0
 cudaError_t launch_step_host_limits(const StepArgs& a);    // step_host_limits.cu: NOISE=2, TILE=1
 cudaError_t launch_step_multicast_limits(const StepArgs& a);  // step_multicast_limits.cu: NOISE=2, TILE=2
+cudaError_t launch_step_device_spine(const StepArgs& a);  // step_device_spine.cu: NOISE=3 (spine timing), TILE=0
+cudaError_t launch_step_host_spine(const StepArgs& a);    // step_host_spine.cu: NOISE=3, TILE=1
 
 }  // namespace upkie_b200

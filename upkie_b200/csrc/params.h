@@ -191,6 +191,11 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.rand_omega_x = float(c.rand_omega_x);
   P.rand_omega_y = float(c.rand_omega_y);
   for (int k = 0; k < 3; ++k) P.rand_linvel[k] = float(c.rand_linear_velocity[k]);
+  P.spine_mode = c.spine_mode ? 1 : 0;
+  if (P.spine_mode && P.joint_limits == 0) {
+    err = "config: spine_mode needs joint_limits != 0 (it lives in the extras + limits kernels)";
+    return UPKIE_B200_EINVAL;
+  }
   for (int j = 0; j < 6; ++j) P.init_q[j] = float(c.init_joint_configuration[j]);
   for (int k = 0; k < 3; ++k) {
     P.init_angvel[k] = float(c.init_angular_velocity[k]);

@@ -97,6 +97,7 @@ struct SimParams {
   float limit_erp, limit_max_impulse;
   // nominal joint configuration / base velocities of the initial state (RobotState.sample_state keeps / adds them)
   float init_q[6], init_angvel[3], init_linvel[3];
+  int spine_mode;  // 1: timing of the C++ Bullet spine in simulate() mode (include/upkie_b200.h: spine_mode)
 };
 
 // per-robot state in registers
@@ -821,11 +822,12 @@ namespace upkie_b200 {
 // `wext`: external wrench on the base (moment about the base origin, force; base coordinates) or null
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu, AnyFn warp_any,
-                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr, int limits = 0) {
+                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr, int limits = 0, bool locked = false) {
 #if UPKIE_PAIRED_LEGS
-  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext, limits);
+  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext, limits, locked);
 #else
   (void)limits;  // the scalar-leg build has no joint-limit rows
+  (void)locked;
   physics_substep(P, S, tau, eps, mu, warp_any, phase_sync, wext);
 #endif
 }
@@ -1222,6 +1224,183 @@ UPKIE_HD void reset_robot(const SimParams& P, RobotState& S, const float init[UP
   substep(P, S, zero, eps, mu, warp_any, NoSync(), nullptr, limits);  // one stepSimulation (:228)
   observe_update(P, S);
   reset_wrapper_state(S);
+}
+
+// ---- spine mode: the timing of the C++ Bullet spine in simulate() mode ----------------------------------------------
+// What the spine's actuation interface holds between cycles (layout UPKIE_LAG_*, include/upkie_b200.h), plus the last
+// observation the spine assembled (what get_spine_observation / the env observation report).
+struct SpineLag {
+  float rep1[18], rep2[18];  // servo replies of the latest cycle and of the one before: [6][position, velocity, torque]
+  float imu[13];             // latest IMU reading: orientation_imu_in_ars wxyz, angular velocity, acceleration, raw
+  float obs_rep[18], obs_imu[13];  // the assembled observation: replies of two cycles ago, IMU of the last cycle
+  float obs_base[10];        // "sim" ground truth at that instant: base quaternion wxyz, linear, angular velocity (world)
+  float obs_contact;
+};
+
+// bullet::read_imu_data (upkie/cpp/interfaces/bullet/read_imu_data.h:25-89) on the current state; the acceleration is
+// differentiated against the IMU velocity of the previous cycle over one cycle (inv_h)
+UPKIE_HD void spine_read_imu(const SimParams& P, RobotState& S, float imu[13]) {
+  float R[9];
+  quat_to_rot(S.quat, R);
+  float rp[3], w[3], acc[3];
+  rot_mul(R, P.imu_pos, rp);
+  cross3(S.angvel, rp, w);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float v = S.linvel[i] + w[i];
+    acc[i] = (v - S.prev_imu_vel[i]) * P.inv_h;
+    S.prev_imu_vel[i] = v;
+    S.imu_acc[i] = acc[i];
+  }
+  float Riw[9], Ria[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      Riw[3 * i + j] = R[3 * i + 0] * P.Rbi[3 * j + 0] + R[3 * i + 1] * P.Rbi[3 * j + 1] + R[3 * i + 2] * P.Rbi[3 * j + 2];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { Ria[j] = Riw[j]; Ria[3 + j] = -Riw[3 + j]; Ria[6 + j] = -Riw[6 + j]; }
+  quat_from_rot(Ria, &imu[0]);
+  rot_tmul(Riw, S.angvel, &imu[4]);
+  rot_tmul(Riw, acc, &imu[7]);
+  const float praw[3] = {acc[0], acc[1], acc[2] + 9.81f};
+  rot_tmul(Riw, praw, &imu[10]);
+}
+
+// BulletInterface::cycle (BulletInterface.cpp:228-250): read_joint_sensors, read_imu, send_commands - torques from the
+// readings just taken, tau_max = min(maximum_torque, URDF effort), no joint friction (:278-352) - and one
+// stepSimulation. `stopped`: the servos are in moteus kStopped mode (locked joints, zero torque).
+template <typename AnyFn, typename SyncFn>
+UPKIE_HD void spine_cycle(const SimParams& P, RobotState& S, SpineLag& L, const float a[UPKIE_ACT_DIM], bool stopped,
+                          const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync, int limits) {
+#pragma unroll
+  for (int k = 0; k < 18; ++k) L.rep2[k] = L.rep1[k];
+  spine_read_imu(P, S, L.imu);
+  float tau[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float* aj = a + j * 6;
+    const float kp = aj[UPKIE_ACT_KP_SCALE] * P.kp, kd = aj[UPKIE_ACT_KD_SCALE] * P.kd;
+    const float tau_max = fminf(aj[UPKIE_ACT_MAXIMUM_TORQUE], P.tau_max[j]);
+    float t = aj[UPKIE_ACT_FEEDFORWARD_TORQUE] + kd * (aj[UPKIE_ACT_VELOCITY] - S.qd[j]);
+    const float tp = aj[UPKIE_ACT_POSITION];
+    if (!(tp != tp)) t += kp * (tp - S.q[j]);
+    t = fmaxf(fminf(t, tau_max), -tau_max);
+    if (stopped) t = 0.f;
+    tau[j] = t;
+    S.torque[j] = t;
+    L.rep1[3 * j + 0] = S.q[j];
+    L.rep1[3 * j + 1] = S.qd[j];
+    L.rep1[3 * j + 2] = t;
+  }
+  substep(P, S, tau, eps, mu, warp_any, phase_sync, nullptr, limits, stopped);
+}
+
+// the observation cycle_actuation assembles before it cycles the simulator (Spine.cpp:185-200)
+UPKIE_HD void spine_assemble_observation(const RobotState& S, SpineLag& L) {
+#pragma unroll
+  for (int k = 0; k < 18; ++k) L.obs_rep[k] = L.rep2[k];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) L.obs_imu[k] = L.imu[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) L.obs_base[k] = S.quat[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { L.obs_base[4 + k] = S.linvel[k]; L.obs_base[7 + k] = S.angvel[k]; }
+  L.obs_contact = S.contact;
+}
+
+// BulletInterface::reset (BulletInterface.cpp:129-163): base pose, velocities (the body-frame angular velocity rotated
+// to the world frame), joint angles; the IMU's previous velocity restarts from the reset state; no simulation step
+UPKIE_HD void reset_pose_spine(const SimParams& P, RobotState& S, const float init[UPKIE_INIT_DIM], SpineLag& L) {
+  reset_pose(S, init);
+  float R[9], wb[3] = {S.angvel[0], S.angvel[1], S.angvel[2]}, rp[3], w[3];
+  quat_to_rot(S.quat, R);
+  rot_mul(R, wb, S.angvel);
+  rot_mul(R, P.imu_pos, rp);
+  cross3(S.angvel, rp, w);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.prev_imu_vel[i] = S.linvel[i] + w[i];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) S.torque[j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 18; ++k) { L.rep1[k] = 0.f; L.rep2[k] = 0.f; L.obs_rep[k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 13; ++k) { L.imu[k] = 0.f; L.obs_imu[k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) L.obs_base[k] = 0.f;
+  L.obs_contact = 0.f;
+}
+
+// Spine::simulate in State::kReset (Spine.cpp:119-125): three cycles with the servos stopped; the observation handed
+// to the agent is the one the third cycle assembled
+template <typename AnyFn>
+UPKIE_HD void reset_robot_spine(const SimParams& P, RobotState& S, SpineLag& L, const float init[UPKIE_INIT_DIM],
+                                const float* eps, float mu, AnyFn warp_any, int limits) {
+  reset_pose_spine(P, S, init, L);
+  float a[UPKIE_ACT_DIM];
+#pragma unroll
+  for (int k = 0; k < UPKIE_ACT_DIM; ++k) a[k] = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    if (c == 2) spine_assemble_observation(S, L);
+    spine_cycle(P, S, L, a, true, eps, mu, warp_any, NoSync(), limits);
+  }
+  reset_wrapper_state(S);
+}
+
+// spine observation row [UPKIE_SPINE_DIM] from the assembled observation of the lag record
+UPKIE_HD void spine_observation_from_lag(const SimParams& P, const SpineLag& L, float* o) {
+  float R[9];
+  quat_to_rot(L.obs_base, R);
+  float om_b[3];
+  rot_tmul(R, &L.obs_base[7], om_b);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o[UPKIE_SP_BASE_ANGVEL + i] = om_b[i];
+    o[UPKIE_SP_BASE_LINVEL + i] = L.obs_base[4 + i];
+  }
+  o[UPKIE_SP_PITCH] = asinf(2.f * (L.obs_base[0] * L.obs_base[2] - L.obs_base[3] * L.obs_base[1]));
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[UPKIE_SP_ROT + i] = R[i];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[UPKIE_SP_IMU_QUAT + k] = L.obs_imu[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o[UPKIE_SP_IMU_ANGVEL + k] = L.obs_imu[4 + k];
+    o[UPKIE_SP_IMU_LINACC + k] = L.obs_imu[7 + k];
+    o[UPKIE_SP_IMU_RAWACC + k] = L.obs_imu[10 + k];
+  }
+  o[UPKIE_SP_CONTACT] = L.obs_contact;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float* so = o + UPKIE_SP_SERVO + j * UPKIE_OBS_KEYS;
+    so[UPKIE_OBS_POSITION] = L.obs_rep[3 * j];
+    so[UPKIE_OBS_VELOCITY] = L.obs_rep[3 * j + 1];
+    so[UPKIE_OBS_TORQUE] = L.obs_rep[3 * j + 2];
+    so[UPKIE_OBS_TEMPERATURE] = 20.0f;  // BulletInterface.cpp:70
+    so[UPKIE_OBS_VOLTAGE] = 18.0f;
+  }
+  const float signed_radius = P.left_sign * P.wheel_radius;
+  o[UPKIE_SP_ODOM_POS] = 0.5f * (L.obs_rep[3 * 2] - L.obs_rep[3 * 5]) * signed_radius;
+  o[UPKIE_SP_ODOM_VEL] = 0.5f * (L.obs_rep[3 * 2 + 1] - L.obs_rep[3 * 5 + 1]) * signed_radius;
+}
+
+UPKIE_HD void lag_from_row(const float* r, SpineLag& L) {
+#pragma unroll
+  for (int k = 0; k < 18; ++k) { L.rep1[k] = r[UPKIE_LAG_REPLY1 + k]; L.rep2[k] = r[UPKIE_LAG_REPLY2 + k]; L.obs_rep[k] = r[UPKIE_LAG_OBS_REPLY + k]; }
+#pragma unroll
+  for (int k = 0; k < 13; ++k) { L.imu[k] = r[UPKIE_LAG_IMU + k]; L.obs_imu[k] = r[UPKIE_LAG_OBS_IMU + k]; }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) L.obs_base[k] = r[UPKIE_LAG_OBS_BASE + k];
+  L.obs_contact = r[UPKIE_LAG_OBS_CONTACT];
+}
+UPKIE_HD void lag_to_row(const SpineLag& L, float* r) {
+#pragma unroll
+  for (int k = 0; k < 18; ++k) { r[UPKIE_LAG_REPLY1 + k] = L.rep1[k]; r[UPKIE_LAG_REPLY2 + k] = L.rep2[k]; r[UPKIE_LAG_OBS_REPLY + k] = L.obs_rep[k]; }
+#pragma unroll
+  for (int k = 0; k < 13; ++k) { r[UPKIE_LAG_IMU + k] = L.imu[k]; r[UPKIE_LAG_OBS_IMU + k] = L.obs_imu[k]; }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) r[UPKIE_LAG_OBS_BASE + k] = L.obs_base[k];
+  r[UPKIE_LAG_OBS_CONTACT] = L.obs_contact;
 }
 
 // ---- counter-based RNG (Philox4x32-10) for on-device init-state sampling and noise ----

@@ -19,13 +19,6 @@
 
 #include <type_traits>
 
-#ifndef UPKIE_TENROW_V1
-#define UPKIE_TENROW_V1 0
-#endif
-#ifndef UPKIE_TENROW_PAIRED_COLS
-#define UPKIE_TENROW_PAIRED_COLS 1
-#endif
-
 namespace upkie_b200 {
 
 UPKIE_HD f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
@@ -92,8 +85,13 @@ UPKIE_HD void ldl6_solve2(const float A[21], const float nA[21], f2 x[6]) {
 }
 
 // Both legs of leg_pass12 at once.
+// `locked`: every joint is held (spine mode, servos stopped: Bullet velocity motors holding 0 rad/s with 100 N m,
+// BulletInterface.cpp:296-301, restated as locked joints): 1 / D -> 0, so that a joint transmits everything - no
+// reduction of the articulated inertia, no joint acceleration, no joint response to impulses further down the file.
 UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6], const float tau[6], const float V0[6],
-                          const float* eps, LegCache2& lc, f2 cc[3][6], f2 uu[3], float IA0[21], float pA0[6]) {
+                          const float* eps, LegCache2& lc, f2 cc[3][6], f2 uu[3], float IA0[21], float pA0[6],
+                          bool locked = false) {
+  const f2 free2 = bc2(locked ? 0.f : 1.f);
   f2 cphi[3], sphi[3];
   f2 V[3][6];
   {
@@ -245,11 +243,11 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
 #pragma unroll
       for (int r = 0; r < 6; ++r) U[r] = bc2(0.f);
       U[1] = mul2(s, Iyy);
-      invD = mk2(1.f / Iyy.x, 1.f / Iyy.y);
+      invD = mul2(free2, mk2(1.f / Iyy.x, 1.f / Iyy.y));
       u = sub2(mk2(tau[k], tau[k + 3]), mul2(s, spin_damp));
       lc.ninvD[k] = neg2(invD);
       // Ia = IA - U U^T / D: the rotor stops resisting rotation about its own axis; pa = pA + Ia c + S u
-      IA[SI(1, 1)] = sub2(IA[SI(1, 1)], Iyy);
+      IA[SI(1, 1)] = fma2(neg2(free2), Iyy, IA[SI(1, 1)]);
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         f2 acc = pA[r];
@@ -259,12 +257,12 @@ UPKIE_HD void legs_pass12(const SimParams& P, const float q[6], const float qd[6
         }
         p[r] = acc;
       }
-      p[1] = fma2(s, u, p[1]);
+      p[1] = fma2(mul2(s, free2), u, p[1]);
     } else {
 #pragma unroll
       for (int r = 0; r < 6; ++r) U[r] = mul2(s, fma2(ox, IA[SI(r, 5)], fma2(noz, IA[SI(r, 3)], IA[SI(r, 1)])));
       const f2 D = sdot2(s, ox, noz, U);
-      invD = mk2(1.f / D.x, 1.f / D.y);
+      invD = mul2(free2, mk2(1.f / D.x, 1.f / D.y));
       u = sub2(mk2(tau[k], tau[k + 3]), sdot2(s, ox, noz, pA));
       // Ia = IA - U U^T / D ; pa = pA + Ia c + U u / D
       const f2 ninvD = neg2(invD);
@@ -608,9 +606,12 @@ UPKIE_HD void legs_impulse_up_general(const SimParams& P, const LegCache2& lc, c
   for (int i = 0; i < 6; ++i) nptop[i] = q[i];
 }
 
-#if UPKIE_TENROW_V1  // round-2 starting point, kept for A/B timing (tools/variants.py)
+// Round-2 A/B on a B200 (profiles/r02_variants.md): two rewrites that cut ~280 instructions per substep out of this
+// function - closed-form up-passes for the joint-limit directions, the Delassus matrix stored as paired columns and
+// scaled in place - measured SLOWER (0.1423 / 0.1484 ms against 0.1403 ms per 65 536-env tick): they lengthen live
+// ranges in a kernel that already spills, and ptxas' schedule matters more than the instruction count here. Kept as is.
 template <typename AnyFn, typename SyncFn>
-UPKIE_HD void contact_solve_ten_rows_v1(const SimParams& P, RobotState& S, const LegCache2& lc, const float IA0[21],
+UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const LegCache2& lc, const float IA0[21],
                                      const float nIA0[21], const float R[9], const float zb[3], float inv_n,
                                      const f2 Pc[3], const f2& dist, bool actL, bool actR, float mu, AnyFn warp_any,
                                      SyncFn phase_sync) {
@@ -796,288 +797,6 @@ UPKIE_HD void contact_solve_ten_rows_v1(const SimParams& P, RobotState& S, const
     sweep(false, false);  // even iteration: the non-contact rows are walked backwards
     if (it + 1 >= P.pgs_iterations) break;
     const bool changed = sweep(true, true);
-    if (!warp_any(changed)) break;
-  }
-  S.lam_n[0] = lam[4];
-  S.lam_n[1] = lam[5];
-  f2 F[6];
-  {
-    const f2 ln = mk2(lam[4], lam[5]), l1 = mk2(lam[6], lam[8]), l2 = mk2(lam[7], lam[9]);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) F[i] = fma2(ln, J[0][i], fma2(l1, J[1][i], mul2(l2, J[2][i])));
-  }
-  f2 u[3], nptop[6];
-  legs_impulse_up_general(P, lc, F, mul2(dirH, mk2(lam[0], lam[2])), mul2(dirK, mk2(lam[1], lam[3])), u, nptop);
-  float da0[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) da0[i] = nptop[i].x + nptop[i].y;
-  ldl6_solve(IA0, da0);
-  f2 da2[6], aw[6], dq[3];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) da2[i] = bc2(da0[i]);
-  legs_impulse_down<false>(P, lc, u, da2, aw, dq);
-  float dw[3], dv[3];
-  rot_mul(R, &da0[0], dw);
-  rot_mul(R, &da0[3], dv);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    S.angvel[i] = clampf(S.angvel[i] + dw[i], -P.vmax, P.vmax);
-    S.linvel[i] = clampf(S.linvel[i] + dv[i], -P.vmax, P.vmax);
-    S.qd[i] = clampf(S.qd[i] + dq[i].x, -P.vmax, P.vmax);
-    S.qd[3 + i] = clampf(S.qd[3 + i] + dq[i].y, -P.vmax, P.vmax);
-  }
-  phase_sync();  // 6
-}
-
-#endif
-template <typename AnyFn, typename SyncFn>
-UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const LegCache2& lc, const float IA0[21],
-                                     const float nIA0[21], const float R[9], const float zb[3], float inv_n,
-                                     const f2 Pc[3], const f2& dist, bool actL, bool actR, float mu, AnyFn warp_any,
-                                     SyncFn phase_sync) {
-  // limit slots: dir = +1 at the lower bound, -1 at the upper one, 0 when the joint is inside its range
-  f2 dirH, dirK, penH, penK;
-  {
-    float d[4], pn[4];
-    const int js[4] = {0, 1, 3, 4};
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int j = js[a];
-      const float lo = S.q[j] - P.q_lower[j], hi = P.q_upper[j] - S.q[j];
-      d[a] = lo <= 0.f ? 1.f : (hi <= 0.f ? -1.f : 0.f);
-      pn[a] = lo <= 0.f ? lo : (hi <= 0.f ? hi : 0.f);
-    }
-    dirH = mk2(d[0], d[2]); dirK = mk2(d[1], d[3]);
-    penH = mk2(pn[0], pn[2]); penK = mk2(pn[1], pn[3]);
-  }
-  const bool any_limit = dirH.x != 0.f || dirH.y != 0.f || dirK.x != 0.f || dirK.y != 0.f;
-  if (!warp_any(actL || actR || any_limit)) {
-    S.lam_n[0] = 0.f;
-    S.lam_n[1] = 0.f;
-    phase_sync();  // 3
-    phase_sync();  // 4
-    phase_sync();  // 5
-    phase_sync();  // 6
-    return;
-  }
-  const float t1[3] = {zb[2] * inv_n, 0.f, -zb[0] * inv_n};
-  float t2[3];
-  cross3(zb, t1, t2);
-  const f2 sw = P.sgn2[2];
-  f2 J[3][6];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    f2 dir[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) dir[i] = d == 0 ? bc2(zb[i]) : mul2(sw, bc2(d == 1 ? t1[i] : t2[i]));
-    cross3_2(Pc, dir, &J[d][0]);
-    J[d][3] = dir[0]; J[d][4] = dir[1]; J[d][5] = dir[2];
-  }
-  f2 Vw[6];
-  {
-    float Vb[6];
-    rot_tmul(R, S.angvel, &Vb[0]);
-    rot_tmul(R, S.linvel, &Vb[3]);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) Vw[i] = bc2(Vb[i]);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const f2 w = mul2(P.sgn2[k], mk2(S.qd[k], S.qd[k + 3]));
-      Vw[1] = add2(Vw[1], w);
-      Vw[3] = fma2(lc.noz[k], w, Vw[3]);
-      Vw[5] = fma2(lc.ox[k], w, Vw[5]);
-    }
-  }
-  // Delassus matrix over the five direction pairs (normal, t1, t2, hip, knee). The up-pass of a joint impulse has a
-  // closed form (it enters at its own level with nothing below it): with nUd_k = -U_k / D_k,
-  //   hip  impulse g: u = (g, 0, 0),        -ptop = g nUd_0
-  //   knee impulse g: u = (g sigma, g, 0),  -ptop = g (nUd_1 + sigma nUd_0),  sigma = S_0 . nUd_1
-  // (indices hip, knee, wheel), which replaces two generic up-passes (262 instructions in the round-2 profile).
-  // Stored as paired columns: Wc[k][p] = (W[row(p, L)][k], W[row(p, R)][k]) - the layout the sweep's residual update
-  // wants - so that the row scaling below is 50 packed multiplies in place (round 2; was a scalar 10 x 10 matrix plus
-  // a second, scaled copy).
-#if UPKIE_TENROW_PAIRED_COLS
-  f2 Wc[10][5];
-#else
-  float W[10][10];
-#endif
-  {
-    f2 uu_[5][3], pt_[5][6];
-#pragma unroll
-    for (int d = 0; d < 5; ++d) {
-      if (d == 3) {  // hip rows (computed here, not before the loop: shorter live ranges)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) pt_[3][i] = mul2(dirH, mul2(lc.U[0][i], lc.ninvD[0]));
-        uu_[3][0] = dirH; uu_[3][1] = bc2(0.f); uu_[3][2] = bc2(0.f);
-      }
-      if (d == 4) {  // knee rows
-        f2 nUd1[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) nUd1[i] = mul2(lc.U[1][i], lc.ninvD[1]);
-        const f2 sigma = sdot2(P.sgn2[0], lc.ox[0], lc.noz[0], nUd1);
-        const f2 sn0 = mul2(sigma, lc.ninvD[0]);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) pt_[4][i] = mul2(dirK, fma2(sn0, lc.U[0][i], nUd1[i]));
-        uu_[4][0] = mul2(dirK, sigma); uu_[4][1] = dirK; uu_[4][2] = bc2(0.f);
-      }
-      if (d < 3) legs_impulse_up(P, lc, J[d], uu_[d], pt_[d]);
-      f2 da0[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) da0[i] = pt_[d][i];
-      ldl6_solve2(IA0, nIA0, da0);
-#pragma unroll
-      for (int e = 0; e <= d; ++e) {
-        f2 wo = bc2(0.f), wc = bc2(0.f);
-        // sum_k u_k(e) u_k(d) / D_k over the levels where both are non-zero: hip rows only at level 0, knee rows at 0, 1
-        const int kmax = (d == 3 || e == 3) ? 1 : ((d == 4 || e == 4) ? 2 : 3);
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < kmax) wo = fma2(mul2(uu_[e][k], lc.invD[k]), uu_[d][k], wo);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          wo = fma2(pt_[e][i], da0[i], wo);
-          wc = fma2(swp2(pt_[e][i]), da0[i], wc);
-        }
-        // wo = (W[eL][dL], W[eR][dR]), wc = (W[eR][dL], W[eL][dR]); W is symmetric
-#if UPKIE_TENROW_PAIRED_COLS
-        Wc[row10_of(d, 0)][e] = mk2(wo.x, wc.x);
-        Wc[row10_of(d, 1)][e] = mk2(wc.y, wo.y);
-        if (e != d) {
-          Wc[row10_of(e, 0)][d] = mk2(wo.x, wc.y);
-          Wc[row10_of(e, 1)][d] = mk2(wc.x, wo.y);
-        }
-#else
-        W[row10_of(e, 0)][row10_of(d, 0)] = wo.x;
-        W[row10_of(e, 1)][row10_of(d, 1)] = wo.y;
-        W[row10_of(e, 1)][row10_of(d, 0)] = wc.x;
-        W[row10_of(e, 0)][row10_of(d, 1)] = wc.y;
-        if (e != d) {
-          W[row10_of(d, 0)][row10_of(e, 0)] = wo.x;
-          W[row10_of(d, 1)][row10_of(e, 1)] = wo.y;
-          W[row10_of(d, 0)][row10_of(e, 1)] = wc.x;
-          W[row10_of(d, 1)][row10_of(e, 0)] = wc.y;
-        }
-#endif
-      }
-      if (d < 3) phase_sync();  // 3, 4, 5
-    }
-  }
-#if UPKIE_TENROW_PAIRED_COLS
-  auto Wdiag = [&](int k) { return lane_of_row10(k) == 0 ? Wc[k][pair_of_row10(k)].x : Wc[k][pair_of_row10(k)].y; };
-#else
-  auto Wdiag = [&](int k) { return W[k][k]; };
-#endif
-  float rhs[10], jdi[10], lam[10];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    f2 rel = bc2(0.f);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) rel = fma2(J[d][i], Vw[i], rel);
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const int k = row10_of(d, side);
-      const float r = side == 0 ? rel.x : rel.y;
-      lam[k] = d == 0 ? ((side == 0 ? actL : actR) ? P.warm * S.lam_n[side] : 0.f) : 0.f;
-      if (d == 0) {
-        const float pen = side == 0 ? dist.x : dist.y;
-        jdi[k] = 1.f / (Wdiag(k) + P.cfm);
-        float pos_err = 0.f, vel_err = -r;
-        if (pen > 0.f) vel_err -= pen * P.inv_h;
-        else pos_err = -pen * P.erp * P.inv_h;
-        rhs[k] = (pos_err + vel_err) * jdi[k];
-      } else {
-        jdi[k] = Wdiag(k) > 0.f ? 1.f / Wdiag(k) : 0.f;
-        rhs[k] = -r * jdi[k];
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {  // limit rows 0 hipL, 1 kneeL, 2 hipR, 3 kneeR
-    const int j = a == 0 ? 0 : a == 1 ? 1 : a == 2 ? 3 : 4;
-    const float dir = a == 0 ? dirH.x : a == 1 ? dirK.x : a == 2 ? dirH.y : dirK.y;
-    const float pen = a == 0 ? penH.x : a == 1 ? penK.x : a == 2 ? penH.y : penK.y;
-    lam[a] = 0.f;
-    jdi[a] = Wdiag(a) > 1.1920929e-7f ? 1.f / Wdiag(a) : 0.f;
-    rhs[a] = (-pen * P.limit_erp * P.inv_h - dir * S.qd[j]) * jdi[a];
-  }
-  const float cfmrow = P.cfm;
-  const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
-#if !UPKIE_TENROW_PAIRED_COLS
-  f2 Gc[10][5];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    float g[10];
-#pragma unroll
-    for (int m = 0; m < 10; ++m)
-      g[m] = -jdi[m] * W[m][k] + (m == k ? 1.f - ((k == 4 || k == 5) ? cfmrow * jdi[k] : 0.f) : 0.f);
-#pragma unroll
-    for (int p = 0; p < 5; ++p) Gc[k][p] = mk2(g[row10_of(p, 0)], g[row10_of(p, 1)]);
-  }
-#else
-  // scaled columns in place: G[m][k] = -jdi[m] W[m][k] (+ 1 - cfm jdi on the diagonal of the normal rows)
-  f2 (&Gc)[10][5] = Wc;
-  {
-    f2 njdi2[5];
-#pragma unroll
-    for (int p = 0; p < 5; ++p) njdi2[p] = mk2(-jdi[row10_of(p, 0)], -jdi[row10_of(p, 1)]);
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-#pragma unroll
-      for (int p = 0; p < 5; ++p) Gc[k][p] = mul2(Gc[k][p], njdi2[p]);
-      const float dg = 1.f - ((k == 4 || k == 5) ? cfmrow * jdi[k] : 0.f);
-      if (lane_of_row10(k) == 0) Gc[k][pair_of_row10(k)].x += dg;
-      else Gc[k][pair_of_row10(k)].y += dg;
-    }
-  }
-#endif
-  if (!actL) {
-    rhs[4] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) Gc[k][0].x = 0.f;
-  }
-  if (!actR) {
-    rhs[5] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) Gc[k][0].y = 0.f;
-  }
-  f2 r2[5];
-#pragma unroll
-  for (int p = 0; p < 5; ++p) r2[p] = mk2(rhs[row10_of(p, 0)], rhs[row10_of(p, 1)]);
-#pragma unroll
-  for (int l = 4; l < 6; ++l)  // warm-started normals
-#pragma unroll
-    for (int p = 0; p < 5; ++p) r2[p] = fma2(Gc[l][p], bc2(lam[l]), r2[p]);
-  auto update = [&](int k, bool with_test, bool& changed) {
-    const f2 rp = r2[pair_of_row10(k)];
-    const float rk = lane_of_row10(k) == 0 ? rp.x : rp.y;
-    float nl;
-    if (k < 4) {
-      nl = fminf(fmaxf(rk, 0.f), P.limit_max_impulse);
-    } else if (k < 6) {
-      nl = fmaxf(rk, 0.f);
-    } else {
-      const float hi = mu * lam[(k < 8) ? 4 : 5];
-      nl = fminf(fmaxf(rk, -hi), hi);
-    }
-    const float delta = nl - lam[k];
-    const f2 d2 = bc2(delta);
-#pragma unroll
-    for (int p = 0; p < 5; ++p) r2[p] = fma2(Gc[k][p], d2, r2[p]);
-    if (with_test) changed = changed | (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
-    lam[k] = nl;
-  };
-  auto sweep = [&](bool forward, bool with_test) -> bool {
-    bool changed = false;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) update(forward ? a : 3 - a, with_test, changed);
-#pragma unroll
-    for (int k = 4; k < 10; ++k) update(k, with_test, changed);
-    return changed;
-  };
-  for (int it = 0; it < P.pgs_iterations; it += 2) {
-    sweep(false, false);  // even iteration: the non-contact rows are walked backwards
-    if (it + 1 >= P.pgs_iterations) break;
-    const bool changed = sweep(true, true);
 #ifdef UPKIE_PGS_STATS
     if (!changed) { upkie_pgs_stats(100 + it + 2); break; }
     if (it + 2 >= P.pgs_iterations) upkie_pgs_stats(100 + it + 3);
@@ -1122,7 +841,7 @@ UPKIE_HD constexpr int row_of(int side, int d) { return d == 0 ? side : 2 + 2 * 
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
                                      AnyFn warp_any, SyncFn phase_sync = SyncFn(), const float* wext = nullptr,
-                                     int limits = 0) {
+                                     int limits = 0, bool locked = false) {
   float R[9];
   quat_to_rot(S.quat, R);
   float V0[6];
@@ -1133,7 +852,7 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   base_inertia_bias(P, V0, IA0, pA0);
   LegCache2 lc;
   f2 cc[3][6], uu[3];
-  legs_pass12(P, S.q, S.qd, tau, V0, eps, lc, cc, uu, IA0, pA0);
+  legs_pass12(P, S.q, S.qd, tau, V0, eps, lc, cc, uu, IA0, pA0, locked);
   phase_sync();  // 1
   ldl6(IA0);
   float nIA0[21];  // negated factors for the packed solves (ldl6_solve2)
@@ -1206,11 +925,7 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
     ten_rows = warp_any(on_bound);
   }
   if (ten_rows) {
-#if UPKIE_TENROW_V1
-    contact_solve_ten_rows_v1(P, S, lc, IA0, nIA0, R, zb, inv_n, Pc, dist, inL, inR, mu, warp_any, phase_sync);
-#else
     contact_solve_ten_rows(P, S, lc, IA0, nIA0, R, zb, inv_n, Pc, dist, inL, inR, mu, warp_any, phase_sync);
-#endif
   } else if (!warp_any(actL || actR)) {
     S.lam_n[0] = 0.f;
     S.lam_n[1] = 0.f;

@@ -4,6 +4,7 @@
 
 namespace upkie_b200 {
 cudaError_t launch_step_device(const StepArgs& a) {
+  if (a.noise == 3) return launch_step_device_spine(a);  // step_device_spine.cu
   if (a.noise == 2) return launch_step_device_limits(a);  // step_device_limits.cu
   return launch_step_kernels<0>(a);
 }

@@ -4,6 +4,7 @@
 
 namespace upkie_b200 {
 cudaError_t launch_step_host(const StepArgs& a) {
+  if (a.noise == 3) return launch_step_host_spine(a);  // step_host_spine.cu
   if (a.noise == 2) return launch_step_host_limits(a);  // step_host_limits.cu
   return launch_step_kernels<1>(a);
 }

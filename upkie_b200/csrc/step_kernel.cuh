@@ -16,6 +16,9 @@
 #ifndef UPKIE_STEP_LIMITS_TU
 #define UPKIE_STEP_LIMITS_TU 0
 #endif
+#ifndef UPKIE_STEP_SPINE_TU
+#define UPKIE_STEP_SPINE_TU 0  // 1 in step_*_spine.cu: the NOISE=3 instantiations (extras + limits + spine timing), UpkieServos
+#endif
 #ifndef UPKIE_ACTION_IN_TILE
 #define UPKIE_ACTION_IN_TILE 0  // build-time experiment (tools/variants.py)
 #endif
@@ -44,7 +47,8 @@ __device__ __forceinline__ void step_env(
     uint8_t* __restrict__ truncated, const float* __restrict__ eps_all, const float* __restrict__ mu_all,
     uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev, uint32_t* __restrict__ episode,
     uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset, const float* __restrict__ ext,
-    uint32_t ext_local, float4* tile4, bool full, bool compact, const PeerPtrs* peers = nullptr) {
+    uint32_t ext_local, float4* tile4, bool full, bool compact, const PeerPtrs* peers = nullptr,
+    float* __restrict__ lag = nullptr) {
   const bool live = tid < n;
   const int i = live ? tid : n - 1;  // tail lanes shadow the last robot, stores masked
   const int lane = threadIdx.x & 31;
@@ -104,13 +108,28 @@ __device__ __forceinline__ void step_env(
   // external forces ride on the NOISE ("extras") instantiations so the plain kernels stay untouched
   const ExtForces xf{ext ? ext + i : nullptr, size_t(n_pad), ext_local};
   int nsub = P.nb_substeps;
+  // spine mode (config.spine_mode, UpkieServos, the NOISE=2 kernels): every substep is one cycle of the Bullet spine
+  // (NOISE = 3: its own instantiations, step_*_spine.cu, so that the other kernels do not carry the lag record)
+  constexpr bool spine = NOISE == 3 && MODE == MODE_SERVOS;
+  SpineLag L;
+  if (spine) {
+    float lr[UPKIE_LAG_DIM];
+#pragma unroll
+    for (int k = 0; k < UPKIE_LAG_DIM; ++k) lr[k] = lag[size_t(k) * n_pad + i];
+    lag_from_row(lr, L);
+  }
   if (resetting) {
     const uint32_t ep = episode[i] + 1u;
     if (live) episode[i] = ep;
     float init[UPKIE_INIT_DIM];
     sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
-    reset_pose(S, init);
-    nsub = 1;
+    if (spine) {
+      reset_pose_spine(P, S, init, L);
+      nsub = 3;  // three cycles with the servos stopped (Spine.cpp:119-125)
+    } else {
+      reset_pose(S, init);
+      nsub = 1;
+    }
   } else {
     if (MODE != MODE_SERVOS) e |= gyropod_action(P, S, a0, a1, a);
     e |= clamp_servo_action(P, a);
@@ -126,7 +145,9 @@ __device__ __forceinline__ void step_env(
     __syncwarp();
   }
 #endif
-  for (int sub = 0; sub < P.nb_substeps; ++sub) {
+  if (spine && !resetting) spine_assemble_observation(S, L);  // the first cycle's observation (Spine.cpp:126-131)
+  const int nloop = (AUTORESET == AUTORESET_NEXT_STEP && spine && P.nb_substeps < 3) ? 3 : P.nb_substeps;
+  for (int sub = 0; sub < nloop; ++sub) {
 #if UPKIE_PHASE_SYNC_LEVEL >= 1
     __syncthreads();  // once per substep: all threads are converged here
 #endif
@@ -140,14 +161,19 @@ __device__ __forceinline__ void step_env(
     }
 #endif
     if (sub < nsub) {
-      servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
-                    (NOISE && ext) ? &xf : nullptr, NOISE == 2 ? (P.joint_limits >= 1 ? P.joint_limits : 1) : 0);
+      if (spine) {
+        if (resetting && sub == 2) spine_assemble_observation(S, L);
+        spine_cycle(P, S, L, a, resetting, eps, mu, WarpAny(), PhaseSync(), P.joint_limits >= 1 ? P.joint_limits : 1);
+      } else {
+        servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
+                      (NOISE && ext) ? &xf : nullptr, NOISE >= 2 ? (P.joint_limits >= 1 ? P.joint_limits : 1) : 0);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < kPhaseSyncs; ++k) PhaseSync()();
     }
   }
-  observe_update(P, S);
+  if (!spine) observe_update(P, S);  // spine mode: the cycles read the IMU
   if (resetting) {
     reset_wrapper_state(S);
   } else {
@@ -175,12 +201,19 @@ __device__ __forceinline__ void step_env(
       if (live) episode[i] = ep;
       float init[UPKIE_INIT_DIM];
       sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
-      reset_robot(P, S, init, eps, mu, WarpAny(), NOISE == 2 ? P.joint_limits : 0);
+      if (spine) reset_robot_spine(P, S, L, init, eps, mu, WarpAny(), P.joint_limits);
+      else reset_robot(P, S, init, eps, mu, WarpAny(), NOISE >= 2 ? P.joint_limits : 0);
       if (MODE != MODE_SERVOS) gyropod_obs(P, S, o6);
     }
   }
 
   if (live) store_state(state, n_pad, i, S);
+  if (spine && live) {
+    float lr[UPKIE_LAG_DIM];
+    lag_to_row(L, lr);
+#pragma unroll
+    for (int k = 0; k < UPKIE_LAG_DIM; ++k) lag[size_t(k) * n_pad + i] = lr[k];
+  }
   if (MODE == MODE_SERVOS) {
     float o[UPKIE_OBS_DIM];
     float tq[6];
@@ -190,6 +223,13 @@ __device__ __forceinline__ void step_env(
       o[j * 5 + 0] = S.q[j]; o[j * 5 + 1] = S.qd[j]; o[j * 5 + 2] = tq[j];
       o[j * 5 + 3] = 42.0f;  // pybullet_backend.py:471
       o[j * 5 + 4] = 18.0f;  // pybullet_backend.py:472
+    }
+    if (spine) {  // the replies of two cycles ago, as the spine's observation reports them
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        o[j * 5 + 0] = L.obs_rep[3 * j]; o[j * 5 + 1] = L.obs_rep[3 * j + 1]; o[j * 5 + 2] = L.obs_rep[3 * j + 2];
+        o[j * 5 + 3] = 20.0f;  // BulletInterface.cpp:70
+      }
     }
     if (TILE && compact) {
       // compact rows [6 joints][position, velocity, torque]: temperature / voltage are constants the
@@ -312,12 +352,13 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
        uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated, const float* __restrict__ eps_all,
        const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
        uint32_t* __restrict__ episode, uint32_t* __restrict__ tick, uint64_t seed, uint64_t env_offset,
-       const float* __restrict__ ext, uint32_t ext_local, int coalesce, const __grid_constant__ PeerPtrs peers) {
+       const float* __restrict__ ext, uint32_t ext_local, int coalesce, const __grid_constant__ PeerPtrs peers,
+       float* __restrict__ lag) {
   // this launch covers the envs [i0, n)
   if (!TILE) {
     step_env<MODE, AUTORESET, NOISE, 0>(P, i0 + blockIdx.x * blockDim.x + threadIdx.x, n, n_pad, state, action, obs,
                                         reward, terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick,
-                                        seed, env_offset, ext, ext_local, nullptr, false, false);
+                                        seed, env_offset, ext, ext_local, nullptr, false, false, nullptr, lag);
     return;
   }
   extern __shared__ float4 s_tile[];
@@ -350,7 +391,7 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
     step_env<MODE, AUTORESET, NOISE, TILE>(P, i0 + t * blockDim.x + threadIdx.x, n, n_pad, state, action, obs, reward,
                                         terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick, seed,
                                         env_offset, ext, ext_local, buf[it & 1], warp_full(t), (coalesce & 2) != 0,
-                                        TILE == 2 ? &peers : nullptr);
+                                        TILE == 2 ? &peers : nullptr, lag);
     __syncwarp();  // the tile is free again before the next prefetch lands in it
   }
 }
@@ -368,8 +409,10 @@ cudaError_t launch_step_mode(const StepArgs& a) {
 #define LAUNCH_N(AR, NZ)                                                                                         \
   k_step<MODE, AR, NZ, TILE><<<grid, a.block, smem, a.stream>>>(                                                 \
       *a.P, a.i0, a.i0 + a.cnt, a.n_pad, a.state, a.action, a.obs, a.reward, a.terminated, a.truncated, a.eps,   \
-      a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, a.ext, a.ext_local, coalesce, a.peers)
-#if UPKIE_STEP_LIMITS_TU
+      a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, a.ext, a.ext_local, coalesce, a.peers, a.lag)
+#if UPKIE_STEP_SPINE_TU
+#define LAUNCH(AR) LAUNCH_N(AR, 3)
+#elif UPKIE_STEP_LIMITS_TU
 #define LAUNCH(AR) LAUNCH_N(AR, 2)
 #else
 #define LAUNCH(AR)                \

@@ -6,6 +6,7 @@
 
 namespace upkie_b200 {
 cudaError_t launch_step_multicast(const StepArgs& a) {
+  if (a.noise == 3) return cudaErrorNotSupported;  // no spine-timing instantiation of the in-kernel transports
   if (a.noise == 2) return launch_step_multicast_limits(a);  // step_multicast_limits.cu
   return launch_step_mode<2, MODE_SERVOS>(a);
 }

@@ -59,6 +59,7 @@ struct Handle {
   uint32_t* episode = nullptr;   // [n]
   uint32_t* tick = nullptr;      // [n] env ticks since create: counter of the noise generator
   float* ext = nullptr;          // [7 * 3][n_pad] external forces, null = none
+  float* lag = nullptr;          // [UPKIE_LAG_DIM][n_pad] spine-mode lag records (config.spine_mode), else null
   uint32_t ext_local = 0;
   int autoreset = AUTORESET_DISABLED;
   uint64_t seed = 0, env_offset = 0;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(128)
 k_reset(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict__ state,
         const uint8_t* __restrict__ mask, const float* __restrict__ init_state, const float* __restrict__ eps_all,
         const float* __restrict__ mu_all, uint32_t* __restrict__ err, uint8_t* __restrict__ done_prev,
-        uint32_t* __restrict__ episode, uint64_t seed, uint64_t env_offset) {
+        uint32_t* __restrict__ episode, uint64_t seed, uint64_t env_offset, float* __restrict__ lag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (mask && !mask[i]) return;
@@ -116,23 +117,41 @@ k_reset(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict
     episode[i] = ep;
     sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
   }
-  reset_robot(P, S, init, eps, mu, WarpAny(), P.joint_limits);
+  if (P.spine_mode && lag) {
+    SpineLag L;
+    reset_robot_spine(P, S, L, init, eps, mu, WarpAny(), P.joint_limits);
+    float lr[UPKIE_LAG_DIM];
+    lag_to_row(L, lr);
+    for (int k = 0; k < UPKIE_LAG_DIM; ++k) lag[size_t(k) * n_pad + i] = lr[k];
+  } else {
+    reset_robot(P, S, init, eps, mu, WarpAny(), P.joint_limits);
+  }
   store_state(state, n_pad, i, S);
   err[i] = 0;
   done_prev[i] = 0;
 }
 
 __global__ void k_spine_obs(const __grid_constant__ SimParams P, int n, int n_pad, const float* __restrict__ state,
-                            const uint32_t* __restrict__ tick, uint64_t env_offset, float* __restrict__ out) {
+                            const uint32_t* __restrict__ tick, uint64_t env_offset, float* __restrict__ out,
+                            const float* __restrict__ lag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  RobotState S;
-  load_state(state, n_pad, i, S);
   float o[UPKIE_SPINE_DIM];
-  float tq[6];
   const NoiseCtx nz{env_offset + uint64_t(i), tick[i]};  // same draw as the step that produced this state
-  measured_torques(P, S, &nz, tq);
-  spine_observation(P, S, o, tq);
+  if (P.spine_mode && lag) {
+    // the observation the spine assembled in the first cycle of the last step / the last cycle of the reset
+    float lr[UPKIE_LAG_DIM];
+    for (int k = 0; k < UPKIE_LAG_DIM; ++k) lr[k] = lag[size_t(k) * n_pad + i];
+    SpineLag L;
+    lag_from_row(lr, L);
+    spine_observation_from_lag(P, L, o);
+  } else {
+    RobotState S;
+    load_state(state, n_pad, i, S);
+    float tq[6];
+    measured_torques(P, S, &nz, tq);
+    spine_observation(P, S, o, tq);
+  }
   apply_imu_uncertainty(P, nz, o);
 #pragma unroll
   for (int k = 0; k < UPKIE_SPINE_DIM; ++k) out[size_t(i) * UPKIE_SPINE_DIM + k] = o[k];
@@ -140,11 +159,19 @@ __global__ void k_spine_obs(const __grid_constant__ SimParams P, int n, int n_pa
 
 __global__ void k_reset_obs(const __grid_constant__ SimParams P, int n, int n_pad, const float* __restrict__ state,
                             const uint32_t* __restrict__ tick, uint64_t env_offset, int obs_dim,
-                            float* __restrict__ out) {
+                            float* __restrict__ out, const float* __restrict__ lag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   RobotState S;
   load_state(state, n_pad, i, S);
+  if (obs_dim == UPKIE_OBS_DIM && P.spine_mode && lag) {
+    for (int j = 0; j < 6; ++j) {
+      float* o = out + size_t(i) * UPKIE_OBS_DIM + j * 5;
+      for (int k = 0; k < 3; ++k) o[k] = lag[size_t(UPKIE_LAG_OBS_REPLY + 3 * j + k) * n_pad + i];
+      o[3] = 20.0f; o[4] = 18.0f;
+    }
+    return;
+  }
   if (obs_dim == UPKIE_OBS_DIM) {
     float tq[6];
     const NoiseCtx nz{env_offset + uint64_t(i), tick[i]};
@@ -218,6 +245,13 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
   a.mode = mode;
   a.autoreset = h->autoreset;
   a.noise = h->P.joint_limits ? 2 : ((h->P.any_ctrl_noise || h->P.any_meas_noise || h->ext) ? 1 : 0);  // "extras" kernels
+  a.lag = nullptr;
+  if (h->P.spine_mode) {
+    if (mode != MODE_SERVOS) return fail(UPKIE_B200_EINVAL, "spine_mode supports UpkieServos steps only");
+    if (multicast) return fail(UPKIE_B200_EINVAL, "spine_mode has no in-kernel rollout transport");
+    a.noise = 3;
+    a.lag = h->lag;
+  }
   a.ext = h->ext;
   a.ext_local = h->ext_local;
   a.i0 = i0;
@@ -474,6 +508,10 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
   if (e == cudaSuccess) e = cudaMemset(h->err, 0, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(h->done_prev, 0, size_t(n_envs));
   if (e == cudaSuccess) e = cudaMemset(h->episode, 0, size_t(n_envs) * sizeof(uint32_t));
+  if (e == cudaSuccess && h->P.spine_mode) {
+    e = cudaMalloc(&h->lag, size_t(UPKIE_LAG_DIM) * h->n_pad * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(h->lag, 0, size_t(UPKIE_LAG_DIM) * h->n_pad * sizeof(float));
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->tick, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(h->tick, 0, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) {
@@ -495,7 +533,7 @@ void upkie_b200_destroy(void* handle) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->state); cudaFree(h->eps); cudaFree(h->mu); cudaFree(h->err); cudaFree(h->done_prev); cudaFree(h->episode);
-  cudaFree(h->tick); cudaFree(h->ext);
+  cudaFree(h->tick); cudaFree(h->ext); cudaFree(h->lag);
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_term); cudaFreeHost(h->h_trunc);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
   for (int k = 0; k < kHostStreams; ++k)
@@ -519,6 +557,7 @@ int upkie_b200_set_config(void* handle, const UpkieSimConfig* config) {
   std::string err;
   int rc = make_sim_params(h->model, *config, P, err);
   if (rc) return fail(rc, err);
+  if (P.spine_mode != h->P.spine_mode) return fail(UPKIE_B200_EINVAL, "set_config: spine_mode is fixed at creation");
   // kernels read the parameter block by value at launch: steps already enqueued keep the old one
   h->P = P;
   return UPKIE_B200_OK;
@@ -567,7 +606,7 @@ int upkie_b200_reset(void* handle, const uint8_t* mask, const float* init_state,
   const int rblock = 128;
   const int grid = (h->n + rblock - 1) / rblock;
   k_reset<<<grid, rblock, 0, s>>>(h->P, h->n, h->n_pad, h->state, mask, init_state, h->eps, h->mu, h->err,
-                                    h->done_prev, h->episode, seed, env_offset);
+                                    h->done_prev, h->episode, seed, env_offset, h->lag);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }
@@ -656,7 +695,7 @@ int upkie_b200_spine_obs(void* handle, float* out, void* stream) {
   Handle* h = as_handle(handle);
   if (!h || !out) return fail(UPKIE_B200_EINVAL, "spine_obs: invalid argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  k_spine_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, h->tick, h->env_offset, out);
+  k_spine_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, h->tick, h->env_offset, out, h->lag);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }
@@ -666,7 +705,7 @@ int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream) {
   if (!h || !obs) return fail(UPKIE_B200_EINVAL, "reset_obs: invalid argument");
   if (obs_dim != 4 && obs_dim != 6 && obs_dim != UPKIE_OBS_DIM) return fail(UPKIE_B200_EINVAL, "reset_obs: obs_dim must be 4, 6 or 30");
   CUDA_TRY(cudaSetDevice(h->device));
-  k_reset_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, h->tick, h->env_offset, obs_dim, obs);
+  k_reset_obs<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->P, h->n, h->n_pad, h->state, h->tick, h->env_offset, obs_dim, obs, h->lag);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }
@@ -685,6 +724,34 @@ int upkie_b200_set_state(void* handle, const float* state, void* stream) {
   if (!h || !state) return fail(UPKIE_B200_EINVAL, "set_state: invalid argument");
   CUDA_TRY(cudaSetDevice(h->device));
   k_set_state<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, h->n_pad, h->state, state);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+
+__global__ void k_lag_copy(int n, int n_pad, float* __restrict__ lag, float* __restrict__ rows, int to_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < UPKIE_LAG_DIM; ++k) {
+    if (to_rows) rows[size_t(i) * UPKIE_LAG_DIM + k] = lag[size_t(k) * n_pad + i];
+    else lag[size_t(k) * n_pad + i] = rows[size_t(i) * UPKIE_LAG_DIM + k];
+  }
+}
+
+int upkie_b200_get_lag(void* handle, float* lag_rows, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !lag_rows) return fail(UPKIE_B200_EINVAL, "get_lag: invalid argument");
+  if (!h->lag) return fail(UPKIE_B200_EINVAL, "get_lag: the handle was not created with spine_mode");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_lag_copy<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, h->n_pad, h->lag, lag_rows, 1);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
+}
+int upkie_b200_set_lag(void* handle, const float* lag_rows, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !lag_rows) return fail(UPKIE_B200_EINVAL, "set_lag: invalid argument");
+  if (!h->lag) return fail(UPKIE_B200_EINVAL, "set_lag: the handle was not created with spine_mode");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_lag_copy<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->n, h->n_pad, h->lag, const_cast<float*>(lag_rows), 0);
   CUDA_TRY(cudaGetLastError());
   return UPKIE_B200_OK;
 }

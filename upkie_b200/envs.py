@@ -225,6 +225,7 @@ def make_config(
     init_state: Optional[RobotState] = None,
     noise_seed: int = 0,
     joint_limits: Union[bool, int] = True,
+    spine_mode: bool = False,
 ) -> _abi.UpkieSimConfig:
     """Split of the keyword arguments the reference's factories forward to the
     backend, the servo env and the wrappers (``upkie/envs/entry_points.py:41-61,99-109``)."""
@@ -248,6 +249,8 @@ def make_config(
     # multibody PyBullet's importer builds (pybullet_backend.py:121). True -> 3 (the packed ten-row solver for the warps
     # that hold a robot on a bound); 2 = ten-row solver for every warp; False / 0 = no limit rows (round-1 behaviour)
     cfg.joint_limits = 3 if joint_limits is True else int(joint_limits)
+    # timing of the C++ Bullet spine in simulate() mode instead of PyBulletBackend's (include/upkie_b200.h: spine_mode)
+    cfg.spine_mode = 1 if spine_mode else 0
     cfg.max_gain_scale = max_gain_scale
     cfg.fall_pitch = fall_pitch
     cfg.leg_gain_scale = leg_gain_scale
@@ -289,6 +292,7 @@ class B200VectorEnv(VectorEnv):
         noise_seed: int = 0,
         joint_limits: Union[bool, int] = True,
         copy: bool = True,
+        spine_mode: bool = False,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")
@@ -314,9 +318,12 @@ class B200VectorEnv(VectorEnv):
             config = make_config(
                 frequency, nb_substeps, torque_control_kp, torque_control_kd, joint_properties, max_gain_scale,
                 fall_pitch, leg_gain_scale, max_ground_velocity, max_yaw_velocity, self.init_state, noise_seed,
-                joint_limits,
+                joint_limits, spine_mode,
             )
         self.config = config
+        if self.config.spine_mode and env_type != "servos":
+            raise UpkieException("spine_mode is available for env_type='servos' (the wrappers of a spine read observer "
+                                 "outputs: feed info['spine_observation'] to upkie_b200.observers.ObserverPipeline)")
         (
             servo_act, servo_obs, self._neutral_action, self._max_action, self._min_action,
         ) = make_servo_spaces(self.model, max_gain_scale)
@@ -418,7 +425,8 @@ class B200VectorEnv(VectorEnv):
             n = self.num_envs
             const = getattr(self, "_obs_constants", None)
             if const is None:
-                temperature = np.full((n, 1), 42.0, dtype=np.float32)
+                # pybullet_backend.py:471 (42.0) / BulletInterface.cpp:70 in spine mode (20.0)
+                temperature = np.full((n, 1), 20.0 if self.config.spine_mode else 42.0, dtype=np.float32)
                 voltage = np.full((n, 1), 18.0, dtype=np.float32)
                 temperature.flags.writeable = False
                 voltage.flags.writeable = False

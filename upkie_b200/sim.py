@@ -316,6 +316,17 @@ class UpkieSim:
         check(lib().upkie_b200_get_state(self._h, _ptr(out), self._stream()))
         return out
 
+    def get_lag(self) -> torch.Tensor:
+        """Spine mode: the lag records ``[N, LAG_DIM]`` (servo replies of the last two cycles, last IMU reading, the
+        last assembled observation; ``include/upkie_b200.h`` ``UPKIE_LAG_*``)."""
+        out = torch.empty((self.n, _abi.LAG_DIM), dtype=torch.float32, device=self.device)
+        check(lib().upkie_b200_get_lag(self._h, _ptr(out), self._stream()))
+        return out
+
+    def set_lag(self, lag: torch.Tensor) -> None:
+        self._check_tensor(lag, (self.n, _abi.LAG_DIM), name="lag")
+        check(lib().upkie_b200_set_lag(self._h, _ptr(lag), self._stream()))
+
     def set_state(self, state: torch.Tensor) -> None:
         self._check_tensor(state, (self.n, _abi.STATE_DIM), name="state")
         check(lib().upkie_b200_set_state(self._h, _ptr(state), self._stream()))
