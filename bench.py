@@ -39,7 +39,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # algorithmic bytes per env-step (DESIGN.md "Roofline")
-B_ALG = {"servos": 542 + 284 + 3 * 4 * 2, "pendulum": 346 + 3 * 4 * 2 + 16, "mpc": 157}
+# + 24 B: three IMU-acceleration floats kept in the state row; + 32 B: four friction impulses (get_contact_points)
+B_ALG = {"servos": 542 + 284 + 3 * 4 * 2 + 4 * 4 * 2, "pendulum": 346 + 3 * 4 * 2 + 16 + 4 * 4 * 2, "mpc": 157}
 # compact rollout records: observation rows 72 B instead of 120 B, no reward (4 B) / truncated (1 B) stores
 B_ALG_SERVOS_COMPACT = B_ALG["servos"] - 48 - 5
 N_ACTION_BUFFERS = 16

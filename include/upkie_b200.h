@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UPKIE_B200_ABI_VERSION 3
+#define UPKIE_B200_ABI_VERSION 4
 
 #define UPKIE_NJ 6 /* actuated joints */
 #define UPKIE_NB 7 /* moving bodies: base lump + 2 x (upper leg, lower leg, wheel) */
@@ -84,7 +84,8 @@ extern "C" {
 #define UPKIE_ST_CONTACT 40     /* floor contact seen by the last collision pass (0/1) */
 #define UPKIE_ST_IMU_ACC 41     /* world-frame IMU linear acceleration of the last observation [3] (pybullet_backend.py:405-408) */
 #define UPKIE_ST_CONTACT_IMPULSE 44 /* normal contact impulses of the last substep (left, right wheel): PGS warm start */
-#define UPKIE_STATE_DIM 46
+#define UPKIE_ST_FRICTION_IMPULSE 46 /* friction impulses of the last substep: rolling / lateral direction of the left wheel, then of the right wheel [4] (what getContactPoints reports as lateralFriction1 / 2, pybullet_backend.py:696-709) */
+#define UPKIE_STATE_DIM 50
 
 /* spine_obs[N][UPKIE_SPINE_DIM]: the observation dictionary of
  * PyBulletBackend.get_spine_observation (pybullet_backend.py:313-331), flattened. */

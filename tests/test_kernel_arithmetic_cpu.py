@@ -442,7 +442,7 @@ def test_wheel_contact_points_follow_the_collision_pass(model, oracle_lib):
         assert (len(pts) > 0) == (rows[i, _abi.ST_CONTACT] > 0.5), i
         agree += 1
         for side, p, force in pts:
-            assert p[2] < 0.02 and force >= 0.0
+            assert p[2] < 0.02 and force[2] >= 0.0
     assert agree > 0.9 * n
     # a robot standing still on its wheels
     osim1 = oracle_lib.OracleSim(model, cfg, 1)
@@ -455,8 +455,9 @@ def test_wheel_contact_points_follow_the_collision_pass(model, oracle_lib):
         osim1.step_servos(hold)
     pts = wheel_contact_points(model, osim1.get_state()[0], h)
     assert [s for s, _, _ in pts] == [0, 1]
-    total = sum(f for _, _, f in pts)
+    total = sum(f[2] for _, _, f in pts)
     assert abs(total - float(np.sum(model.mass)) * cfg.gravity) < 0.15 * float(np.sum(model.mass)) * cfg.gravity
+    assert all(np.linalg.norm(f[:2]) < 0.05 * f[2] for _, _, f in pts)  # at rest on flat ground: hardly any friction
     (_, pl, _), (_, pr, _) = pts
     assert abs(pl[2]) < 5e-3 and abs(pr[2]) < 5e-3 and abs((pl[1] - pr[1]) - model.wheel_base) < 1e-3
     from upkie_b200.model import contact_points_from_state
@@ -464,10 +465,42 @@ def test_wheel_contact_points_follow_the_collision_pass(model, oracle_lib):
     row = osim1.get_state()[0]
     contacts = contact_points_from_state(model, row, cfg)
     assert [c.link_name for c in contacts] == ["left_wheel_tire", "right_wheel_tire"]
-    assert contacts[0].force_in_world[2] == pytest.approx(pts[0][2]) and contacts[0].force_in_world[0] == 0.0
+    assert np.allclose(contacts[0].force_in_world, pts[0][2])
     assert [c.link_name for c in contact_points_from_state(model, row, cfg, "right_wheel_tire")] == ["right_wheel_tire"]
     assert contact_points_from_state(model, row, cfg, "imu") == [] == contact_points_from_state(model, row, cfg, "nope")
     assert "PointContact(link_name='left_wheel_tire'" in repr(contacts[0])
+
+
+def test_contact_points_report_the_friction_force(model, oracle_lib):
+    """``get_contact_points`` sums normal force and the two friction components (pybullet_backend.py:696-709). A robot
+    held upright by its servos and pushed sideways with 10 N (below mu W = 52 N) stays put: the tires' friction forces
+    balance the push, the normal forces the weight - for the oracle and for the kernels' arithmetic."""
+    from upkie_b200.model import contact_points_from_state
+
+    cfg = _abi.default_sim_config()
+    push = np.zeros((1, 7, 3))
+    push[0, 0] = [0.0, 10.0, 0.0]  # newtons on the base, world frame
+    hold = np.zeros((1, 6, 6))
+    hold[:, :, 3], hold[:, :, 4], hold[:, :, 5] = 1.0, 1.0, np.asarray(model.tau_max)
+    init = np.zeros((1, _abi.INIT_DIM))
+    init[:, 2], init[:, 3] = 0.6, 1.0
+    osim = oracle_lib.OracleSim(model, cfg, 1)
+    osim.reset(init)
+    hs = HostSim(model, cfg, 1)
+    hs.reset(init.astype(np.float32))
+    osim.set_external_forces(push)
+    for _ in range(60):
+        osim.step_servos(hold)
+        hs.step_servos_ext(hold.astype(np.float32), push.astype(np.float32))
+    weight = float(np.sum(model.mass)) * cfg.gravity
+    for row in (osim.get_state()[0], hs.state[0]):
+        contacts = contact_points_from_state(model, row, cfg)
+        assert len(contacts) == 2
+        total = sum(c.force_in_world for c in contacts)
+        assert abs(total[1] + 10.0) < 1.5, total   # friction balances the push
+        assert abs(total[2] - weight) < 0.15 * weight
+        assert abs(total[0]) < 2.0
+        assert abs(row[8]) < 5e-3  # and the robot does not slide (base y velocity)
 
 
 def test_imu_uncertainty_known_answers(model):

@@ -388,8 +388,8 @@ def test_resting_contact_is_the_implicit_spring_of_the_tire(model, oracle_lib):
         points = wheel_contact_points(model, row, h)
         assert [side for side, _, _ in points] == [0, 1]
         for _, position, force in points:
-            assert force == pytest.approx(weight / 2, rel=0.01)  # the robot leans 0.03 rad by now: not exactly half
-            assert -position[2] == pytest.approx(force / cfg.contact_stiffness, rel=tol)
+            assert force[2] == pytest.approx(weight / 2, rel=0.01)  # the robot leans 0.03 rad by now: not exactly half
+            assert -position[2] == pytest.approx(force[2] / cfg.contact_stiffness, rel=tol)
 
 
 def test_lateral_push_obeys_coulomb_friction(model, oracle_lib):

@@ -46,7 +46,8 @@ def test_reset_sampling_through_the_reference_env(cases, model, oracle_lib):
         osim = oracle_lib.OracleSim(model, cfg, 1, threads=1)
         row = _init_state().sample_state(np.random.default_rng(case["seed"])).to_row()
         osim.reset(row.reshape(1, -1))
-        assert np.allclose(osim.get_state()[0], np.asarray(case["state_after_reset"]), rtol=0, atol=1e-12), case["kind"]
+        ref_row = np.asarray(case["state_after_reset"])  # recorded before the friction impulses joined the row (46 words)
+        assert np.allclose(osim.get_state()[0][:len(ref_row)], ref_row, rtol=0, atol=1e-12), case["kind"]
 
 
 @pytest.mark.parametrize("index", [0, 1, 2])
@@ -94,7 +95,9 @@ def test_kernel_arithmetic_follows_the_reference_wrappers(cases, model, index):
     act_dim = 2 if case["kind"] == "gyropod" else 1
     cfg = _abi.default_sim_config()
     hs = HostSim(model, cfg, 1)
-    hs.set_state(np.asarray(case["state_after_reset"], dtype=np.float32).reshape(1, -1))
+    row = np.zeros((1, _abi.STATE_DIM), dtype=np.float32)
+    row[0, :len(case["state_after_reset"])] = np.asarray(case["state_after_reset"], dtype=np.float32)
+    hs.set_state(row)
     worst = 0.0
     fell_at = None
     for t, (a, o, term) in enumerate(zip(case["actions"], case["obs"], case["terminated"])):

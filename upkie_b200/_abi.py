@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LAG_REPLY1, LAG_REPLY2, LAG_IMU, LAG_OBS_REPLY, LAG_OBS_IMU, LAG_OBS_BASE, LAG_OBS_CONTACT, LAG_DIM = 0, 18, 36, 49, 67, 80, 90, 91  # spine-mode lag record (include/upkie_b200.h)
 
 NJ = 6
@@ -41,7 +41,7 @@ WHEEL_JOINTS = (2, 5)
 ACT_DIM = 36
 OBS_DIM = 30
 INIT_DIM = 25
-STATE_DIM = 46
+STATE_DIM = 50
 SPINE_DIM = 62
 
 # init_state offsets
@@ -51,6 +51,7 @@ ST_POS, ST_QUAT, ST_LINVEL, ST_ANGVEL, ST_Q, ST_QD = 0, 3, 7, 10, 13, 19
 ST_PREV_IMU_VEL, ST_TORQUE, ST_LEG_TARGET, ST_YAW, ST_YAW_VEL, ST_CONTACT = 25, 28, 34, 38, 39, 40
 ST_IMU_ACC = 41
 ST_CONTACT_IMPULSE = 44
+ST_FRICTION_IMPULSE = 46  # rolling / lateral friction impulses of the last substep, left wheel then right wheel
 # spine observation offsets
 SP_BASE_ANGVEL, SP_BASE_LINVEL, SP_PITCH, SP_ROT = 0, 3, 6, 7
 SP_IMU_QUAT, SP_IMU_ANGVEL, SP_IMU_LINACC, SP_IMU_RAWACC = 16, 20, 23, 26

@@ -227,6 +227,7 @@ UPKIE_HD void state_from_row(const float* r, RobotState& S) {
   S.contact = r[UPKIE_ST_CONTACT];
   S.lam_n[0] = r[UPKIE_ST_CONTACT_IMPULSE];
   S.lam_n[1] = r[UPKIE_ST_CONTACT_IMPULSE + 1];
+  for (int k = 0; k < 4; ++k) S.lam_t[k] = r[UPKIE_ST_FRICTION_IMPULSE + k];
 }
 
 UPKIE_HD void state_to_row(const RobotState& S, float* r) {
@@ -251,6 +252,7 @@ UPKIE_HD void state_to_row(const RobotState& S, float* r) {
   r[UPKIE_ST_CONTACT] = S.contact;
   r[UPKIE_ST_CONTACT_IMPULSE] = S.lam_n[0];
   r[UPKIE_ST_CONTACT_IMPULSE + 1] = S.lam_n[1];
+  for (int k = 0; k < 4; ++k) r[UPKIE_ST_FRICTION_IMPULSE + k] = S.lam_t[k];
 }
 
 }  // namespace upkie_b200

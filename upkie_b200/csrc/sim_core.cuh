@@ -111,6 +111,7 @@ struct RobotState {
   float contact;
   float imu_acc[3];  // world-frame IMU acceleration of the last observation
   float lam_n[2];    // normal contact impulses of the last substep (warm start)
+  float lam_t[4];    // friction impulses of the last substep: (rolling, lateral) of the left wheel, of the right wheel
 };
 
 // packed upper-triangular index of a symmetric 6x6
@@ -645,6 +646,8 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
   if (!warp_any(actL || actR)) {
     S.lam_n[0] = 0.f;
     S.lam_n[1] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) S.lam_t[k] = 0.f;
     phase_sync();  // 3
     phase_sync();  // 4
     phase_sync();  // 5
@@ -759,6 +762,8 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
     pgs_solve(P, W, rhs, lam, mu, hiL, hiR, pgs_atol, warp_any);
     S.lam_n[0] = lam[0];
     S.lam_n[1] = lam[1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) S.lam_t[k] = lam[2 + k];
     // apply the total wheel impulses
     float fL[6], fR[6];
 #pragma unroll
@@ -1206,6 +1211,8 @@ UPKIE_HD void reset_pose(RobotState& S, const float init[UPKIE_INIT_DIM]) {
   }
   S.lam_n[0] = 0.f;  // new contact points carry no cached impulse
   S.lam_n[1] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) S.lam_t[k] = 0.f;
 }
 
 // UpkieGyropod.reset (upkie_gyropod.py:216-244), after the reset's stepSimulation + observation

@@ -550,12 +550,15 @@ UPKIE_HD void limit_contact_solve(const SimParams& P, RobotState& S, const LegCa
   for (int i = 0; i < 6; ++i) { fw[0][i] = 0.f; fw[1][i] = 0.f; g[i] = 0.f; }
   S.lam_n[0] = 0.f;
   S.lam_n[1] = 0.f;
+  for (int k = 0; k < 4; ++k) S.lam_t[k] = 0.f;
+  int nfric[2] = {0, 0};
   for (int k = 0; k < n; ++k) {
     if (kind[k] == 2) {
       g[joint[k]] += dirj[k] * lam[k];
     } else {
       for (int i = 0; i < 6; ++i) fw[side[k]][i] += J[k][i] * lam[k];
       if (kind[k] == 0) S.lam_n[side[k]] = lam[k];
+      else S.lam_t[2 * side[k] + nfric[side[k]]++] = lam[k];  // rolling row first, then lateral (add_contact_row order)
     }
   }
   impulse_response_generic(P, lc, IA0, fw, g, da0, dqd, aw);
@@ -634,6 +637,8 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
   if (!warp_any(actL || actR || any_limit)) {
     S.lam_n[0] = 0.f;
     S.lam_n[1] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) S.lam_t[k] = 0.f;
     phase_sync();  // 3
     phase_sync();  // 4
     phase_sync();  // 5
@@ -806,6 +811,8 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
   }
   S.lam_n[0] = lam[4];
   S.lam_n[1] = lam[5];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) S.lam_t[k] = lam[6 + k];
   f2 F[6];
   {
     const f2 ln = mk2(lam[4], lam[5]), l1 = mk2(lam[6], lam[8]), l2 = mk2(lam[7], lam[9]);
@@ -929,6 +936,8 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   } else if (!warp_any(actL || actR)) {
     S.lam_n[0] = 0.f;
     S.lam_n[1] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) S.lam_t[k] = 0.f;
     phase_sync();  // 3
     phase_sync();  // 4
     phase_sync();  // 5
@@ -1102,6 +1111,8 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
     }
     S.lam_n[0] = lam[0];
     S.lam_n[1] = lam[1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) S.lam_t[k] = lam[2 + k];
     // apply the total wheel impulses: both wheels up their legs at once, one base solve, both legs down
     f2 F[6];
     {

@@ -363,7 +363,10 @@ def wheel_contact_points(model, state_row, substep_dt: float, breaking_threshold
     Restates the collision pass of the step kernel on the host (``physics_substep_paired``, sim_pair.cuh: the
     lowest point of the tire circle against the plane z = 0, a contact while it is closer than Bullet's contact
     breaking threshold) and reads the normal impulses the last substep applied (``UPKIE_ST_CONTACT_IMPULSE``).
-    Returns ``[(side, position_in_world[3], normal_force), ...]``; ``side`` is 0 (left) or 1 (right)."""
+    Returns ``[(side, position_in_world[3], force_in_world[3]), ...]``; ``side`` is 0 (left) or 1 (right). The force is
+    the one the ground exerted on the tire during the last substep: normal impulse along +z and the two friction
+    impulses (``UPKIE_ST_FRICTION_IMPULSE``) along the contact's rolling and lateral directions - what
+    ``getContactPoints`` reports as normalForce, lateralFriction1 / 2 (``pybullet_backend.py:696-709``)."""
     row = np.asarray(state_row, dtype=float)
     pos = row[_abi.ST_POS:_abi.ST_POS + 3]
     w, x, y, z = row[_abi.ST_QUAT:_abi.ST_QUAT + 4]
@@ -391,7 +394,14 @@ def wheel_contact_points(model, state_row, substep_dt: float, breaking_threshold
         if p_world[2] >= breaking_threshold:
             continue
         impulse = float(row[_abi.ST_CONTACT_IMPULSE + side])
-        out.append((side, p_world, impulse / substep_dt))
+        # friction directions of the kernels (sim_pair.cuh): t1 = s (zb.z, 0, -zb.x) / |.| (rolling), t2 = s (zb x t1)
+        # (lateral), s = sign of the wheel's joint axis; both lie in the ground plane
+        sgn = float(model.joint_axis[3 * side + 2][1])
+        t1 = sgn * np.array([zb[2], 0.0, -zb[0]]) / n_xz
+        t2 = np.cross(zb, t1)
+        lam_t = row[_abi.ST_FRICTION_IMPULSE + 2 * side:_abi.ST_FRICTION_IMPULSE + 2 * side + 2] if len(row) > _abi.ST_FRICTION_IMPULSE else (0.0, 0.0)
+        force = (impulse * np.array([0.0, 0.0, 1.0]) + R @ (float(lam_t[0]) * t1 + float(lam_t[1]) * t2)) / substep_dt
+        out.append((side, p_world, force))
     return out
 
 TIRE_LINKS = ("left_wheel_tire", "right_wheel_tire")
@@ -400,14 +410,14 @@ TIRE_LINKS = ("left_wheel_tire", "right_wheel_tire")
 def contact_points_from_state(model, state_row, config, link_name=None):
     """``PyBulletBackend.get_contact_points`` (``pybullet_backend.py:660-716``) for one robot from its state row:
     ``PointContact`` instances on ``left_wheel_tire`` / ``right_wheel_tire``, filtered by ``link_name``. A link
-    without simulated contacts, or one the robot does not have, yields ``[]`` like the reference. ``force_in_world``
-    holds the normal force of the last substep (friction components: DESIGN.md section 8)."""
+    without simulated contacts, or one the robot does not have, yields ``[]`` like the reference. ``force_in_world`` =
+    normal + two friction components of the last substep, as the reference sums them (``pybullet_backend.py:696-709``)."""
     if link_name is not None and link_name not in TIRE_LINKS:
         return []
     h = float(config.dt) / int(config.nb_substeps)
     contacts = wheel_contact_points(model, state_row, h, breaking_threshold=float(config.contact_breaking_threshold))
     return [
-        PointContact(TIRE_LINKS[side], position, np.array([0.0, 0.0, force]))
+        PointContact(TIRE_LINKS[side], position, np.asarray(force, dtype=float))
         for side, position, force in contacts
         if link_name is None or TIRE_LINKS[side] == link_name
     ]
