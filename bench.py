@@ -397,7 +397,7 @@ def main():
     value = total_units / (t_ms * 1e-3)
     b_alg = B_ALG_SERVOS_COMPACT if config.get("rollout_record", "").startswith("compact") else B_ALG[args.workload]
     achieved = b_alg * n_per_gpu / (kernel_ms * 1e-3) / 1e9  # GB/s per GPU, dominant kernel
-    side = ncu_sidecar(args.workload, config, n_per_gpu)
+    side = ncu_sidecar(args.workload, config, n_per_gpu, "early" if W + K <= 64 else "steady")
     line = {
         "metric": "env-steps/sec" if args.workload != "mpc" else "qp-solves/sec",
         "value": value,
@@ -467,13 +467,15 @@ def main():
         dist.destroy_process_group()
 
 
-def ncu_sidecar(workload, config, n_per_gpu):
+def ncu_sidecar(workload, config, n_per_gpu, regime):
     """Per-launch DRAM bytes and warp instructions per env-step of the benchmarked kernel, from the sidecar that
-    tools/ncu_summary.py writes from an `ncu --set full` capture, valid only for the build it was captured on."""
+    tools/ncu_summary.py writes from an `ncu --set full` capture, valid only for the build it was captured on.
+    `regime`: the work per env-step depends on where the episodes are - "early" (the driver's 25 steps after a reset:
+    robots still falling from their initial pitch) or "steady" (falling, tumbling, resetting mix after ~100 steps)."""
     from upkie_b200 import build as b
 
     path = os.path.join(ROOT, "profiles", "ncu_sidecar.json")
-    key = f"{workload}:limits{config.get('joint_limit_solver', 0)}:n{n_per_gpu}"
+    key = f"{workload}:limits{config.get('joint_limit_solver', 0)}:n{n_per_gpu}:{regime}"
     try:
         with open(path) as f:
             data = json.load(f)
@@ -536,7 +538,30 @@ def other_workloads(torch, dev, model):
                                      "workload": "BASELINE configs[3]" + (" at the reference's default horizon" if H == 50 else "")}
     except Exception as exc:  # secondary lines must never take the headline down
         out["error"] = repr(exc)
+    out["servos_65536_exact_mode"] = exact_mode_line()
     return out
+
+
+def exact_mode_line():
+    """The servos workload on the exact-arithmetic companion library (no --use_fast_math, upkie_b200/build.py) with
+    pgs_tolerance = 0 (50 sweeps every substep, as the oracle and Bullet): what the two shortcuts of the headline
+    kernel buy. Own process (a second copy of the library cannot be the package's singleton), device buffers, full
+    records (the exact library has the TILE=0 kernels only)."""
+    try:
+        from upkie_b200 import build as b
+
+        if not os.path.exists(b.EXACT_LIB_PATH):
+            return {"unavailable": "libupkie_b200_exact.so not built"}
+        env = dict(os.environ, UPKIE_B200_LIB=b.EXACT_LIB_PATH, UPKIE_BENCH_PGS_TOL="0", UPKIE_BENCH_ROLLOUT="full",
+                   UPKIE_BENCH_DEVICE_ONLY="1")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10",
+                            "--no-cpu-baseline", "--no-other-workloads"], env=env, capture_output=True, text=True, timeout=300)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"metric": "env-steps/sec", "value": j["value"], "ms_per_step": j["ms_per_step"],
+                "kernel_ms_median": j["roofline"]["kernel_ms"],
+                "workload": "headline workload, exact arithmetic: no fast-math, pgs_tolerance 0 (50 sweeps), full 126 B records"}
+    except Exception as exc:
+        return {"error": repr(exc)}
 
 
 def bench_env(args, torch, dist, dev, rank, world, model, K, W):
@@ -720,6 +745,10 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     t_ms = float(t.item()) / K
     launches = env.sim.launches - launches0
 
+    if os.environ.get("UPKIE_BENCH_DEVICE_ONLY") == "1":  # exact-mode companion run: no host-buffer kernels in that library
+        config = {"workload": "device-only run", "envs_per_gpu": n, "rollout_record": "full",
+                  "joint_limit_solver": int(getattr(env.config, "joint_limits", 0))}
+        return n * K, t_ms * K, kernel_ms, {"value": None}, launches, clk.summary(), config, n
     # e2e through the public VectorEnv API with HOST buffers (H2D + kernel + D2H per step)
     # this step's inputs live in pinned host memory (4 rotating buffers), outputs land in pinned memory
     host_acts = [a.cpu().pin_memory().numpy() for a in acts[:4]]

@@ -46,6 +46,41 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+# ---- exact-arithmetic build (test / measurement companion of the product library) ------------------------------------
+# Same sources WITHOUT --use_fast_math (IEEE division / sqrt / sincos, no flush-to-zero), device-buffer kernels only
+# (TILE=0: plain, extras, extras + limits); the other launchers are stubs that return cudaErrorNotSupported. Used by
+# tests/test_gpu_exact_mode.py and bench.py's `exact_mode` line together with pgs_tolerance = 0 (exactly 50 sweeps):
+# what the two shortcuts of the timed kernel cost in accuracy and buy in time.
+EXACT_LIB_PATH = os.path.join(_HERE, "libupkie_b200_exact.so")
+EXACT_SOURCES = ["upkie_b200.cu", "step_device.cu", "step_device_limits.cu", "exact_stubs.cu"]
+EXACT_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math"] + ["-DUPKIE_EXACT_BUILD=1"]
+
+
+def exact_is_stale() -> bool:
+    if not os.path.exists(EXACT_LIB_PATH):
+        return True
+    t = os.path.getmtime(EXACT_LIB_PATH)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS + ["exact_stubs.cu"])
+
+
+def build_exact(force: bool = False) -> str:
+    if not force and not exact_is_stale():
+        return EXACT_LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objdir = os.path.join(_HERE, "build", "exact")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for src in EXACT_SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc] + EXACT_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]))
+    failed = [src for src, p in zip(EXACT_SOURCES, procs) if p.wait() != 0]
+    if failed:
+        raise RuntimeError(f"nvcc (exact build) failed on {failed}")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", EXACT_LIB_PATH] + objs)
+    return EXACT_LIB_PATH
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA library (cross-compiles without a GPU)."""
     if not force and not is_stale():
