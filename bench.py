@@ -649,6 +649,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     # stalls of the simulation stream waiting for the gather of the buffer it is about to overwrite
     stall_events = []
     counters = {"gathers": 0}
+    pending = {"push": None}
+    # UPKIE_BENCH_PUSH=now: the immediate in-kernel transports (rows leave at the END of the launch that produced them)
+    deferred = os.environ.get("UPKIE_BENCH_PUSH", "deferred") != "now"
 
     def wait_for(cur, record):
         """The gather that last read buffer `cur` must be done before its slots are overwritten."""
@@ -674,9 +677,14 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         if k % T_roll == 0:
             wait_for(cur, timed)
         a = acts[k % N_ACTION_BUFFERS]
-        if gather_mode == "multicast":
-            # the kernel's rows go to the NVSwitch multicast address of this rank's slot and land in every GPU's
-            # buffer; a barrier per rollout replaces the gather
+        if gather_mode in ("multicast", "peerstore") and deferred:
+            # this step's rows go to the local slot; the PROLOGUE of the same launch sends the previous step's rows to
+            # every GPU (NVSwitch multicast store, or stores into the peers' buffers), so that their NVLink latency
+            # hides under the simulation; a barrier per rollout replaces the gather
+            env.sim.step_servos_push(a, *rollouts[cur].local_slot(k), pending["push"])
+            pending["push"] = rollouts[cur].push_descriptor(k, multicast=gather_mode == "multicast")
+        elif gather_mode == "multicast":
+            # immediate form: the kernel's rows go to the multicast address of this rank's slot at the end of the launch
             env.sim.step_servos_multicast(a, *rollouts[cur].multicast_slot(k))
         elif gather_mode == "peerstore":
             # no multicast object: the kernel stores each row into every peer's buffer over NVLink itself
@@ -689,6 +697,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
             if timed:
                 counters["gathers"] += 1
             if gather_mode in ("multicast", "peerstore"):
+                if deferred and pending["push"] is not None:
+                    env.sim.push_rows(pending["push"])  # the rollout's last rows have no later launch to ride on
+                    pending["push"] = None
                 rollouts[cur].publish()
                 works[cur] = True
             elif gather_mode == "peer":
@@ -790,10 +801,11 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     transport = {
         "none": "",
         "peer": "; rollout buffer pushed to the peers' symmetric-memory buffers by the copy engines over NVLink",
-        "multicast": "; the step kernel stores its rollout rows to the NVSwitch multicast address of the symmetric "
-                     "rollout buffer (multimem.st): every GPU receives them, one barrier per rollout, no collective kernel",
-        "peerstore": "; the step kernel stores its rollout rows into every peer's symmetric rollout buffer over "
-                     "NVLink, one barrier per rollout, no collective kernel",
+        "multicast": "; the step kernel sends the previous step's rollout rows to the NVSwitch multicast address of the "
+                     "symmetric rollout buffer (multimem.st in the launch's prologue): every GPU receives them, one "
+                     "barrier per rollout, no collective kernel",
+        "peerstore": "; the step kernel stores the previous step's rollout rows into every peer's symmetric rollout "
+                     "buffer over NVLink (in the launch's prologue), one barrier per rollout, no collective kernel",
         "nccl": "; NCCL all_gather_into_tensor of the rollout buffer",
     }[gather_mode]
     config = {
@@ -819,7 +831,8 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     }
     if world > 1:
         config["gather"] = {
-            "transport": gather_mode, "rollout_steps": T_roll, "gathers_in_timed_region": gathers,
+            "transport": gather_mode + (" (deferred push)" if deferred and gather_mode in ("multicast", "peerstore") else ""),
+            "rollout_steps": T_roll, "gathers_in_timed_region": gathers,
             "bytes_per_rank_and_gather": int(rollouts[0].nbytes),
             # time the simulation stream spent waiting for a gather before re-using its buffer, inside the timed region
             "sim_stream_stall_ms_total": gather_stall_ms,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UPKIE_B200_ABI_VERSION 4
+#define UPKIE_B200_ABI_VERSION 5
 
 #define UPKIE_NJ 6 /* actuated joints */
 #define UPKIE_NB 7 /* moving bodies: base lump + 2 x (upper leg, lower leg, wheel) */
@@ -390,6 +390,28 @@ int upkie_b200_step_servos_multicast(void* handle, const float* action, float* o
 #define UPKIE_MAX_PEERS 8
 int upkie_b200_step_servos_peers(void* handle, const float* action, float* const* obs_ptrs,
                                  uint8_t* const* terminated_ptrs, int n_peers, void* stream);
+
+/* Deferred form of the two transports above (what bench.py runs): this step's compact rows and `terminated` bytes go
+ * to LOCAL buffers (obs / terminated: this rank's slot of the step, plain stores), and the prologue of the same launch
+ * sends the rows of an EARLIER step - read from src_obs / src_terminated, this rank's local slot of that step - to
+ * every GPU: to the multicast addresses mc_obs / mc_terminated when n_peers == 0, else into the n_peers buffers
+ * peer_obs[p] / peer_terminated[p]. The remote stores then drain under the ~0.1 ms of simulation instead of holding up
+ * the completion of the launch (measured at 8 GPUs: the immediate form costs 8 % of kernel time at 20-step runs).
+ * src_obs == NULL: nothing to send (first step). upkie_b200_push_rows sends a slot on its own (last step of a
+ * rollout, before the ranks' barrier). Alignment as above; n_envs a multiple of 32. */
+typedef struct UpkiePush {
+  const float* src_obs;
+  const uint8_t* src_terminated;
+  float* mc_obs;
+  uint8_t* mc_terminated;
+  float* peer_obs[UPKIE_MAX_PEERS];
+  uint8_t* peer_terminated[UPKIE_MAX_PEERS];
+  int32_t n_peers;
+  int32_t reserved;
+} UpkiePush;
+int upkie_b200_step_servos_push(void* handle, const float* action, float* obs, uint8_t* terminated,
+                                const UpkiePush* push, void* stream);
+int upkie_b200_push_rows(void* handle, const UpkiePush* push, void* stream);
 
 /* Same calls with HOST buffers and a stream synchronisation inside the call
  * (the `e2e` path of bench.py). When every buffer is pinned and mapped

@@ -227,3 +227,114 @@ def test_spine_mode_vector_env_and_fused_autoreset(model):
         prev_term = term.copy()
     assert seen_reset.any()
     env.close()
+
+
+@pytest.mark.gpu
+def test_spine_pipeline_balances_on_lagged_observations(model):
+    """The whole spine of `spines/bullet_spine.cpp --pipeline wheel_balancer` on the device, with the spine's timing:
+    simulator in spine mode (one cycle per agent step at 1 kHz, `--nb-substeps 1`) -> lagged spine observation ->
+    observer pipeline (BaseOrientation, FloorContact, WheelOdometry) -> WheelStopper + WheelBalancer -> servo action.
+    Rows a14, a15, f1, f2 together: 256 robots started with up to 0.15 rad of pitch are upright after the transient."""
+    import torch
+
+    from upkie_b200.controllers import WheelBalancerPipeline
+    from upkie_b200.observers import ObserverPipeline
+    from upkie_b200.sim import UpkieSim
+
+    n = 256
+    cfg = _cfg(nb_substeps=1, frequency=1000.0)
+    sim = UpkieSim(n, model=model, config=cfg)
+    init = np.zeros((n, _abi.INIT_DIM), dtype=np.float32)
+    init[:, 2] = 0.58
+    pitch0 = np.random.default_rng(3).uniform(-0.15, 0.15, n)
+    init[:, 3], init[:, 5] = np.cos(pitch0 / 2), np.sin(pitch0 / 2)
+    sim.reset(init_state=torch.from_numpy(init).cuda())
+    obs_pipe = ObserverPipeline(n, model=model, spine_frequency=1000.0)
+    wbc = _abi.default_wheel_balancer_config(1000.0)
+    wbc.wheel_radius = float(model.wheel_radius)
+    wb = WheelBalancerPipeline(n, config=wbc)
+    neutral = torch.zeros((n, 6, 6), device="cuda")
+    neutral[:, :, 3:5] = 1.0
+    neutral[:, :, 5] = torch.tensor(model.tau_max, device="cuda", dtype=torch.float32)
+    worst = []
+    for k in range(3000):  # 3 s of spine cycles
+        rows = obs_pipe.step(sim.spine_obs())  # the observation the spine assembled in its last cycle (lagged)
+        act = wb.step(rows, neutral.clone())
+        sim.step_servos(act)
+        if k % 50 == 0:
+            worst.append(rows[:, _abi.OBSV_PITCH].abs().max().item())
+    st = sim.get_state().cpu().numpy()
+    assert max(worst[20:]) < 0.3, max(worst[20:])
+    assert (st[:, _abi.ST_POS + 2] > 0.4).all()
+
+
+@pytest.mark.gpu
+def test_peer_store_step_on_one_gpu_equals_the_compact_step(model):
+    """`upkie_b200_step_servos_peers` (the in-kernel rollout transport without a multicast object) with this GPU's own
+    buffer as the only "peer": same rows and `terminated` bytes as `upkie_b200_step_servos_compact`, bit for bit; two
+    peers = two copies. (The multi-GPU form is validated by tools/multicast_check.py on 2 and 8 GPUs.)"""
+    import torch
+
+    from upkie_b200.sim import UpkieSim
+
+    n = 4096
+    cfg = _abi.default_sim_config()
+    sims = [UpkieSim(n, model=model, config=cfg) for _ in range(2)]
+    for s_ in sims:
+        s_.reset(seed=4)
+    act = torch.from_numpy(random_servo_actions(n, model, seed=9).astype(np.float32)).cuda()
+    bufs = [torch.zeros(n * 18, dtype=torch.float32, device="cuda") for _ in range(2)]
+    terms = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    for t in range(3):
+        ref_obs, ref_term = sims[0].step_servos_compact(act)
+        sims[1].step_servos_peers(act, [b.data_ptr() for b in bufs], [t_.data_ptr() for t_ in terms])
+        torch.cuda.synchronize()
+        for b, t_ in zip(bufs, terms):
+            assert torch.equal(b.view(n, 6, 3), ref_obs) and torch.equal(t_, ref_term)
+
+
+@pytest.mark.gpu
+def test_deferred_push_on_one_gpu_equals_the_compact_step(model):
+    """`upkie_b200_step_servos_push` / `upkie_b200_push_rows` (deferred rollout transport): every step writes its rows to
+    a local slot and the NEXT launch's prologue copies them to the destination buffers (here: two local "peer" buffers);
+    after the final `push_rows` the destinations hold the same rows as the compact step produced, slot by slot."""
+    import torch
+
+    from upkie_b200 import _abi as A
+    from upkie_b200.sim import UpkieSim
+
+    n, T = 4096, 4
+    cfg = A.default_sim_config()
+    sims = [UpkieSim(n, model=model, config=cfg) for _ in range(2)]
+    for s_ in sims:
+        s_.reset(seed=4)
+    act = torch.from_numpy(random_servo_actions(n, model, seed=9).astype(np.float32)).cuda()
+    local_obs = torch.zeros((T, n * 18), dtype=torch.float32, device="cuda")
+    local_term = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+    dst_obs = [torch.zeros((T, n * 18), dtype=torch.float32, device="cuda") for _ in range(2)]
+    dst_term = [torch.zeros((T, n), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    ref = []
+
+    def descriptor(t):
+        d = A.UpkiePush()
+        d.src_obs, d.src_terminated = local_obs[t].data_ptr(), local_term[t].data_ptr()
+        for p in range(2):
+            d.peer_obs[p], d.peer_terminated[p] = dst_obs[p][t].data_ptr(), dst_term[p][t].data_ptr()
+        d.n_peers = 2
+        return d
+
+    pending = None
+    for t in range(T):
+        o, te = sims[0].step_servos_compact(act)
+        ref.append((o.clone(), te.clone()))
+        sims[1].step_servos_push(act, local_obs[t].data_ptr(), local_term[t].data_ptr(), pending)
+        pending = descriptor(t)
+        torch.cuda.synchronize()
+        if t > 0:  # the previous step's rows arrived with this launch, this step's have not left yet
+            assert torch.equal(dst_obs[0][t - 1].view(n, 6, 3), ref[t - 1][0]) and not dst_obs[0][t].any()
+    sims[1].push_rows(pending)
+    torch.cuda.synchronize()
+    for t in range(T):
+        for p in range(2):
+            assert torch.equal(dst_obs[p][t].view(n, 6, 3), ref[t][0]) and torch.equal(dst_term[p][t], ref[t][1])
+        assert torch.equal(local_obs[t].view(n, 6, 3), ref[t][0])

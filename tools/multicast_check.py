@@ -28,7 +28,7 @@ def main():
     n, T = 4096, 8
     model = Model.standard_upkie()
     cfg = _abi.default_sim_config()
-    sims = [UpkieSim(n, model=model, config=cfg, device=local) for _ in range(3)]
+    sims = [UpkieSim(n, model=model, config=cfg, device=local) for _ in range(5)]
     for s in sims:
         s.set_autoreset(0, 0, rank * n)
         s.reset(seed=100 + rank, env_offset=rank * n)
@@ -38,6 +38,9 @@ def main():
     local_buf = RolloutBuffer(T, n, 18, dev, compact=True)
     peer = PeerRolloutBuffer(T, n, 18, dev, compact=True)   # multicast stores
     peer2 = PeerRolloutBuffer(T, n, 18, dev, compact=True)  # peer stores
+    peer3 = PeerRolloutBuffer(T, n, 18, dev, compact=True)  # deferred multicast push
+    peer4 = PeerRolloutBuffer(T, n, 18, dev, compact=True)  # deferred peer stores
+    pend3 = pend4 = None
     mc = peer.multicast_supported
     if not mc:
         print(f"rank {rank}: symmetric memory reports no multicast support on this box", flush=True)
@@ -51,14 +54,24 @@ def main():
         if mc:
             sims[1].step_servos_multicast(a, *peer.multicast_slot(t))
         sims[2].step_servos_peers(a, *peer2.peer_slots(t))
+        if mc:
+            sims[3].step_servos_push(a, *peer3.local_slot(t), pend3)
+            pend3 = peer3.push_descriptor(t, multicast=True)
+        sims[4].step_servos_push(a, *peer4.local_slot(t), pend4)
+        pend4 = peer4.push_descriptor(t, multicast=False)
     if mc:
+        sims[3].push_rows(pend3)
         peer.publish()
+        peer3.publish()
+    sims[4].push_rows(pend4)
     peer2.publish()
+    peer4.publish()
     torch.cuda.synchronize()
     expect = local_buf.gather_raw()  # [world, nbytes] through NCCL, for the comparison only
     nb = local_buf.nbytes
     ok = True
-    for name, buf in (("multicast", peer if mc else None), ("peerstore", peer2)):
+    for name, buf in (("multicast", peer if mc else None), ("peerstore", peer2),
+                      ("deferred multicast", peer3 if mc else None), ("deferred peerstore", peer4)):
         if buf is None:
             continue
         got = buf.gathered()

@@ -12,7 +12,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LAG_REPLY1, LAG_REPLY2, LAG_IMU, LAG_OBS_REPLY, LAG_OBS_IMU, LAG_OBS_BASE, LAG_OBS_CONTACT, LAG_DIM = 0, 18, 36, 49, 67, 80, 90, 91  # spine-mode lag record (include/upkie_b200.h)
 
 NJ = 6
@@ -277,6 +277,21 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.spine_mode = 0  # 1: timing of the C++ Bullet spine in simulate() mode (include/upkie_b200.h)
     c.reserved_spine_mode = 0
     return c
+
+
+class UpkiePush(C.Structure):
+    """``UpkiePush`` of include/upkie_b200.h: which earlier slot a launch sends to the other GPUs, and where."""
+
+    _fields_ = [
+        ("src_obs", C.c_void_p),
+        ("src_terminated", C.c_void_p),
+        ("mc_obs", C.c_void_p),
+        ("mc_terminated", C.c_void_p),
+        ("peer_obs", C.c_void_p * 8),
+        ("peer_terminated", C.c_void_p * 8),
+        ("n_peers", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
 
 
 def default_mpc_config() -> UpkieMpcConfig:

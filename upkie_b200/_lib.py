@@ -43,6 +43,8 @@ SYMBOLS = {
     "upkie_b200_step_servos_compact": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_servos_multicast": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_servos_peers": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "upkie_b200_step_servos_push": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_abi.UpkiePush), _vp]),
+    "upkie_b200_push_rows": (C.c_int, [_vp, C.POINTER(_abi.UpkiePush), _vp]),
     "upkie_b200_step_servos_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_gyropod_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "upkie_b200_step_servos_host_compact": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -66,10 +66,20 @@ __device__ __forceinline__ void store_state(float* __restrict__ st, int n_pad, i
 // TILE=2 (rollout rows leave the GPU from inside the step kernel): n = 0 -> `obs` / `terminated` are NVSwitch multicast
 // addresses (multimem.st, the switch replicates the store into every GPU's buffer); n > 0 -> plain stores into the n
 // peer buffers listed here (peer-mapped symmetric memory over NVLink; the list includes this rank's own buffer).
+//
+// `deferred` (round 2, the default of bench.py): the rows this launch sends are those of an EARLIER step - read from
+// `src_obs` / `src_term` (this rank's local slot of that step) and sent in the PROLOGUE of the kernel, so that their
+// NVLink latency hides under the ~0.1 ms of simulation instead of holding up the completion of the launch - while this
+// step's rows go to the local slot (`obs` / `terminated` of the launch) with plain stores.
 struct PeerPtrs {
   float* obs[UPKIE_MAX_PEERS];
   uint8_t* term[UPKIE_MAX_PEERS];
   int n;
+  int deferred;
+  float* mc_obs;          // deferred + multicast: multicast address of the earlier step's slot (null with peer stores)
+  uint8_t* mc_term;
+  const float* src_obs;   // deferred: local rows of the earlier step, null = nothing to send in this launch
+  const uint8_t* src_term;
 };
 
 // One launch of the env-step kernel over the envs [i0, i0 + cnt) of a handle.
@@ -105,6 +115,7 @@ cudaError_t launch_step_multicast(const StepArgs& a);  // step_multicast.cu: TIL
 cudaError_t launch_step_device_limits(const StepArgs& a);  // step_device_limits.cu: NOISE=2 (joint-limit rows), TILE=0
 cudaError_t launch_step_host_limits(const StepArgs& a);    // step_host_limits.cu: NOISE=2, TILE=1
 cudaError_t launch_step_multicast_limits(const StepArgs& a);  // step_multicast_limits.cu: NOISE=2, TILE=2
+cudaError_t launch_push_rows(const PeerPtrs& pp, int n, cudaStream_t stream);  // step_multicast.cu: flush of a rollout's last rows
 cudaError_t launch_step_device_spine(const StepArgs& a);  // step_device_spine.cu: NOISE=3 (spine timing), TILE=0
 cudaError_t launch_step_host_spine(const StepArgs& a);    // step_host_spine.cu: NOISE=3, TILE=1
 

@@ -247,7 +247,7 @@ __device__ __forceinline__ void step_env(
         for (int k = 0; k < 5; ++k) {
           const int idx = k * 32 + lane;
           if (idx < 32 * 18 / 4) {
-            if (TILE == 2) {
+            if (TILE == 2 && !peers->deferred) {
               const float4 v = tile4[idx];
               if (peers->n == 0) {
                 mc_store4(op + idx, v);
@@ -303,12 +303,14 @@ __device__ __forceinline__ void step_env(
   }
   if (TILE == 2) {
     // the host only launches this variant on full, aligned warps (n % 32 == 0): the warp's 32 `terminated` bytes go
-    // out as eight multicast words built from the ballot (multimem.st has no byte form)
+    // out as eight words built from the ballot (multimem.st has no byte form)
     const unsigned m = __ballot_sync(0xffffffffu, term);
     if (lane < 8) {
       const unsigned nib = (m >> (4 * lane)) & 0xFu;
       const uint32_t word = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-      if (peers->n == 0) {
+      if (peers->deferred) {
+        reinterpret_cast<uint32_t*>(terminated + wb)[lane] = word;  // local slot; sent by a later launch's prologue
+      } else if (peers->n == 0) {
         mc_store_u32(reinterpret_cast<uint32_t*>(terminated + wb) + lane, word);
       } else {
         for (int p = 0; p < peers->n; ++p) reinterpret_cast<uint32_t*>(peers->term[p] + wb)[lane] = word;
@@ -321,6 +323,33 @@ __device__ __forceinline__ void step_env(
   if (truncated) truncated[i] = 0;
   if (e) err[i] |= e;
   if (AUTORESET == AUTORESET_NEXT_STEP) done_prev[i] = term ? 1 : 0;
+}
+
+// Deferred rollout transport: send the warp's 32 compact rows (and `terminated` bytes) of an EARLIER step, read from
+// this rank's local slot of that step, to every GPU - NVSwitch multicast store or plain stores into the peers'
+// buffers. Called at the top of a tile, before its physics: the stores drain while the warp simulates.
+__device__ __forceinline__ void push_rows(const PeerPtrs& pp, int wb, int lane) {
+  const float4* src = reinterpret_cast<const float4*>(pp.src_obs + size_t(wb) * 18);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int idx = k * 32 + lane;
+    if (idx < 32 * 18 / 4) {
+      const float4 v = src[idx];
+      if (pp.n == 0) {
+        mc_store4(reinterpret_cast<float4*>(pp.mc_obs + size_t(wb) * 18) + idx, v);
+      } else {
+        for (int p = 0; p < pp.n; ++p) reinterpret_cast<float4*>(pp.obs[p] + size_t(wb) * 18)[idx] = v;
+      }
+    }
+  }
+  if (lane < 8) {
+    const uint32_t word = reinterpret_cast<const uint32_t*>(pp.src_term + wb)[lane];
+    if (pp.n == 0) {
+      mc_store_u32(reinterpret_cast<uint32_t*>(pp.mc_term + wb) + lane, word);
+    } else {
+      for (int p = 0; p < pp.n; ++p) reinterpret_cast<uint32_t*>(pp.term[p] + wb)[lane] = word;
+    }
+  }
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -388,6 +417,9 @@ k_step(const __grid_constant__ SimParams P, int i0, int n, int n_pad, float* __r
       cp_async_wait<0>();
     }
     __syncwarp();
+    if (TILE == 2) {
+      if (peers.deferred && peers.src_obs) push_rows(peers, i0 + t * int(blockDim.x) + warp * 32, lane);
+    }
     step_env<MODE, AUTORESET, NOISE, TILE>(P, i0 + t * blockDim.x + threadIdx.x, n, n_pad, state, action, obs, reward,
                                         terminated, truncated, eps_all, mu_all, err, done_prev, episode, tick, seed,
                                         env_offset, ext, ext_local, buf[it & 1], warp_full(t), (coalesce & 2) != 0,

@@ -239,7 +239,7 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
                uint8_t* trunc, cudaStream_t s, bool tile = false, bool persistent = true, bool compact = false,
                bool multicast = false, const PeerPtrs* peers = nullptr) {
   StepArgs a;
-  a.peers.n = 0;
+  std::memset(&a.peers, 0, sizeof(a.peers));
   if (peers) a.peers = *peers;
   a.P = &h->P;
   a.mode = mode;
@@ -648,6 +648,7 @@ int upkie_b200_step_servos_peers(void* handle, const float* action, float* const
   if (n_peers < 1 || n_peers > UPKIE_MAX_PEERS) return fail(UPKIE_B200_EINVAL, "step_servos_peers: 1 <= n_peers <= UPKIE_MAX_PEERS");
   if (h->n % 32 != 0) return fail(UPKIE_B200_EINVAL, "step_servos_peers: the number of envs must be a multiple of 32");
   PeerPtrs pp;
+  std::memset(&pp, 0, sizeof(pp));
   pp.n = n_peers;
   for (int p = 0; p < UPKIE_MAX_PEERS; ++p) {
     pp.obs[p] = p < n_peers ? obs_ptrs[p] : nullptr;
@@ -660,6 +661,62 @@ int upkie_b200_step_servos_peers(void* handle, const float* action, float* const
   CUDA_TRY(cudaSetDevice(h->device));
   return step_range(h, MODE_SERVOS, 0, h->n, action, pp.obs[0], nullptr, pp.term[0], nullptr, static_cast<cudaStream_t>(stream),
                     /*tile=*/true, /*persistent=*/false, /*compact=*/true, /*multicast=*/true, &pp);
+}
+
+namespace {
+int fill_push(const Handle* h, const UpkiePush* push, PeerPtrs& pp, const char* who) {
+  std::memset(&pp, 0, sizeof(pp));
+  pp.deferred = 1;
+  if (!push) return UPKIE_B200_OK;  // nothing to send
+  if (push->n_peers < 0 || push->n_peers > UPKIE_MAX_PEERS) return fail(UPKIE_B200_EINVAL, std::string(who) + ": 0 <= n_peers <= UPKIE_MAX_PEERS");
+  if (h->n % 32 != 0) return fail(UPKIE_B200_EINVAL, std::string(who) + ": the number of envs must be a multiple of 32");
+  auto bad = [](const void* q, uintptr_t mask) { return !q || (reinterpret_cast<uintptr_t>(q) & mask) != 0; };
+  if (push->src_obs) {
+    if (bad(push->src_obs, 15) || bad(push->src_terminated, 3)) return fail(UPKIE_B200_EINVAL, std::string(who) + ": source slot misaligned or null");
+    pp.src_obs = push->src_obs;
+    pp.src_term = push->src_terminated;
+    pp.n = push->n_peers;
+    if (pp.n == 0) {
+      if (bad(push->mc_obs, 15) || bad(push->mc_terminated, 3)) return fail(UPKIE_B200_EINVAL, std::string(who) + ": multicast slot misaligned or null");
+      pp.mc_obs = push->mc_obs;
+      pp.mc_term = push->mc_terminated;
+    }
+    for (int p = 0; p < pp.n; ++p) {
+      if (bad(push->peer_obs[p], 15) || bad(push->peer_terminated[p], 3)) return fail(UPKIE_B200_EINVAL, std::string(who) + ": peer slot misaligned or null");
+      pp.obs[p] = push->peer_obs[p];
+      pp.term[p] = push->peer_terminated[p];
+    }
+  }
+  return UPKIE_B200_OK;
+}
+}  // namespace
+
+int upkie_b200_step_servos_push(void* handle, const float* action, float* obs, uint8_t* terminated,
+                                const UpkiePush* push, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h) return fail(UPKIE_B200_EINVAL, "invalid handle");
+  if (!action || !obs || !terminated) return fail(UPKIE_B200_EINVAL, "step_servos_push: null buffer");
+  if (h->n % 32 != 0) return fail(UPKIE_B200_EINVAL, "step_servos_push: the number of envs must be a multiple of 32");
+  if (((reinterpret_cast<uintptr_t>(action) | reinterpret_cast<uintptr_t>(obs)) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(terminated) & 3) != 0)
+    return fail(UPKIE_B200_EINVAL, "step_servos_push: action / obs rows must be 16-byte, terminated 4-byte aligned");
+  PeerPtrs pp;
+  int rc = fill_push(h, push, pp, "step_servos_push");
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return step_range(h, MODE_SERVOS, 0, h->n, action, obs, nullptr, terminated, nullptr, static_cast<cudaStream_t>(stream),
+                    /*tile=*/true, /*persistent=*/false, /*compact=*/true, /*multicast=*/true, &pp);
+}
+
+int upkie_b200_push_rows(void* handle, const UpkiePush* push, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !push || !push->src_obs) return fail(UPKIE_B200_EINVAL, "push_rows: invalid argument");
+  PeerPtrs pp;
+  int rc = fill_push(h, push, pp, "push_rows");
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(launch_push_rows(pp, h->n, static_cast<cudaStream_t>(stream)));
+  return UPKIE_B200_OK;
 }
 
 int upkie_b200_step_gyropod(void* handle, const float* action, int act_dim, float* obs, float* reward,

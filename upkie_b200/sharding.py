@@ -210,6 +210,36 @@ class PeerRolloutBuffer(RolloutBuffer):
         bases = [p_.data_ptr() for p_ in self._peers]
         return [b + obs_off for b in bases], [b + term_off for b in bases]
 
+    def local_slot(self, t: int):
+        """``(obs_ptr, terminated_ptr)``: LOCAL device addresses of this rank's slot at time step ``t`` (the deferred
+        transport writes a step's rows there and sends them with a later launch)."""
+        if not self.compact:
+            raise ValueError("deferred slots carry compact records")
+        k = t % self.T
+        base = self.raw.data_ptr()
+        return base + k * self.n * self.obs_dim * 4, base + self.T * self.n * self.obs_dim * 4 + k * self.n
+
+    def push_descriptor(self, t: int, multicast: bool):
+        """``_abi.UpkiePush`` that sends this rank's slot of step ``t`` to every rank: to the multicast address of the
+        slot, or (``multicast=False``) into every PEER's buffer (this rank's own copy is already in place)."""
+        from . import _abi
+
+        d = _abi.UpkiePush()
+        d.src_obs, d.src_terminated = self.local_slot(t)
+        if multicast:
+            d.mc_obs, d.mc_terminated = self.multicast_slot(t)
+            d.n_peers = 0
+        else:
+            obs_ptrs, term_ptrs = self.peer_slots(t)
+            k = 0
+            for p in range(self.world):
+                if p == self.rank:
+                    continue
+                d.peer_obs[k], d.peer_terminated[k] = obs_ptrs[p], term_ptrs[p]
+                k += 1
+            d.n_peers = k
+        return d
+
     def publish(self) -> None:
         """After the last multicast step of a rollout: cross-rank barrier on the current stream; once it has
         passed, ``gathered()`` holds every rank's records on every rank."""

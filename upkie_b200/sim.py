@@ -199,6 +199,19 @@ class UpkieSim:
         ta = (C.c_void_p * k)(*[C.c_void_p(int(x)) for x in terminated_ptrs])
         check(lib().upkie_b200_step_servos_peers(self._h, _ptr(action), oa, ta, k, self._stream()))
 
+    def step_servos_push(self, action: torch.Tensor, obs_ptr: int, terminated_ptr: int, push=None) -> None:
+        """Deferred rollout transport (``upkie_b200_step_servos_push``): this step's compact rows go to the local slot
+        at ``obs_ptr`` / ``terminated_ptr``; ``push`` (an ``_abi.UpkiePush`` from ``PeerRolloutBuffer.push_descriptor``)
+        names an earlier slot the same launch sends to every GPU in its prologue, or None."""
+        self._check_tensor(action, (self.n, 6, 6), name="action")
+        check(lib().upkie_b200_step_servos_push(
+            self._h, _ptr(action), C.c_void_p(int(obs_ptr)), C.c_void_p(int(terminated_ptr)),
+            C.byref(push) if push is not None else None, self._stream()))
+
+    def push_rows(self, push) -> None:
+        """Send one slot on its own (last step of a rollout): ``upkie_b200_push_rows``."""
+        check(lib().upkie_b200_push_rows(self._h, C.byref(push), self._stream()))
+
     def step_gyropod(self, action: torch.Tensor, obs: Optional[torch.Tensor] = None, reward=None, terminated=None,
                      truncated=None):
         self._check_tensor(action, (self.n, 2), name="action")
@@ -345,6 +358,7 @@ class UpkieSim:
         friction, eps = getattr(self, "_randomization", (None, None))
         force, local_mask = getattr(self, "_external", (None, 0))
         return {
+            "lag": self.get_lag() if self.config.spine_mode else None,  # spine mode: replies / IMU of the last cycles
             "state": self.get_state(), "episode": episode, "tick": tick, "pending_reset": pending, "error_flags": flags,
             "friction": friction, "inertia_eps": eps, "external_force": force, "external_local_mask": local_mask,
             "autoreset": getattr(self, "_autoreset", (AUTORESET_DISABLED, 0, 0)),
@@ -353,6 +367,8 @@ class UpkieSim:
     def load_state_dict(self, sd: dict) -> None:
         dev = self.device
         self.set_state(sd["state"].to(dev))
+        if sd.get("lag") is not None:
+            self.set_lag(sd["lag"].to(dev))
         check(lib().upkie_b200_set_counters(
             self._h, _ptr(sd["episode"].to(dev)), _ptr(sd["tick"].to(dev)), _ptr(sd["pending_reset"].to(dev)),
             _ptr(sd["error_flags"].to(dev)), self._stream()))
