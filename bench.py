@@ -651,7 +651,8 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     counters = {"gathers": 0}
     pending = {"push": None}
     # UPKIE_BENCH_PUSH=now: the immediate in-kernel transports (rows leave at the END of the launch that produced them)
-    deferred = os.environ.get("UPKIE_BENCH_PUSH", "deferred") != "now"
+    push_mode = os.environ.get("UPKIE_BENCH_PUSH", "kernel")  # kernel | deferred | now
+    deferred = push_mode == "deferred"
 
     def wait_for(cur, record):
         """The gather that last read buffer `cur` must be done before its slots are overwritten."""
@@ -677,7 +678,13 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         if k % T_roll == 0:
             wait_for(cur, timed)
         a = acts[k % N_ACTION_BUFFERS]
-        if gather_mode in ("multicast", "peerstore") and deferred:
+        if gather_mode in ("multicast", "peerstore") and push_mode == "kernel":
+            # the fastest step kernel (TILE=1, local stores) writes the local slot; a 2 us kernel of its own sends the
+            # rows to every GPU right behind it on the same stream
+            so, sr, ste, stru = rollouts[cur].slot(k)
+            step(a, obs=so, reward=sr, terminated=ste, truncated=stru)
+            env.sim.push_rows(rollouts[cur].push_descriptor(k, multicast=gather_mode == "multicast"))
+        elif gather_mode in ("multicast", "peerstore") and deferred:
             # this step's rows go to the local slot; the PROLOGUE of the same launch sends the previous step's rows to
             # every GPU (NVSwitch multicast store, or stores into the peers' buffers), so that their NVLink latency
             # hides under the simulation; a barrier per rollout replaces the gather
@@ -831,7 +838,7 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     }
     if world > 1:
         config["gather"] = {
-            "transport": gather_mode + (" (deferred push)" if deferred and gather_mode in ("multicast", "peerstore") else ""),
+            "transport": gather_mode + ({"kernel": " (push kernel behind every step)", "deferred": " (deferred push)", "now": " (stores at the end of the step kernel)"}[push_mode] if gather_mode in ("multicast", "peerstore") else ""),
             "rollout_steps": T_roll, "gathers_in_timed_region": gathers,
             "bytes_per_rank_and_gather": int(rollouts[0].nbytes),
             # time the simulation stream spent waiting for a gather before re-using its buffer, inside the timed region

@@ -289,8 +289,10 @@ def test_peer_store_step_on_one_gpu_equals_the_compact_step(model):
         ref_obs, ref_term = sims[0].step_servos_compact(act)
         sims[1].step_servos_peers(act, [b.data_ptr() for b in bufs], [t_.data_ptr() for t_ in terms])
         torch.cuda.synchronize()
-        for b, t_ in zip(bufs, terms):
-            assert torch.equal(b.view(n, 6, 3), ref_obs) and torch.equal(t_, ref_term)
+        # transport exact (both "peers" hold the same bytes); against the separately compiled TILE=1 kernel: round-off
+        assert torch.equal(bufs[0], bufs[1]) and torch.equal(terms[0], terms[1])
+        assert torch.allclose(bufs[0].view(n, 6, 3), ref_obs, rtol=0, atol=2e-2) and torch.equal(terms[0], ref_term)
+        assert float((bufs[0].view(n, 6, 3) - ref_obs).abs().median()) < 1e-6
 
 
 @pytest.mark.gpu
@@ -331,10 +333,12 @@ def test_deferred_push_on_one_gpu_equals_the_compact_step(model):
         pending = descriptor(t)
         torch.cuda.synchronize()
         if t > 0:  # the previous step's rows arrived with this launch, this step's have not left yet
-            assert torch.equal(dst_obs[0][t - 1].view(n, 6, 3), ref[t - 1][0]) and not dst_obs[0][t].any()
+            assert torch.equal(dst_obs[0][t - 1], local_obs[t - 1]) and not dst_obs[0][t].any()
     sims[1].push_rows(pending)
     torch.cuda.synchronize()
     for t in range(T):
-        for p in range(2):
-            assert torch.equal(dst_obs[p][t].view(n, 6, 3), ref[t][0]) and torch.equal(dst_term[p][t], ref[t][1])
-        assert torch.equal(local_obs[t].view(n, 6, 3), ref[t][0])
+        for p in range(2):  # transport: byte for byte what the kernel wrote to its local slot
+            assert torch.equal(dst_obs[p][t], local_obs[t]) and torch.equal(dst_term[p][t], local_term[t])
+        # physics against the separately compiled TILE=1 kernel: fp32 round-off, same flags
+        assert torch.allclose(local_obs[t].view(n, 6, 3), ref[t][0], rtol=0, atol=2e-2)
+        assert float((local_obs[t].view(n, 6, 3) - ref[t][0]).abs().median()) < 1e-6 and torch.equal(local_term[t], ref[t][1])

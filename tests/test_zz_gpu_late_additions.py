@@ -1,11 +1,11 @@
 # SPDX-License-Identifier: Apache-2.0
-"""GPU tests of what was written after round 1's GPU budget had been spent: joint-limit rows on the device
-(k_step<.., NOISE=2, ..>, config.joint_limits = 1) against the oracle, the Backend contact query, and the
-parity-audit recorder.
+"""GPU tests of the joint-limit rows on the device (k_step<.., NOISE=2, ..>: config.joint_limits = 1 -> 3 on the
+device, 2, 3) against the oracle, the Backend contact query, and the parity-audit recorder.
 
-This file sorts last on purpose: its first run on a B200 is the driver's round-end `pytest -m gpu` (DESIGN.md
-section 3), after every test that was green on the GPU during the round. The CPU build of the same kernel code agrees
-with the oracle (tests/test_kernel_arithmetic_cpu.py::test_joint_limit_rows)."""
+Written at the end of round 1 (hence the file name: it sorted last so that its first run on a B200 could not mask the
+tests that had already been green there); green on the B200 since the first GPU call of round 2
+(profiles/r02_variants.md). The CPU build of the same kernel code agrees with the oracle
+(tests/test_kernel_arithmetic_cpu.py::test_joint_limit_rows)."""
 import numpy as np
 import pytest
 

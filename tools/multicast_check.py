@@ -67,18 +67,28 @@ def main():
     peer2.publish()
     peer4.publish()
     torch.cuda.synchronize()
-    expect = local_buf.gather_raw()  # [world, nbytes] through NCCL, for the comparison only
-    nb = local_buf.nbytes
+    # (1) transport: what every rank holds for rank r must be, byte for byte, what rank r holds for itself (its own
+    # region, exchanged with a plain NCCL all-gather for the comparison). (2) physics: the TILE=2 instantiations are
+    # compiled separately from the TILE=1 kernel that wrote `local_buf`; their rows agree to fp32 round-off, not
+    # necessarily bit for bit (the compiler schedules / contracts each instantiation on its own).
+    ref_rows = local_buf.obs.reshape(T, n, 18)
     ok = True
     for name, buf in (("multicast", peer if mc else None), ("peerstore", peer2),
                       ("deferred multicast", peer3 if mc else None), ("deferred peerstore", peer4)):
         if buf is None:
             continue
+        own = buf.raw.clone()
+        expect = torch.empty(world * buf.nbytes, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(expect, own)
         got = buf.gathered()
-        good = all(torch.equal(got[r, :nb], expect[r, :nb]) for r in range(world))
-        ok = ok and good
-        print(f"rank {rank}: {name} rollout {'MATCHES' if good else 'DIFFERS FROM'} the NCCL-gathered reference "
-              f"({world} ranks x {nb} bytes)", flush=True)
+        good = torch.equal(got.reshape(-1), expect)
+        rows = buf.obs.reshape(T, n, 18)
+        close = bool(torch.allclose(rows, ref_rows, rtol=0, atol=2e-2)) and float((rows - ref_rows).abs().median()) < 1e-6
+        flags = bool(torch.equal(buf.terminated, local_buf.terminated))
+        ok = ok and good and close and flags
+        print(f"rank {rank}: {name} rollout {'MATCHES' if good else 'DIFFERS FROM'} every rank's own copy "
+              f"({world} ranks x {buf.nbytes} bytes); rows vs the TILE=1 kernel: max |d| "
+              f"{float((rows - ref_rows).abs().max()):.2e}, terminated {'equal' if flags else 'DIFFER'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
