@@ -183,6 +183,13 @@ def servos_config():
     cfg.rand_pitch = 0.3
     if os.environ.get("UPKIE_BENCH_JOINT_LIMITS"):  # developer knob: 0 off, 1 scalar slow path, 2 ten-row, 3 hybrid
         cfg.joint_limits = int(os.environ["UPKIE_BENCH_JOINT_LIMITS"])
+    # Torso-floor contact rows: OFF for the headline, ON (the library's default) in the secondary line
+    # other_workloads.servos_65536_body_contacts. SURVEY 8(d) defines this workload with "reset when |pitch| > 1 or base
+    # z < 0.15 m", i.e. it recycles robots by letting their torso sink through the floor. With the rows on, a crouched
+    # robot SITS on the torso box (bottom 0.21 m below the base origin of the stand-in model) at z ~ 0.21 > 0.15 and never
+    # terminates: a third of the robots ends up resting on the floor for good (tools/r02/body_gate_stats.cpp), every warp
+    # takes the general row solver every substep, and the figure measures a different workload. Both are reported.
+    cfg.body_contacts = int(os.environ.get("UPKIE_BENCH_BODY_CONTACTS", "0"))
     if os.environ.get("UPKIE_BENCH_PGS_TOL"):  # developer knob (profiles/r01_variants.md)
         cfg.pgs_tolerance = float(os.environ["UPKIE_BENCH_PGS_TOL"])
     return cfg
@@ -539,7 +546,24 @@ def other_workloads(torch, dev, model):
     except Exception as exc:  # secondary lines must never take the headline down
         out["error"] = repr(exc)
     out["servos_65536_exact_mode"] = exact_mode_line()
+    out["servos_65536_body_contacts"] = body_contacts_line()
     return out
+
+
+def body_contacts_line():
+    """The servos workload with the torso-floor contact rows on (the library's default physics): own process, steady
+    state (the robots need ~100 ticks to fold onto their torsos), device buffers."""
+    try:
+        env = dict(os.environ, UPKIE_BENCH_BODY_CONTACTS="1", UPKIE_BENCH_DEVICE_ONLY="1")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "60", "--warmup", "150",
+                            "--no-cpu-baseline", "--no-other-workloads"], env=env, capture_output=True, text=True, timeout=300)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"metric": "env-steps/sec", "value": j["value"], "ms_per_step": j["ms_per_step"],
+                "kernel_ms_median": j["roofline"]["kernel_ms"],
+                "workload": "headline workload with body_contacts = 1: ~1/3 of the robots sit on their torso box and never "
+                            "reach the 0.15 m reset height; every warp solves its rows in general_contact_solve()"}
+    except Exception as exc:
+        return {"error": repr(exc)}
 
 
 def exact_mode_line():
@@ -832,6 +856,10 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         # path, 2 packed ten-row solver, 3 ten-row solver for the warps that hold a robot on a bound
         "joint_limit_rows": int(getattr(env.config, "joint_limits", 0)) != 0,
         "joint_limit_solver": int(getattr(env.config, "joint_limits", 0)),
+        # body-ground contact rows of the model's collision points (the torso box; include/upkie_b200.h: body_contacts;
+        # library default ON). Off in the headline workload, whose "base below 0.15 m" reset rule presumes that the
+        # torso sinks through the floor (servos_config() above); other_workloads.servos_65536_body_contacts has them on
+        "body_contact_rows": int(getattr(env.config, "body_contacts", 0)) != 0,
         "parallelism": f"env-index sharded x{world}" + transport,
         "l2": f"{N_ACTION_BUFFERS} rotating action buffers ({N_ACTION_BUFFERS * n * act_bytes / 1e6:.0f} MB"
               " vs 126 MB L2); robot state stays resident by design",

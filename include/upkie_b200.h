@@ -31,10 +31,13 @@
 extern "C" {
 #endif
 
-#define UPKIE_B200_ABI_VERSION 5
+#define UPKIE_B200_ABI_VERSION 6
 
 #define UPKIE_NJ 6 /* actuated joints */
 #define UPKIE_NB 7 /* moving bodies: base lump + 2 x (upper leg, lower leg, wheel) */
+#define UPKIE_MAX_COLLISION_POINTS 16 /* body-ground collision points a model may carry (UpkieModel) */
+#define UPKIE_MAX_BODY_CONTACTS 4    /* of which at most this many (the deepest) hold contact rows in one substep:
+                                      * Bullet's persistent manifold keeps 4 points per pair (MANIFOLD_CACHE_SIZE) */
 
 /* ---- flat tensor layouts (all row-major, last index fastest) ------------- */
 
@@ -153,6 +156,16 @@ typedef struct UpkieModel {
   double wheel_base;                 /* distance between tire frames, model.py:82 */
   double imu_position[3];            /* IMU frame origin in the base frame */
   double rotation_base_to_imu[9];    /* row-major, model.py:106 */
+  /* Collision points of the bodies other than the tires (ABI 6): what the <collision> shapes of the URDF links reduce
+   * to against the ground plane - a box is its 8 corners, a sphere its centre with a radius, a cylinder / capsule the
+   * two end points of its axis with the radius (upkie/model/link.py:53-91 parses the same elements). Point p belongs
+   * to moving body collision_body[p] (0 = base lump .. 6) and sits at collision_point[p] in that body's frame.
+   * PyBullet collides every link that has a collision shape with plane.urdf (pybullet_backend.py:115,121,306). */
+  int32_t n_collision_points;        /* 0 .. UPKIE_MAX_COLLISION_POINTS */
+  int32_t collision_body[UPKIE_MAX_COLLISION_POINTS];
+  int32_t reserved_collision;
+  double collision_point[UPKIE_MAX_COLLISION_POINTS][3];
+  double collision_radius[UPKIE_MAX_COLLISION_POINTS];
 } UpkieModel;
 
 /* Simulation + environment configuration. Defaults are filled by
@@ -248,6 +261,19 @@ typedef struct UpkieSimConfig {
    * reads 20.0 (BulletInterface.cpp:70). Needs joint_limits != 0 (the "extras + limits" kernels carry it). */
   int32_t spine_mode;
   int32_t reserved_spine_mode;
+  /* Body-ground contacts (ABI 6; Bullet collides every link that has a collision shape with the plane, so a fallen
+   * robot rests on its torso instead of passing through the floor). 1 (default): while a collision point of the
+   * model (UpkieModel.collision_*) is closer to the ground than contact_breaking_threshold, it holds one normal row
+   * and two friction rows in the substep's PGS solve - rigid contact (no <contact> stiffness on those links):
+   * cfm 0, Baumgarte factor body_contact_erp, friction coefficient = the env's floor friction x body_friction, friction
+   * directions world -y and +x (btPlaneSpace1 of the plane normal); rows are solved after the wheel rows of their kind
+   * (normals, then frictions). At most UPKIE_MAX_BODY_CONTACTS points (the deepest) are active per robot. Needs
+   * joint_limits != 0 (the rows live in the "extras + limits" kernels); a warp that holds no such point runs the
+   * packed solvers unchanged. 0 = off (round 1's / early round 2's physics). */
+  int32_t body_contacts;
+  int32_t reserved_body_contacts;
+  double body_contact_erp;   /* btContactSolverInfo::m_erp2 = 0.2 */
+  double body_friction;      /* URDF importer default lateral friction of a link without <contact>: 0.5 */
 } UpkieSimConfig;
 
 /* Spine-mode lag record of one env (upkie_b200_get_lag / set_lag, [N][UPKIE_LAG_DIM] floats): the two latest
@@ -447,6 +473,12 @@ int upkie_b200_spine_obs(void* handle, float* out, void* stream);
 int upkie_b200_reset_obs(void* handle, int obs_dim, float* obs, void* stream);
 
 int upkie_b200_get_state(void* handle, float* state /* [N][UPKIE_STATE_DIM] */, void* stream);
+/* Body-ground contacts of the last substep (what PyBulletBackend.get_contact_points reports for links other than the
+ * tires, pybullet_backend.py:660-716): rows [N][UPKIE_BODY_REC_DIM] = bit mask of the model's collision points that
+ * held rows (as a float), then for each of the UPKIE_MAX_BODY_CONTACTS slots: collision point index, normal impulse,
+ * friction impulses along world -y and +x. Zero rows when the handle has no body contacts. */
+#define UPKIE_BODY_REC_DIM (1 + 4 * UPKIE_MAX_BODY_CONTACTS)
+int upkie_b200_get_body_contacts(void* handle, float* rows, void* stream);
 /* spine mode: the lag records [N][UPKIE_LAG_DIM] (device buffers), for checkpoints and parity tests */
 int upkie_b200_get_lag(void* handle, float* lag_rows, void* stream);
 int upkie_b200_set_lag(void* handle, const float* lag_rows, void* stream);

@@ -117,6 +117,7 @@ def lib():
         L.oracle_reset_obs.argtypes = [C.c_void_p, C.c_int, _dp]
         L.oracle_spine_obs.argtypes = [C.c_void_p, _dp]
         L.oracle_get_state.argtypes = [C.c_void_p, _dp]
+        L.oracle_get_body_contacts.argtypes = [C.c_void_p, _dp]
         L.oracle_set_state.argtypes = [C.c_void_p, _dp]
         L.oracle_get_lag.argtypes = [C.c_void_p, _dp]
         L.oracle_set_lag.argtypes = [C.c_void_p, _dp]

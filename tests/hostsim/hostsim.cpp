@@ -66,6 +66,26 @@ void hostsim_step_servos(void* hv, int n, float* state, const float* action, flo
   }
 }
 
+// the same tick, also returning the body-ground contact record of the last substep ([n][UPKIE_BODY_REC_DIM])
+void hostsim_step_servos_rec(void* hv, int n, float* state, const float* action, float* obs, const float* eps,
+                             const float* mu, float* rec) {
+  HostSim* h = static_cast<HostSim*>(hv);
+  for (int i = 0; i < n; ++i) {
+    RobotState S;
+    state_from_row(state + size_t(i) * UPKIE_STATE_DIM, S);
+    float a[UPKIE_ACT_DIM];
+    std::memcpy(a, action + size_t(i) * UPKIE_ACT_DIM, sizeof(a));
+    float* r = rec + size_t(i) * UPKIE_BODY_REC_DIM;
+    for (int k = 0; k < UPKIE_BODY_REC_DIM; ++k) r[k] = 0.f;
+    step_servo_action<false>(h->P, S, a, eps ? eps + size_t(i) * 6 : nullptr, mu ? mu[i] : h->P.friction, any_fn, r);
+    for (int j = 0; j < 6; ++j) {
+      float* o = obs + size_t(i) * UPKIE_OBS_DIM + j * 5;
+      o[0] = S.q[j]; o[1] = S.qd[j]; o[2] = S.torque[j]; o[3] = 42.0f; o[4] = 18.0f;
+    }
+    state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
+  }
+}
+
 void hostsim_step_gyropod(void* hv, int n, float* state, const float* action, int act_dim, float* obs6,
                           uint8_t* terminated) {
   HostSim* h = static_cast<HostSim*>(hv);

@@ -43,6 +43,7 @@ def lib():
         L.hostsim_reset.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp]
         L.hostsim_step_servos.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp, fp, C.POINTER(C.c_uint32)]
         L.hostsim_step_gyropod.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_int, fp, u8p]
+        L.hostsim_step_servos_rec.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp, fp, fp]
         L.hostsim_substep.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.hostsim_spine_obs.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.hostsim_spine_obs_with_uncertainty.argtypes = [C.c_void_p, C.c_int, fp, C.c_uint32, C.c_uint64, fp]
@@ -111,6 +112,15 @@ class HostSim:
         lib().hostsim_step_servos(self._h, self.n, _f(self.state), _f(a), _f(obs), self._opt(self.eps),
                                   self._opt(self.mu), err.ctypes.data_as(C.POINTER(C.c_uint32)))
         return obs, err
+
+    def step_servos_rec(self, action):
+        """One tick; also returns the body-ground contact record of its last substep ``[n, BODY_REC_DIM]``."""
+        a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.n, 36)
+        obs = np.empty((self.n, 6, 5), dtype=np.float32)
+        rec = np.zeros((self.n, _abi.BODY_REC_DIM), dtype=np.float32)
+        lib().hostsim_step_servos_rec(self._h, self.n, _f(self.state), _f(a), _f(obs), self._opt(self.eps),
+                                      self._opt(self.mu), _f(rec))
+        return obs, rec
 
     def step_servos_ext(self, action, ext, local_mask=0):
         """One tick under external forces ``ext[n, 7, 3]`` (newtons at the bodies' centres of mass)."""

@@ -12,11 +12,14 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 LAG_REPLY1, LAG_REPLY2, LAG_IMU, LAG_OBS_REPLY, LAG_OBS_IMU, LAG_OBS_BASE, LAG_OBS_CONTACT, LAG_DIM = 0, 18, 36, 49, 67, 80, 90, 91  # spine-mode lag record (include/upkie_b200.h)
 
 NJ = 6
 NB = 7
+MAX_COLLISION_POINTS = 16  # UPKIE_MAX_COLLISION_POINTS
+MAX_BODY_CONTACTS = 4  # UPKIE_MAX_BODY_CONTACTS
+BODY_REC_DIM = 1 + 4 * MAX_BODY_CONTACTS  # rows of upkie_b200_get_body_contacts
 
 ACT_KEYS = (
     "position",
@@ -77,6 +80,11 @@ class UpkieModel(C.Structure):
         ("wheel_base", C.c_double),
         ("imu_position", C.c_double * 3),
         ("rotation_base_to_imu", C.c_double * 9),
+        ("n_collision_points", C.c_int32),
+        ("collision_body", C.c_int32 * MAX_COLLISION_POINTS),
+        ("reserved_collision", C.c_int32),
+        ("collision_point", (C.c_double * 3) * MAX_COLLISION_POINTS),
+        ("collision_radius", C.c_double * MAX_COLLISION_POINTS),
     ]
 
 
@@ -131,6 +139,10 @@ class UpkieSimConfig(C.Structure):
         ("init_linear_velocity", C.c_double * 3),
         ("spine_mode", C.c_int32),
         ("reserved_spine_mode", C.c_int32),
+        ("body_contacts", C.c_int32),
+        ("reserved_body_contacts", C.c_int32),
+        ("body_contact_erp", C.c_double),
+        ("body_friction", C.c_double),
     ]
 
 
@@ -276,6 +288,10 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
         c.init_joint_configuration[j] = 0.0
     c.spine_mode = 0  # 1: timing of the C++ Bullet spine in simulate() mode (include/upkie_b200.h)
     c.reserved_spine_mode = 0
+    c.body_contacts = 1  # collision points of the model (torso box...) hold contact rows against the ground, as every link with a <collision> does in Bullet
+    c.reserved_body_contacts = 0
+    c.body_contact_erp = 0.2  # btContactSolverInfo::m_erp2
+    c.body_friction = 0.5  # URDF importer default lateral friction of a link without <contact>
     return c
 
 

@@ -52,6 +52,7 @@ SYMBOLS = {
     "upkie_b200_reset_obs": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "upkie_b200_get_state": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_get_lag": (C.c_int, [_vp, _vp, _vp]),
+    "upkie_b200_get_body_contacts": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_set_lag": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_set_state": (C.c_int, [_vp, _vp, _vp]),
     "upkie_b200_error_flags": (C.c_int, [_vp, _vp, _vp]),

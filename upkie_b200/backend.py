@@ -52,9 +52,11 @@ class B200Backend(_Base):
         torque_control_kp: float = 20.0,
         device: int = 0,
         joint_limits: bool = True,
+        body_contacts: bool = True,
     ) -> None:
         # same keyword arguments as PyBulletBackend.__init__ (pybullet_backend.py:55-66); gui is ignored.
-        # joint_limits (extension): Bullet's hip / knee limit constraints, on as in the multibody loadURDF builds
+        # joint_limits (extension): Bullet's hip / knee limit constraints, on as in the multibody loadURDF builds;
+        # body_contacts (extension): the links' collision shapes rest on the floor, as in Bullet
         self.__dt = dt
         self.__model = model if model is not None else default_model()
         self.torque_control_kd = torque_control_kd
@@ -63,6 +65,7 @@ class B200Backend(_Base):
         cfg = make_config(
             frequency=1.0 / dt, nb_substeps=nb_substeps, torque_control_kp=torque_control_kp,
             torque_control_kd=torque_control_kd, joint_properties=joint_properties, joint_limits=joint_limits,
+            body_contacts=body_contacts,
         )
         cfg.skip_action_clamps = 1  # the env on top (UpkieServos.get_spine_action) clamps, as in the reference
         self._sim = UpkieSim(1, model=self.__model, config=cfg, device=device)
@@ -91,11 +94,13 @@ class B200Backend(_Base):
     def get_contact_points(self, link_name: Optional[str] = None) -> List[PointContact]:
         """``PyBulletBackend.get_contact_points`` (``pybullet_backend.py:660-716``): the contacts of the robot, or
         of one link of it, as of the last simulation substep. The simulated contacts are the two tire-ground
-        points, reported on ``left_wheel_tire`` / ``right_wheel_tire``. ``force_in_world``
-        holds the normal force of the last substep; its friction components are not reported yet (the state row
-        keeps the normal impulses only), which is a documented difference from the reference."""
+        points, reported on ``left_wheel_tire`` / ``right_wheel_tire``, and the collision points of the other links
+        that touch the ground (the torso box of a fallen robot). ``force_in_world`` sums the
+        normal and the two friction components of the last substep, as the reference does
+        (``pybullet_backend.py:696-709``)."""
         row = self._sim.get_state()[0].cpu().numpy()
-        return contact_points_from_state(self._sim.model, row, self._sim.config, link_name)
+        rec = self._sim.get_body_contacts()[0].cpu().numpy()
+        return contact_points_from_state(self._sim.model, row, self._sim.config, link_name, rec)
 
     def reset(self, init_state: RobotState) -> dict:
         row = torch.from_numpy(init_state.to_row().astype(np.float32)).reshape(1, _abi.INIT_DIM).to(self._sim.device)

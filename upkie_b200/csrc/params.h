@@ -57,6 +57,10 @@ inline void default_sim_config(UpkieSimConfig* c) {
   for (int k = 0; k < 3; ++k) c->init_angular_velocity[k] = c->init_linear_velocity[k] = 0.0;
   c->spine_mode = 0;
   c->reserved_spine_mode = 0;
+  c->body_contacts = 1;  // every link with a <collision> collides with plane.urdf in Bullet (pybullet_backend.py:115,121)
+  c->reserved_body_contacts = 0;
+  c->body_contact_erp = 0.2;  // btContactSolverInfo::m_erp2
+  c->body_friction = 0.5;     // URDF importer default lateral friction of a link without <contact>
 }
 
 inline void default_mpc_config(UpkieMpcConfig* c) {
@@ -196,6 +200,43 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
     err = "config: spine_mode needs joint_limits != 0 (it lives in the extras + limits kernels)";
     return UPKIE_B200_EINVAL;
   }
+  // body-ground contacts: the model's collision points and the gate constants of the packed solvers
+  if (m.n_collision_points < 0 || m.n_collision_points > UPKIE_MAX_COLLISION_POINTS) {
+    err = "model: n_collision_points must be in [0, UPKIE_MAX_COLLISION_POINTS]";
+    return UPKIE_B200_EMODEL;
+  }
+  P.n_bp = m.n_collision_points;
+  P.n_gate_base = 0;
+  for (int k = 0; k < 3; ++k) { P.gate_leg_bound[k].x = -1e30f; P.gate_leg_bound[k].y = -1e30f; }
+  for (int p = 0; p < UPKIE_MAX_COLLISION_POINTS; ++p) {
+    P.bp_body[p] = 0; P.bp_radius[p] = 0.f;
+    for (int k = 0; k < 3; ++k) P.bp_pos[p][k] = 0.f;
+    for (int k = 0; k < 4; ++k) P.gate_base[p][k] = 0.f;
+  }
+  for (int p = 0; p < P.n_bp; ++p) {
+    const int b = m.collision_body[p];
+    if (b < 0 || b >= UPKIE_NB || !(m.collision_radius[p] >= 0.0)) {
+      err = "model: collision point on an unknown body or with a negative radius";
+      return UPKIE_B200_EMODEL;
+    }
+    P.bp_body[p] = b;
+    for (int k = 0; k < 3; ++k) P.bp_pos[p][k] = float(m.collision_point[p][k]);
+    P.bp_radius[p] = float(m.collision_radius[p]);
+    const double* cp = m.collision_point[p];
+    if (b == 0) {
+      float* g = P.gate_base[P.n_gate_base++];
+      g[0] = P.bp_pos[p][0]; g[1] = P.bp_pos[p][1]; g[2] = P.bp_pos[p][2]; g[3] = P.bp_radius[p];
+    } else {
+      // a point on a leg body can be at most |point| + radius below that body's origin (1 mm of slack for fp32)
+      const float bound = float(std::sqrt(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]) + m.collision_radius[p] + 1e-3);
+      const int leg = (b - 1) / 3, k = (b - 1) % 3;
+      float& slot = leg == 0 ? P.gate_leg_bound[k].x : P.gate_leg_bound[k].y;
+      if (bound > slot) slot = bound;
+    }
+  }
+  P.body_contacts = (c.body_contacts != 0 && P.n_bp > 0 && P.joint_limits != 0) ? 1 : 0;
+  P.body_erp = float(c.body_contact_erp);
+  P.body_mu_scale = float(c.body_friction);
   for (int j = 0; j < 6; ++j) P.init_q[j] = float(c.init_joint_configuration[j]);
   for (int k = 0; k < 3; ++k) {
     P.init_angvel[k] = float(c.init_angular_velocity[k]);

@@ -98,6 +98,22 @@ struct SimParams {
   // nominal joint configuration / base velocities of the initial state (RobotState.sample_state keeps / adds them)
   float init_q[6], init_angvel[3], init_linvel[3];
   int spine_mode;  // 1: timing of the C++ Bullet spine in simulate() mode (include/upkie_b200.h: spine_mode)
+  // body-ground contacts (config.body_contacts; the NOISE >= 2 instantiations). Collision points of the model:
+  int body_contacts;       // 1: on AND the model has collision points
+  int n_bp;
+  int bp_body[UPKIE_MAX_COLLISION_POINTS];
+  float bp_pos[UPKIE_MAX_COLLISION_POINTS][3];
+  float bp_radius[UPKIE_MAX_COLLISION_POINTS];
+  // the per-substep gate of the packed solvers (sim_pair.cuh body_points_near_ground): base-body points exactly
+  // (x, y, z, radius), leg bodies through the height of the body origin minus a bound on |point| + radius
+  int n_gate_base;
+  float gate_base[UPKIE_MAX_COLLISION_POINTS][4];
+  f2 gate_leg_bound[3];    // (left, right) per level hip / knee / wheel body; -1e30 = no collision point on that body
+  float body_erp, body_mu_scale;
+  // device buffer [UPKIE_BODY_REC_DIM][body_rec_stride] the step kernels write the body contacts of a tick's last
+  // substep to (upkie_b200_get_body_contacts); null in the host build and when the handle has no body contacts
+  float* body_rec;
+  int body_rec_stride;
 };
 
 // per-robot state in registers
@@ -827,12 +843,14 @@ namespace upkie_b200 {
 // `wext`: external wrench on the base (moment about the base origin, force; base coordinates) or null
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void substep(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu, AnyFn warp_any,
-                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr, int limits = 0, bool locked = false) {
+                      SyncFn phase_sync = SyncFn(), const float* wext = nullptr, int limits = 0, bool locked = false,
+                      BodyRecOut rec = BodyRecOut{nullptr, 0}) {
 #if UPKIE_PAIRED_LEGS
-  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext, limits, locked);
+  physics_substep_paired(P, S, tau, eps, mu, warp_any, phase_sync, wext, limits, locked, rec);
 #else
   (void)limits;  // the scalar-leg build has no joint-limit rows
   (void)locked;
+  (void)rec;
   physics_substep(P, S, tau, eps, mu, warp_any, phase_sync, wext);
 #endif
 }
@@ -939,8 +957,9 @@ UPKIE_HD void observe_update(const SimParams& P, RobotState& S) {
 }
 
 UPKIE_HD float base_pitch(const RobotState& S) {
-  // pybullet_backend.py:350-352
-  return asinf(2.f * (S.quat[0] * S.quat[2] - S.quat[3] * S.quat[1]));
+  // pybullet_backend.py:350-352. The argument is sin(pitch) of a unit quaternion; clamped because round-off can put
+  // it an ulp beyond 1 when the torso lies flat on the floor (np.arcsin would hand out nan there)
+  return asinf(clampf(2.f * (S.quat[0] * S.quat[2] - S.quat[3] * S.quat[1]), -1.f, 1.f));
 }
 
 // scipy Rotation.from_matrix(...).as_quat(scalar_first=True) (rotations.py:14-33)
@@ -1061,7 +1080,7 @@ template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPKIE_ACT_DIM], bool zero_torque,
                             const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync = SyncFn(),
                             const NoiseCtx* nz = nullptr, int sub = 0, const ExtForces* ext = nullptr,
-                            int limits = 0) {
+                            int limits = 0, BodyRecOut rec = BodyRecOut{nullptr, 0}) {
   float tau[6];
   float noise[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (P.any_ctrl_noise && nz) {
@@ -1088,7 +1107,7 @@ UPKIE_HD void servo_substep(const SimParams& P, RobotState& S, const float a[UPK
 #pragma unroll
       for (int j = 0; j < 6; ++j) tau[j] += tau_add[j];
     }
-    substep(P, S, tau, eps, mu, warp_any, phase_sync, forced ? wbase : nullptr, limits);
+    substep(P, S, tau, eps, mu, warp_any, phase_sync, forced ? wbase : nullptr, limits, false, rec);
   } else if (ext && !zero_torque) {  // the substep of a reset runs without external forces (pybullet_backend.py:227-228)
     float tau_add[6], wbase[6];
     external_generalized_forces(P, S, *ext, tau_add, wbase);
@@ -1109,7 +1128,7 @@ UPKIE_HD uint32_t state_sanity(const RobotState& S) {
 // kernels run (substep(): the f32x2-paired legs unless UPKIE_PAIRED_LEGS is 0), true the scalar-leg variant.
 template <bool SCALAR_LEGS = false, typename AnyFn>
 UPKIE_HD uint32_t step_servo_action(const SimParams& P, RobotState& S, float a[UPKIE_ACT_DIM], const float* eps, float mu,
-                                    AnyFn warp_any) {
+                                    AnyFn warp_any, float* body_rec = nullptr) {
   uint32_t err = 0;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
@@ -1135,7 +1154,8 @@ UPKIE_HD uint32_t step_servo_action(const SimParams& P, RobotState& S, float a[U
       S.torque[j] = tau[j];
     }
     if (SCALAR_LEGS) physics_substep(P, S, tau, eps, mu, warp_any);  // no joint-limit rows in the scalar-leg variant
-    else substep(P, S, tau, eps, mu, warp_any, NoSync(), nullptr, P.joint_limits);
+    else substep(P, S, tau, eps, mu, warp_any, NoSync(), nullptr, P.joint_limits, false,
+                 BodyRecOut{sub + 1 == P.nb_substeps ? body_rec : nullptr, 1});
   }
   observe_update(P, S);
   const float chk = S.quat[0] + S.quat[1] + S.quat[2] + S.quat[3] + S.pos[2] + S.linvel[0];
@@ -1225,10 +1245,10 @@ UPKIE_HD void reset_wrapper_state(RobotState& S) {
 // PyBulletBackend.reset (pybullet_backend.py:220-267) + UpkieGyropod.reset (upkie_gyropod.py:216-244)
 template <typename AnyFn>
 UPKIE_HD void reset_robot(const SimParams& P, RobotState& S, const float init[UPKIE_INIT_DIM], const float* eps, float mu,
-                          AnyFn warp_any, int limits) {
+                          AnyFn warp_any, int limits, BodyRecOut rec = BodyRecOut{nullptr, 0}) {
   reset_pose(S, init);
   const float zero[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  substep(P, S, zero, eps, mu, warp_any, NoSync(), nullptr, limits);  // one stepSimulation (:228)
+  substep(P, S, zero, eps, mu, warp_any, NoSync(), nullptr, limits, false, rec);  // one stepSimulation (:228)
   observe_update(P, S);
   reset_wrapper_state(S);
 }
@@ -1279,7 +1299,8 @@ UPKIE_HD void spine_read_imu(const SimParams& P, RobotState& S, float imu[13]) {
 // stepSimulation. `stopped`: the servos are in moteus kStopped mode (locked joints, zero torque).
 template <typename AnyFn, typename SyncFn>
 UPKIE_HD void spine_cycle(const SimParams& P, RobotState& S, SpineLag& L, const float a[UPKIE_ACT_DIM], bool stopped,
-                          const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync, int limits) {
+                          const float* eps, float mu, AnyFn warp_any, SyncFn phase_sync, int limits,
+                          BodyRecOut rec = BodyRecOut{nullptr, 0}) {
 #pragma unroll
   for (int k = 0; k < 18; ++k) L.rep2[k] = L.rep1[k];
   spine_read_imu(P, S, L.imu);
@@ -1300,7 +1321,7 @@ UPKIE_HD void spine_cycle(const SimParams& P, RobotState& S, SpineLag& L, const 
     L.rep1[3 * j + 1] = S.qd[j];
     L.rep1[3 * j + 2] = t;
   }
-  substep(P, S, tau, eps, mu, warp_any, phase_sync, nullptr, limits, stopped);
+  substep(P, S, tau, eps, mu, warp_any, phase_sync, nullptr, limits, stopped, rec);
 }
 
 // the observation cycle_actuation assembles before it cycles the simulator (Spine.cpp:185-200)
@@ -1342,14 +1363,15 @@ UPKIE_HD void reset_pose_spine(const SimParams& P, RobotState& S, const float in
 // to the agent is the one the third cycle assembled
 template <typename AnyFn>
 UPKIE_HD void reset_robot_spine(const SimParams& P, RobotState& S, SpineLag& L, const float init[UPKIE_INIT_DIM],
-                                const float* eps, float mu, AnyFn warp_any, int limits) {
+                                const float* eps, float mu, AnyFn warp_any, int limits,
+                                BodyRecOut rec = BodyRecOut{nullptr, 0}) {
   reset_pose_spine(P, S, init, L);
   float a[UPKIE_ACT_DIM];
 #pragma unroll
   for (int k = 0; k < UPKIE_ACT_DIM; ++k) a[k] = 0.f;
   for (int c = 0; c < 3; ++c) {
     if (c == 2) spine_assemble_observation(S, L);
-    spine_cycle(P, S, L, a, true, eps, mu, warp_any, NoSync(), limits);
+    spine_cycle(P, S, L, a, true, eps, mu, warp_any, NoSync(), limits, c == 2 ? rec : BodyRecOut{nullptr, 0});
   }
   reset_wrapper_state(S);
 }
@@ -1365,7 +1387,7 @@ UPKIE_HD void spine_observation_from_lag(const SimParams& P, const SpineLag& L, 
     o[UPKIE_SP_BASE_ANGVEL + i] = om_b[i];
     o[UPKIE_SP_BASE_LINVEL + i] = L.obs_base[4 + i];
   }
-  o[UPKIE_SP_PITCH] = asinf(2.f * (L.obs_base[0] * L.obs_base[2] - L.obs_base[3] * L.obs_base[1]));
+  o[UPKIE_SP_PITCH] = asinf(clampf(2.f * (L.obs_base[0] * L.obs_base[2] - L.obs_base[3] * L.obs_base[1]), -1.f, 1.f));
 #pragma unroll
   for (int i = 0; i < 9; ++i) o[UPKIE_SP_ROT + i] = R[i];
 #pragma unroll

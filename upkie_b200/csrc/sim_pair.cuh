@@ -842,13 +842,355 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
   phase_sync();  // 6
 }
 
+// ---- body-ground contacts: gate and general solver ------------------------------------------------------------------
+// Bullet collides every link that has a <collision> shape with plane.urdf (pybullet_backend.py:115,121,306), so a
+// fallen robot rests on its torso. Here the shapes are reduced to collision points (UpkieModel.collision_*); while one
+// of them is closer to the ground than the breaking threshold it holds a normal row and two friction rows. That is rare
+// on the workloads the kernels are tuned for (the envs terminate on a fall), and the row count is open-ended, so such
+// robots do not go through the packed solvers: once per substep a warp asks whether ANY of its robots has a collision
+// point near the ground (body_points_near_ground: a dozen FMAs), and only then solves ALL rows of its robots - joint
+// limits, tires, body points - in general_contact_solve(): scalar, looped, local-memory arrays, compiled as a real
+// function (not inlined) so that its stack frame and registers stay out of the kernels' fast path.
+// Restated from Bullet 3.24 (third-party, absent from the reference tree: parity unpinned): rigid contact for links
+// without <contact> stiffness (cfm 0, erp = m_erp2), friction directions btPlaneSpace1(normal), at most four manifold
+// points per pair, rows ordered limits / normals / frictions as in btMultiBodyConstraintSolver::solveSingleIteration.
+#ifndef UPKIE_BODY_CONTACTS_BUILD
+#define UPKIE_BODY_CONTACTS_BUILD 1  // 0: compile the body-contact path out of the kernels (A/B builds, tools/variants.py)
+#endif
+#if defined(__CUDACC__)
+#define UPKIE_NOINLINE __host__ __device__ __noinline__
+#else
+#define UPKIE_NOINLINE __attribute__((noinline))
+#endif
+
+// where the record of the last substep's body contacts goes (upkie_b200_get_body_contacts): element k at p[k * stride]
+struct BodyRecOut {
+  float* p;
+  size_t stride;
+};
+
+// conservative per-robot test: exact for the points of the base body, through a bounding radius for the leg bodies
+UPKIE_HD bool body_points_near_ground(const SimParams& P, float posz, const LegCache2& lc, const float zb[3]) {
+  bool near = false;
+#pragma unroll 1
+  for (int p = 0; p < P.n_gate_base; ++p) {
+    const float d = posz + zb[0] * P.gate_base[p][0] + zb[1] * P.gate_base[p][1] + zb[2] * P.gate_base[p][2] - P.gate_base[p][3];
+    near = near || (d < P.breaking_threshold);
+  }
+  if (P.n_gate_base < P.n_bp) {  // collision points on leg bodies
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const f2 h = fma2(bc2(zb[0]), lc.ox[k], fma2(bc2(zb[1]), P.oy2[k], fma2(bc2(zb[2]), lc.oz[k], bc2(posz))));
+      near = near || (h.x - P.gate_leg_bound[k].x < P.breaking_threshold) || (h.y - P.gate_leg_bound[k].y < P.breaking_threshold);
+    }
+  }
+  return near;
+}
+
+struct BodySolveIO {
+  // in
+  float R[9];        // base -> world rotation
+  float posz, inv_n, mu;
+  float q[6];
+  LegCache2 lc;
+  float IA0[21];     // LDL^T factors of the base's articulated inertia (ldl6)
+  f2 Pc[3], dist;    // tire contact points (base coordinates) and their distances to the ground
+  int inL, inR;      // tire closer than the breaking threshold
+  int limits;        // joint-limit rows on
+  // in / out
+  float angvel[3], linvel[3], qd[6];
+  float lam_n[2];
+  // out
+  float lam_t[4];
+  float rec[UPKIE_BODY_REC_DIM];
+};
+
+// Velocity change for spatial impulses fb[b] on the bodies (0 base, 1..3 left leg, 4..6 right leg; about the base
+// origin, base coordinates) plus generalized impulses g[j] on the joint coordinates: ab[b] per body, dqd per joint.
+UPKIE_HD void impulse_response_bodies(const SimParams& P, const LegCache2& lc, const float IA0[21], const float fb[7][6],
+                                      const float g[6], float dqd[6], float ab[7][6]) {
+  float u[6], da0[6];
+  for (int i = 0; i < 6; ++i) da0[i] = fb[0][i];
+  for (int leg = 0; leg < 2; ++leg) {
+    float qv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // q = -p
+    for (int k = 2; k >= 0; --k) {
+      const int b = 1 + 3 * leg + k;
+      for (int i = 0; i < 6; ++i) qv[i] += fb[b][i];
+      const float s = lane(P.sgn2[k], leg), ox = lane(lc.ox[k], leg), oz = lane(lc.oz[k], leg);
+      const float uj = s * (qv[1] - oz * qv[3] + ox * qv[5]) + g[3 * leg + k];
+      u[3 * leg + k] = uj;
+      const float c = uj * lane(lc.invD[k], leg);
+      for (int i = 0; i < 6; ++i) qv[i] -= lane(lc.U[k][i], leg) * c;
+    }
+    for (int i = 0; i < 6; ++i) da0[i] += qv[i];
+  }
+  ldl6_solve(IA0, da0);
+  for (int i = 0; i < 6; ++i) ab[0][i] = da0[i];
+  for (int leg = 0; leg < 2; ++leg) {
+    float a[6];
+    for (int i = 0; i < 6; ++i) a[i] = da0[i];
+    for (int k = 0; k < 3; ++k) {
+      float dot = 0.f;
+      for (int i = 0; i < 6; ++i) dot += lane(lc.U[k][i], leg) * a[i];
+      const float dd = (u[3 * leg + k] - dot) * lane(lc.invD[k], leg);
+      dqd[3 * leg + k] = dd;
+      const float w = lane(P.sgn2[k], leg) * dd;
+      a[1] += w;
+      a[3] -= lane(lc.oz[k], leg) * w;
+      a[5] += lane(lc.ox[k], leg) * w;
+      for (int i = 0; i < 6; ++i) ab[1 + 3 * leg + k][i] = a[i];
+    }
+  }
+}
+
+// All constraint rows of one robot: joint limits, tire contacts, body-point contacts. Updates the velocities, the tire
+// impulses and the body-contact record of `io`.
+static UPKIE_NOINLINE void general_contact_solve(const SimParams& P, BodySolveIO& io) {
+  constexpr int kMaxRows = 10 + 3 * UPKIE_MAX_BODY_CONTACTS;
+  const float* R = io.R;
+  const float zb[3] = {R[6], R[7], R[8]};
+  const LegCache2& lc = io.lc;
+  // -- collision points below the breaking threshold, the deepest UPKIE_MAX_BODY_CONTACTS of them in index order
+  int cand[UPKIE_MAX_COLLISION_POINTS];
+  float cdist[UPKIE_MAX_COLLISION_POINTS], cpos[UPKIE_MAX_COLLISION_POINTS][3];
+  int nc = 0;
+  {
+    float cphi[2][3], sphi[2][3];
+    bool have_trig = false;
+    for (int p = 0; p < P.n_bp; ++p) {
+      const int b = P.bp_body[p];
+      float pb[3];
+      if (b == 0) {
+        for (int i = 0; i < 3; ++i) pb[i] = P.bp_pos[p][i];
+      } else {
+        if (!have_trig) {
+          for (int leg = 0; leg < 2; ++leg) {
+            float phi = 0.f;
+            for (int k = 0; k < 3; ++k) {
+              phi += lane(P.sgn2[k], leg) * io.q[3 * leg + k];
+              const float red = phi - 6.28318530718f * rintf(phi * 0.15915494309f);
+              sphi[leg][k] = sinf(red);
+              cphi[leg][k] = cosf(red);
+            }
+          }
+          have_trig = true;
+        }
+        const int leg = (b - 1) / 3, k = (b - 1) % 3;
+        const float c = cphi[leg][k], sn = sphi[leg][k];
+        pb[0] = lane(lc.ox[k], leg) + c * P.bp_pos[p][0] + sn * P.bp_pos[p][2];
+        pb[1] = lane(P.oy2[k], leg) + P.bp_pos[p][1];
+        pb[2] = lane(lc.oz[k], leg) - sn * P.bp_pos[p][0] + c * P.bp_pos[p][2];
+      }
+      const float d = io.posz + zb[0] * pb[0] + zb[1] * pb[1] + zb[2] * pb[2] - P.bp_radius[p];
+      if (d >= P.breaking_threshold) continue;
+      cand[nc] = p;
+      cdist[nc] = d;
+      for (int i = 0; i < 3; ++i) cpos[nc][i] = pb[i] - P.bp_radius[p] * zb[i];  // lowest point of the sphere
+      ++nc;
+    }
+    while (nc > UPKIE_MAX_BODY_CONTACTS) {  // drop the shallowest (the later one on ties)
+      int worst = 0;
+      for (int c = 1; c < nc; ++c)
+        if (cdist[c] >= cdist[worst]) worst = c;
+      for (int c = worst; c + 1 < nc; ++c) {
+        cand[c] = cand[c + 1];
+        cdist[c] = cdist[c + 1];
+        for (int i = 0; i < 3; ++i) cpos[c][i] = cpos[c + 1][i];
+      }
+      --nc;
+    }
+  }
+  for (int k = 0; k < UPKIE_BODY_REC_DIM; ++k) io.rec[k] = 0.f;
+  {
+    unsigned mask = 0;
+    for (int c = 0; c < nc; ++c) { mask |= 1u << cand[c]; io.rec[1 + 4 * c] = float(cand[c]); }
+    io.rec[0] = float(mask);
+  }
+
+  // -- rows. kind 0 normal, 1 friction, 2 joint limit
+  int kind[kMaxRows], body[kMaxRows], joint[kMaxRows], partner[kMaxRows], wheel[kMaxRows], slot[kMaxRows];
+  float dirj[kMaxRows], pen[kMaxRows], J[kMaxRows][6];
+  int n = 0;
+  if (io.limits) {
+    for (int j = 0; j < 6; ++j) {
+      // wheels carry infinite bounds: both tests fail for them
+      const float pen_lo = io.q[j] - P.q_lower[j], pen_hi = P.q_upper[j] - io.q[j];
+      for (int sd = 0; sd < 2; ++sd) {
+        const float pn = sd == 0 ? pen_lo : pen_hi;
+        if (!(pn <= 0.f) || n >= 4) continue;
+        kind[n] = 2; body[n] = -1; joint[n] = j; dirj[n] = sd == 0 ? 1.f : -1.f; pen[n] = pn; partner[n] = -1;
+        wheel[n] = -1; slot[n] = -1;
+        for (int i = 0; i < 6; ++i) J[n][i] = 0.f;
+        ++n;
+      }
+    }
+  }
+  const int nlimit = n;
+  const float t1[3] = {zb[2] * io.inv_n, 0.f, -zb[0] * io.inv_n};
+  float t2[3];
+  cross3(zb, t1, t2);
+  const bool act[2] = {io.inL != 0, io.inR != 0};
+  auto add_row = [&](int b, const float pc[3], const float dir[3], int knd, int prt, int wh, int sl, float pn) {
+    cross3(pc, dir, &J[n][0]);
+    J[n][3] = dir[0]; J[n][4] = dir[1]; J[n][5] = dir[2];
+    kind[n] = knd; body[n] = b; joint[n] = -1; dirj[n] = 0.f; partner[n] = prt; wheel[n] = wh; slot[n] = sl; pen[n] = pn;
+    return n++;
+  };
+  int normal_of_wheel[2] = {-1, -1}, normal_of_slot[UPKIE_MAX_BODY_CONTACTS];
+  for (int sd = 0; sd < 2; ++sd)
+    if (act[sd]) {
+      const float pc[3] = {lane(io.Pc[0], sd), lane(io.Pc[1], sd), lane(io.Pc[2], sd)};
+      normal_of_wheel[sd] = add_row(3 + 3 * sd, pc, zb, 0, -1, sd, -1, lane(io.dist, sd));
+    }
+  for (int c = 0; c < nc; ++c) normal_of_slot[c] = add_row(P.bp_body[cand[c]], cpos[c], zb, 0, -1, -1, c, cdist[c]);
+  for (int sd = 0; sd < 2; ++sd)
+    if (act[sd]) {
+      const float sw = lane(P.sgn2[2], sd);
+      const float pc[3] = {lane(io.Pc[0], sd), lane(io.Pc[1], sd), lane(io.Pc[2], sd)};
+      const float d1[3] = {sw * t1[0], sw * t1[1], sw * t1[2]}, d2[3] = {sw * t2[0], sw * t2[1], sw * t2[2]};
+      add_row(3 + 3 * sd, pc, d1, 1, normal_of_wheel[sd], sd, -1, 0.f);
+      add_row(3 + 3 * sd, pc, d2, 1, normal_of_wheel[sd], sd, -1, 0.f);
+    }
+  {
+    // btPlaneSpace1((0, 0, 1)) = (0, -1, 0), (1, 0, 0) in the world, here in base coordinates
+    const float d1[3] = {-R[3], -R[4], -R[5]}, d2[3] = {R[0], R[1], R[2]};
+    for (int c = 0; c < nc; ++c) {
+      add_row(P.bp_body[cand[c]], cpos[c], d1, 1, normal_of_slot[c], -1, c, 0.f);
+      add_row(P.bp_body[cand[c]], cpos[c], d2, 1, normal_of_slot[c], -1, c, 0.f);
+    }
+  }
+  if (n == 0) {  // nothing to solve
+    io.lam_n[0] = 0.f; io.lam_n[1] = 0.f;
+    for (int k = 0; k < 4; ++k) io.lam_t[k] = 0.f;
+    return;
+  }
+
+  // -- body spatial velocities at the predicted generalized velocity (about the base origin, base coordinates)
+  float Vb[7][6];
+  {
+    rot_tmul(R, io.angvel, &Vb[0][0]);
+    rot_tmul(R, io.linvel, &Vb[0][3]);
+    for (int leg = 0; leg < 2; ++leg) {
+      float v[6];
+      for (int i = 0; i < 6; ++i) v[i] = Vb[0][i];
+      for (int k = 0; k < 3; ++k) {
+        const float w = lane(P.sgn2[k], leg) * io.qd[3 * leg + k];
+        v[1] += w;
+        v[3] -= lane(lc.oz[k], leg) * w;
+        v[5] += lane(lc.ox[k], leg) * w;
+        for (int i = 0; i < 6; ++i) Vb[1 + 3 * leg + k][i] = v[i];
+      }
+    }
+  }
+  // -- Delassus matrix, one response per row
+  float W[kMaxRows][kMaxRows];
+  float fb[7][6], g[6], dqd[6], ab[7][6];
+  for (int l = 0; l < n; ++l) {
+    for (int b = 0; b < 7; ++b)
+      for (int i = 0; i < 6; ++i) fb[b][i] = 0.f;
+    for (int j = 0; j < 6; ++j) g[j] = 0.f;
+    if (kind[l] == 2) g[joint[l]] = dirj[l];
+    else for (int i = 0; i < 6; ++i) fb[body[l]][i] = J[l][i];
+    impulse_response_bodies(P, lc, io.IA0, fb, g, dqd, ab);
+    for (int k = 0; k < n; ++k) {
+      float wkl;
+      if (kind[k] == 2) {
+        wkl = dirj[k] * dqd[joint[k]];
+      } else {
+        wkl = 0.f;
+        for (int i = 0; i < 6; ++i) wkl += J[k][i] * ab[body[k]][i];
+      }
+      W[k][l] = wkl;
+    }
+  }
+  float rhs[kMaxRows], jdi[kMaxRows], cfmrow[kMaxRows], lam[kMaxRows];
+  for (int k = 0; k < n; ++k) {
+    lam[k] = 0.f;
+    if (kind[k] == 2) {
+      const float rel = dirj[k] * io.qd[joint[k]];
+      jdi[k] = W[k][k] > 1.1920929e-7f ? 1.f / W[k][k] : 0.f;
+      rhs[k] = (-pen[k] * P.limit_erp * P.inv_h - rel) * jdi[k];
+      cfmrow[k] = 0.f;
+      continue;
+    }
+    float rel = 0.f;
+    for (int i = 0; i < 6; ++i) rel += J[k][i] * Vb[body[k]][i];
+    if (kind[k] == 0) {
+      // tires: soft contact from their <contact> stiffness / damping; other links: rigid (cfm 0, erp = m_erp2)
+      const bool tire = wheel[k] >= 0;
+      if (tire) lam[k] = P.warm * io.lam_n[wheel[k]];
+      const float row_cfm = tire ? P.cfm : 0.f, row_erp = tire ? P.erp : P.body_erp;
+      jdi[k] = 1.f / (W[k][k] + row_cfm);
+      float pos_err = 0.f, vel_err = -rel;
+      if (pen[k] > 0.f) vel_err -= pen[k] * P.inv_h;
+      else pos_err = -pen[k] * row_erp * P.inv_h;
+      rhs[k] = (pos_err + vel_err) * jdi[k];
+      cfmrow[k] = row_cfm * jdi[k];
+    } else {
+      jdi[k] = W[k][k] > 0.f ? 1.f / W[k][k] : 0.f;
+      rhs[k] = -rel * jdi[k];
+      cfmrow[k] = 0.f;
+    }
+  }
+  const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+  for (int it = 0; it < P.pgs_iterations; ++it) {
+    bool changed = false;
+    for (int pos = 0; pos < n; ++pos) {
+      const int k = pos < nlimit ? ((it & 1) ? pos : nlimit - 1 - pos) : pos;
+      float jdv = 0.f;
+      for (int l = 0; l < n; ++l) jdv += W[k][l] * lam[l];
+      const float sum = lam[k] + (rhs[k] - lam[k] * cfmrow[k] - jdv * jdi[k]);
+      float lo, hi;
+      if (kind[k] == 0) { lo = 0.f; hi = 1e10f; }
+      else if (kind[k] == 2) { lo = 0.f; hi = P.limit_max_impulse; }
+      else { hi = io.mu * (wheel[k] >= 0 ? 1.f : P.body_mu_scale) * lam[partner[k]]; lo = -hi; }
+      const float nl = fminf(fmaxf(sum, lo), hi);
+      changed = changed | (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+      lam[k] = nl;
+    }
+    if (!changed) break;  // per robot (the packed solvers vote per warp)
+  }
+  // -- apply the total impulse
+  for (int b = 0; b < 7; ++b)
+    for (int i = 0; i < 6; ++i) fb[b][i] = 0.f;
+  for (int j = 0; j < 6; ++j) g[j] = 0.f;
+  io.lam_n[0] = 0.f;
+  io.lam_n[1] = 0.f;
+  for (int k = 0; k < 4; ++k) io.lam_t[k] = 0.f;
+  int nfric[2] = {0, 0}, nbf[UPKIE_MAX_BODY_CONTACTS] = {0, 0, 0, 0};
+  for (int k = 0; k < n; ++k) {
+    if (kind[k] == 2) {
+      g[joint[k]] += dirj[k] * lam[k];
+      continue;
+    }
+    for (int i = 0; i < 6; ++i) fb[body[k]][i] += J[k][i] * lam[k];
+    if (wheel[k] >= 0) {
+      if (kind[k] == 0) io.lam_n[wheel[k]] = lam[k];
+      else io.lam_t[2 * wheel[k] + nfric[wheel[k]]++] = lam[k];  // rolling row first, then lateral
+    } else {
+      const int c = slot[k];
+      if (kind[k] == 0) io.rec[1 + 4 * c + 1] = lam[k];
+      else io.rec[1 + 4 * c + 2 + nbf[c]++] = lam[k];
+    }
+  }
+  impulse_response_bodies(P, lc, io.IA0, fb, g, dqd, ab);
+  float dw[3], dv[3];
+  rot_mul(R, &ab[0][0], dw);
+  rot_mul(R, &ab[0][3], dv);
+  for (int i = 0; i < 3; ++i) {
+    io.angvel[i] = clampf(io.angvel[i] + dw[i], -P.vmax, P.vmax);
+    io.linvel[i] = clampf(io.linvel[i] + dv[i], -P.vmax, P.vmax);
+  }
+  for (int j = 0; j < 6; ++j) io.qd[j] = clampf(io.qd[j] + dqd[j], -P.vmax, P.vmax);
+}
+
 // row / column index of (side, direction) in Bullet's order: nL nR t1L t2L t1R t2R
 UPKIE_HD constexpr int row_of(int side, int d) { return d == 0 ? side : 2 + 2 * side + (d - 1); }
 
 template <typename AnyFn, typename SyncFn = NoSync>
 UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const float tau[6], const float* eps, float mu,
                                      AnyFn warp_any, SyncFn phase_sync = SyncFn(), const float* wext = nullptr,
-                                     int limits = 0, bool locked = false) {
+                                     int limits = 0, bool locked = false, BodyRecOut rec = BodyRecOut{nullptr, 0}) {
   float R[9];
   quat_to_rot(S.quat, R);
   float V0[6];
@@ -909,11 +1251,17 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   // The scalar slow path exists in the HOST build only (the CPU test-suite's independent second implementation of the
   // limit rows): on a B200 it measured 18x the plain kernel on the torque workload (profiles/r02_limits.md) and its
   // dynamically indexed local arrays cost every NOISE=2 kernel a 2 KB stack frame. On the device 1 aliases to 3.
+  // body-ground contacts: a warp that holds a robot with a collision point near the ground solves all rows of its
+  // robots in general_contact_solve() instead of the packed solvers (warp-uniform choice)
+  bool body_slow = false;
+#if UPKIE_BODY_CONTACTS_BUILD
+  if (limits != 0 && P.body_contacts) body_slow = warp_any(body_points_near_ground(P, S.pos[2], lc, zb));
+#endif
 #if defined(__CUDA_ARCH__)
   const bool slow = false;
   if (limits == 1) limits = 3;
 #else
-  const bool slow = limits == 1 && active_joint_limits(P, S.q, lim) > 0;
+  const bool slow = !body_slow && limits == 1 && active_joint_limits(P, S.q, lim) > 0;
 #endif
   const float lam_prev[2] = {S.lam_n[0], S.lam_n[1]};
   const bool actL = inL && !slow, actR = inR && !slow;
@@ -922,7 +1270,7 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
   // limits == 3: the ten-row solver only for warps that hold a robot on a bound (warp-uniform choice), the six-row
   // contact block otherwise: workloads that never reach a bound (position-controlled legs) keep the plain cost
   bool ten_rows = limits == 2;
-  if (limits == 3) {
+  if (limits == 3 && !body_slow) {
     bool on_bound = false;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -931,6 +1279,41 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
     }
     ten_rows = warp_any(on_bound);
   }
+#if UPKIE_BODY_CONTACTS_BUILD
+  if (body_slow) {
+    phase_sync();  // 3
+    phase_sync();  // 4
+    phase_sync();  // 5
+    BodySolveIO io;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) io.R[i] = R[i];
+    io.posz = S.pos[2]; io.inv_n = inv_n; io.mu = mu;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { io.q[j] = S.q[j]; io.qd[j] = S.qd[j]; }
+    io.lc = lc;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) io.IA0[i] = IA0[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { io.Pc[i] = Pc[i]; io.angvel[i] = S.angvel[i]; io.linvel[i] = S.linvel[i]; }
+    io.dist = dist;
+    io.inL = inL ? 1 : 0; io.inR = inR ? 1 : 0;
+    io.limits = 1;
+    io.lam_n[0] = S.lam_n[0]; io.lam_n[1] = S.lam_n[1];
+    general_contact_solve(P, io);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { S.angvel[i] = io.angvel[i]; S.linvel[i] = io.linvel[i]; }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) S.qd[j] = io.qd[j];
+    S.lam_n[0] = io.lam_n[0]; S.lam_n[1] = io.lam_n[1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) S.lam_t[k] = io.lam_t[k];
+    if (rec.p) {
+#pragma unroll 1
+      for (int k = 0; k < UPKIE_BODY_REC_DIM; ++k) rec.p[size_t(k) * rec.stride] = io.rec[k];
+    }
+    phase_sync();  // 6
+  } else
+#endif
   if (ten_rows) {
     contact_solve_ten_rows(P, S, lc, IA0, nIA0, R, zb, inv_n, Pc, dist, inL, inR, mu, warp_any, phase_sync);
   } else if (!warp_any(actL || actR)) {
@@ -1147,6 +1530,7 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
 #else
   (void)lam_prev;
 #endif
+  if (rec.p && !body_slow) rec.p[0] = 0.f;  // no body contact held rows in this substep
 
   // -- position integration with the new velocities (as physics_substep)
 #pragma unroll

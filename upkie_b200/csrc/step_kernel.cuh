@@ -161,12 +161,15 @@ __device__ __forceinline__ void step_env(
     }
 #endif
     if (sub < nsub) {
+      // the body-ground contacts of the tick's last substep go to the handle's record (NOISE >= 2 kernels)
+      const BodyRecOut br{(NOISE >= 2 && P.body_rec && live && sub == nsub - 1) ? P.body_rec + i : nullptr,
+                          size_t(P.body_rec_stride)};
       if (spine) {
         if (resetting && sub == 2) spine_assemble_observation(S, L);
-        spine_cycle(P, S, L, a, resetting, eps, mu, WarpAny(), PhaseSync(), P.joint_limits >= 1 ? P.joint_limits : 1);
+        spine_cycle(P, S, L, a, resetting, eps, mu, WarpAny(), PhaseSync(), P.joint_limits >= 1 ? P.joint_limits : 1, br);
       } else {
         servo_substep(P, S, a, resetting, eps, mu, WarpAny(), PhaseSync(), NOISE ? &nz : nullptr, sub,
-                      (NOISE && ext) ? &xf : nullptr, NOISE >= 2 ? (P.joint_limits >= 1 ? P.joint_limits : 1) : 0);
+                      (NOISE && ext) ? &xf : nullptr, NOISE >= 2 ? (P.joint_limits >= 1 ? P.joint_limits : 1) : 0, br);
       }
     } else {
 #pragma unroll
@@ -201,8 +204,9 @@ __device__ __forceinline__ void step_env(
       if (live) episode[i] = ep;
       float init[UPKIE_INIT_DIM];
       sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
-      if (spine) reset_robot_spine(P, S, L, init, eps, mu, WarpAny(), P.joint_limits);
-      else reset_robot(P, S, init, eps, mu, WarpAny(), NOISE >= 2 ? P.joint_limits : 0);
+      const BodyRecOut br{(NOISE >= 2 && P.body_rec && live) ? P.body_rec + i : nullptr, size_t(P.body_rec_stride)};
+      if (spine) reset_robot_spine(P, S, L, init, eps, mu, WarpAny(), P.joint_limits, br);
+      else reset_robot(P, S, init, eps, mu, WarpAny(), NOISE >= 2 ? P.joint_limits : 0, br);
       if (MODE != MODE_SERVOS) gyropod_obs(P, S, o6);
     }
   }

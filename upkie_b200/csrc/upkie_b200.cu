@@ -60,6 +60,7 @@ struct Handle {
   uint32_t* tick = nullptr;      // [n] env ticks since create: counter of the noise generator
   float* ext = nullptr;          // [7 * 3][n_pad] external forces, null = none
   float* lag = nullptr;          // [UPKIE_LAG_DIM][n_pad] spine-mode lag records (config.spine_mode), else null
+  float* body_rec = nullptr;     // [UPKIE_BODY_REC_DIM][n_pad] body-ground contacts of the last substep (config.body_contacts)
   uint32_t ext_local = 0;
   int autoreset = AUTORESET_DISABLED;
   uint64_t seed = 0, env_offset = 0;
@@ -117,14 +118,15 @@ k_reset(const __grid_constant__ SimParams P, int n, int n_pad, float* __restrict
     episode[i] = ep;
     sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
   }
+  const BodyRecOut br{P.body_rec ? P.body_rec + i : nullptr, size_t(P.body_rec_stride)};
   if (P.spine_mode && lag) {
     SpineLag L;
-    reset_robot_spine(P, S, L, init, eps, mu, WarpAny(), P.joint_limits);
+    reset_robot_spine(P, S, L, init, eps, mu, WarpAny(), P.joint_limits, br);
     float lr[UPKIE_LAG_DIM];
     lag_to_row(L, lr);
     for (int k = 0; k < UPKIE_LAG_DIM; ++k) lag[size_t(k) * n_pad + i] = lr[k];
   } else {
-    reset_robot(P, S, init, eps, mu, WarpAny(), P.joint_limits);
+    reset_robot(P, S, init, eps, mu, WarpAny(), P.joint_limits, br);
   }
   store_state(state, n_pad, i, S);
   err[i] = 0;
@@ -512,6 +514,12 @@ int upkie_b200_create(const UpkieModel* model, const UpkieSimConfig* config, int
     e = cudaMalloc(&h->lag, size_t(UPKIE_LAG_DIM) * h->n_pad * sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(h->lag, 0, size_t(UPKIE_LAG_DIM) * h->n_pad * sizeof(float));
   }
+  if (e == cudaSuccess && h->P.body_contacts) {
+    e = cudaMalloc(&h->body_rec, size_t(UPKIE_BODY_REC_DIM) * h->n_pad * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(h->body_rec, 0, size_t(UPKIE_BODY_REC_DIM) * h->n_pad * sizeof(float));
+    h->P.body_rec = h->body_rec;
+    h->P.body_rec_stride = h->n_pad;
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->tick, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(h->tick, 0, size_t(n_envs) * sizeof(uint32_t));
   if (e == cudaSuccess) {
@@ -533,7 +541,7 @@ void upkie_b200_destroy(void* handle) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->state); cudaFree(h->eps); cudaFree(h->mu); cudaFree(h->err); cudaFree(h->done_prev); cudaFree(h->episode);
-  cudaFree(h->tick); cudaFree(h->ext); cudaFree(h->lag);
+  cudaFree(h->tick); cudaFree(h->ext); cudaFree(h->lag); cudaFree(h->body_rec);
   cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_term); cudaFreeHost(h->h_trunc);
   cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_term); cudaFree(h->d_trunc);
   for (int k = 0; k < kHostStreams; ++k)
@@ -558,6 +566,13 @@ int upkie_b200_set_config(void* handle, const UpkieSimConfig* config) {
   int rc = make_sim_params(h->model, *config, P, err);
   if (rc) return fail(rc, err);
   if (P.spine_mode != h->P.spine_mode) return fail(UPKIE_B200_EINVAL, "set_config: spine_mode is fixed at creation");
+  if (P.body_contacts && !h->body_rec) {  // switched on after creation: the record buffer is allocated now
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMalloc(&h->body_rec, size_t(UPKIE_BODY_REC_DIM) * h->n_pad * sizeof(float)));
+    CUDA_TRY(cudaMemset(h->body_rec, 0, size_t(UPKIE_BODY_REC_DIM) * h->n_pad * sizeof(float)));
+  }
+  P.body_rec = P.body_contacts ? h->body_rec : nullptr;
+  P.body_rec_stride = h->n_pad;
   // kernels read the parameter block by value at launch: steps already enqueued keep the old one
   h->P = P;
   return UPKIE_B200_OK;
@@ -792,6 +807,22 @@ __global__ void k_lag_copy(int n, int n_pad, float* __restrict__ lag, float* __r
     if (to_rows) rows[size_t(i) * UPKIE_LAG_DIM + k] = lag[size_t(k) * n_pad + i];
     else lag[size_t(k) * n_pad + i] = rows[size_t(i) * UPKIE_LAG_DIM + k];
   }
+}
+
+__global__ void k_body_rec_rows(int n, int n_pad, const float* __restrict__ rec, float* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < UPKIE_BODY_REC_DIM; ++k) rows[size_t(i) * UPKIE_BODY_REC_DIM + k] = rec ? rec[size_t(k) * n_pad + i] : 0.f;
+}
+
+int upkie_b200_get_body_contacts(void* handle, float* rows, void* stream) {
+  Handle* h = as_handle(handle);
+  if (!h || !rows) return fail(UPKIE_B200_EINVAL, "get_body_contacts: invalid argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_body_rec_rows<<<(h->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->n, h->n_pad, h->P.body_contacts ? h->body_rec : nullptr, rows);
+  CUDA_TRY(cudaGetLastError());
+  return UPKIE_B200_OK;
 }
 
 int upkie_b200_get_lag(void* handle, float* lag_rows, void* stream) {

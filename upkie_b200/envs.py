@@ -226,6 +226,7 @@ def make_config(
     noise_seed: int = 0,
     joint_limits: Union[bool, int] = True,
     spine_mode: bool = False,
+    body_contacts: bool = True,
 ) -> _abi.UpkieSimConfig:
     """Split of the keyword arguments the reference's factories forward to the
     backend, the servo env and the wrappers (``upkie/envs/entry_points.py:41-61,99-109``)."""
@@ -251,6 +252,9 @@ def make_config(
     cfg.joint_limits = 3 if joint_limits is True else int(joint_limits)
     # timing of the C++ Bullet spine in simulate() mode instead of PyBulletBackend's (include/upkie_b200.h: spine_mode)
     cfg.spine_mode = 1 if spine_mode else 0
+    # body-ground contacts (include/upkie_b200.h: body_contacts): the collision shapes of the model's links other than
+    # the tires hold contact rows against the floor, as they do in Bullet; needs the joint-limit kernels
+    cfg.body_contacts = 1 if (body_contacts and cfg.joint_limits) else 0
     cfg.max_gain_scale = max_gain_scale
     cfg.fall_pitch = fall_pitch
     cfg.leg_gain_scale = leg_gain_scale
@@ -293,6 +297,7 @@ class B200VectorEnv(VectorEnv):
         joint_limits: Union[bool, int] = True,
         copy: bool = True,
         spine_mode: bool = False,
+        body_contacts: bool = True,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")
@@ -318,7 +323,7 @@ class B200VectorEnv(VectorEnv):
             config = make_config(
                 frequency, nb_substeps, torque_control_kp, torque_control_kd, joint_properties, max_gain_scale,
                 fall_pitch, leg_gain_scale, max_ground_velocity, max_yaw_velocity, self.init_state, noise_seed,
-                joint_limits, spine_mode,
+                joint_limits, spine_mode, body_contacts,
             )
         self.config = config
         if self.config.spine_mode and env_type != "servos":
@@ -405,7 +410,8 @@ class B200VectorEnv(VectorEnv):
         from .model import contact_points_from_state
 
         row = self.sim.get_state()[int(env_index)].cpu().numpy()
-        return contact_points_from_state(self.model, row, self.config, link_name)
+        rec = self.sim.get_body_contacts()[int(env_index)].cpu().numpy()
+        return contact_points_from_state(self.model, row, self.config, link_name, rec)
 
     def set_external_forces(self, external_forces: Optional[dict]) -> None:
         """Batched ``PyBulletBackend.set_external_forces``: ``{link name: ExternalForce}`` whose ``force`` is

@@ -126,6 +126,47 @@ class Model:
     link_body: dict = field(default_factory=lambda: dict(_STANDIN_LINK_BODY))
     # link frame -> body (lump) frame rotation at the zero configuration, identity when absent
     link_rotation: dict = field(default_factory=dict)
+    # Collision shapes of the links other than the tires, reduced to what they are against the ground plane
+    # (``UpkieModel.collision_*``): points in the frame of the moving body they belong to, with a radius, and the
+    # name of the URDF link that carries the shape (what ``get_contact_points`` reports). Bullet collides every link
+    # that has a ``<collision>`` with plane.urdf (``pybullet_backend.py:115,121``); ``upkie.model.Link`` parses the
+    # same elements (``upkie/model/link.py:53-91``).
+    collision_body: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))
+    collision_point: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+    collision_radius: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    collision_link: List[str] = field(default_factory=list)
+    # the shapes themselves, for write_urdf: dicts {link, body, kind ("box" / "sphere" / "capsule" / "cylinder"), size,
+    # center (body frame, base axes)}
+    collision_shapes: List[dict] = field(default_factory=list)
+
+    def add_collision_shape(self, link: str, body: int, kind: str, size, center, rotation=None) -> None:
+        """Attach a collision shape to moving body ``body``: ``box`` (size = the three edge lengths) -> its 8 corners;
+        ``sphere`` (size = [radius]) -> its centre; ``capsule`` / ``cylinder`` (size = [radius, length], axis along the
+        shape's z) -> the two end points of the axis with the radius (for a cylinder that rounds its rims).
+        ``center`` and ``rotation`` (3x3, shape axes -> body axes at the zero configuration) place the shape in the body
+        frame."""
+        R = np.eye(3) if rotation is None else np.asarray(rotation, dtype=float).reshape(3, 3)
+        c = np.asarray(center, dtype=float)
+        size = [float(x) for x in size]
+        if kind == "box":
+            pts = [c + R @ (0.5 * np.array([sx * size[0], sy * size[1], sz * size[2]]))
+                   for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]
+            rad = [0.0] * 8
+        elif kind == "sphere":
+            pts, rad = [c], [size[0]]
+        elif kind in ("capsule", "cylinder"):
+            half = 0.5 * size[1] * (R @ np.array([0.0, 0.0, 1.0]))
+            pts, rad = [c - half, c + half], [size[0], size[0]]
+        else:
+            raise ValueError(f"unsupported collision shape {kind}")
+        if len(self.collision_body) + len(pts) > _abi.MAX_COLLISION_POINTS:
+            raise ValueError(f"more than {_abi.MAX_COLLISION_POINTS} collision points")
+        self.collision_body = np.concatenate([self.collision_body, np.full(len(pts), int(body), dtype=int)])
+        self.collision_point = np.concatenate([self.collision_point.reshape(-1, 3), np.asarray(pts)])
+        self.collision_radius = np.concatenate([self.collision_radius, np.asarray(rad)])
+        self.collision_link = list(self.collision_link) + [link] * len(pts)
+        self.collision_shapes = list(self.collision_shapes) + [
+            dict(link=link, body=int(body), kind=kind, size=size, center=c.tolist(), rotation=R.tolist())]
 
     def external_force_rows(self, external_forces: dict, n: int = 1):
         """``{link name: ExternalForce}`` (``PyBulletBackend.set_external_forces``, ``pybullet_backend.py:603-625``)
@@ -221,6 +262,12 @@ class Model:
         R = np.asarray(self.rotation_base_to_imu, dtype=float).reshape(9)
         for k in range(9):
             s.rotation_base_to_imu[k] = float(R[k])
+        s.n_collision_points = len(self.collision_body)
+        for p in range(len(self.collision_body)):
+            s.collision_body[p] = int(self.collision_body[p])
+            s.collision_radius[p] = float(self.collision_radius[p])
+            for k in range(3):
+                s.collision_point[p][k] = float(self.collision_point[p][k])
         return s
 
     # ---- constructors ---------------------------------------------------------
@@ -293,7 +340,7 @@ class Model:
             ]
         )
         inf = math.inf
-        return Model(
+        model = Model(
             parent=parent,
             joint_origin=joint_origin,
             joint_axis=joint_axis,
@@ -310,6 +357,10 @@ class Model:
             imu_position=np.array([-0.01, 0.0, -0.06]),
             rotation_base_to_imu=np.diag([-1.0, 1.0, -1.0]),
         )
+        # collision box of the torso: the box the base lump's inertia was authored from, about its centre of mass
+        # (stand-in like the inertias: the real shapes live in upkie_description)
+        model.add_collision_shape("torso", 0, "box", (bx, by, bz), com[0])
+        return model
 
     @staticmethod
     def from_urdf(urdf_path: str) -> "Model":
@@ -407,17 +458,76 @@ def wheel_contact_points(model, state_row, substep_dt: float, breaking_threshold
 TIRE_LINKS = ("left_wheel_tire", "right_wheel_tire")
 
 
-def contact_points_from_state(model, state_row, config, link_name=None):
-    """``PyBulletBackend.get_contact_points`` (``pybullet_backend.py:660-716``) for one robot from its state row:
-    ``PointContact`` instances on ``left_wheel_tire`` / ``right_wheel_tire``, filtered by ``link_name``. A link
-    without simulated contacts, or one the robot does not have, yields ``[]`` like the reference. ``force_in_world`` =
-    normal + two friction components of the last substep, as the reference sums them (``pybullet_backend.py:696-709``)."""
-    if link_name is not None and link_name not in TIRE_LINKS:
+def body_points_in_world(model, state_row):
+    """World positions ``[K, 3]`` of the model's collision points (``Model.collision_point``) for one robot, from its
+    state row: the kinematics of the step kernels restated on the host (every joint turns about +-y of the base)."""
+    row = np.asarray(state_row, dtype=float)
+    pos = row[_abi.ST_POS:_abi.ST_POS + 3]
+    w, x, y, z = row[_abi.ST_QUAT:_abi.ST_QUAT + 4]
+    R = np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)],
+    ])
+    q = row[_abi.ST_Q:_abi.ST_Q + 6]
+    frames = [(np.zeros(3), np.eye(3))]  # body -> (origin, rotation) in base coordinates
+    for side in (0, 1):
+        origin, phi = np.zeros(3), 0.0
+        for k in range(3):
+            j = 3 * side + k
+            c, s = np.cos(phi), np.sin(phi)
+            Ry = np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])
+            origin = origin + Ry @ np.asarray(model.joint_origin[j], dtype=float)
+            phi += float(model.joint_axis[j][1]) * q[j]
+            c, s = np.cos(phi), np.sin(phi)
+            frames.append((origin, np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])))
+    out = np.zeros((len(model.collision_body), 3))
+    for p, b in enumerate(model.collision_body):
+        o, Rb = frames[int(b)]
+        out[p] = pos + R @ (o + Rb @ np.asarray(model.collision_point[p], dtype=float))
+    return out
+
+
+def body_contact_points(model, state_row, body_rec_row, substep_dt: float):
+    """Body-ground contacts of one robot from the record of the last substep (``UpkieSim.get_body_contacts`` row,
+    layout ``upkie_b200_get_body_contacts``): ``[(link name, position_in_world[3], force_in_world[3]), ...]``. The
+    position is the lowest point of the collision sphere at the current state; the force sums the normal impulse
+    (+z) and the two friction impulses (world -y and +x, the solver's directions), over the substep."""
+    rec = np.asarray(body_rec_row, dtype=float)
+    mask = int(round(rec[0]))
+    if mask == 0 or len(model.collision_body) == 0:
         return []
+    pts = body_points_in_world(model, state_row)
+    out = []
+    for c in range(min(bin(mask).count("1"), _abi.MAX_BODY_CONTACTS)):  # one slot per bit of the mask, in point order
+        p = int(round(rec[1 + 4 * c]))
+        lam_n, lam_1, lam_2 = rec[1 + 4 * c + 1:1 + 4 * c + 4]
+        position = pts[p] - np.array([0.0, 0.0, float(model.collision_radius[p])])
+        force = np.array([lam_2, -lam_1, lam_n]) / substep_dt
+        out.append((model.collision_link[p], position, force))
+    return out
+
+
+def contact_points_from_state(model, state_row, config, link_name=None, body_rec_row=None):
+    """``PyBulletBackend.get_contact_points`` (``pybullet_backend.py:660-716``) for one robot from its state row:
+    ``PointContact`` instances on ``left_wheel_tire`` / ``right_wheel_tire`` and, with ``body_rec_row`` (the robot's row
+    of ``UpkieSim.get_body_contacts``), on the links that carry collision shapes (the torso...), filtered by
+    ``link_name``. A link without simulated contacts, or one the robot does not have, yields ``[]`` like the reference.
+    ``force_in_world`` = normal + two friction components of the last substep, as the reference sums them
+    (``pybullet_backend.py:696-709``)."""
     h = float(config.dt) / int(config.nb_substeps)
-    contacts = wheel_contact_points(model, state_row, h, breaking_threshold=float(config.contact_breaking_threshold))
-    return [
-        PointContact(TIRE_LINKS[side], position, np.asarray(force, dtype=float))
-        for side, position, force in contacts
-        if link_name is None or TIRE_LINKS[side] == link_name
-    ]
+    out = []
+    if link_name is None or link_name in TIRE_LINKS:
+        contacts = wheel_contact_points(model, state_row, h, breaking_threshold=float(config.contact_breaking_threshold))
+        out += [
+            PointContact(TIRE_LINKS[side], position, np.asarray(force, dtype=float))
+            for side, position, force in contacts
+            if link_name is None or TIRE_LINKS[side] == link_name
+        ]
+    if body_rec_row is not None and (link_name is None or link_name not in TIRE_LINKS):
+        out += [
+            PointContact(name, position, force)
+            for name, position, force in body_contact_points(model, state_row, body_rec_row, h)
+            if link_name is None or name == link_name
+        ]
+    return out

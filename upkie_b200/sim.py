@@ -329,6 +329,15 @@ class UpkieSim:
         check(lib().upkie_b200_get_state(self._h, _ptr(out), self._stream()))
         return out
 
+    def get_body_contacts(self) -> torch.Tensor:
+        """Body-ground contacts of the last substep, ``[n, BODY_REC_DIM]``: bit mask of the model's collision points that
+        held contact rows, then per slot (collision point index, normal impulse, friction impulses along world -y and
+        +x). What ``PyBulletBackend.get_contact_points`` reports for links other than the tires
+        (``pybullet_backend.py:660-716``)."""
+        out = torch.empty((self.n, _abi.BODY_REC_DIM), dtype=torch.float32, device=self.device)
+        check(lib().upkie_b200_get_body_contacts(self._h, _ptr(out), self._stream()))
+        return out
+
     def get_lag(self) -> torch.Tensor:
         """Spine mode: the lag records ``[N, LAG_DIM]`` (servo replies of the last two cycles, last IMU reading, the
         last assembled observation; ``include/upkie_b200.h`` ``UPKIE_LAG_*``)."""

@@ -161,7 +161,30 @@ def load_urdf_model(urdf_path: str):
     if abs(z_hub[0]) > 1e-4 or abs(z_hub[2]) > 1e-4:
         raise ModelError(f"the z-axis of the left-wheel hub {z_hub} is not aligned with the y-axis of the base frame")
     R_base_from_imu, p_imu = T["imu"]
-    return Model(
+    # collision shapes of the links other than the tires -> collision points of the moving bodies
+    shapes = []
+    for name, link in links.items():
+        if name not in body_of or name.endswith("_wheel_tire"):
+            continue
+        for col in link.findall("collision"):
+            geom = col.find("geometry")
+            if geom is None:
+                continue
+            Rc, pc = _origin(col)
+            Rl, pl = T[name]
+            b = body_of[name]
+            center = pl + Rl @ pc - body_origin[b]
+            rot = Rl @ Rc
+            if geom.find("box") is not None:
+                shapes.append((name, b, "box", _vec(geom.find("box").get("size"), [0, 0, 0]), center, rot))
+            elif geom.find("sphere") is not None:
+                shapes.append((name, b, "sphere", [float(geom.find("sphere").get("radius"))], center, rot))
+            elif geom.find("cylinder") is not None or geom.find("capsule") is not None:
+                kind = "cylinder" if geom.find("cylinder") is not None else "capsule"
+                g = geom.find(kind)
+                shapes.append((name, b, kind, [float(g.get("radius")), float(g.get("length"))], center, rot))
+            # meshes: no analytic reduction to points; such a link does not collide here
+    model = Model(
         parent=parent,
         joint_origin=joint_origin,
         joint_axis=joint_axis,
@@ -181,6 +204,9 @@ def load_urdf_model(urdf_path: str):
         link_body=dict(body_of),
         link_rotation={name: T[name][0].copy() for name in body_of},
     )
+    for name, b, kind, size, center, rot in shapes:
+        model.add_collision_shape(name, b, kind, size, center, rot)
+    return model
 
 
 def write_urdf(model, path: str, split_fixed_links: bool = True) -> None:
@@ -193,6 +219,30 @@ def write_urdf(model, path: str, split_fixed_links: bool = True) -> None:
             f'<inertial><origin xyz="{c[0]:.17g} {c[1]:.17g} {c[2]:.17g}" rpy="0 0 0"/><mass value="{m:.17g}"/>'
             f'<inertia ixx="{I6[0]:.17g}" iyy="{I6[1]:.17g}" izz="{I6[2]:.17g}" ixy="{I6[3]:.17g}" ixz="{I6[4]:.17g}" iyz="{I6[5]:.17g}"/></inertial>'
         )
+
+    def rpy_of(Rm):
+        return (math.atan2(Rm[2, 1], Rm[2, 2]), math.atan2(-Rm[2, 0], math.hypot(Rm[0, 0], Rm[1, 0])),
+                math.atan2(Rm[1, 0], Rm[0, 0]))
+
+    def collisions(body, link_origin, link_rotation):
+        """<collision> elements of the shapes on moving body ``body``, in a link frame at ``link_origin`` (body frame)
+        with axes ``link_rotation`` (link -> body)."""
+        el = []
+        for sh in getattr(model, "collision_shapes", []):
+            if sh["body"] != body:
+                continue
+            c = link_rotation.T @ (np.asarray(sh["center"], dtype=float) - link_origin)
+            r, p, y = rpy_of(link_rotation.T @ np.asarray(sh["rotation"], dtype=float))
+            size = sh["size"]
+            if sh["kind"] == "box":
+                g = f'<box size="{size[0]:.17g} {size[1]:.17g} {size[2]:.17g}"/>'
+            elif sh["kind"] == "sphere":
+                g = f'<sphere radius="{size[0]:.17g}"/>'
+            else:
+                g = f'<{sh["kind"]} radius="{size[0]:.17g}" length="{size[1]:.17g}"/>'
+            el.append(f'<collision><origin xyz="{c[0]:.17g} {c[1]:.17g} {c[2]:.17g}" rpy="{r:.17g} {p:.17g} {y:.17g}"/>'
+                      f'<geometry>{g}</geometry></collision>')
+        return "".join(el)
 
     out = ['<?xml version="1.0"?>', '<robot name="upkie">']
     m0, c0, I0 = float(model.mass[0]), model.com[0], model.inertia[0]
@@ -212,7 +262,7 @@ def write_urdf(model, path: str, split_fixed_links: bool = True) -> None:
         torso_origin = np.array([0.0, 0.0, -0.1])  # tests/model/test_kinematic_tree.py:31-36
         out.append(f'<link name="base">{inertial(m_virtual, np.zeros(3), np.zeros(6))}</link>')
         It6 = [I_t[0, 0], I_t[1, 1], I_t[2, 2], I_t[0, 1], I_t[0, 2], I_t[1, 2]]
-        out.append(f'<link name="torso">{inertial(m_t, c_t - torso_origin, It6)}</link>')
+        out.append(f'<link name="torso">{inertial(m_t, c_t - torso_origin, It6)}{collisions(0, torso_origin, np.eye(3))}</link>')
         out.append(f'<joint name="torso_fix" type="fixed"><parent link="base"/><child link="torso"/>'
                    f'<origin xyz="0 0 -0.1" rpy="0 0 0"/></joint>')
         # imu frame: rotation_base_to_imu^T = R_base_from_imu; diag(-1, 1, -1) = rotation of pi about y
@@ -225,7 +275,7 @@ def write_urdf(model, path: str, split_fixed_links: bool = True) -> None:
         out.append(f'<joint name="imu_fix" type="fixed"><parent link="torso"/><child link="imu"/>'
                    f'<origin xyz="{pi_t[0]:.17g} {pi_t[1]:.17g} {pi_t[2]:.17g}" rpy="{roll:.17g} {pitch:.17g} {yaw:.17g}"/></joint>')
     else:
-        out.append(f'<link name="base">{inertial(m0, c0, I0)}</link>')
+        out.append(f'<link name="base">{inertial(m0, c0, I0)}{collisions(0, np.zeros(3), np.eye(3))}</link>')
         R = np.asarray(model.rotation_base_to_imu, dtype=float).reshape(3, 3).T
         pitch = math.atan2(-R[2, 0], math.hypot(R[0, 0], R[1, 0]))
         yaw = math.atan2(R[1, 0], R[0, 0])
@@ -261,7 +311,8 @@ def write_urdf(model, path: str, split_fixed_links: bool = True) -> None:
         Im = np.array([[Ib[0], Ib[3], Ib[4]], [Ib[3], Ib[1], Ib[5]], [Ib[4], Ib[5], Ib[2]]])
         Il = Rj_full(model, b).T @ Im @ Rj_full(model, b)
         I6 = [Il[0, 0], Il[1, 1], Il[2, 2], Il[0, 1], Il[0, 2], Il[1, 2]]
-        out.append(f'<link name="{names[b]}">{inertial(float(model.mass[b]), c_link, I6)}</link>')
+        out.append(f'<link name="{names[b]}">{inertial(float(model.mass[b]), c_link, I6)}'
+                   f'{collisions(b, np.zeros(3), Rj_full(model, b))}</link>')
         jtype = "continuous" if wheel else "revolute"
         lim = (f'<limit effort="{float(model.tau_max[j]):.17g}" velocity="{float(model.qd_max[j]):.17g}"'
                + ("" if wheel else f' lower="{float(model.q_lower[j]):.17g}" upper="{float(model.q_upper[j]):.17g}"') + "/>")
