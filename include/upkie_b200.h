@@ -262,14 +262,17 @@ typedef struct UpkieSimConfig {
   int32_t spine_mode;
   int32_t reserved_spine_mode;
   /* Body-ground contacts (ABI 6; Bullet collides every link that has a collision shape with the plane, so a fallen
-   * robot rests on its torso instead of passing through the floor). 1 (default): while a collision point of the
+   * robot rests on its torso instead of passing through the floor). 1: while a collision point of the
    * model (UpkieModel.collision_*) is closer to the ground than contact_breaking_threshold, it holds one normal row
    * and two friction rows in the substep's PGS solve - rigid contact (no <contact> stiffness on those links):
    * cfm 0, Baumgarte factor body_contact_erp, friction coefficient = the env's floor friction x body_friction, friction
    * directions world -y and +x (btPlaneSpace1 of the plane normal); rows are solved after the wheel rows of their kind
    * (normals, then frictions). At most UPKIE_MAX_BODY_CONTACTS points (the deepest) are active per robot. Needs
-   * joint_limits != 0 (the rows live in the "extras + limits" kernels); a warp that holds no such point runs the
-   * packed solvers unchanged. 0 = off (round 1's / early round 2's physics). */
+   * joint_limits != 0. Handles with body_contacts = 1 run their own kernel instantiations (step_*_body.cu); there a
+   * warp that holds no such point runs the packed solvers, one that does solves ALL rows of its 32 robots in a general
+   * scalar solver - measured ~50x the packed cost for that warp and substep on a B200, which is
+   * why the default is 0 = off (a fallen robot's torso passes through the floor, as in round 1) for batched handles:
+   * RL workloads reset fallen robots anyway. B200Backend, the single-env drop-in for PyBulletBackend, turns it on. */
   int32_t body_contacts;
   int32_t reserved_body_contacts;
   double body_contact_erp;   /* btContactSolverInfo::m_erp2 = 0.2 */

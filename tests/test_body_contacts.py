@@ -25,6 +25,14 @@ def _oracle_rec(oracle_lib, osim):
     return out
 
 
+def _on():
+    """Default configuration with the body-ground contact rows on (what B200Backend runs; batched handles opt in)."""
+    cfg = _abi.default_sim_config()
+    assert cfg.body_contacts == 0 and cfg.joint_limits == 3
+    cfg.body_contacts = 1
+    return cfg
+
+
 def _falling_setup(model, n, pitch_lo=0.05, pitch_hi=0.4):
     init = np.zeros((n, _abi.INIT_DIM))
     init[:, 2] = 0.6
@@ -68,8 +76,7 @@ def test_urdf_round_trip_of_collision_shapes():
 
 def test_fallen_robot_rests_on_its_torso(model, oracle_lib):
     n = 8
-    cfg = _abi.default_sim_config()
-    assert cfg.body_contacts == 1 and cfg.joint_limits == 3  # the defaults a user gets
+    cfg = _on()
     init, act = _falling_setup(model, n)
     osim = oracle_lib.OracleSim(model, cfg, n)
     osim.reset(init)
@@ -170,7 +177,7 @@ def test_collision_points_on_leg_bodies(oracle_lib):
     m.add_collision_shape("right_lower_leg", 5, "sphere", [0.04], [0.0, 0.0, 0.0])
     m.add_collision_shape("left_upper_leg", 1, "capsule", [0.03, 0.12], [0.0, 0.0, -0.085])
     n = 6
-    cfg = _abi.default_sim_config()
+    cfg = _on()
     init, act = _falling_setup(m, n, 0.2, 0.5)
     init[:, _abi.INIT_Q + 0] = init[:, _abi.INIT_Q + 3] = 0.9    # crouched: knees forward
     init[:, _abi.INIT_Q + 1] = init[:, _abi.INIT_Q + 4] = -1.8
@@ -196,7 +203,7 @@ def test_body_contacts_need_the_limit_kernels(model):
     """The rows live in the "extras + limits" kernels: with joint_limits = 0 they are off, as the header says."""
     n = 2
     init, act = _falling_setup(model, n, 0.3, 0.4)
-    cfg = _abi.default_sim_config()
+    cfg = _on()
     cfg.joint_limits = 0
     hs = HostSim(model, cfg, n)
     hs.reset(init.astype(np.float32))
@@ -215,7 +222,7 @@ def test_gpu_fallen_robots_rest_on_the_floor(model, oracle_lib):
     from upkie_b200.sim import UpkieSim
 
     n = 96  # three warps: one falls early, one late, one mixed with robots that stay up for a while
-    cfg = _abi.default_sim_config()
+    cfg = _on()
     init, act = _falling_setup(model, n, 0.0, 0.45)
     init[64:, 3], init[64:, 5] = 1.0, 0.0
     init[64::3, 3], init[64::3, 5] = np.cos(0.2), np.sin(0.2)
@@ -234,7 +241,8 @@ def test_gpu_fallen_robots_rest_on_the_floor(model, oracle_lib):
     down = orec[:, 0] != 0
     assert down.sum() >= 64
     np.testing.assert_array_equal(rec[down, 0], orec[down, 0])
-    assert np.abs(sg[down, 2] - so[down, 2]).max() < 1e-3
+    dz = np.abs(sg[down, 2] - so[down, 2])
+    assert np.quantile(dz, 0.9) < 1e-5 and dz.max() < 1e-2, (np.quantile(dz, 0.9), dz.max())  # a robot may still be rocking on an edge
     pts_z = np.stack([body_points_in_world(model, sg[i]) for i in range(n)])[:, :, 2]
     assert (pts_z.min(axis=1) > -5e-3).all()  # nobody tunnels
     h = cfg.dt / cfg.nb_substeps

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round 2, session 2, GPU call 1: the GPU test-suite on the body-contact build, smoke, the bench line at steady state
+# (rows off headline + rows on secondary via other_workloads) and at the driver's settings.
+mkdir -p gpurun_out/r02b
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/r02b/gpu.txt
+( time timeout 900 python -m pytest tests -m gpu -q -x ) > gpurun_out/r02b/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r02b/pytest_gpu.log
+tail -5 gpurun_out/r02b/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02b/smoke.log 2>&1; tail -2 gpurun_out/r02b/smoke.log
+timeout 600 python bench.py --steps 300 --warmup 20 > gpurun_out/r02b/bench_steady.json 2> gpurun_out/r02b/bench_steady.err
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-other-workloads > gpurun_out/r02b/bench_driver.json 2> gpurun_out/r02b/bench_driver.err
+python - <<'P'
+import json
+for f in ("bench_steady","bench_driver"):
+    try:
+        j=json.loads(open(f"gpurun_out/r02b/{f}.json").read().strip().splitlines()[-1])
+        print(f, "value %.4g ms %.4f e2e %.4g kernel_ms %.4f" % (j["value"], j["ms_per_step"], j["e2e"]["value"], j["roofline"]["kernel_ms"]))
+        ow=j.get("other_workloads",{})
+        for k,v in ow.items(): print("   ",k, {kk:vv for kk,vv in v.items() if kk!="workload"} if isinstance(v,dict) else v)
+    except Exception as e: print(f, "ERR", e)
+P

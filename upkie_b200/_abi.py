@@ -288,7 +288,7 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
         c.init_joint_configuration[j] = 0.0
     c.spine_mode = 0  # 1: timing of the C++ Bullet spine in simulate() mode (include/upkie_b200.h)
     c.reserved_spine_mode = 0
-    c.body_contacts = 1  # collision points of the model (torso box...) hold contact rows against the ground, as every link with a <collision> does in Bullet
+    c.body_contacts = 0  # 1: collision points of the model (torso box...) hold contact rows against the ground, as every link with a <collision> does in Bullet; B200Backend turns it on, batched envs opt in (include/upkie_b200.h)
     c.reserved_body_contacts = 0
     c.body_contact_erp = 0.2  # btContactSolverInfo::m_erp2
     c.body_friction = 0.5  # URDF importer default lateral friction of a link without <contact>

@@ -8,4 +8,5 @@ cudaError_t launch_step_host(const StepArgs&) { return cudaErrorNotSupported; }
 cudaError_t launch_step_multicast(const StepArgs&) { return cudaErrorNotSupported; }
 cudaError_t launch_push_rows(const PeerPtrs&, int, cudaStream_t) { return cudaErrorNotSupported; }
 cudaError_t launch_step_device_spine(const StepArgs&) { return cudaErrorNotSupported; }
+cudaError_t launch_step_device_body(const StepArgs&) { return cudaErrorNotSupported; }
 }  // namespace upkie_b200

@@ -85,7 +85,7 @@ struct PeerPtrs {
 // One launch of the env-step kernel over the envs [i0, i0 + cnt) of a handle.
 struct StepArgs {
   const SimParams* P;
-  int mode, autoreset, noise;  // noise: 1 = the "extras" instantiation (torque noise models, external forces), 2 = extras + joint-limit rows, 3 = 2 + spine timing
+  int mode, autoreset, noise;  // noise: 1 = the "extras" instantiation (torque noise models, external forces), 2 = extras + joint-limit rows, 3 = 2 + spine timing, 4 = 2 + body-ground contact rows
   int i0, cnt, n_pad, block;
   int compact_obs;      // TILE=1, servos: observation rows [6][3] (position, velocity, torque) instead of [6][5]
   int grid;             // TILE=1: number of persistent blocks (0 = one block per tile)
@@ -116,6 +116,8 @@ cudaError_t launch_step_device_limits(const StepArgs& a);  // step_device_limits
 cudaError_t launch_step_host_limits(const StepArgs& a);    // step_host_limits.cu: NOISE=2, TILE=1
 cudaError_t launch_step_multicast_limits(const StepArgs& a);  // step_multicast_limits.cu: NOISE=2, TILE=2
 cudaError_t launch_push_rows(const PeerPtrs& pp, int n, cudaStream_t stream);  // step_multicast.cu: flush of a rollout's last rows
+cudaError_t launch_step_device_body(const StepArgs& a);  // step_device_body.cu: NOISE=4 (limits + body-ground contact rows), TILE=0
+cudaError_t launch_step_host_body(const StepArgs& a);    // step_host_body.cu: NOISE=4, TILE=1
 cudaError_t launch_step_device_spine(const StepArgs& a);  // step_device_spine.cu: NOISE=3 (spine timing), TILE=0
 cudaError_t launch_step_host_spine(const StepArgs& a);    // step_host_spine.cu: NOISE=3, TILE=1
 

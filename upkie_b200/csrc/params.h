@@ -57,7 +57,7 @@ inline void default_sim_config(UpkieSimConfig* c) {
   for (int k = 0; k < 3; ++k) c->init_angular_velocity[k] = c->init_linear_velocity[k] = 0.0;
   c->spine_mode = 0;
   c->reserved_spine_mode = 0;
-  c->body_contacts = 1;  // every link with a <collision> collides with plane.urdf in Bullet (pybullet_backend.py:115,121)
+  c->body_contacts = 0;  // opt-in for batched handles (B200Backend, the single-env drop-in, turns it on): see include/upkie_b200.h
   c->reserved_body_contacts = 0;
   c->body_contact_erp = 0.2;  // btContactSolverInfo::m_erp2
   c->body_friction = 0.5;     // URDF importer default lateral friction of a link without <contact>

@@ -854,8 +854,11 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
 // Restated from Bullet 3.24 (third-party, absent from the reference tree: parity unpinned): rigid contact for links
 // without <contact> stiffness (cfm 0, erp = m_erp2), friction directions btPlaneSpace1(normal), at most four manifold
 // points per pair, rows ordered limits / normals / frictions as in btMultiBodyConstraintSolver::solveSingleIteration.
+// 0 in the translation units whose kernels never take the body-contact path (step_device.cu, step_host.cu,
+// step_multicast.cu and the three *_limits.cu units: their SASS is what it was before the rows existed); 1 in the
+// *_body.cu / *_spine.cu units, in upkie_b200.cu (reset kernels) and in the host build
 #ifndef UPKIE_BODY_CONTACTS_BUILD
-#define UPKIE_BODY_CONTACTS_BUILD 1  // 0: compile the body-contact path out of the kernels (A/B builds, tools/variants.py)
+#define UPKIE_BODY_CONTACTS_BUILD 1
 #endif
 #if defined(__CUDACC__)
 #define UPKIE_NOINLINE __host__ __device__ __noinline__
@@ -1530,7 +1533,12 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
 #else
   (void)lam_prev;
 #endif
+#if UPKIE_BODY_CONTACTS_BUILD
   if (rec.p && !body_slow) rec.p[0] = 0.f;  // no body contact held rows in this substep
+#else
+  (void)rec;
+  (void)body_slow;
+#endif
 
   // -- position integration with the new velocities (as physics_substep)
 #pragma unroll

@@ -4,7 +4,8 @@
 //   k_step<MODE, AUTORESET, NOISE, TILE>   one 5 ms env tick: action front-end, 5 x (moteus torque law,
 //       articulated-body dynamics, wheel-ground contact solve, semi-implicit integration), observation,
 //       termination; optional fused auto-reset; optional torque noise models.
-//       NOISE: 0 plain, 1 "extras" (noise models, external forces), 2 extras + joint-limit rows.
+//       NOISE: 0 plain, 1 "extras" (noise models, external forces), 2 extras + joint-limit rows, 3 = 2 + spine timing
+//       (+ body-ground contact rows), 4 = 2 + body-ground contact rows.
 // Included by step_device.cu (TILE=0), step_host.cu (TILE=1), step_multicast.cu (TILE=2) and the two *_limits.cu
 // units (NOISE=2), see kernel_common.cuh.
 #pragma once
@@ -18,6 +19,9 @@
 #endif
 #ifndef UPKIE_STEP_SPINE_TU
 #define UPKIE_STEP_SPINE_TU 0  // 1 in step_*_spine.cu: the NOISE=3 instantiations (extras + limits + spine timing), UpkieServos
+#endif
+#ifndef UPKIE_STEP_BODY_TU
+#define UPKIE_STEP_BODY_TU 0  // 1 in step_*_body.cu: the NOISE=4 instantiations (extras + limits + body-ground contact rows)
 #endif
 #ifndef UPKIE_ACTION_IN_TILE
 #define UPKIE_ACTION_IN_TILE 0  // build-time experiment (tools/variants.py)
@@ -161,8 +165,8 @@ __device__ __forceinline__ void step_env(
     }
 #endif
     if (sub < nsub) {
-      // the body-ground contacts of the tick's last substep go to the handle's record (NOISE >= 2 kernels)
-      const BodyRecOut br{(NOISE >= 2 && P.body_rec && live && sub == nsub - 1) ? P.body_rec + i : nullptr,
+      // the body-ground contacts of the tick's last substep go to the handle's record (NOISE >= 3 kernels)
+      const BodyRecOut br{(NOISE >= 3 && P.body_rec && live && sub == nsub - 1) ? P.body_rec + i : nullptr,
                           size_t(P.body_rec_stride)};
       if (spine) {
         if (resetting && sub == 2) spine_assemble_observation(S, L);
@@ -204,7 +208,7 @@ __device__ __forceinline__ void step_env(
       if (live) episode[i] = ep;
       float init[UPKIE_INIT_DIM];
       sample_init_state(P, seed, env_offset + uint64_t(i), uint64_t(ep), init);
-      const BodyRecOut br{(NOISE >= 2 && P.body_rec && live) ? P.body_rec + i : nullptr, size_t(P.body_rec_stride)};
+      const BodyRecOut br{(NOISE >= 3 && P.body_rec && live) ? P.body_rec + i : nullptr, size_t(P.body_rec_stride)};
       if (spine) reset_robot_spine(P, S, L, init, eps, mu, WarpAny(), P.joint_limits, br);
       else reset_robot(P, S, init, eps, mu, WarpAny(), NOISE >= 2 ? P.joint_limits : 0, br);
       if (MODE != MODE_SERVOS) gyropod_obs(P, S, o6);
@@ -448,6 +452,8 @@ cudaError_t launch_step_mode(const StepArgs& a) {
       a.mu, a.err, a.done_prev, a.episode, a.tick, a.seed, a.env_offset, a.ext, a.ext_local, coalesce, a.peers, a.lag)
 #if UPKIE_STEP_SPINE_TU
 #define LAUNCH(AR) LAUNCH_N(AR, 3)
+#elif UPKIE_STEP_BODY_TU
+#define LAUNCH(AR) LAUNCH_N(AR, 4)
 #elif UPKIE_STEP_LIMITS_TU
 #define LAUNCH(AR) LAUNCH_N(AR, 2)
 #else

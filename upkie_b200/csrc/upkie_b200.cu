@@ -247,6 +247,10 @@ int step_range(Handle* h, int mode, int i0, int cnt, const float* action, float*
   a.mode = mode;
   a.autoreset = h->autoreset;
   a.noise = h->P.joint_limits ? 2 : ((h->P.any_ctrl_noise || h->P.any_meas_noise || h->ext) ? 1 : 0);  // "extras" kernels
+  if (h->P.body_contacts) {  // the model's collision points hold contact rows: the NOISE=4 kernels (step_*_body.cu)
+    if (multicast) return fail(UPKIE_B200_EINVAL, "body_contacts has no in-kernel rollout transport (use upkie_b200_step_servos_compact)");
+    a.noise = 4;
+  }
   a.lag = nullptr;
   if (h->P.spine_mode) {
     if (mode != MODE_SERVOS) return fail(UPKIE_B200_EINVAL, "spine_mode supports UpkieServos steps only");

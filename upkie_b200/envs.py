@@ -226,7 +226,7 @@ def make_config(
     noise_seed: int = 0,
     joint_limits: Union[bool, int] = True,
     spine_mode: bool = False,
-    body_contacts: bool = True,
+    body_contacts: bool = False,
 ) -> _abi.UpkieSimConfig:
     """Split of the keyword arguments the reference's factories forward to the
     backend, the servo env and the wrappers (``upkie/envs/entry_points.py:41-61,99-109``)."""
@@ -297,7 +297,7 @@ class B200VectorEnv(VectorEnv):
         joint_limits: Union[bool, int] = True,
         copy: bool = True,
         spine_mode: bool = False,
-        body_contacts: bool = True,
+        body_contacts: bool = False,
     ):
         if env_type not in ENV_TYPES:
             raise UpkieException(f"env_type must be one of {ENV_TYPES}")
