@@ -190,8 +190,8 @@ def servos_config():
     # terminates: a third of the robots ends up resting on the floor for good (tools/r02/body_gate_stats.cpp), every warp
     # takes the general row solver every substep, and the figure measures a different workload. Both are reported.
     cfg.body_contacts = int(os.environ.get("UPKIE_BENCH_BODY_CONTACTS", "0"))
-    if os.environ.get("UPKIE_BENCH_PGS_TOL"):  # developer knob (profiles/r01_variants.md)
-        cfg.pgs_tolerance = float(os.environ["UPKIE_BENCH_PGS_TOL"])
+    if os.environ.get("UPKIE_BENCH_RESIDUAL_THRESHOLD"):  # developer knob: 0 = always 50 sweeps (Bullet's own default; PyBullet sets 1e-7)
+        cfg.solver_residual_threshold = float(os.environ["UPKIE_BENCH_RESIDUAL_THRESHOLD"])
     return cfg
 
 
@@ -567,23 +567,22 @@ def body_contacts_line():
 
 
 def exact_mode_line():
-    """The servos workload on the exact-arithmetic companion library (no --use_fast_math, upkie_b200/build.py) with
-    pgs_tolerance = 0 (50 sweeps every substep, as the oracle and Bullet): what the two shortcuts of the headline
-    kernel buy. Own process (a second copy of the library cannot be the package's singleton), device buffers, full
-    records (the exact library has the TILE=0 kernels only)."""
+    """The servos workload on the exact-arithmetic companion library (no --use_fast_math, upkie_b200/build.py): what
+    the one shortcut of the headline kernel buys. Own process (a second copy of the library cannot be the package's
+    singleton), device buffers, full records (the exact library has the TILE=0 kernels only)."""
     try:
         from upkie_b200 import build as b
 
         if not os.path.exists(b.EXACT_LIB_PATH):
             return {"unavailable": "libupkie_b200_exact.so not built"}
-        env = dict(os.environ, UPKIE_B200_LIB=b.EXACT_LIB_PATH, UPKIE_BENCH_PGS_TOL="0", UPKIE_BENCH_ROLLOUT="full",
+        env = dict(os.environ, UPKIE_B200_LIB=b.EXACT_LIB_PATH, UPKIE_BENCH_ROLLOUT="full",
                    UPKIE_BENCH_DEVICE_ONLY="1")
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10",
                             "--no-cpu-baseline", "--no-other-workloads"], env=env, capture_output=True, text=True, timeout=300)
         j = json.loads(r.stdout.strip().splitlines()[-1])
         return {"metric": "env-steps/sec", "value": j["value"], "ms_per_step": j["ms_per_step"],
                 "kernel_ms_median": j["roofline"]["kernel_ms"],
-                "workload": "headline workload, exact arithmetic: no fast-math, pgs_tolerance 0 (50 sweeps), full 126 B records"}
+                "workload": "headline workload, exact arithmetic: no fast-math, full 126 B records"}
     except Exception as exc:
         return {"error": repr(exc)}
 
@@ -856,6 +855,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
         # path, 2 packed ten-row solver, 3 ten-row solver for the warps that hold a robot on a bound
         "joint_limit_rows": int(getattr(env.config, "joint_limits", 0)) != 0,
         "joint_limit_solver": int(getattr(env.config, "joint_limits", 0)),
+        # Bullet's solver exit rule with PyBullet's default threshold (solverResidualThreshold = 1e-7): a robot's PGS
+        # sweeps end once no row changed its relative velocity by more than sqrt(threshold) in a sweep; 0 = 50 sweeps
+        "solver_residual_threshold": float(getattr(env.config, "solver_residual_threshold", 0.0)),
         # body-ground contact rows of the model's collision points (the torso box; include/upkie_b200.h: body_contacts;
         # library default ON). Off in the headline workload, whose "base below 0.15 m" reset rule presumes that the
         # torso sinks through the floor (servos_config() above); other_workloads.servos_65536_body_contacts has them on

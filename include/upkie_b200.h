@@ -210,7 +210,8 @@ typedef struct UpkieSimConfig {
    * which receives actions the reference's own UpkieServos already clamped) */
   int32_t skip_action_clamps;
   double min_base_height;
-  /* PGS sweeps stop early once every impulse of a warp changed by less than
+  /* DEPRECATED, ignored since ABI 6 (superseded by solver_residual_threshold, Bullet's own exit rule, at the end of
+   * this struct). Was: PGS sweeps stop early once every impulse of a warp changed by less than
    * pgs_tolerance * |impulse| + 1e-9 in one sweep (Bullet: m_leastSquaresResidualThreshold-style
    * exit); 0 = always run pgs_iterations sweeps. Default 1e-5: ~50 ulp of the fp32 impulses, the converged
    * contact impulses then differ from 50 full sweeps by < 1e-6 m/s on velocities (profiles/r01_variants.md) */
@@ -277,6 +278,15 @@ typedef struct UpkieSimConfig {
   int32_t reserved_body_contacts;
   double body_contact_erp;   /* btContactSolverInfo::m_erp2 = 0.2 */
   double body_friction;      /* URDF importer default lateral friction of a link without <contact>: 0.5 */
+  /* Bullet's solver exit rule (btSequentialImpulseConstraintSolver::solveGroupCacheFriendlyIterations): after every
+   * sweep the solver compares the largest squared velocity-level change of a row, (delta_impulse / jacDiagABInv)^2,
+   * with btContactSolverInfo::m_leastSquaresResidualThreshold and stops at or below it. Bullet's own default is 0
+   * (all numIterations sweeps); PyBullet's physics server sets 1e-7 (setPhysicsEngineParameter solverResidualThreshold,
+   * "default 1e-7") and the reference changes neither (it only calls setTimeStep, pybullet_backend.py:112,
+   * BulletInterface.cpp:129): a robot's solve ends once no row moved its relative velocity by more than 3.2e-4 m/s in a
+   * sweep. Default 1e-7; 0 = always pgs_iterations sweeps. Evaluated per robot after every sweep: a robot that has
+   * met the threshold keeps its impulses while the other robots of its warp finish. */
+  double solver_residual_threshold;
 } UpkieSimConfig;
 
 /* Spine-mode lag record of one env (upkie_b200_get_lag / set_lag, [N][UPKIE_LAG_DIM] floats): the two latest

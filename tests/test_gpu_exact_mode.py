@@ -1,8 +1,8 @@
 # SPDX-License-Identifier: Apache-2.0
 """Exact-mode parity: the device-buffer kernels compiled WITHOUT --use_fast_math (libupkie_b200_exact.so,
-upkie_b200/build.py: build_exact) with pgs_tolerance = 0 (exactly 50 PGS sweeps, like the oracle) against the fp64
-oracle, next to the product library with its two shortcuts (fast-math, early PGS exit) on the same inputs. Through
-the C ABI of include/upkie_b200.h, loaded a second time with ctypes."""
+upkie_b200/build.py: build_exact) against the fp64 oracle, next to the product library with its shortcut (fast-math)
+on the same inputs; both stop their PGS sweeps by Bullet's residual rule (solver_residual_threshold), like the oracle.
+Through the C ABI of include/upkie_b200.h, loaded a second time with ctypes."""
 import ctypes as C
 import os
 
@@ -63,7 +63,6 @@ def test_exact_mode_one_tick_against_the_oracle(model, oracle_lib):
     st32 = random_states(n, seed=3).astype(np.float32)
     act32 = random_servo_actions(n, model, seed=4).astype(np.float32)
     cfg_exact = _abi.default_sim_config()
-    cfg_exact.pgs_tolerance = 0.0  # exactly pgs_iterations sweeps, as the oracle and as Bullet
     cfg_fast = _abi.default_sim_config()
     osim = oracle_lib.OracleSim(model, cfg_exact, n, threads=8)
     osim.set_state(st32.astype(np.float64))

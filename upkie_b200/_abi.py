@@ -143,6 +143,7 @@ class UpkieSimConfig(C.Structure):
         ("reserved_body_contacts", C.c_int32),
         ("body_contact_erp", C.c_double),
         ("body_friction", C.c_double),
+        ("solver_residual_threshold", C.c_double),
     ]
 
 
@@ -271,7 +272,7 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.servos_fall_termination = 0
     c.skip_action_clamps = 0
     c.min_base_height = 0.0
-    c.pgs_tolerance = 1e-5
+    c.pgs_tolerance = 0.0  # deprecated, ignored (see solver_residual_threshold)
     c.warmstarting_factor = 0.0  # measured: no fewer sweeps (friction rows dominate); Bullet's value would be 0.85
     c.joint_limits = 3  # Bullet's hip / knee limit rows on (0 off, 1 scalar reference path [host build], 2 ten-row, 3 ten-row per warp on demand)
     c.joint_limit_erp = 0.2
@@ -292,6 +293,7 @@ def default_sim_config(frequency: float = 200.0) -> UpkieSimConfig:
     c.reserved_body_contacts = 0
     c.body_contact_erp = 0.2  # btContactSolverInfo::m_erp2
     c.body_friction = 0.5  # URDF importer default lateral friction of a link without <contact>
+    c.solver_residual_threshold = 1e-7  # PyBullet's solverResidualThreshold default (Bullet's m_leastSquaresResidualThreshold)
     return c
 
 

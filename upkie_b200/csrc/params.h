@@ -42,7 +42,7 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->servos_fall_termination = 0;
   c->skip_action_clamps = 0;
   c->min_base_height = 0.0;
-  c->pgs_tolerance = 1e-5;
+  c->pgs_tolerance = 0.0;  // deprecated, ignored (see solver_residual_threshold)
   c->warmstarting_factor = 0.0;  // off by default (Bullet's m_warmstartingFactor is 0.85)
   c->joint_limits = 3;  // Bullet's hip / knee limit constraints ON (pybullet_backend.py:121 loadURDF): ten-row solver for warps with a robot on a bound
   c->reserved_joint_limits = 0;
@@ -61,6 +61,7 @@ inline void default_sim_config(UpkieSimConfig* c) {
   c->reserved_body_contacts = 0;
   c->body_contact_erp = 0.2;  // btContactSolverInfo::m_erp2
   c->body_friction = 0.5;     // URDF importer default lateral friction of a link without <contact>
+  c->solver_residual_threshold = 1e-7;  // PyBullet: getSolverInfo().m_leastSquaresResidualThreshold = 1e-7
 }
 
 inline void default_mpc_config(UpkieMpcConfig* c) {
@@ -160,7 +161,7 @@ inline int make_sim_params(const UpkieModel& m, const UpkieSimConfig& c, SimPara
   P.inv_h = float(1.0 / h);
   P.nb_substeps = c.nb_substeps;
   P.pgs_iterations = c.pgs_iterations;
-  P.pgs_rtol = float(c.pgs_tolerance);
+  P.res_thr = float(c.solver_residual_threshold);
   P.warm = float(c.warmstarting_factor);
   P.joint_limits = c.joint_limits < 0 ? 0 : (c.joint_limits > 3 ? 3 : c.joint_limits);
   P.limit_erp = float(c.joint_limit_erp);

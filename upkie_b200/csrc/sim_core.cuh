@@ -70,7 +70,8 @@ struct SimParams {
   // backend
   float dt, inv_dt, h, inv_h;
   int nb_substeps, pgs_iterations;
-  float pgs_rtol;          // early-exit tolerance of the PGS sweeps (0 = fixed count)
+  float res_thr;           // Bullet's m_leastSquaresResidualThreshold: a robot's solve ends once the largest squared
+                           // velocity-level row change of a sweep is at or below it (0 = all sweeps)
   float warm;              // warm-starting factor of the normal contact impulses (Bullet: 0.85)
   int skip_action_clamps;
   float gravity, kp, kd;
@@ -561,9 +562,15 @@ constexpr int kPhaseSyncs = 6;
 // iterates as the textbook sweep that re-sums each row, but the dependent chain per row is clamp -> delta -> one
 // FMA instead of a six-term sum (the solver is latency-bound: ~1.75 warps per scheduler), and the six updates
 // pair into three f32x2 FMAs in the paired build (sim_pair.cuh).
+//
+// Exit rule (Bullet's, btSequentialImpulseConstraintSolver::solveGroupCacheFriendlyIterations): after every sweep the
+// largest squared velocity-level change of a row, (delta_k * dinv_k)^2 with dinv_k = 1 / jacDiagABInv_k, is compared with
+// m_leastSquaresResidualThreshold (P.res_thr; PyBullet: 1e-7); at or below it the robot's solve is over. A lane that
+// has met it is frozen (its updates become no-ops) while the other lanes of the warp finish, so that every robot keeps
+// exactly the impulses Bullet would have left it with.
 template <typename AnyFn>
 UPKIE_HD void pgs_solve(const SimParams& P, const float G[6][6], const float rhs[6], float lam[6], float mu,
-                        float hiL, float hiR, float pgs_atol, AnyFn warp_any) {
+                        float hiL, float hiR, const float dinv[6], AnyFn warp_any) {
   float r[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -571,30 +578,31 @@ UPKIE_HD void pgs_solve(const SimParams& P, const float G[6][6], const float rhs
 #pragma unroll
     for (int l = 0; l < 2; ++l) r[k] += G[k][l] * lam[l];  // warm-started normals; frictions start from 0
   }
-  // the exit test runs on every second sweep (as in the paired build, sim_pair.cuh)
+  bool frozen = false;
   for (int it = 0; it < P.pgs_iterations; ++it) {
-    const bool test = (it & 1) != 0;
-    bool changed = false;
+    float res = 0.f;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       float lo, hi;
       if (k == 0) { lo = 0.f; hi = hiL; }
       else if (k == 1) { lo = 0.f; hi = hiR; }
       else { hi = mu * lam[(k < 4) ? 0 : 1]; lo = -hi; }
-      const float nl = fminf(fmaxf(r[k], lo), hi);
+      const float nl = frozen ? lam[k] : fminf(fmaxf(r[k], lo), hi);
       const float delta = nl - lam[k];
-      if (test) changed = changed | (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+      res = fmaxf(res, fabsf(delta) * dinv[k]);
       lam[k] = nl;
 #pragma unroll
       for (int m = 0; m < 6; ++m) r[m] += G[m][k] * delta;
     }
-    if (!test) continue;
+    const bool was_frozen = frozen;
+    frozen = frozen || (res * res <= P.res_thr);
 #ifdef UPKIE_PGS_STATS
-    if (!changed) { upkie_pgs_stats(it + 1); break; }
-    if (it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 2);
+    if (frozen && !was_frozen) upkie_pgs_stats(it + 1);
+    else if (!frozen && it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 1);
 #else
-    if (!warp_any(changed)) break;
+    (void)was_frozen;
 #endif
+    if (!warp_any(!frozen)) break;
   }
 }
 
@@ -762,11 +770,10 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
     }
     const float cfmrow = P.cfm;  // m_cfm = cfm * jacDiagABInv
     const float hiL = actL ? 1e10f : 0.f, hiR = actR ? 1e10f : 0.f;
-    // Projected Gauss-Seidel, at most Bullet's iteration count. The sweep is a
-    // contraction towards a fixed point; the loop leaves once a sweep changed no
-    // impulse of the warp by more than pgs_rtol * |impulse| + 1e-9 (with
-    // pgs_rtol = 0 and the 1e-9 floor removed it runs all sweeps).
-    const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+    // Projected Gauss-Seidel, at most Bullet's iteration count, with Bullet's residual exit rule (pgs_solve)
+    float dinv[6];  // 1 / jacDiagABInv: turns an impulse change into the row's velocity change
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dinv[k] = W[k][k] + (k < 2 ? P.cfm : 0.f);
     // row update lam_k <- clamp(lam_k + rhs_k - cfm_k lam_k - jdi_k sum_l W_kl lam_l) with the
     // row pre-scaled: G_kl = -jdi_k W_kl (l != k), G_kk = 1 - cfm_k - jdi_k W_kk
 #pragma unroll
@@ -775,7 +782,7 @@ UPKIE_HD void physics_substep(const SimParams& P, RobotState& S, const float tau
       for (int l = 0; l < 6; ++l) W[k][l] = -jdi[k] * W[k][l];
       W[k][k] += 1.f - (k < 2 ? cfmrow * jdi[k] : 0.f);
     }
-    pgs_solve(P, W, rhs, lam, mu, hiL, hiR, pgs_atol, warp_any);
+    pgs_solve(P, W, rhs, lam, mu, hiL, hiR, dinv, warp_any);
     S.lam_n[0] = lam[0];
     S.lam_n[1] = lam[1];
 #pragma unroll

@@ -527,9 +527,8 @@ UPKIE_HD void limit_contact_solve(const SimParams& P, RobotState& S, const LegCa
       cfmrow[k] = 0.f;
     }
   }
-  const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
   for (int it = 0; it < P.pgs_iterations; ++it) {
-    bool changed = false;
+    float res = 0.f;  // largest velocity-level row change of the sweep (Bullet's residual, see pgs_solve())
     for (int pos = 0; pos < n; ++pos) {
       const int k = pos < nlimit ? ((it & 1) ? pos : nlimit - 1 - pos) : pos;
       float jdv = 0.f;
@@ -540,10 +539,10 @@ UPKIE_HD void limit_contact_solve(const SimParams& P, RobotState& S, const LegCa
       else if (kind[k] == 2) { lo = 0.f; hi = P.limit_max_impulse; }
       else { hi = mu * lam[partner[k]]; lo = -hi; }
       const float nl = fminf(fmaxf(sum, lo), hi);
-      changed = changed | (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+      if (jdi[k] != 0.f) res = fmaxf(res, fabsf(nl - lam[k]) / jdi[k]);
       lam[k] = nl;
     }
-    if (!changed) break;  // per robot here (the packed solver votes per warp)
+    if (res * res <= P.res_thr) break;  // per robot
   }
   // apply the total impulse
   float fw[2][6], g[6], da0[6], dqd[6], aw[2][6];
@@ -743,7 +742,9 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
     rhs[a] = (-pen * P.limit_erp * P.inv_h - dir * S.qd[j]) * jdi[a];
   }
   const float cfmrow = P.cfm;
-  const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+  float dinv[10];  // 1 / jacDiagABInv per row: impulse change -> velocity change (Bullet's residual, see pgs_solve())
+#pragma unroll
+  for (int k = 0; k < 10; ++k) dinv[k] = W[k][k] + ((k == 4 || k == 5) ? P.cfm : 0.f);
   f2 Gc[10][5];
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
@@ -771,7 +772,8 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
   for (int l = 4; l < 6; ++l)  // warm-started normals
 #pragma unroll
     for (int p = 0; p < 5; ++p) r2[p] = fma2(Gc[l][p], bc2(lam[l]), r2[p]);
-  auto update = [&](int k, bool with_test, bool& changed) {
+  bool frozen = false;  // this lane has met Bullet's residual threshold: its updates are no-ops from here on
+  auto update = [&](int k, float& res) {
     const f2 rp = r2[pair_of_row10(k)];
     const float rk = lane_of_row10(k) == 0 ? rp.x : rp.y;
     float nl;
@@ -783,31 +785,46 @@ UPKIE_HD void contact_solve_ten_rows(const SimParams& P, RobotState& S, const Le
       const float hi = mu * lam[(k < 8) ? 4 : 5];
       nl = fminf(fmaxf(rk, -hi), hi);
     }
+    if (frozen) nl = lam[k];
     const float delta = nl - lam[k];
     const f2 d2 = bc2(delta);
 #pragma unroll
     for (int p = 0; p < 5; ++p) r2[p] = fma2(Gc[k][p], d2, r2[p]);
-    if (with_test) changed = changed | (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+    res = fmaxf(res, fabsf(delta) * dinv[k]);
     lam[k] = nl;
   };
-  auto sweep = [&](bool forward, bool with_test) -> bool {
-    bool changed = false;
+  auto sweep = [&](bool forward) -> float {
+    float res = 0.f;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) update(forward ? a : 3 - a, with_test, changed);
+    for (int a = 0; a < 4; ++a) update(forward ? a : 3 - a, res);
 #pragma unroll
-    for (int k = 4; k < 10; ++k) update(k, with_test, changed);
-    return changed;
+    for (int k = 4; k < 10; ++k) update(k, res);
+    return res;
   };
-  for (int it = 0; it < P.pgs_iterations; it += 2) {
-    sweep(false, false);  // even iteration: the non-contact rows are walked backwards
-    if (it + 1 >= P.pgs_iterations) break;
-    const bool changed = sweep(true, true);
+  // two sweeps per trip, each followed by the per-lane residual test (the lane freezes exactly where Bullet would stop);
+  // the warp votes once per trip - at most one no-op sweep more than needed, half the votes and branches
+  auto after_sweep = [&](float res, int it) {
+    const bool was_frozen = frozen;
+    frozen = frozen || (res * res <= P.res_thr);
 #ifdef UPKIE_PGS_STATS
-    if (!changed) { upkie_pgs_stats(100 + it + 2); break; }
-    if (it + 2 >= P.pgs_iterations) upkie_pgs_stats(100 + it + 3);
+    if (frozen && !was_frozen) upkie_pgs_stats(100 + it + 1);
+    else if (!frozen && it + 1 == P.pgs_iterations) upkie_pgs_stats(100 + it + 1);
 #else
-    if (!warp_any(changed)) break;
+    (void)was_frozen;
+    (void)it;
 #endif
+  };
+#ifndef UPKIE_SWEEPS_PER_TRIP
+#define UPKIE_SWEEPS_PER_TRIP 2  // measured on a B200, 65 536-env torque workload: 1 -> 0.1465, 2 -> 0.1384, 4 -> 0.1419 ms per tick
+#endif
+  for (int it = 0; it < P.pgs_iterations; it += UPKIE_SWEEPS_PER_TRIP) {
+    after_sweep(sweep(false), it);  // even iteration: the non-contact rows are walked backwards
+    if (it + 1 < P.pgs_iterations) after_sweep(sweep(true), it + 1);
+#if UPKIE_SWEEPS_PER_TRIP == 4
+    if (it + 2 < P.pgs_iterations) after_sweep(sweep(false), it + 2);
+    if (it + 3 < P.pgs_iterations) after_sweep(sweep(true), it + 3);
+#endif
+    if (!warp_any(!frozen)) break;
   }
   S.lam_n[0] = lam[4];
   S.lam_n[1] = lam[5];
@@ -1106,12 +1123,14 @@ static UPKIE_NOINLINE void general_contact_solve(const SimParams& P, BodySolveIO
       W[k][l] = wkl;
     }
   }
-  float rhs[kMaxRows], jdi[kMaxRows], cfmrow[kMaxRows], lam[kMaxRows];
+  float rhs[kMaxRows], jdi[kMaxRows], cfmrow[kMaxRows], lam[kMaxRows], dinv[kMaxRows];
   for (int k = 0; k < n; ++k) {
     lam[k] = 0.f;
+    dinv[k] = W[k][k] + ((kind[k] == 0 && wheel[k] >= 0) ? P.cfm : 0.f);
     if (kind[k] == 2) {
       const float rel = dirj[k] * io.qd[joint[k]];
       jdi[k] = W[k][k] > 1.1920929e-7f ? 1.f / W[k][k] : 0.f;
+      if (jdi[k] == 0.f) dinv[k] = 0.f;
       rhs[k] = (-pen[k] * P.limit_erp * P.inv_h - rel) * jdi[k];
       cfmrow[k] = 0.f;
       continue;
@@ -1135,9 +1154,8 @@ static UPKIE_NOINLINE void general_contact_solve(const SimParams& P, BodySolveIO
       cfmrow[k] = 0.f;
     }
   }
-  const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
   for (int it = 0; it < P.pgs_iterations; ++it) {
-    bool changed = false;
+    float res = 0.f;  // largest velocity-level row change of the sweep (Bullet's residual, see pgs_solve())
     for (int pos = 0; pos < n; ++pos) {
       const int k = pos < nlimit ? ((it & 1) ? pos : nlimit - 1 - pos) : pos;
       float jdv = 0.f;
@@ -1148,10 +1166,10 @@ static UPKIE_NOINLINE void general_contact_solve(const SimParams& P, BodySolveIO
       else if (kind[k] == 2) { lo = 0.f; hi = P.limit_max_impulse; }
       else { hi = io.mu * (wheel[k] >= 0 ? 1.f : P.body_mu_scale) * lam[partner[k]]; lo = -hi; }
       const float nl = fminf(fmaxf(sum, lo), hi);
-      changed = changed | (fabsf(nl - lam[k]) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+      res = fmaxf(res, fabsf(nl - lam[k]) * dinv[k]);
       lam[k] = nl;
     }
-    if (!changed) break;  // per robot (the packed solvers vote per warp)
+    if (res * res <= P.res_thr) break;  // per robot
   }
   // -- apply the total impulse
   for (int b = 0; b < 7; ++b)
@@ -1428,8 +1446,10 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
       }
     }
     const float cfmrow = P.cfm;  // m_cfm = cfm * jacDiagABInv
-    // Projected Gauss-Seidel, see physics_substep() for the exit rule
-    const float pgs_atol = P.pgs_rtol > 0.f ? 1e-9f : -1.f;
+    // Projected Gauss-Seidel with Bullet's residual exit rule, see pgs_solve() (sim_core.cuh)
+    float dinv[6];  // 1 / jacDiagABInv: turns an impulse change into the row's velocity change
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dinv[k] = W[k][k] + (k < 2 ? P.cfm : 0.f);
     // residual-form sweep of pgs_solve() (sim_core.cuh) with the six residuals as three (left, right) pairs:
     // r2[0] = (nL, nR), r2[1] = (t1L, t1R), r2[2] = (t2L, t2R); column k of the scaled matrix in the same pairing
     f2 Gc[6][3];
@@ -1460,11 +1480,11 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
 #pragma unroll
       for (int p = 0; p < 3; ++p) r2[p] = fma2(Gc[l][p], bc2(lam[l]), r2[p]);
     // One sweep = six row updates in Bullet's order: clamp the row's residual, push the change into all six
-    // residuals (three FFMA2). The exit test costs as much as a third of a sweep, so it runs on every second
-    // sweep only; robots standing on both wheels use all pgs_iterations sweeps anyway (their two lateral
-    // friction rows are nearly redundant and converge slowly), flying or rolling ones leave after a few.
-    auto sweep = [&](auto with_test) -> bool {
-      bool changed = false;
+    // residuals (three FFMA2), keep the largest velocity-level change of the sweep. A lane whose sweep stayed at or
+    // below Bullet's residual threshold is frozen (its later updates are no-ops) until the warp's last lane is done.
+    bool frozen = false;
+    auto sweep = [&]() -> float {
+      float res = 0.f;
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const float rk = k == 0 ? r2[0].x : k == 1 ? r2[0].y : k == 2 ? r2[1].x : k == 3 ? r2[2].x : k == 4 ? r2[1].y : r2[2].y;
@@ -1475,25 +1495,32 @@ UPKIE_HD void physics_substep_paired(const SimParams& P, RobotState& S, const fl
           const float hi = mu * lam[(k < 4) ? 0 : 1];
           nl = fminf(fmaxf(rk, -hi), hi);
         }
+        if (frozen) nl = lam[k];
         const float delta = nl - lam[k];
         const f2 d2 = bc2(delta);
 #pragma unroll
         for (int p = 0; p < 3; ++p) r2[p] = fma2(Gc[k][p], d2, r2[p]);
-        if (decltype(with_test)::value) changed = changed | (fabsf(delta) > P.pgs_rtol * fabsf(nl) + pgs_atol);
+        res = fmaxf(res, fabsf(delta) * dinv[k]);
         lam[k] = nl;
       }
-      return changed;
+      return res;
     };
-    for (int it = 0; it < P.pgs_iterations; it += 2) {
-      sweep(std::false_type());
-      if (it + 1 >= P.pgs_iterations) break;
-      const bool changed = sweep(std::true_type());
+    auto after_sweep = [&](float res, int it) {
+      const bool was_frozen = frozen;
+      frozen = frozen || (res * res <= P.res_thr);
 #ifdef UPKIE_PGS_STATS
-      if (!changed) { upkie_pgs_stats(it + 2); break; }
-      if (it + 2 >= P.pgs_iterations) upkie_pgs_stats(it + 3);
+      if (frozen && !was_frozen) upkie_pgs_stats(it + 1);
+      else if (!frozen && it + 1 == P.pgs_iterations) upkie_pgs_stats(it + 1);
 #else
-      if (!warp_any(changed)) break;
+      (void)was_frozen;
+      (void)it;
 #endif
+    };
+    // two sweeps per trip, one warp vote (see contact_solve_ten_rows)
+    for (int it = 0; it < P.pgs_iterations; it += 2) {
+      after_sweep(sweep(), it);
+      if (it + 1 < P.pgs_iterations) after_sweep(sweep(), it + 1);
+      if (!warp_any(!frozen)) break;
     }
     S.lam_n[0] = lam[0];
     S.lam_n[1] = lam[1];
