@@ -520,6 +520,30 @@ def other_workloads(torch, dev, model):
             torch.cuda.synchronize()
             return ev[0].elapsed_time(ev[k]) / k, float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(k)]))
 
+        def timed_graph(fn, k=48, reps=8):
+            """Device time per call with the launches replayed from a CUDA graph: at 4 096 problems a kernel is as
+            short as the Python / ctypes launch cadence (~10-20 us), which the event intervals above then measure
+            instead of the kernel. Returns None when the capture is not possible."""
+            try:
+                s = torch.cuda.Stream(device=dev)
+                s.wait_stream(torch.cuda.current_stream(dev))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    for i in range(k):
+                        fn(i)
+                torch.cuda.synchronize()
+                g.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / (k * reps)
+            except Exception:
+                return None
+
         n = 4096
         gen = torch.Generator(device=dev)
         gen.manual_seed(7)
@@ -531,6 +555,9 @@ def other_workloads(torch, dev, model):
         ms, med = timed(lambda i: env.sim.step_pendulum(acts[i % 8]))
         out["pendulum_4096"] = {"metric": "env-steps/sec", "value": n / (ms * 1e-3), "ms_per_step": ms,
                                 "kernel_ms_median": med, "workload": "BASELINE configs[1]"}
+        gms = timed_graph(lambda i: env.sim.step_pendulum(acts[i % 8]))
+        if gms:
+            out["pendulum_4096"].update({"graph_replay_ms_per_step": gms, "graph_replay_value": n / (gms * 1e-3)})
         env.close()
         for H in (16, 50):
             cfg = _abi.default_mpc_config()
@@ -543,6 +570,9 @@ def other_workloads(torch, dev, model):
             out[f"mpc_4096_h{H}"] = {"metric": "qp-solves/sec", "value": n / (ms * 1e-3), "ms_per_step": ms,
                                      "kernel_ms_median": med,
                                      "workload": "BASELINE configs[3]" + (" at the reference's default horizon" if H == 50 else "")}
+            gms = timed_graph(lambda i: mpc.step_tensors(xs[i % 8], vt, contact, 0.005))
+            if gms:
+                out[f"mpc_4096_h{H}"].update({"graph_replay_ms_per_step": gms, "graph_replay_value": n / (gms * 1e-3)})
     except Exception as exc:  # secondary lines must never take the headline down
         out["error"] = repr(exc)
     out["servos_65536_exact_mode"] = exact_mode_line()

@@ -19,7 +19,11 @@ struct HostSim {
   int scalar_legs = 0;  // 1: step with the scalar-leg substep instead of the paired one the kernels run
 };
 
-static bool any_fn(bool p) { return p; }
+// The warp vote of the kernels. g_vote_always: every vote says "some other lane still needs this" - the robot stays
+// in the PGS loops for all pgs_iterations trips, as a lane does whose warp-mates converge late; its result must not
+// change (per-lane freeze of Bullet's residual rule, sim_pair.cuh).
+static int g_vote_always = 0;
+static bool any_fn(bool p) { return g_vote_always ? true : p; }
 
 extern "C" {
 
@@ -42,6 +46,8 @@ void hostsim_reset(void* hv, int n, float* state, const float* init, const float
     state_to_row(S, state + size_t(i) * UPKIE_STATE_DIM);
   }
 }
+
+void hostsim_set_vote_always(int on) { g_vote_always = on ? 1 : 0; }
 
 void hostsim_set_scalar_legs(void* hv, int on) { static_cast<HostSim*>(hv)->scalar_legs = on ? 1 : 0; }
 
@@ -275,26 +281,38 @@ static void fill_mpc_params(const UpkieMpcConfig& c, MpcParams<T>& M) {
 template <typename T>
 static void hostsim_mpc_impl(const UpkieMpcConfig* c, int n, const double* x0, const double* v_target,
                              const uint8_t* contact, double dt, double* v_cmd, double* plan, uint8_t* found,
-                             int* iterations) {
+                             int* iterations, uint64_t* active = nullptr, int* work = nullptr) {
   MpcParams<T> M;
   fill_mpc_params(*c, M);
+  MpcParams<double> Md;
+  fill_mpc_params(*c, Md);
+  std::vector<T> tabv(size_t(M.N) * kMpcTabRow);
+  mpc_build_tables(Md, tabv.data());
+  const T* tab = tabv.data();
   std::vector<T> scratch(size_t(5) * M.N);
   for (int i = 0; i < n; ++i) {
     MpcScratch<T> sc{scratch.data(), 1};
     const T x[4] = {T(x0[4 * i]), T(x0[4 * i + 1]), T(x0[4 * i + 2]), T(x0[4 * i + 3])};
-    uint64_t up = 0, lo = 0;
+    // `active` ([2][n], in / out): warm start from the previous call's active sets, as k_mpc_step does
+    uint64_t up = active ? active[i] : 0, lo = active ? active[size_t(n) + i] : 0;
     T u0 = 0;
     // count iterations by running the solver with increasing caps is wasteful; replicate the loop here
     bool ok = false;
     int it = 0;
     for (; it < M.max_iterations; ++it) {
-      mpc_backward(M, x[0], T(v_target[i]), up, lo, sc);
+      if (work) {  // steps of the sweep in the explicit recursion / in the tabulated free tail (cost model)
+        const int kmax = mpc_last_bound(up | lo);
+        work[2 * i] += kmax + 1;
+        work[2 * i + 1] += M.N - 1 - kmax;
+      }
+      mpc_backward(M, tab, x[0], T(v_target[i]), up, lo, sc);
       uint64_t nu, nl;
-      mpc_forward(M, x, up, lo, sc, nu, nl, u0);
+      mpc_forward(M, tab, x, up, lo, sc, nu, nl, u0);
       if (nu == up && nl == lo) { ok = true; break; }
       up = nu; lo = nl;
     }
     if (iterations) iterations[i] = it + 1;
+    if (active) { active[i] = ok ? up : 0; active[size_t(n) + i] = ok ? lo : 0; }
     for (int k = 0; k < M.N; ++k) {
       double u = double(sc.at(k, 4));
       if (u > c->max_ground_accel) u = c->max_ground_accel;
@@ -314,6 +332,12 @@ void hostsim_mpc_step_f32(const UpkieMpcConfig* c, int n, const double* x0, cons
 void hostsim_mpc_step_f64(const UpkieMpcConfig* c, int n, const double* x0, const double* v_target, const uint8_t* contact,
                           double dt, double* v_cmd, double* plan, uint8_t* found, int* iterations) {
   hostsim_mpc_impl<double>(c, n, x0, v_target, contact, dt, v_cmd, plan, found, iterations);
+}
+// warm-started form: active[2][n] in / out (the kernel's warm start), work[n][2] += (explicit, tabulated) sweep steps
+void hostsim_mpc_step_warm_f32(const UpkieMpcConfig* c, int n, const double* x0, const double* v_target, const uint8_t* contact,
+                               double dt, double* v_cmd, double* plan, uint8_t* found, int* iterations, uint64_t* active,
+                               int* work) {
+  hostsim_mpc_impl<float>(c, n, x0, v_target, contact, dt, v_cmd, plan, found, iterations, active, work);
 }
 }
 

@@ -43,6 +43,7 @@ def lib():
         L.hostsim_reset.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp]
         L.hostsim_step_servos.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp, fp, C.POINTER(C.c_uint32)]
         L.hostsim_step_gyropod.argtypes = [C.c_void_p, C.c_int, fp, fp, C.c_int, fp, u8p]
+        L.hostsim_set_vote_always.argtypes = [C.c_int]
         L.hostsim_step_servos_rec.argtypes = [C.c_void_p, C.c_int, fp, fp, fp, fp, fp, fp]
         L.hostsim_substep.argtypes = [C.c_void_p, C.c_int, fp, fp]
         L.hostsim_spine_obs.argtypes = [C.c_void_p, C.c_int, fp, fp]

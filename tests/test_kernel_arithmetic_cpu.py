@@ -805,3 +805,42 @@ def test_external_forces_match_oracle(model, oracle_lib, local_mask):
             expect = (f4[i].sum(axis=0) + np.array([0.0, 0.0, -mass * cfg.gravity])) * 1e-5
             # O(h^2) slack: the momentum is read after the position update
             assert np.allclose(o2.energy(i)["linear_momentum"], expect, atol=1e-8, rtol=1e-4)
+
+
+def test_frozen_lanes_keep_bullets_result(model, oracle_lib):
+    """Bullet's residual exit rule per lane: a robot whose sweep met the threshold is frozen while
+    the rest of its warp finishes. With the warp vote forced to "somebody is still sweeping" the robot stays in the loop
+    for all 50 trips - its state must come out bit for bit as when it leaves on its own, for the six-row, the ten-row
+    and the scalar solvers; and with the threshold at 0 nobody leaves early."""
+    import hostsim_wrap
+
+    n = 96
+    st = random_states(n, seed=21).astype(np.float32)
+    st[:48] = at_joint_bounds(model, 48, seed=22)  # robots on a hip / knee bound: the ten-row solver
+    act = random_servo_actions(n, model, seed=23).astype(np.float32)
+    results = {}
+    for limits in (3, 1, 0):
+        for vote in (0, 1):
+            cfg = _abi.default_sim_config()
+            cfg.joint_limits = limits
+            hs = HostSim(model, cfg, n)
+            hs.set_state(st)
+            hostsim_wrap.lib().hostsim_set_vote_always(vote)
+            try:
+                for _ in range(3):
+                    hs.step_servos(act)
+            finally:
+                hostsim_wrap.lib().hostsim_set_vote_always(0)
+            results[(limits, vote)] = hs.state.copy()
+        np.testing.assert_array_equal(results[(limits, 0)], results[(limits, 1)])
+    # the threshold matters: all 50 sweeps give (slightly) different impulses, and still match the oracle run the same way
+    cfg0 = _abi.default_sim_config()
+    cfg0.solver_residual_threshold = 0.0
+    hs0, osim0 = HostSim(model, cfg0, n), oracle_lib.OracleSim(model, cfg0, n, threads=4)
+    hs0.set_state(st)
+    osim0.set_state(st.astype(np.float64))
+    hs0.step_servos(act)
+    osim0.step_servos(act.astype(np.float64))
+    assert np.abs(hs0.state[:, 19:25] - results[(3, 0)][:, 19:25]).max() > 0  # not the same iteration count
+    d = np.abs(hs0.state[:, :25].astype(np.float64) - osim0.get_state()[:, :25])
+    assert np.median(d[:, 19:25].max(axis=1)) < 5e-4

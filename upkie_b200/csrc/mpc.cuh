@@ -3,7 +3,9 @@
 // mpc.cuh -- batched MPC balancer: kernel + handle management.
 // One thread = one robot's horizon-N box-constrained LQ problem; the per-step
 // Riccati gains (5 N floats per robot) live in shared memory laid out
-// [5 N][blockDim] (conflict-free: consecutive robots hit consecutive banks).
+// [5 N][blockDim] (conflict-free: consecutive robots hit consecutive banks),
+// followed by the handle's free-tail tables (20 N floats, mpc_core.cuh), which
+// every block copies from global memory once.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -18,7 +20,8 @@
 
 namespace upkie_b200 {
 
-inline int make_mpc_params(const UpkieMpcConfig& c, MpcParams<float>& M, std::string& err) {
+template <typename Real>
+inline int make_mpc_params(const UpkieMpcConfig& c, MpcParams<Real>& M, std::string& err) {
   if (c.nb_timesteps < 1 || c.nb_timesteps > 64) {
     err = "mpc: nb_timesteps must be in [1, 64]";
     return UPKIE_B200_EINVAL;
@@ -28,23 +31,23 @@ inline int make_mpc_params(const UpkieMpcConfig& c, MpcParams<float>& M, std::st
     return UPKIE_B200_EINVAL;
   }
   // qpmpc WheeledInvertedPendulum discretisation (third-party, restated; see oracle/upkie_oracle.cpp MpcOracle)
-  const double T = c.sampling_period, g = c.gravity;
+  const double Ts = c.sampling_period, g = c.gravity;
   const double om = std::sqrt(g / c.leg_length);
-  const double ch = std::cosh(T * om), sh = std::sinh(T * om);
-  M.Ts = float(T);
-  M.ch = float(ch);
-  M.sho = float(sh / om);
-  M.osh = float(om * sh);
-  M.b0 = float(T * T / 2.0);
-  M.b1 = float(-ch / g + 1.0 / g);
-  M.b2 = float(T);
-  M.b3 = float(-om * sh / g);
-  M.w_u = float(c.stage_input_cost_weight);
-  M.w_x = float(c.stage_state_cost_weight);
-  M.w_T = float(c.terminal_cost_weight);
-  M.a_max = float(c.max_ground_accel);
-  M.v_max = float(c.max_ground_velocity);
-  M.fall_pitch = float(c.fall_pitch);
+  const double ch = std::cosh(Ts * om), sh = std::sinh(Ts * om);
+  M.Ts = Real(Ts);
+  M.ch = Real(ch);
+  M.sho = Real(sh / om);
+  M.osh = Real(om * sh);
+  M.b0 = Real(Ts * Ts / 2.0);
+  M.b1 = Real(-ch / g + 1.0 / g);
+  M.b2 = Real(Ts);
+  M.b3 = Real(-om * sh / g);
+  M.w_u = Real(c.stage_input_cost_weight);
+  M.w_x = Real(c.stage_state_cost_weight);
+  M.w_T = Real(c.terminal_cost_weight);
+  M.a_max = Real(c.max_ground_accel);
+  M.v_max = Real(c.max_ground_velocity);
+  M.fall_pitch = Real(c.fall_pitch);
   M.N = c.nb_timesteps;
   M.max_iterations = c.max_iterations > 0 ? c.max_iterations : 30;
   return 0;
@@ -55,6 +58,7 @@ struct MpcHandle {
   int n, device, block;
   MpcParams<float> M;
   float* plan = nullptr;      // [N][n] last optimal input sequence
+  float* tab = nullptr;       // [N][kMpcTabRow] free-tail tables (mpc_core.cuh), built in double precision at create
   uint64_t* active = nullptr;  // [2][n] warm-start active sets (upper, lower)
   size_t smem;
 };
@@ -63,8 +67,20 @@ constexpr uint32_t kMpcMagic = 0x55504D43u;
 __global__ void k_mpc_step(const __grid_constant__ MpcParams<float> M, int n, const float* __restrict__ x0_all,
                            const float* __restrict__ v_target, const uint8_t* __restrict__ floor_contact, float dt,
                            float* __restrict__ v_cmd, float* __restrict__ first_input, uint8_t* __restrict__ found,
-                           float* __restrict__ plan, uint64_t* __restrict__ active) {
+                           float* __restrict__ plan, uint64_t* __restrict__ active, const float* __restrict__ tab_g) {
   extern __shared__ float smem[];
+  float* tab = smem + size_t(5) * M.N * blockDim.x;
+  {
+    // 20 N floats = 5 N float4 (both 16 B aligned): all loads of a lane are issued before the first store, so the copy
+    // costs one L2 round trip instead of one per element (ncu: the dependent LDG -> STS pairs of the scalar loop were
+    // a quarter of the kernel's stall samples)
+    const float4* src = reinterpret_cast<const float4*>(tab_g);
+    float4* dst = reinterpret_cast<float4*>(tab);
+    const int n4 = M.N * (kMpcTabRow / 4);
+#pragma unroll 4
+    for (int k = threadIdx.x; k < n4; k += blockDim.x) dst[k] = __ldg(src + k);
+  }
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   MpcScratch<float> sc{smem + threadIdx.x, int(blockDim.x)};
@@ -73,7 +89,7 @@ __global__ void k_mpc_step(const __grid_constant__ MpcParams<float> M, int n, co
   // warm start: previous tick's active set (the receding horizon barely moves at 200 Hz)
   uint64_t up = active[i], lo = active[size_t(n) + i];
   float u0 = 0.f;
-  const bool ok = mpc_solve(M, x0, v_target[i], sc, u0, up, lo);
+  const bool ok = mpc_solve(M, tab, x0, v_target[i], sc, u0, up, lo);
   active[i] = ok ? up : 0ull;
   active[size_t(n) + i] = ok ? lo : 0ull;
   for (int k = 0; k < M.N; ++k) plan[size_t(k) * n + i] = fminf(fmaxf(sc.at(k, 4), -M.a_max), M.a_max);
@@ -108,6 +124,7 @@ inline void mpc_destroy_impl(void* p) {
   cudaSetDevice(h->device);
   cudaFree(h->plan);
   cudaFree(h->active);
+  cudaFree(h->tab);
   h->magic = 0;
   delete h;
 }
@@ -130,7 +147,7 @@ inline int mpc_create_impl(const UpkieMpcConfig& c, int n, int device, void** ou
   // 5 N floats of gains per robot in shared memory; keep blocks small so that
   // several fit per SM (227 KB) and the grid covers all 148 SMs at N = 4096
   h->block = 32;
-  h->smem = size_t(5) * h->M.N * h->block * sizeof(float);
+  h->smem = (size_t(5) * h->M.N * h->block + size_t(h->M.N) * kMpcTabRow) * sizeof(float);
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess && h->smem > 48 * 1024)
     e = cudaFuncSetAttribute(k_mpc_step, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem));
@@ -138,6 +155,15 @@ inline int mpc_create_impl(const UpkieMpcConfig& c, int n, int device, void** ou
   if (e == cudaSuccess) e = cudaMalloc(&h->active, size_t(2) * n * sizeof(uint64_t));
   if (e == cudaSuccess) e = cudaMemset(h->plan, 0, size_t(h->M.N) * n * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(h->active, 0, size_t(2) * n * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&h->tab, size_t(h->M.N) * kMpcTabRow * sizeof(float));
+  if (e == cudaSuccess) {
+    MpcParams<double> Md;
+    std::string e2;
+    make_mpc_params(c, Md, e2);
+    float host_tab[64 * kMpcTabRow];
+    mpc_build_tables(Md, host_tab);
+    e = cudaMemcpy(h->tab, host_tab, size_t(h->M.N) * kMpcTabRow * sizeof(float), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     err = std::string("mpc_create: ") + cudaGetErrorString(e);
     mpc_destroy_impl(h);
@@ -165,7 +191,7 @@ inline int mpc_step_impl(void* p, const float* x0, const float* v_target, const 
   cudaSetDevice(h->device);
   const int grid = (h->n + h->block - 1) / h->block;
   k_mpc_step<<<grid, h->block, h->smem, s>>>(h->M, h->n, x0, v_target, contact, dt, v_cmd, first_input, found,
-                                             h->plan, h->active);
+                                             h->plan, h->active, h->tab);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = cudaGetErrorString(e); return UPKIE_B200_ECUDA; }
   return 0;

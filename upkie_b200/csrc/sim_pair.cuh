@@ -1102,8 +1102,11 @@ static UPKIE_NOINLINE void general_contact_solve(const SimParams& P, BodySolveIO
       }
     }
   }
-  // -- Delassus matrix, one response per row
-  float W[kMaxRows][kMaxRows];
+  // -- Delassus matrix, one response per row. Rows padded to a multiple of four columns (zeros) and 16 B aligned: the
+  // row . impulse products of the sweeps below read them as 128-bit local-memory loads
+  constexpr int kPad = (kMaxRows + 3) / 4 * 4;
+  struct alignas(16) Quad { float x, y, z, w; };
+  alignas(16) float W[kMaxRows][kPad];
   float fb[7][6], g[6], dqd[6], ab[7][6];
   for (int l = 0; l < n; ++l) {
     for (int b = 0; b < 7; ++b)
@@ -1123,7 +1126,12 @@ static UPKIE_NOINLINE void general_contact_solve(const SimParams& P, BodySolveIO
       W[k][l] = wkl;
     }
   }
-  float rhs[kMaxRows], jdi[kMaxRows], cfmrow[kMaxRows], lam[kMaxRows], dinv[kMaxRows];
+  float rhs[kMaxRows], jdi[kMaxRows], cfmrow[kMaxRows], dinv[kMaxRows];
+  alignas(16) float lam[kPad];
+  const int n4 = (n + 3) & ~3;
+  for (int l = 0; l < kPad; ++l) lam[l] = 0.f;
+  for (int k = 0; k < n; ++k)
+    for (int l = n; l < n4; ++l) W[k][l] = 0.f;
   for (int k = 0; k < n; ++k) {
     lam[k] = 0.f;
     dinv[k] = W[k][k] + ((kind[k] == 0 && wheel[k] >= 0) ? P.cfm : 0.f);
@@ -1158,8 +1166,16 @@ static UPKIE_NOINLINE void general_contact_solve(const SimParams& P, BodySolveIO
     float res = 0.f;  // largest velocity-level row change of the sweep (Bullet's residual, see pgs_solve())
     for (int pos = 0; pos < n; ++pos) {
       const int k = pos < nlimit ? ((it & 1) ? pos : nlimit - 1 - pos) : pos;
-      float jdv = 0.f;
-      for (int l = 0; l < n; ++l) jdv += W[k][l] * lam[l];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four partial sums: no 22-deep dependent chain
+      {
+        const Quad* wr = reinterpret_cast<const Quad*>(W[k]);
+        const Quad* lv = reinterpret_cast<const Quad*>(lam);
+        for (int q = 0; q < n4 / 4; ++q) {
+          const Quad w4 = wr[q], l4 = lv[q];
+          a0 += w4.x * l4.x; a1 += w4.y * l4.y; a2 += w4.z * l4.z; a3 += w4.w * l4.w;
+        }
+      }
+      const float jdv = (a0 + a1) + (a2 + a3);
       const float sum = lam[k] + (rhs[k] - lam[k] * cfmrow[k] - jdv * jdi[k]);
       float lo, hi;
       if (kind[k] == 0) { lo = 0.f; hi = 1e10f; }
