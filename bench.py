@@ -704,7 +704,9 @@ def bench_env(args, torch, dist, dev, rank, world, model, K, W):
     counters = {"gathers": 0}
     pending = {"push": None}
     # UPKIE_BENCH_PUSH=now: the immediate in-kernel transports (rows leave at the END of the launch that produced them)
-    push_mode = os.environ.get("UPKIE_BENCH_PUSH", "kernel")  # kernel | deferred | now
+    # Default "now" since the second session of round 2: measured best at 2 and at 4 GPUs with the final kernels
+    # (profiles/r02_multigpu.md, last section: 20-step run at N = 4: now 2.15e9, deferred 2.05e9, kernel 1.84e9 env-steps/s)
+    push_mode = os.environ.get("UPKIE_BENCH_PUSH", "now")  # now | deferred | kernel
     deferred = push_mode == "deferred"
 
     def wait_for(cur, record):
