@@ -72,6 +72,20 @@ def test_urdf_round_trip_of_collision_shapes():
         assert m2.collision_link[8:] == ["left_lower_leg", "right_upper_leg", "right_upper_leg"]
     with pytest.raises(ValueError):
         m.add_collision_shape("torso", 0, "box", (0.1, 0.1, 0.1), [0, 0, 0])  # 11 + 8 > UPKIE_MAX_COLLISION_POINTS
+    # a URDF with more shapes than UpkieModel carries still loads: the surplus is reported and does not collide
+    m3 = Model.standard_upkie()
+    m3.add_collision_shape("left_lower_leg", 2, "box", (0.02, 0.02, 0.1), [0.0, 0.0, -0.08])
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "u.urdf")
+        write_urdf(m3, path, True)
+        text = open(path).read().replace(
+            '<link name="right_lower_leg">',
+            '<link name="right_lower_leg"><collision><origin xyz="0 0 0" rpy="0 0 0"/><geometry><box size="0.02 0.02 0.1"/>'
+            "</geometry></collision>")
+        open(path, "w").write(text)
+        with pytest.warns(UserWarning, match="ignored"):
+            m4 = Model.from_urdf(path)
+    assert len(m4.collision_body) == 16
 
 
 def test_fallen_robot_rests_on_its_torso(model, oracle_lib):

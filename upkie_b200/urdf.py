@@ -205,7 +205,12 @@ def load_urdf_model(urdf_path: str):
         link_rotation={name: T[name][0].copy() for name in body_of},
     )
     for name, b, kind, size, center, rot in shapes:
-        model.add_collision_shape(name, b, kind, size, center, rot)
+        try:
+            model.add_collision_shape(name, b, kind, size, center, rot)
+        except ValueError as exc:  # more points than UpkieModel carries: the remaining shapes do not collide
+            import warnings
+
+            warnings.warn(f"collision shape of link '{name}' ignored ({exc})")
     return model
 
 
