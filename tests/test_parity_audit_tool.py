@@ -96,3 +96,22 @@ def test_record_and_compare_on_the_reference_backend(audit, tmp_path):
         for k in [k for k in sys.modules if k.split(".")[0] in names]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_constants_report_flags_differences(audit):
+    """`parity_audit.py constants`: the report logic on a made-up PyBullet answer (a real one needs a machine that has
+    pybullet): every restated Bullet constant of UpkieSimConfig is looked up under its PyBullet name."""
+    from upkie_b200 import _abi
+
+    cfg = _abi.default_sim_config()
+    physics = {"numSolverIterations": 50, "solverResidualThreshold": 1e-7, "contactBreakingThreshold": 0.02,
+               "contactERP": 0.2, "erp": 0.2}
+    dynamics = {"left_wheel_tire": {"contactStiffness": 30000.0, "contactDamping": 1000.0, "lateralFriction": 1.0},
+                "torso": {"lateralFriction": 0.5}, "": {"linearDamping": 0.04, "angularDamping": 0.04}}
+    rows = {field: (ours, key, theirs) for field, ours, key, theirs in audit.constants_report(cfg, physics, dynamics)}
+    assert rows["solver_residual_threshold"] == (1e-7, "solverResidualThreshold", 1e-7)
+    assert rows["pgs_iterations"][2] == 50.0 and rows["contact_stiffness"][2] == 30000.0
+    assert rows["warmstarting_factor"][2] is None  # a key this PyBullet did not report
+    assert all(theirs is None or abs(theirs - ours) < 1e-9 for ours, _, theirs in rows.values())
+    for field, _, _ in audit.RESTATED_CONSTANTS:
+        assert hasattr(cfg, field)

@@ -24,6 +24,9 @@ depend on the observations), so that both backends receive bit-identical inputs:
   squat     hips / knees follow a slow squat, wheels as above
   torques   seeded random feedforward torques on every joint (kp = kd = 0), from a 1 m drop
 
+    # on the machine with a real pybullet: the third-party constants this repo restates from memory, next to Bullet's own
+    python tools/parity_audit.py constants [--urdf upkie.urdf]
+
 Differences to expect: the stand-in inertias of ``Model.standard_upkie()`` (pass ``--urdf`` with the real
 ``upkie_description`` URDF on the B200 side to remove them), Bullet's up-to-four-point tire manifold against one point
 here, and chaotic divergence after a touchdown.
@@ -165,6 +168,68 @@ def print_table(table: dict) -> None:
         print(f"{key:48s}" + "".join(f"{table[key].get(t, float('nan')):10.2e}" for t in ticks))
 
 
+# what UpkieSimConfig restates from memory of Bullet / PyBullet -> the key of pybullet.getPhysicsEngineParameters()
+# (or of getDynamicsInfo of a link) that holds the real value
+RESTATED_CONSTANTS = (
+    ("pgs_iterations", "numSolverIterations", "physics"),
+    ("solver_residual_threshold", "solverResidualThreshold", "physics"),
+    ("contact_breaking_threshold", "contactBreakingThreshold", "physics"),
+    ("body_contact_erp", "contactERP", "physics"),
+    ("joint_limit_erp", "erp", "physics"),
+    ("warmstarting_factor", "warmStartingFactor", "physics"),
+    ("linear_damping", "linearDamping", "dynamics"),
+    ("angular_damping", "angularDamping", "dynamics"),
+    ("contact_stiffness", "contactStiffness", "dynamics:left_wheel_tire"),
+    ("contact_damping", "contactDamping", "dynamics:left_wheel_tire"),
+    ("body_friction", "lateralFriction", "dynamics:torso"),
+)
+
+
+def constants_report(our_config, physics: dict, dynamics: dict) -> list:
+    """Rows ``(field of UpkieSimConfig, value here, PyBullet key, value there or None)``. ``physics`` is the dictionary
+    ``pybullet.getPhysicsEngineParameters()`` returns, ``dynamics`` maps a link name ("" = any) to a dictionary of the
+    named entries of ``pybullet.getDynamicsInfo`` (lateralFriction, contactStiffness, contactDamping, linearDamping...)."""
+    rows = []
+    for field, key, where in RESTATED_CONSTANTS:
+        ours = getattr(our_config, field)
+        if where == "physics":
+            theirs = physics.get(key)
+        else:
+            link = where.split(":", 1)[1] if ":" in where else ""
+            theirs = (dynamics.get(link) or dynamics.get("") or {}).get(key)
+        rows.append((field, float(ours), key, None if theirs is None else float(theirs)))
+    return rows
+
+
+def pybullet_constants(urdf: str = None):
+    """Load plane + robot in a DIRECT PyBullet like ``PyBulletBackend.__init__`` does (``pybullet_backend.py:100-125``:
+    no solver parameter is changed) and read the constants back."""
+    import pybullet
+    import pybullet_data
+
+    if urdf is None:
+        import upkie_description
+
+        urdf = upkie_description.URDF_PATH
+    client = pybullet.connect(pybullet.DIRECT)
+    pybullet.setAdditionalSearchPath(pybullet_data.getDataPath())
+    pybullet.loadURDF("plane.urdf")
+    robot = pybullet.loadURDF(urdf, basePosition=[0, 0, 0.6])
+    physics = dict(pybullet.getPhysicsEngineParameters())
+    names = ("mass", "lateralFriction", "localInertiaDiagonal", "localInertialPos", "localInertialOrn", "restitution",
+             "rollingFriction", "spinningFriction", "contactDamping", "contactStiffness", "bodyType", "collisionMargin")
+    dynamics = {}
+    for idx in range(-1, pybullet.getNumJoints(robot)):
+        link = "base" if idx < 0 else pybullet.getJointInfo(robot, idx)[12].decode()
+        info = pybullet.getDynamicsInfo(robot, idx)
+        dynamics[link] = {k: v for k, v in zip(names, info) if isinstance(v, (int, float))}
+        shapes = pybullet.getCollisionShapeData(robot, idx)
+        dynamics[link]["collisionShapes"] = len(shapes)
+    dynamics[""] = dynamics.get("base", {})
+    pybullet.disconnect(client)
+    return physics, dynamics
+
+
 def main(argv=None) -> int:
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -179,7 +244,21 @@ def main(argv=None) -> int:
     cmp_ = sub.add_parser("compare")
     cmp_.add_argument("a")
     cmp_.add_argument("b")
+    con = sub.add_parser("constants", help="print the Bullet / PyBullet constants restated in UpkieSimConfig next to a real PyBullet's")
+    con.add_argument("--urdf", default=None)
     args = ap.parse_args(argv)
+    if args.cmd == "constants":
+        from upkie_b200 import _abi
+
+        physics, dynamics = pybullet_constants(args.urdf)
+        print(f"{'UpkieSimConfig field':32s}{'here':>14s}  {'PyBullet':28s}{'there':>14s}")
+        for field, ours, key, theirs in constants_report(_abi.default_sim_config(), physics, dynamics):
+            there = "n/a" if theirs is None else f"{theirs:.6g}"
+            flag = "" if theirs is None or abs(theirs - ours) <= 1e-9 + 1e-6 * abs(ours) else "   <-- differs"
+            print(f"{field:32s}{ours:14.6g}  {key:28s}{there:>14s}{flag}")
+        links = sorted(k for k, v in dynamics.items() if k and v.get("collisionShapes"))
+        print("links with collision shapes:", ", ".join(links) or "none")
+        return 0
     if args.cmd == "record":
         dt = 1.0 / args.frequency
         backend, robot_state_cls, tau_max = make_backend(args.backend, dt, args.urdf)
