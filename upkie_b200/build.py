@@ -50,8 +50,8 @@ def is_stale() -> bool:
 # ---- exact-arithmetic build (test / measurement companion of the product library) ------------------------------------
 # Same sources WITHOUT --use_fast_math (IEEE division / sqrt / sincos, no flush-to-zero), device-buffer kernels only
 # (TILE=0: plain, extras, extras + limits); the other launchers are stubs that return cudaErrorNotSupported. Used by
-# tests/test_gpu_exact_mode.py and bench.py's `exact_mode` line together with pgs_tolerance = 0 (exactly 50 sweeps):
-# what the two shortcuts of the timed kernel cost in accuracy and buy in time.
+# tests/test_gpu_exact_mode.py and bench.py's `exact_mode` line: what the one shortcut of the timed kernel (fast-math)
+# costs in accuracy and buys in time.
 EXACT_LIB_PATH = os.path.join(_HERE, "libupkie_b200_exact.so")
 EXACT_SOURCES = ["upkie_b200.cu", "step_device.cu", "step_device_limits.cu", "exact_stubs.cu"]
 EXACT_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math"] + ["-DUPKIE_EXACT_BUILD=1"]
