@@ -23,6 +23,8 @@ depend on the observations), so that both backends receive bit-identical inputs:
   stand     legs held at zero by the position controller, wheels velocity-controlled along a slow sine
   squat     hips / knees follow a slow squat, wheels as above
   torques   seeded random feedforward torques on every joint (kp = kd = 0), from a 1 m drop
+  fall      no action at all from an initial pitch of 0.4 rad: the robot topples and comes to rest on whatever collision
+            shapes its links carry (body-ground contact rows; compare the resting base height and pitch)
 
     # on the machine with a real pybullet: the third-party constants this repo restates from memory, next to Bullet's own
     python tools/parity_audit.py constants [--urdf upkie.urdf]
@@ -43,7 +45,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 JOINTS = ("left_hip", "left_knee", "left_wheel", "right_hip", "right_knee", "right_wheel")
-SCENARIOS = ("stand", "squat", "torques")
+SCENARIOS = ("stand", "squat", "torques", "fall")
 
 
 def scenario_actions(name: str, ticks: int, dt: float, seed: int, tau_max) -> list:
@@ -53,6 +55,9 @@ def scenario_actions(name: str, ticks: int, dt: float, seed: int, tau_max) -> li
     actions = []
     for k in range(ticks):
         t = k * dt
+        if name == "fall":
+            actions.append({})  # step(action={}) is legal = no torques (tests/envs/backends/test_pybullet_backend.py:28-31)
+            continue
         servo = {}
         wheel_velocity = 2.0 * np.sin(2.0 * np.pi * 0.5 * t)  # rad/s
         squat = 0.3 * (1.0 - np.cos(2.0 * np.pi * 0.5 * t)) if name == "squat" else 0.0
@@ -117,7 +122,12 @@ def record(backend, robot_state_cls, actions: list, header: dict, out_path: str)
     from upkie_b200 import wire
 
     height = 1.0 if header["scenario"] == "torques" else 0.6
-    init = robot_state_cls(position_base_in_world=np.array([0.0, 0.0, height]))
+    kwargs = {}
+    if header["scenario"] == "fall":
+        from scipy.spatial.transform import Rotation
+
+        kwargs["orientation_base_in_world"] = Rotation.from_euler("y", 0.4)
+    init = robot_state_cls(position_base_in_world=np.array([0.0, 0.0, height]), **kwargs)
     with open(out_path, "wb") as f:
         f.write(wire.pack_dict(header))
         observation = backend.reset(init)
