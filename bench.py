@@ -190,6 +190,8 @@ def servos_config():
     # terminates: a third of the robots ends up resting on the floor for good (tools/r02/body_gate_stats.cpp), every warp
     # takes the general row solver every substep, and the figure measures a different workload. Both are reported.
     cfg.body_contacts = int(os.environ.get("UPKIE_BENCH_BODY_CONTACTS", "0"))
+    if os.environ.get("UPKIE_BENCH_MIN_BASE_HEIGHT"):  # developer knob: reset height of the workload (0.15 m)
+        cfg.min_base_height = float(os.environ["UPKIE_BENCH_MIN_BASE_HEIGHT"])
     if os.environ.get("UPKIE_BENCH_RESIDUAL_THRESHOLD"):  # developer knob: 0 = always 50 sweeps (Bullet's own default; PyBullet sets 1e-7)
         cfg.solver_residual_threshold = float(os.environ["UPKIE_BENCH_RESIDUAL_THRESHOLD"])
     return cfg
