@@ -316,6 +316,8 @@ def run_reference_arm(args, rank, world):
             "envs_per_step": n,
             "same_config_as_gpu_arm": n == 65536,
             "joint_limit_rows": int(servos_config().joint_limits),
+            "solver_residual_threshold": float(servos_config().solver_residual_threshold),
+            "body_contact_rows": int(servos_config().body_contacts) != 0,
         },
         "cpu_baseline": {
             "value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
